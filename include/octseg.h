@@ -1,0 +1,136 @@
+/*
+ * octseg.h -- C ABI of the B200-native U-Net hot path (liboctseg.so).
+ *
+ * The reference (NIH-NEI/oct-image-segmentation-models) has no FFI of its own: every
+ * FLOP of this path runs inside TensorFlow, reached through Keras objects.  Each entry
+ * point below therefore cites the reference *call site* it replaces; the Python-side
+ * mirror (oct_image_segmentation_models_b200/) binds these with ctypes and keeps the
+ * reference's Python surface (load_model_and_config / predict / evaluate_model /
+ * train_model / *Params) unchanged.  See INTEGRATION.md for the binding stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures
+ *     (`stream` is a cudaStream_t passed as void*, NULL = the handle's own stream);
+ *   - every call returns 0 on success, non-zero on failure; octseg_last_error()
+ *     returns a thread-local message for the last failure;
+ *   - a handle is bound to one CUDA device and is not thread-safe (one host thread
+ *     per GPU, as the reference's single-threaded loops are);
+ *   - host tensors are NHWC, row-major, owned by the caller.  On the device the
+ *     library keeps activations in an internal channel-blocked layout
+ *     [N][C/8][H][W][8]; callers never see it.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef OCTSEG_H_
+#define OCTSEG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct octseg_net octseg_net;
+
+/* Graph hyper-parameters == keys of the reference's model_config.json
+ * (reference: models/unet.py:62-104, models/base_model.py:27-33). */
+typedef struct octseg_config {
+  int32_t input_channels;
+  int32_t num_classes;
+  int32_t start_neurons;   /* default 8  */
+  int32_t pool_layers;     /* default 4  */
+  int32_t conv_layers;     /* default 2  */
+  int32_t enc_kh, enc_kw;  /* default 3,3 */
+  int32_t dec_kh, dec_kw;  /* default 2,2 */
+} octseg_config;
+
+enum { OCTSEG_FP32 = 0, OCTSEG_BF16 = 1 };          /* precision modes            */
+enum { OCTSEG_U8 = 0, OCTSEG_F32 = 1 };             /* host/device image dtypes   */
+
+/* ---- library / device ---------------------------------------------------------- */
+int32_t     octseg_version(void);
+const char *octseg_last_error(void);
+/* number of visible CUDA devices; 0 (not an error) when there is no driver/GPU */
+int32_t     octseg_device_count(void);
+
+/* ---- static graph description (no GPU needed) ----------------------------------- *
+ * Replaces introspection of the Keras model built by UNet.build_model()
+ * (reference models/unet.py:106-153): weight tensors in `model.get_weights()` order. */
+int32_t octseg_param_count(const octseg_config *cfg, int32_t *n_tensors);
+int32_t octseg_param_info(const octseg_config *cfg, int32_t index, char *name, int32_t name_cap,
+                          int32_t *ndim, int64_t shape[4], int32_t *trainable);
+
+/* ---- lifetime ------------------------------------------------------------------- *
+ * Replaces `model_class(**config).build_model()` (reference training/training.py:243-260)
+ * and the model object returned by tf.keras.models.load_model (common/utils.py:63-67). */
+int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precision, octseg_net **out);
+int32_t octseg_destroy(octseg_net *net);
+
+/* ---- weights (Keras get_weights()/set_weights() order, float32 host arrays) ------ */
+int32_t octseg_set_param(octseg_net *net, int32_t index, const float *host, int64_t count);
+int32_t octseg_get_param(octseg_net *net, int32_t index, float *host, int64_t count);
+
+/* ---- inference ------------------------------------------------------------------ *
+ * Replaces `loaded_model.predict(preprocess(x))`
+ * (reference prediction/prediction.py:75-81, evaluation/evaluation.py:129-135, with
+ * the x/255 preprocessing of models/unet.py:87-91 applied on the device).
+ *   images : [n,h,w,input_channels], dtype OCTSEG_U8 or OCTSEG_F32 (raw 0..255 values)
+ *   probs  : [n,h,w,num_classes] float32 softmax output, may be NULL
+ *   labels : [n,h,w] uint8 argmax (first max on ties, as np.argmax), may be NULL
+ * *_host: pageable or pinned host pointers, copies are part of the call.
+ * *_device: device pointers on the handle's device; asynchronous on `stream`. */
+int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
+                            int32_t w, float *probs, uint8_t *labels);
+int32_t octseg_predict_device(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
+                              int32_t w, float *probs, uint8_t *labels, void *stream);
+/* wait for all work queued on the handle's stream */
+int32_t octseg_synchronize(octseg_net *net);
+
+/* ---- training ------------------------------------------------------------------- *
+ * Replaces one step of `model.fit` after `model.compile(optimizer, loss)`
+ * (reference training/training.py:262-266, 401-407): forward with batch-statistics
+ * BatchNorm and Dropout(0.5), weighted categorical cross-entropy
+ * (common/custom_losses.py:27-35, mean over all pixels of the GLOBAL batch),
+ * backward, gradient all-reduce across ranks (MirroredStrategy, training.py:185),
+ * Keras-Adam update, BN moving-statistics update. */
+typedef struct octseg_train_config {
+  float   learning_rate;     /* 1e-3  */
+  float   beta_1, beta_2;    /* 0.9, 0.999 */
+  float   epsilon;           /* 1e-7 (outside the bias correction, Keras optimizer_v2) */
+  float   dropout_rate;      /* 0.5; 0 disables */
+  uint64_t dropout_seed;
+  int32_t global_batch;      /* samples over all ranks (loss denominator) */
+} octseg_train_config;
+
+int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc,
+                           const float *class_weights /* [num_classes] */);
+/* NCCL communicator for data-parallel training: `unique_id` is the 128-byte
+ * ncclUniqueId produced by octseg_comm_unique_id on rank 0 and broadcast by the host. */
+int32_t octseg_comm_unique_id(uint8_t id_out[128]);
+int32_t octseg_comm_init(octseg_net *net, const uint8_t unique_id[128], int32_t rank, int32_t world);
+/* images: [n,h,w,Cin] (this rank's shard), labels: [n,h,w] uint8 class ids,
+ * dropout_mask: NULL or [n, h/2^P, w/2^P, C_mid] uint8 {0,1} (injected for parity tests).
+ * loss_out receives this rank's contribution sum(per_pixel)/(global_batch*h*w). */
+int32_t octseg_train_step_host(octseg_net *net, const void *images, int32_t dtype, const uint8_t *labels,
+                               int32_t n, int32_t h, int32_t w, const uint8_t *dropout_mask,
+                               float *loss_out);
+int32_t octseg_train_step_device(octseg_net *net, const void *images, int32_t dtype, const uint8_t *labels,
+                                 int32_t n, int32_t h, int32_t w, const uint8_t *dropout_mask,
+                                 float *loss_out_device, void *stream);
+/* flat float32 gradient of the last step, Keras trainable-weight order (tests) */
+int32_t octseg_get_grad(octseg_net *net, int32_t index, float *host, int64_t count);
+
+/* ---- introspection for bench / tests -------------------------------------------- */
+/* number of kernels this library launched on the handle since creation */
+int64_t octseg_launch_count(octseg_net *net);
+/* 1 if conv layer `conv_index` runs on the tcgen05 path at (h,w) in the current mode */
+int32_t octseg_layer_uses_tensor_core(octseg_net *net, int32_t conv_index, int32_t h, int32_t w);
+/* run ONE conv block (index in Keras order) on caller data, for per-layer parity tests:
+ *   in  : float32 NHWC [n,h,w,cin] host;  out: float32 NHWC host [n,h_out,w_out,cout]
+ *   path: 0 = CUDA-core kernel, 1 = tcgen05 kernel (bf16 mode only) */
+int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t path, const float *in,
+                                int32_t n, int32_t h, int32_t w, float *out, float *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCTSEG_H_ */

@@ -1,0 +1,84 @@
+// Shared declarations for the liboctseg kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+
+namespace octseg {
+
+// ---------------------------------------------------------------------------------
+// Device activation layout: channel-blocked [N][C/8][H][W][8]  ("plane" = 8 channels).
+// A view may address a slice of planes inside a wider buffer (skip-concat written in
+// place: reference models/unet.py:52 concatenates [up, skip]; here both producers
+// write straight into their plane ranges of one buffer).
+// ---------------------------------------------------------------------------------
+template <typename T>
+struct View {
+  T *ptr;            // first element of plane 0 of image 0 of this view
+  int n, planes, h, w;
+  long long img_stride;   // elements between consecutive images
+};
+
+template <typename T>
+__host__ __device__ inline View<T> make_view(T *base, int n, int planes_total, int plane0, int planes,
+                                             int h, int w) {
+  View<T> v;
+  v.ptr = base + (long long)plane0 * h * w * 8;
+  v.n = n; v.planes = planes; v.h = h; v.w = w;
+  v.img_stride = (long long)planes_total * h * w * 8;
+  return v;
+}
+
+struct Vec8f { float v[8]; };
+
+__device__ __forceinline__ Vec8f load8(const float *p) {
+  Vec8f r;
+  float4 a = *reinterpret_cast<const float4 *>(p);
+  float4 b = *reinterpret_cast<const float4 *>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ Vec8f load8(const __nv_bfloat16 *p) {
+  Vec8f r;
+  uint4 u = *reinterpret_cast<const uint4 *>(p);
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void store8(float *p, const Vec8f &r) {
+  *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  *reinterpret_cast<float4 *>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16 *p, const Vec8f &r) {
+  uint4 u;
+  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+  *reinterpret_cast<uint4 *>(p) = u;
+}
+__device__ __forceinline__ Vec8f zero8() {
+  Vec8f r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
+  return r;
+}
+
+// error plumbing -------------------------------------------------------------------
+void set_error(const std::string &msg);
+#define OCTSEG_CUDA(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      octseg::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " +  \
+                        __FILE__ + ":" + std::to_string(__LINE__));                    \
+      return 1;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+}  // namespace octseg

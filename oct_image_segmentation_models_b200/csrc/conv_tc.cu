@@ -1,0 +1,531 @@
+// tcgen05 implicit-GEMM convolution for sm_100a.
+//
+// GEMM view of one conv block (reference models/unet.py:26-29, 41-44):
+//   D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * W[tap, cin, cout]
+//   M = 128 output pixels (an 8 px x 16 row tile), N = cout (padded to 16), K = taps*cin.
+//
+// B200-first design (this is not how cuDNN/CUTLASS stage a convolution):
+//   * activations live in HBM as [N][C/8][H][W][8]; ONE TMA box load brings the
+//     (8+kw-1) x (16+kh-1) halo tile of every 8-channel plane of the chunk into smem
+//     as [plane][row][px][8ch] -- TMA zero-fills out-of-image coordinates, which IS
+//     Keras "same" padding;
+//   * that layout is already the canonical no-swizzle K-major UMMA operand: 8 pixels x
+//     16 B form a core matrix, SBO = tile row pitch, LBO = plane pitch.  Every filter
+//     tap is the same smem tile viewed through a descriptor whose start address is
+//     shifted by (dy*pitch + dx*16) bytes, so the halo tile is read from L2/HBM once
+//     and never duplicated in smem (no im2col);
+//   * for Cin = 8 one K=16 MMA covers two taps (LBO = distance between the taps);
+//   * the x2 nearest up-sampling in front of the decoder 2x2 conv is folded into the
+//     weights: the four output parities are four column groups of one GEMM on the
+//     LOW-res tile and the epilogue scatters them (pixel shuffle) straight into the
+//     up-conv's plane range of the concat buffer;
+//   * accumulators sit in TMEM (double buffered), the epilogue applies the folded
+//     BatchNorm scale/shift + ReLU and stores one 16 B vector per pixel per plane.
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer (A halo tiles + packed weight stages)
+//   warp 1 lane 0 : MMA issuer (tcgen05.mma, commits to mbarriers)
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue (TMEM lane quarter = warp % 4)
+#include "conv_tc.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace octseg {
+
+// ----------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a broken pipeline must end in an error code, never in a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int *status, int code) {
+  const long long t0 = clock64();
+  for (uint32_t it = 1;; ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return true;
+    if ((it & 0x3FFu) == 0) {
+      // ~2 s at 2 GHz, or another role already gave up
+      if (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int *>(status) != 0) break;
+    }
+  }
+  atomicCAS(status, 0, code);
+  return false;
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                 "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (sm_100 "version 1").
+//   core matrix = 8 rows x 16 B, rows 16 B apart; SBO = bytes between 8-row groups,
+//   LBO = bytes between the two 8-element K halves of one K=16 step.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+constexpr int kMaxStages = 8;
+
+struct __align__(8) TcBarriers {
+  uint64_t a_full[kMaxStages], a_empty[kMaxStages];
+  uint64_t b_full[kMaxStages], b_empty[kMaxStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ void decode_tile(const TcConvParams &p, int tile, int &n_tile, int &tx,
+                                            int &ty, int &img) {
+  n_tile = tile % p.n_tiles_n;
+  int t = tile / p.n_tiles_n;
+  tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  ty = t % p.tiles_y;
+  img = t / p.tiles_y;
+}
+
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ TcConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_stride = (p.a_stage_bytes + 127u) & ~127u;
+  const uint32_t b_stride = (p.b_stage_bytes + 127u) & ~127u;
+  uint8_t *a_smem = smem;
+  uint8_t *b_smem = smem + (size_t)a_stride * p.a_stages;
+  TcBarriers *bars = reinterpret_cast<TcBarriers *>(b_smem + (size_t)b_stride * p.b_stages);
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)p.n_cols) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
+        int n_tile, tx, ty, img;
+        decode_tile(p, tile, n_tile, tx, ty, img);
+        const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.wpack) +
+                              (size_t)n_tile * p.cin_chunks * p.ksteps * 32u * p.n_cols;
+        for (int ch = 0; ok && ch < p.cin_chunks; ++ch) {
+          ok = mbar_wait(smem_u32(&bars->a_empty[as]), aph ^ 1u, p.status, 1);
+          if (!ok) break;
+          const uint32_t afull = smem_u32(&bars->a_full[as]);
+          mbar_expect_tx(afull, p.a_stage_bytes);
+          tma_load_4d(smem_u32(a_smem + (size_t)as * a_stride), &tmap_a, afull,
+                      (tx * kTcTileW - p.pad_x) * 8, ty * kTcTileH - p.pad_y, ch * p.planes_per_chunk, img);
+          if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+          for (int g = 0; g < p.ksteps; g += p.bgroup) {
+            ok = mbar_wait(smem_u32(&bars->b_empty[bs]), bph ^ 1u, p.status, 2);
+            if (!ok) break;
+            const uint32_t bfull = smem_u32(&bars->b_full[bs]);
+            mbar_expect_tx(bfull, p.b_stage_bytes);
+            bulk_load(smem_u32(b_smem + (size_t)bs * b_stride),
+                      wsrc + ((size_t)ch * p.ksteps + g) * 32u * p.n_cols, p.b_stage_bytes, bfull);
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_cols >> 3) << 17) |
+                             ((128u >> 4) << 24);
+      const uint32_t sbo_a = (uint32_t)p.box_w * 16u;
+      const uint32_t lbo_b = (uint32_t)p.n_cols * 16u;
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, accph = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
+        ok = mbar_wait(smem_u32(&bars->acc_empty[acc]), accph ^ 1u, p.status, 3);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_cols);
+        for (int ch = 0; ok && ch < p.cin_chunks; ++ch) {
+          ok = mbar_wait(smem_u32(&bars->a_full[as]), aph, p.status, 4);
+          if (!ok) break;
+          const uint32_t a_base = smem_u32(a_smem + (size_t)as * a_stride);
+          for (int g = 0; g < p.ksteps; g += p.bgroup) {
+            ok = mbar_wait(smem_u32(&bars->b_full[bs]), bph, p.status, 5);
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(b_smem + (size_t)bs * b_stride);
+            for (int s = 0; s < p.bgroup; ++s) {
+              const int ks = g + s;
+              const uint64_t da = make_desc(a_base + p.a_off[ks], p.a_lbo[ks], sbo_a);
+              const uint64_t db = make_desc(b_base + (uint32_t)s * 32u * p.n_cols, lbo_b, 128u);
+              umma_bf16(d_tmem, da, db, idesc, (ch | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&bars->b_empty[bs]));
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+          }
+          umma_commit(smem_u32(&bars->a_empty[as]));
+          if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+        }
+        umma_commit(smem_u32(&bars->acc_full[acc]));
+        if (++acc == 2) { acc = 0; accph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int m = q * 32 + lane;            // GEMM row == TMEM lane
+    const int r = m >> 3, px = m & 7;       // tile row / px
+    int acc = 0;
+    uint32_t accph = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
+      int n_tile, tx, ty, img;
+      decode_tile(p, tile, n_tile, tx, ty, img);
+      ok = mbar_wait(smem_u32(&bars->acc_full[acc]), accph, p.status, 6);
+      if (!ok) break;
+      tc_fence_after();
+      const int y = ty * kTcTileH + r, x = tx * kTcTileW + px;
+      const bool inside = (y < p.h) && (x < p.w);
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_cols);
+      for (int j = 0; j < p.n_cols; j += 8) {
+        const int col = n_tile * p.n_cols + j;   // warp-uniform
+        if (col >= p.cols_valid) break;
+        uint32_t v[8];
+        tmem_ld8(t_base + (uint32_t)j, v);
+        tmem_ld_wait();
+        if (inside) {
+          int co0, oy, ox;
+          if (p.mode == 0) { co0 = col; oy = y; ox = x; }
+          else {
+            const int par = col / p.cout;
+            co0 = col - par * p.cout;
+            oy = 2 * y + (par >> 1);
+            ox = 2 * x + (par & 1);
+          }
+          Vec8f o;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float f = fmaf(__uint_as_float(v[k]), __ldg(p.scale + co0 + k), __ldg(p.shift + co0 + k));
+            o.v[k] = p.relu ? fmaxf(f, 0.f) : f;
+          }
+          __nv_bfloat16 *dst = p.out + (long long)img * p.out_img_stride +
+                               (((long long)(co0 >> 3) * p.out_h + oy) * p.out_w + ox) * 8;
+          store8(dst, o);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
+      if (++acc == 2) { acc = 0; accph ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------
+static inline int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w) {
+  if (cin % 8 || cout % 8) return false;
+  const int cg = cin / 8;
+  if (cg != 1 && (cg & 1)) return false;
+  if (cg > 8 && cg % 8) return false;
+  if (kh < 1 || kw < 1 || kh > 3 || kw > 3) return false;
+  if (cg == 1 && kh * kw == 1) return false;
+  // (h, w) is the GEMM-row grid (the low-res grid for the up-conv)
+  if (h < kTcTileH || w < kTcTileW) return false;
+  (void)ups;
+  return true;
+}
+
+int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g) {
+  std::memset(g, 0, sizeof(*g));
+  g->kh = kh; g->kw = kw; g->cin = cin; g->cout = cout; g->ups = ups;
+  const int pt = (kh - 1) / 2, pl = (kw - 1) / 2;
+  if (!ups) {
+    g->dy_min = -pt; g->dy_max = kh - 1 - pt; g->dx_min = -pl; g->dx_max = kw - 1 - pl;
+  } else {
+    g->dy_min = floordiv2(0 - pt); g->dy_max = floordiv2(1 + kh - 1 - pt);
+    g->dx_min = floordiv2(0 - pl); g->dx_max = floordiv2(1 + kw - 1 - pl);
+  }
+  const int nty = g->dy_max - g->dy_min + 1, ntx = g->dx_max - g->dx_min + 1;
+  g->box_h = kTcTileH + nty - 1;
+  g->box_w = kTcTileW + ntx - 1;
+  const int cg = cin / 8;
+  g->planes_per_chunk = std::min(cg, 8);
+  g->cin_chunks = cg / g->planes_per_chunk;
+  const int cols = ups ? 4 * cout : cout;
+  g->cols_valid = cols;
+  const int cols_pad = (cols + 15) / 16 * 16;
+  int nc = 256;
+  while (cols_pad % nc) nc >>= 1;
+  g->n_cols = nc;
+  g->n_tiles_n = cols_pad / nc;
+  int ks = 0;
+  if (g->planes_per_chunk == 1) {
+    // pair taps in raster order (byte offsets increase, so LBO stays positive)
+    std::vector<std::pair<int, int>> taps;
+    for (int ty = 0; ty < nty; ++ty)
+      for (int tx = 0; tx < ntx; ++tx) taps.push_back({ty, tx});
+    size_t i = 0;
+    if (taps.size() & 1) {
+      // odd count: first step = (zero-weight dummy, tap0) is impossible (nothing before
+      // tap 0), so put the dummy in front of the LAST tap: (last-1 position, last)
+      for (; i + 2 < taps.size(); i += 2) {
+        g->half_ty[ks][0] = taps[i].first; g->half_tx[ks][0] = taps[i].second; g->half_pl[ks][0] = 0;
+        g->half_ty[ks][1] = taps[i + 1].first; g->half_tx[ks][1] = taps[i + 1].second; g->half_pl[ks][1] = 0;
+        ++ks;
+      }
+      const auto last = taps.back();
+      int dty = last.first, dtx = last.second - 1;
+      if (dtx < 0) { dtx = last.second; dty = last.first - 1; }
+      if (dty < 0) return 1;
+      g->half_ty[ks][0] = -1 - dty; g->half_tx[ks][0] = dtx; g->half_pl[ks][0] = 0;   // dummy (encoded ty<0)
+      g->half_ty[ks][1] = last.first; g->half_tx[ks][1] = last.second; g->half_pl[ks][1] = 0;
+      ++ks;
+    } else {
+      for (; i < taps.size(); i += 2) {
+        g->half_ty[ks][0] = taps[i].first; g->half_tx[ks][0] = taps[i].second; g->half_pl[ks][0] = 0;
+        g->half_ty[ks][1] = taps[i + 1].first; g->half_tx[ks][1] = taps[i + 1].second; g->half_pl[ks][1] = 0;
+        ++ks;
+      }
+    }
+  } else {
+    for (int ty = 0; ty < nty; ++ty)
+      for (int tx = 0; tx < ntx; ++tx)
+        for (int jj = 0; jj < g->planes_per_chunk / 2; ++jj) {
+          for (int hf = 0; hf < 2; ++hf) {
+            g->half_ty[ks][hf] = ty; g->half_tx[ks][hf] = tx; g->half_pl[ks][hf] = 2 * jj + hf;
+          }
+          ++ks;
+        }
+  }
+  if (ks > kTcMaxKSteps) return 1;
+  g->ksteps = ks;
+  g->bgroup = (ks * 32 * nc <= 32768) ? ks : g->planes_per_chunk / 2;
+  if (ks % g->bgroup) return 1;
+  return 0;
+}
+
+static inline uint16_t f2bf(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+  u += 0x7fffu + ((u >> 16) & 1u);   // round to nearest even
+  return (uint16_t)(u >> 16);
+}
+
+void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> *out) {
+  const int pt = (g.kh - 1) / 2, pl = (g.kw - 1) / 2;
+  const size_t per_step = (size_t)2 * g.n_cols * 8;
+  out->assign((size_t)g.n_tiles_n * g.cin_chunks * g.ksteps * per_step, 0);
+  for (int nt = 0; nt < g.n_tiles_n; ++nt)
+    for (int ch = 0; ch < g.cin_chunks; ++ch)
+      for (int s = 0; s < g.ksteps; ++s)
+        for (int hf = 0; hf < 2; ++hf) {
+          if (g.half_ty[s][hf] < 0) continue;   // dummy half: zero weights
+          const int dy = g.half_ty[s][hf] + g.dy_min, dx = g.half_tx[s][hf] + g.dx_min;
+          for (int n = 0; n < g.n_cols; ++n) {
+            const int col = nt * g.n_cols + n;
+            if (col >= g.cols_valid) continue;
+            for (int kk = 0; kk < 8; ++kk) {
+              const int ci = (ch * g.planes_per_chunk + g.half_pl[s][hf]) * 8 + kk;
+              float val = 0.f;
+              if (!g.ups) {
+                const int a = dy + pt, b = dx + pl;
+                val = w[(((size_t)a * g.kw + b) * g.cin + ci) * g.cout + col];
+              } else {
+                const int par = col / g.cout, co = col % g.cout;
+                const int py = par >> 1, px = par & 1;
+                for (int a = 0; a < g.kh; ++a)
+                  for (int b = 0; b < g.kw; ++b)
+                    if (floordiv2(py + a - pt) == dy && floordiv2(px + b - pl) == dx)
+                      val += w[(((size_t)a * g.kw + b) * g.cin + ci) * g.cout + co];
+              }
+              (*out)[(((size_t)(nt * g.cin_chunks + ch) * g.ksteps + s) * 2 + hf) * g.n_cols * 8 +
+                     (size_t)n * 8 + kk] = f2bf(val);
+            }
+          }
+        }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, size_t *smem_bytes) {
+  TcConvParams &p = *pp;
+  std::memset(&p, 0, sizeof(p));
+  p.n = n; p.h = h; p.w = w;
+  p.tiles_x = (w + kTcTileW - 1) / kTcTileW;
+  p.tiles_y = (h + kTcTileH - 1) / kTcTileH;
+  p.n_tiles_n = g.n_tiles_n;
+  p.num_tiles = n * p.tiles_x * p.tiles_y * p.n_tiles_n;
+  p.cin_chunks = g.cin_chunks;
+  p.planes_per_chunk = g.planes_per_chunk;
+  p.ksteps = g.ksteps;
+  p.bgroup = g.bgroup;
+  p.n_cols = g.n_cols;
+  p.cols_valid = g.cols_valid;
+  p.pad_y = -g.dy_min; p.pad_x = -g.dx_min;
+  p.box_w = g.box_w; p.box_h = g.box_h;
+  const uint32_t pitch = (uint32_t)g.box_w * 16u;
+  const uint32_t plane = pitch * (uint32_t)g.box_h;
+  p.a_stage_bytes = plane * (uint32_t)g.planes_per_chunk;
+  p.b_stage_bytes = (uint32_t)g.bgroup * 32u * (uint32_t)g.n_cols;
+  for (int s = 0; s < g.ksteps; ++s) {
+    uint32_t off[2];
+    for (int hf = 0; hf < 2; ++hf) {
+      int ty = g.half_ty[s][hf];
+      if (ty < 0) ty = -1 - ty;   // dummy half: valid in-tile address, zero weights
+      off[hf] = (uint32_t)g.half_pl[s][hf] * plane + (uint32_t)ty * pitch + (uint32_t)g.half_tx[s][hf] * 16u;
+    }
+    if (off[1] <= off[0]) { set_error("tc plan: non-positive LBO"); return 1; }
+    p.a_off[s] = off[0];
+    p.a_lbo[s] = off[1] - off[0];
+  }
+  const uint32_t a_stride = (p.a_stage_bytes + 127u) & ~127u, b_stride = (p.b_stage_bytes + 127u) & ~127u;
+  const size_t budget = 200 * 1024;
+  p.b_stages = 4;
+  p.a_stages = 4;
+  while (p.b_stages > 2 && (size_t)p.b_stages * b_stride > budget / 2) --p.b_stages;
+  while (p.a_stages > 1 &&
+         (size_t)p.a_stages * a_stride + (size_t)p.b_stages * b_stride + sizeof(TcBarriers) + 1024 > budget)
+    --p.a_stages;
+  *smem_bytes = (size_t)p.a_stages * a_stride + (size_t)p.b_stages * b_stride + sizeof(TcBarriers) + 1024;
+  if (*smem_bytes > 227 * 1024) { set_error("tc plan: smem budget exceeded"); return 1; }
+  p.mode = g.ups ? 1 : 0;
+  p.cout = g.cout;
+  return 0;
+}
+
+int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int w,
+                 const __nv_bfloat16 *wpack_dev, const float *scale, const float *shift, int relu,
+                 View<__nv_bfloat16> out, int *status_dev, TcPlan *plan) {
+  TcConvParams &p = plan->p;
+  if (tc_fill_params(g, n, h, w, &p, &plan->smem_bytes)) return 1;
+  p.relu = relu;
+  p.scale = scale; p.shift = shift;
+  p.out = out.ptr; p.out_img_stride = out.img_stride; p.out_h = out.h; p.out_w = out.w;
+  p.wpack = wpack_dev;
+  p.status = status_dev;
+
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return 1; }
+  const int cg = g.cin / 8;
+  cuuint64_t dims[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)cg, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)cg * h * w * 16};
+  cuuint32_t box[4] = {(cuuint32_t)g.box_w * 8, (cuuint32_t)g.box_h, (cuuint32_t)g.planes_per_chunk, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&plan->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16 *>(in), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return 1; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  plan->grid = std::min(p.num_tiles, sms);
+  plan->valid = true;
+  return 0;
+}
+
+int tc_launch(const TcPlan &plan, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    OCTSEG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_tc_kernel<<<plan.grid, 256, plan.smem_bytes, st>>>(plan.tmap, plan.p);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace octseg

@@ -1,0 +1,72 @@
+// tcgen05 implicit-GEMM convolution ("tap-shifted descriptors over one TMA halo tile").
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+#include <vector>
+
+namespace octseg {
+
+constexpr int kTcMaxKSteps = 40;   // k-steps (K=16 each) per input-channel chunk
+constexpr int kTcTileW = 8;        // output tile: 8 px wide x 16 rows = 128 GEMM rows
+constexpr int kTcTileH = 16;
+
+// Kernel parameters (passed by value as __grid_constant__).
+struct TcConvParams {
+  int n, h, w;                 // GEMM-row grid (== input grid; the low-res grid for up-conv)
+  int tiles_x, tiles_y, n_tiles_n, num_tiles;
+  int cin_chunks;              // number of input-channel chunks
+  int planes_per_chunk;        // 8-channel planes per chunk
+  int ksteps;                  // MMA k-steps per chunk
+  int bgroup;                  // k-steps per weight stage
+  int n_cols;                  // MMA N per n-tile (multiple of 16, <= 256)
+  int cols_valid;              // total valid GEMM columns over all n-tiles
+  int pad_y, pad_x;            // halo before (rows / px)
+  int box_w, box_h;            // halo tile size in px / rows
+  int a_stages, b_stages;
+  uint32_t a_stage_bytes, b_stage_bytes;
+  uint32_t a_off[kTcMaxKSteps];   // byte offset of the k-step's first 8-channel half
+  uint32_t a_lbo[kTcMaxKSteps];   // byte distance to its second half
+  // epilogue
+  int mode;                    // 0: plain NHWC-blocked store, 1: 2x2 pixel-shuffle store (up-conv)
+  int cout;                    // channels per parity (mode 1) or total (mode 0)
+  int relu;
+  const float *scale, *shift;  // [cout]
+  __nv_bfloat16 *out;          // plane 0 of image 0 of the destination view
+  long long out_img_stride;    // elements
+  int out_h, out_w;
+  const __nv_bfloat16 *wpack;  // packed weights [n_tile][chunk][kstep][2][n_cols][8]
+  int *status;                 // device word: non-zero = pipeline timeout code
+};
+
+// Host-side plan for one conv block at one (n,h,w).
+struct TcPlan {
+  bool valid = false;
+  TcConvParams p{};
+  CUtensorMap tmap{};
+  size_t smem_bytes = 0;
+  int grid = 0;
+};
+
+// Describes how GEMM K and N map to taps / channels; shared by the weight packer and
+// the kernel's A-descriptor table.
+struct TcGeometry {
+  int kh, kw, cin, cout, ups;          // conv block
+  int dy_min, dy_max, dx_min, dx_max;  // low-res tap range
+  int planes_per_chunk, cin_chunks, ksteps, n_cols, n_tiles_n, cols_valid, bgroup;
+  int box_w, box_h;
+  // per k-step, per half: tap (dy,dx relative to dy_min/dx_min) and plane within chunk; tap -1 = zero
+  int half_ty[kTcMaxKSteps][2], half_tx[kTcMaxKSteps][2], half_pl[kTcMaxKSteps][2];
+};
+
+bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w);
+int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g);
+// packs fp32 HWIO weights into the bf16 smem image the kernel streams (host memory)
+void tc_pack_weights(const TcGeometry &g, const float *w_hwio, std::vector<uint16_t> *out);
+// pure host part of the plan (no CUDA driver needed): tiling, stage sizes, A-descriptor table
+int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *p, size_t *smem_bytes);
+int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int w,
+                 const __nv_bfloat16 *wpack_dev, const float *scale, const float *shift, int relu,
+                 View<__nv_bfloat16> out, int *status_dev, TcPlan *plan);
+int tc_launch(const TcPlan &plan, cudaStream_t st);
+
+}  // namespace octseg

@@ -1,0 +1,112 @@
+// Host-only emulation of conv_tc_kernel's address arithmetic: builds the smem halo tile the
+// TMA box would deliver, reads it back through the (a_off, LBO, SBO) descriptor table and the
+// packed-weight image exactly as the UMMA would, and compares with a direct convolution.
+// Validates geometry + weight packing + epilogue indexing without a GPU.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+#include "../conv_tc.cuh"
+
+using namespace octseg;
+namespace octseg { void set_error(const std::string &m) { fprintf(stderr, "error: %s\n", m.c_str()); } }
+
+static float bf2f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+static uint16_t f2bf(float f) { uint32_t u; memcpy(&u, &f, 4); u += 0x7fffu + ((u >> 16) & 1u); return (uint16_t)(u >> 16); }
+
+static int run(int kh, int kw, int cin, int cout, int ups, int n, int h, int w) {
+  TcGeometry g;
+  if (tc_make_geometry(kh, kw, cin, cout, ups, &g)) { printf("geometry failed\n"); return 1; }
+  TcConvParams p; size_t smem;
+  if (tc_fill_params(g, n, h, w, &p, &smem)) return 1;
+  std::mt19937 rng(1);
+  std::uniform_real_distribution<float> U(-1, 1);
+  std::vector<float> wt((size_t)kh * kw * cin * cout);
+  for (auto &v : wt) v = U(rng);
+  std::vector<uint16_t> x((size_t)n * cin * h * w);   // blocked [n][cg][h][w][8]
+  for (auto &v : x) v = f2bf(U(rng));
+  std::vector<uint16_t> wp;
+  tc_pack_weights(g, wt.data(), &wp);
+  const int oh = ups ? 2 * h : h, ow = ups ? 2 * w : w, cg = cin / 8;
+  std::vector<double> out((size_t)n * oh * ow * cout, 1e30), ref((size_t)n * oh * ow * cout, 0);
+  // reference (double, bf16 inputs, fp32 weights)
+  const int pt = (kh - 1) / 2, pl = (kw - 1) / 2;
+  for (int b = 0; b < n; ++b) for (int y = 0; y < oh; ++y) for (int xx = 0; xx < ow; ++xx)
+    for (int co = 0; co < cout; ++co) {
+      double acc = 0;
+      for (int a = 0; a < kh; ++a) for (int c = 0; c < kw; ++c) {
+        int iy = y + a - pt, ix = xx + c - pl;
+        if (iy < 0 || iy >= oh || ix < 0 || ix >= ow) continue;
+        if (ups) { iy >>= 1; ix >>= 1; }
+        for (int ci = 0; ci < cin; ++ci)
+          acc += (double)bf2f(x[((((size_t)b * cg + ci / 8) * h + iy) * w + ix) * 8 + (ci & 7)]) *
+                 wt[(((size_t)a * kw + c) * cin + ci) * cout + co];
+      }
+      ref[(((size_t)b * oh + y) * ow + xx) * cout + co] = acc;
+    }
+  // emulated kernel
+  std::vector<uint8_t> stage(p.a_stage_bytes + 4096, 0xFF);
+  for (int tile = 0; tile < p.num_tiles; ++tile) {
+    int n_tile = tile % p.n_tiles_n, t = tile / p.n_tiles_n;
+    int tx = t % p.tiles_x; t /= p.tiles_x; int ty = t % p.tiles_y; int img = t / p.tiles_y;
+    std::vector<double> D((size_t)128 * p.n_cols, 0.0);
+    for (int ch = 0; ch < p.cin_chunks; ++ch) {
+      // TMA box: dims (W*8, H, CG, N), start ((tx*8-pad_x)*8, ty*16-pad_y, ch*CGC, img)
+      uint16_t *s16 = reinterpret_cast<uint16_t *>(stage.data());
+      for (int pc = 0; pc < p.planes_per_chunk; ++pc) for (int r = 0; r < p.box_h; ++r) for (int e = 0; e < p.box_w * 8; ++e) {
+        int gx = (tx * kTcTileW - p.pad_x) * 8 + e, gy = ty * kTcTileH - p.pad_y + r, gp = ch * p.planes_per_chunk + pc;
+        uint16_t v = 0;
+        if (gx >= 0 && gx < w * 8 && gy >= 0 && gy < h) v = x[(((size_t)img * cg + gp) * h + gy) * w * 8 + gx];
+        s16[((size_t)pc * p.box_h + r) * p.box_w * 8 + e] = v;
+      }
+      for (int ks = 0; ks < p.ksteps; ++ks) {
+        const uint16_t *bbase = wp.data() + ((size_t)(n_tile * p.cin_chunks + ch) * p.ksteps + ks) * 2 * p.n_cols * 8;
+        for (int m = 0; m < 128; ++m) for (int k = 0; k < 16; ++k) {
+          size_t aoff = p.a_off[ks] + (size_t)(k / 8) * p.a_lbo[ks] + (size_t)(m / 8) * p.box_w * 16 + (m % 8) * 16 + (k % 8) * 2;
+          if (aoff + 2 > p.a_stage_bytes) { printf("A read out of stage: ks %d m %d k %d off %zu\n", ks, m, k, aoff); return 1; }
+          float av = bf2f(*reinterpret_cast<uint16_t *>(stage.data() + aoff));
+          for (int nn = 0; nn < p.n_cols; ++nn) {
+            size_t boff = (size_t)(k / 8) * p.n_cols * 16 + (size_t)(nn / 8) * 128 + (nn % 8) * 16 + (k % 8) * 2;
+            D[(size_t)m * p.n_cols + nn] += (double)av * bf2f(bbase[boff / 2]);
+          }
+        }
+      }
+    }
+    for (int m = 0; m < 128; ++m) {
+      int r = m >> 3, px = m & 7, y = ty * kTcTileH + r, xx = tx * kTcTileW + px;
+      if (y >= h || xx >= w) continue;
+      for (int j = 0; j < p.n_cols; ++j) {
+        int col = n_tile * p.n_cols + j;
+        if (col >= p.cols_valid) break;
+        int co, oy, ox;
+        if (p.mode == 0) { co = col; oy = y; ox = xx; }
+        else { int par = col / p.cout; co = col - par * p.cout; oy = 2 * y + (par >> 1); ox = 2 * xx + (par & 1); }
+        out[(((size_t)img * oh + oy) * ow + ox) * cout + co] = D[(size_t)m * p.n_cols + j];
+      }
+    }
+  }
+  double maxerr = 0, maxref = 0;
+  for (size_t i = 0; i < ref.size(); ++i) { maxerr = std::max(maxerr, std::fabs(out[i] - ref[i])); maxref = std::max(maxref, std::fabs(ref[i])); }
+  printf("k%dx%d cin %d cout %d ups %d %dx%dx%d: ksteps %d bgroup %d n_cols %d n_tiles %d chunks %d a_st %d b_st %d smem %zu | max err %.4g (ref max %.3g) %s\n",
+         kh, kw, cin, cout, ups, n, h, w, p.ksteps, p.bgroup, p.n_cols, p.n_tiles_n, p.cin_chunks, p.a_stages, p.b_stages, smem,
+         maxerr, maxref, maxerr < 0.02 * maxref ? "OK" : "MISMATCH");
+  return maxerr < 0.02 * maxref ? 0 : 1;
+}
+
+int main() {
+  int bad = 0;
+  bad += run(3, 3, 8, 8, 0, 2, 32, 24);
+  bad += run(3, 3, 8, 16, 0, 1, 16, 16);
+  bad += run(3, 3, 16, 16, 0, 1, 32, 16);
+  bad += run(3, 3, 32, 64, 0, 1, 16, 8);
+  bad += run(3, 3, 128, 128, 0, 1, 16, 8);
+  bad += run(3, 3, 128, 64, 0, 1, 16, 16);
+  bad += run(2, 2, 128, 64, 1, 1, 16, 8);
+  bad += run(2, 2, 16, 8, 1, 2, 32, 24);
+  bad += run(3, 3, 16, 8, 0, 1, 20, 12);   // ragged tiles
+  bad += run(3, 3, 512, 512, 0, 1, 16, 8); // wide net: n-tiles + chunks
+  bad += run(2, 2, 256, 128, 1, 1, 16, 8); // wide up-conv: 512 columns
+  printf(bad ? "FAILED %d\n" : "ALL OK\n", bad);
+  return bad;
+}

@@ -1,0 +1,39 @@
+// Launchers of the CUDA-core kernels (memory-bound ops + the fp32-exact conv path).
+#pragma once
+#include "common.cuh"
+
+namespace octseg {
+
+// x/255 preprocessing table: lut[u] = float32(float64(u)/255)  (reference models/unet.py:87-91)
+int init_preprocess_lut();
+
+// First conv block: reads the raw NHWC image (u8 or f32), applies x/255, kxk "same" conv,
+// epilogue y = acc*scale + shift (+ReLU), writes blocked output.
+template <typename T>
+int launch_conv_first(const void *img, int img_dtype, int n, int h, int w, int cin_img,
+                      const float *wgt, int kh, int kw, int cout, const float *scale,
+                      const float *shift, int relu, View<T> out, cudaStream_t st);
+
+// Generic kxk "same" conv on blocked input (CUDA cores, fp32 accumulate).
+// ups=1: the input is first nearest-upsampled x2 (never materialised): reference
+// models/unet.py:41-44 (UpSampling2D + Conv2D(dec_kernel, "same")).
+template <typename T>
+int launch_conv_direct(View<const T> in, const float *wgt, int kh, int kw, int cin, int cout,
+                       int ups, const float *scale, const float *shift, int relu, View<T> out,
+                       cudaStream_t st);
+
+// 2x2/stride-2 max pool (reference models/unet.py:37)
+template <typename T>
+int launch_maxpool2(View<const T> in, View<T> out, cudaStream_t st);
+
+// 1x1 conv + bias + softmax head (reference models/unet.py:142-147); probs NHWC fp32,
+// labels = first-max argmax (np.argmax semantics, reference common/utils.py:104)
+template <typename T>
+int launch_head(View<const T> in, const float *wgt /*[cin][K]*/, const float *bias, int cin, int K,
+                float *probs, uint8_t *labels, cudaStream_t st);
+
+// BN folding for inference: scale = gamma*rsqrt(var+eps), shift = (bias-mean)*scale+beta
+int launch_bn_fold(const float *bias, const float *gamma, const float *beta, const float *mean,
+                   const float *var, float eps, int c, float *scale, float *shift, cudaStream_t st);
+
+}  // namespace octseg

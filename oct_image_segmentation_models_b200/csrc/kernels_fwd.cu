@@ -1,0 +1,322 @@
+// CUDA-core forward kernels: first conv (raw image in), generic direct conv (fp32-exact
+// path and fallback), max-pool, 1x1+softmax head, BN fold.  All tensors use the blocked
+// [N][C/8][H][W][8] layout so every pixel access is one 16 B (bf16) / 32 B (fp32) vector
+// and consecutive threads touch consecutive vectors (fully coalesced).
+#include "kernels.cuh"
+
+namespace octseg {
+
+__constant__ float c_lut255[256];
+
+int init_preprocess_lut() {
+  float h[256];
+  for (int i = 0; i < 256; ++i) h[i] = (float)((double)i / 255.0);
+  OCTSEG_CUDA(cudaMemcpyToSymbol(c_lut255, h, sizeof(h)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// first conv: thread = (pixel, output plane)
+// ---------------------------------------------------------------------------------
+template <typename T, typename IMG>
+__global__ void __launch_bounds__(256) conv_first_kernel(
+    const IMG *__restrict__ img, int n, int h, int w, int cin, const float *__restrict__ wgt, int kh,
+    int kw, int cout, const float *__restrict__ scale, const float *__restrict__ shift, int relu,
+    View<T> out) {
+  extern __shared__ float wsm[];  // [kh*kw*cin][8] for this output plane
+  const int cog = blockIdx.y;
+  const int taps = kh * kw * cin;
+  for (int i = threadIdx.x; i < taps * 8; i += blockDim.x) {
+    int t = i >> 3, co = i & 7;
+    wsm[i] = wgt[(long long)t * cout + cog * 8 + co];
+  }
+  __syncthreads();
+  const long long total = (long long)n * h * w;
+  const int pt = (kh - 1) / 2, pl = (kw - 1) / 2;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % w);
+    const int y = (int)((pix / w) % h);
+    const int b = (int)(pix / ((long long)w * h));
+    Vec8f acc = zero8();
+    for (int dy = 0; dy < kh; ++dy) {
+      const int iy = y + dy - pt;
+      if (iy < 0 || iy >= h) continue;
+      for (int dx = 0; dx < kw; ++dx) {
+        const int ix = x + dx - pl;
+        if (ix < 0 || ix >= w) continue;
+        const IMG *px = img + (((long long)b * h + iy) * w + ix) * cin;
+        for (int ci = 0; ci < cin; ++ci) {
+          float v;
+          if constexpr (sizeof(IMG) == 1) v = c_lut255[px[ci]];
+          else v = (float)((double)px[ci] / 255.0);
+          const float *wr = wsm + ((dy * kw + dx) * cin + ci) * 8;
+#pragma unroll
+          for (int co = 0; co < 8; ++co) acc.v[co] = fmaf(v, wr[co], acc.v[co]);
+        }
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < 8; ++co) {
+      float v = fmaf(acc.v[co], scale[cog * 8 + co], shift[cog * 8 + co]);
+      acc.v[co] = relu ? fmaxf(v, 0.f) : v;
+    }
+    T *dst = out.ptr + b * out.img_stride + (((long long)cog * h + y) * w + x) * 8;
+    store8(dst, acc);
+  }
+}
+
+template <typename T>
+int launch_conv_first(const void *img, int img_dtype, int n, int h, int w, int cin_img,
+                      const float *wgt, int kh, int kw, int cout, const float *scale,
+                      const float *shift, int relu, View<T> out, cudaStream_t st) {
+  const long long total = (long long)n * h * w;
+  dim3 grid((unsigned)std::min<long long>((total + 255) / 256, 148 * 16), cout / 8);
+  size_t smem = (size_t)kh * kw * cin_img * 8 * sizeof(float);
+  if (img_dtype == 0)
+    conv_first_kernel<T, uint8_t><<<grid, 256, smem, st>>>((const uint8_t *)img, n, h, w, cin_img, wgt,
+                                                           kh, kw, cout, scale, shift, relu, out);
+  else
+    conv_first_kernel<T, float><<<grid, 256, smem, st>>>((const float *)img, n, h, w, cin_img, wgt, kh,
+                                                         kw, cout, scale, shift, relu, out);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// generic direct conv: block = 32x4 threads, tile = 64 px x 4 rows, 2 px / thread,
+// one output plane (8 couts) per blockIdx.y; weights of the plane staged in smem per
+// 64-channel input chunk.
+// ---------------------------------------------------------------------------------
+constexpr int kDirectChunk = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(128) conv_direct_kernel(
+    View<const T> in, const float *__restrict__ wgt, int kh, int kw, int cin, int cout, int ups,
+    const float *__restrict__ scale, const float *__restrict__ shift, int relu, View<T> out,
+    int tiles_x) {
+  extern __shared__ float wsm[];  // [kh*kw][chunk][8]
+  const int cog = blockIdx.y;
+  const int b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+  const int x0 = tile_x * 64 + tx * 2;
+  const int y = tile_y * 4 + ty;
+  const int H = out.h, W = out.w;           // output grid
+  const int Hin = in.h, Win = in.w;         // input grid (H/2 when ups)
+  const int pt = (kh - 1) / 2, pl = (kw - 1) / 2;
+  const int ntap = kh * kw;
+  const bool active = (y < H) && (x0 < W);
+  Vec8f acc0 = zero8(), acc1 = zero8();
+
+  for (int c0 = 0; c0 < cin; c0 += kDirectChunk) {
+    const int chunk = min(kDirectChunk, cin - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ntap * chunk * 8; i += blockDim.x) {
+      const int co = i & 7;
+      const int ci = (i >> 3) % chunk;
+      const int t = (i >> 3) / chunk;
+      wsm[i] = wgt[((long long)t * cin + c0 + ci) * cout + cog * 8 + co];
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int cgl = 0; cgl < chunk / 8; ++cgl) {
+      const T *plane = in.ptr + b * in.img_stride + (long long)(c0 / 8 + cgl) * Hin * Win * 8;
+      for (int dy = 0; dy < kh; ++dy) {
+        int iy = y + dy - pt;
+        if (iy < 0 || iy >= H) continue;
+        if (ups) iy >>= 1;
+        for (int dx = 0; dx < kw; ++dx) {
+          int ix0 = x0 + dx - pl, ix1 = ix0 + 1;
+          const bool v0ok = (ix0 >= 0 && ix0 < W);
+          const bool v1ok = (ix1 >= 0 && ix1 < W) && (x0 + 1 < W);
+          if (ups) { ix0 >>= 1; ix1 >>= 1; }
+          Vec8f v0 = v0ok ? load8(plane + ((long long)iy * Win + ix0) * 8) : zero8();
+          Vec8f v1 = v1ok ? load8(plane + ((long long)iy * Win + ix1) * 8) : zero8();
+          const float *wt = wsm + ((dy * kw + dx) * chunk + cgl * 8) * 8;
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci) {
+            const float4 wa = *reinterpret_cast<const float4 *>(wt + ci * 8);
+            const float4 wb = *reinterpret_cast<const float4 *>(wt + ci * 8 + 4);
+            const float a = v0.v[ci], c = v1.v[ci];
+            acc0.v[0] = fmaf(a, wa.x, acc0.v[0]); acc0.v[1] = fmaf(a, wa.y, acc0.v[1]);
+            acc0.v[2] = fmaf(a, wa.z, acc0.v[2]); acc0.v[3] = fmaf(a, wa.w, acc0.v[3]);
+            acc0.v[4] = fmaf(a, wb.x, acc0.v[4]); acc0.v[5] = fmaf(a, wb.y, acc0.v[5]);
+            acc0.v[6] = fmaf(a, wb.z, acc0.v[6]); acc0.v[7] = fmaf(a, wb.w, acc0.v[7]);
+            acc1.v[0] = fmaf(c, wa.x, acc1.v[0]); acc1.v[1] = fmaf(c, wa.y, acc1.v[1]);
+            acc1.v[2] = fmaf(c, wa.z, acc1.v[2]); acc1.v[3] = fmaf(c, wa.w, acc1.v[3]);
+            acc1.v[4] = fmaf(c, wb.x, acc1.v[4]); acc1.v[5] = fmaf(c, wb.y, acc1.v[5]);
+            acc1.v[6] = fmaf(c, wb.z, acc1.v[6]); acc1.v[7] = fmaf(c, wb.w, acc1.v[7]);
+          }
+        }
+      }
+    }
+  }
+  if (!active) return;
+#pragma unroll
+  for (int co = 0; co < 8; ++co) {
+    const float s = scale[cog * 8 + co], t = shift[cog * 8 + co];
+    float a = fmaf(acc0.v[co], s, t), c = fmaf(acc1.v[co], s, t);
+    acc0.v[co] = relu ? fmaxf(a, 0.f) : a;
+    acc1.v[co] = relu ? fmaxf(c, 0.f) : c;
+  }
+  T *dst = out.ptr + b * out.img_stride + (((long long)cog * H + y) * W + x0) * 8;
+  store8(dst, acc0);
+  if (x0 + 1 < W) store8(dst + 8, acc1);
+}
+
+template <typename T>
+int launch_conv_direct(View<const T> in, const float *wgt, int kh, int kw, int cin, int cout,
+                       int ups, const float *scale, const float *shift, int relu, View<T> out,
+                       cudaStream_t st) {
+  const int tiles_x = (out.w + 63) / 64, tiles_y = (out.h + 3) / 4;
+  dim3 grid(tiles_x * tiles_y, cout / 8, out.n);
+  size_t smem = (size_t)kh * kw * std::min(cin, kDirectChunk) * 8 * sizeof(float);
+  conv_direct_kernel<T><<<grid, 128, smem, st>>>(in, wgt, kh, kw, cin, cout, ups, scale, shift, relu, out,
+                                               tiles_x);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// 2x2 max pool: thread = output (pixel, plane) vector
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_kernel(View<const T> in, View<T> out) {
+  const int Ho = out.h, Wo = out.w;
+  const long long total = (long long)out.n * out.planes * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wo);
+    const int y = (int)((i / Wo) % Ho);
+    const int pl = (int)((i / ((long long)Wo * Ho)) % out.planes);
+    const int b = (int)(i / ((long long)Wo * Ho * out.planes));
+    const T *src = in.ptr + b * in.img_stride + (((long long)pl * in.h + 2 * y) * in.w + 2 * x) * 8;
+    Vec8f a = load8(src), c = load8(src + 8);
+    Vec8f d = load8(src + (long long)in.w * 8), e = load8(src + (long long)in.w * 8 + 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.v[k] = fmaxf(fmaxf(a.v[k], c.v[k]), fmaxf(d.v[k], e.v[k]));
+    store8(out.ptr + b * out.img_stride + (((long long)pl * Ho + y) * Wo + x) * 8, a);
+  }
+}
+
+template <typename T>
+int launch_maxpool2(View<const T> in, View<T> out, cudaStream_t st) {
+  const long long total = (long long)out.n * out.planes * out.h * out.w;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  maxpool2_kernel<T><<<grid, 256, 0, st>>>(in, out);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// head: 1x1 conv + softmax (+ first-max argmax).  thread = pixel.
+// ---------------------------------------------------------------------------------
+constexpr int kMaxClasses = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) head_kernel(View<const T> in, const float *__restrict__ wgt,
+                                                   const float *__restrict__ bias, int cin, int K,
+                                                   float *__restrict__ probs,
+                                                   uint8_t *__restrict__ labels) {
+  extern __shared__ float wsm[];  // [cin][K] + [K]
+  for (int i = threadIdx.x; i < cin * K; i += blockDim.x) wsm[i] = wgt[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) wsm[cin * K + i] = bias[i];
+  __syncthreads();
+  const int H = in.h, W = in.w;
+  const long long total = (long long)in.n * H * W;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const long long hw = pix % ((long long)H * W);
+    const int b = (int)(pix / ((long long)H * W));
+    float z[kMaxClasses];
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) z[k] = (k < K) ? wsm[cin * K + k] : 0.f;
+    for (int pl = 0; pl < cin / 8; ++pl) {
+      Vec8f v = load8(in.ptr + b * in.img_stride + ((long long)pl * H * W + hw) * 8);
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) {
+        const float *wr = wsm + (pl * 8 + ci) * K;
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k)
+          if (k < K) z[k] = fmaf(v.v[ci], wr[k], z[k]);
+      }
+    }
+    float m = z[0];
+    int am = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxClasses; ++k)
+      if (k < K && z[k] > m) { m = z[k]; am = k; }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < K) { z[k] = expf(z[k] - m); s += z[k]; }
+    const float inv = 1.f / s;
+    if (probs) {
+      float *dst = probs + pix * K;
+      if (K == 4) {
+        *reinterpret_cast<float4 *>(dst) = make_float4(z[0] * inv, z[1] * inv, z[2] * inv, z[3] * inv);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k)
+          if (k < K) dst[k] = z[k] * inv;
+      }
+    }
+    if (labels) {
+      // np.argmax runs on the float32 probabilities: recompute on p so that ties created
+      // by rounding resolve exactly as they would on the returned array
+      float pm = z[0] * inv;
+      int pa = 0;
+#pragma unroll
+      for (int k = 1; k < kMaxClasses; ++k)
+        if (k < K && z[k] * inv > pm) { pm = z[k] * inv; pa = k; }
+      labels[pix] = (uint8_t)pa;
+      (void)am;
+    }
+  }
+}
+
+template <typename T>
+int launch_head(View<const T> in, const float *wgt, const float *bias, int cin, int K, float *probs,
+                uint8_t *labels, cudaStream_t st) {
+  if (K > kMaxClasses) { set_error("num_classes > 16 not supported"); return 1; }
+  const long long total = (long long)in.n * in.h * in.w;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+  size_t smem = (size_t)(cin * K + K) * sizeof(float);
+  head_kernel<T><<<grid, 256, smem, st>>>(in, wgt, bias, cin, K, probs, labels);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+__global__ void bn_fold_kernel(const float *bias, const float *gamma, const float *beta,
+                               const float *mean, const float *var, float eps, int c, float *scale,
+                               float *shift) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  // same operation order as the oracle: inv = rsqrt(var+eps); y = (z-mean)*(inv*gamma)+beta
+  float s = (1.0f / sqrtf(var[i] + eps)) * gamma[i];
+  scale[i] = s;
+  shift[i] = (bias[i] - mean[i]) * s + beta[i];
+}
+
+int launch_bn_fold(const float *bias, const float *gamma, const float *beta, const float *mean,
+                   const float *var, float eps, int c, float *scale, float *shift, cudaStream_t st) {
+  bn_fold_kernel<<<(c + 127) / 128, 128, 0, st>>>(bias, gamma, beta, mean, var, eps, c, scale, shift);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// explicit instantiations
+#define INST(T)                                                                                        \
+  template int launch_conv_first<T>(const void *, int, int, int, int, int, const float *, int, int,    \
+                                    int, const float *, const float *, int, View<T>, cudaStream_t);    \
+  template int launch_conv_direct<T>(View<const T>, const float *, int, int, int, int, int,            \
+                                     const float *, const float *, int, View<T>, cudaStream_t);        \
+  template int launch_maxpool2<T>(View<const T>, View<T>, cudaStream_t);                               \
+  template int launch_head<T>(View<const T>, const float *, const float *, int, int, float *,          \
+                              uint8_t *, cudaStream_t);
+INST(float)
+INST(__nv_bfloat16)
+
+}  // namespace octseg

@@ -1,0 +1,615 @@
+// C ABI (inference half) + network object.  See include/octseg.h for the contract.
+#include "net.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels.cuh"
+
+namespace octseg {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+static const float kBnEps = 1e-3f;   // Keras BatchNormalization() default
+
+// ---------------------------------------------------------------------------------
+// graph (structure only) -- reference models/unet.py:106-153
+// ---------------------------------------------------------------------------------
+int build_graph(const octseg_config &c, std::vector<BlockSpec> *blocks, std::vector<ParamSpec> *params,
+                int64_t *total_floats) {
+  if (c.input_channels < 1 || c.num_classes < 1 || c.start_neurons < 1 || c.pool_layers < 0 ||
+      c.conv_layers < 1 || c.enc_kh < 1 || c.enc_kw < 1 || c.dec_kh < 1 || c.dec_kw < 1) {
+    set_error("invalid octseg_config");
+    return 1;
+  }
+  blocks->clear();
+  int idx = 0, cin = c.input_channels;
+  const int P = c.pool_layers, L = c.conv_layers, s = c.start_neurons;
+  auto add = [&](int role, int level, int kh, int kw, int ci, int co, int j) -> BlockSpec & {
+    BlockSpec b;
+    b.index = idx++; b.role = role; b.level = level; b.kh = kh; b.kw = kw; b.cin = ci; b.cout = co;
+    b.conv_j = j;
+    blocks->push_back(b);
+    return blocks->back();
+  };
+  for (int i = 0; i < P; ++i) {
+    const int f = s << i;
+    for (int j = 0; j < L; ++j) {
+      BlockSpec &b = add(0, i, c.enc_kh, c.enc_kw, cin, f, j);
+      b.pool_after = (j == L - 1);
+      cin = f;
+    }
+  }
+  {
+    const int f = s << P;
+    for (int j = 0; j < L; ++j) {
+      BlockSpec &b = add(1, P, c.enc_kh, c.enc_kw, cin, f, j);
+      b.dropout_after = (j == L - 1);
+      cin = f;
+    }
+  }
+  for (int i = 0; i < P; ++i) {
+    const int lvl = P - 1 - i, f = s << lvl;
+    BlockSpec &u = add(2, lvl, c.dec_kh, c.dec_kw, cin, f, 0);
+    u.ups = true;
+    cin = 2 * f;
+    for (int j = 0; j < L; ++j) {
+      BlockSpec &b = add(3, lvl, c.enc_kh, c.enc_kw, cin, f, j);
+      if (j == 0) b.concat_level = lvl;
+      cin = f;
+    }
+  }
+  {
+    BlockSpec &h = add(4, 0, 1, 1, cin, c.num_classes, 0);
+    h.has_bn = false;
+  }
+  params->clear();
+  int64_t off = 0;
+  auto addp = [&](const std::string &name, int block, bool trainable, int nd, int64_t a, int64_t b2,
+                  int64_t c2, int64_t d) {
+    ParamSpec p;
+    p.name = name; p.ndim = nd; p.block = block; p.trainable = trainable;
+    p.shape[0] = a; p.shape[1] = b2; p.shape[2] = c2; p.shape[3] = d;
+    p.count = 1;
+    for (int i = 0; i < nd; ++i) p.count *= p.shape[i];
+    p.offset = off;
+    off += (p.count + 15) / 16 * 16;
+    params->push_back(p);
+    return (int)params->size() - 1;
+  };
+  for (auto &b : *blocks) {
+    const std::string sfx = b.index == 0 ? "" : "_" + std::to_string(b.index);
+    b.p_kernel = addp("conv2d" + sfx + "/kernel:0", b.index, true, 4, b.kh, b.kw, b.cin, b.cout);
+    b.p_bias = addp("conv2d" + sfx + "/bias:0", b.index, true, 1, b.cout, 0, 0, 0);
+    if (b.has_bn) {
+      const std::string bn = "batch_normalization" + sfx;
+      b.p_gamma = addp(bn + "/gamma:0", b.index, true, 1, b.cout, 0, 0, 0);
+      b.p_beta = addp(bn + "/beta:0", b.index, true, 1, b.cout, 0, 0, 0);
+      b.p_mean = addp(bn + "/moving_mean:0", b.index, false, 1, b.cout, 0, 0, 0);
+      b.p_var = addp(bn + "/moving_variance:0", b.index, false, 1, b.cout, 0, 0, 0);
+    }
+  }
+  *total_floats = off;
+  return 0;
+}
+
+static size_t elem_size(const octseg_net *net) { return net->precision == OCTSEG_BF16 ? 2 : 4; }
+
+static int check_supported(const octseg_net *net) {
+  for (auto &b : net->blocks) {
+    if (b.role != 4 && b.cout % 8) { set_error("start_neurons must be a multiple of 8"); return 1; }
+    if (b.index > 0 && b.cin % 8) { set_error("channel counts must be multiples of 8"); return 1; }
+  }
+  if (net->cfg.num_classes > 16) { set_error("num_classes > 16 not supported"); return 1; }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// derived state: folded BN + packed tensor-core weights
+// ---------------------------------------------------------------------------------
+static int sync_host_mirror(octseg_net *net) {
+  if (!net->host_stale) return 0;
+  OCTSEG_CUDA(cudaMemcpyAsync(net->h_params.data(), net->d_params, net->total_floats * sizeof(float),
+                              cudaMemcpyDeviceToHost, net->stream));
+  OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+  net->host_stale = false;
+  return 0;
+}
+
+int prepare_derived(octseg_net *net) {
+  if (!net->derived_dirty) return 0;
+  if (sync_host_mirror(net)) return 1;
+  for (auto &b : net->blocks) {
+    BlockState &st = net->bstate[b.index];
+    if (!b.has_bn) continue;
+    const float *P = net->d_params;
+    if (launch_bn_fold(P + net->params[b.p_bias].offset, P + net->params[b.p_gamma].offset,
+                       P + net->params[b.p_beta].offset, P + net->params[b.p_mean].offset,
+                       P + net->params[b.p_var].offset, kBnEps, b.cout, st.scale, st.shift, net->stream))
+      return 1;
+    ++net->launches;
+    if (net->precision == OCTSEG_BF16 && st.geo_ok) {
+      std::vector<uint16_t> packed;
+      tc_pack_weights(st.geo, net->h_params.data() + net->params[b.p_kernel].offset, &packed);
+      if (packed.size() != st.wpack_elems) { set_error("internal: wpack size"); return 1; }
+      OCTSEG_CUDA(cudaMemcpyAsync(st.wpack, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice,
+                                  net->stream));
+      OCTSEG_CUDA(cudaStreamSynchronize(net->stream));   // `packed` is a stack-lifetime buffer
+    }
+  }
+  net->derived_dirty = false;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// workspace planning
+// ---------------------------------------------------------------------------------
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; }
+};
+
+int ensure_workspace(octseg_net *net, int n, int h, int w) {
+  if (net->ws && net->ws_n == n && net->ws_h == h && net->ws_w == w) return 0;
+  const int P = net->cfg.pool_layers, L = net->cfg.conv_layers, s = net->cfg.start_neurons;
+  if ((h % (1 << P)) || (w % (1 << P))) {
+    set_error("image height/width must be multiples of 2^pool_layers");
+    return 1;
+  }
+  const size_t es = elem_size(net);
+  auto bytes = [&](int ch, int lvl) { return (size_t)n * ch * (h >> lvl) * (w >> lvl) * es; };
+  Bump bump;
+  std::vector<size_t> cat(P), pooled(P), encT0(P), encT1(P), decT0(P), decT1(P);
+  for (int l = 0; l < P; ++l) {
+    const int f = s << l;
+    cat[l] = bump.take(bytes(2 * f, l));
+    pooled[l] = bump.take(bytes(f, l + 1));
+    encT0[l] = bump.take(bytes(f, l));
+    encT1[l] = bump.take(bytes(f, l));
+    decT0[l] = bump.take(bytes(f, l));
+    decT1[l] = bump.take(bytes(f, l));
+  }
+  const int fm = s << P;
+  size_t midT0 = bump.take(bytes(fm, P)), midT1 = bump.take(bytes(fm, P));
+  if (bump.off > net->ws_bytes) {
+    if (net->ws) OCTSEG_CUDA(cudaFree(net->ws));
+    net->ws = nullptr;
+    OCTSEG_CUDA(cudaMalloc(&net->ws, bump.off));
+    net->ws_bytes = bump.off;
+  }
+  uint8_t *base = reinterpret_cast<uint8_t *>(net->ws);
+  net->io.assign(net->blocks.size(), BlockIO());
+  void *prev = nullptr;
+  int prev_planes = 0, prev_h = h, prev_w = w;
+  for (auto &b : net->blocks) {
+    BlockIO &io = net->io[b.index];
+    const int lh = h >> b.level, lw = w >> b.level;
+    const int f = b.cout;
+    // ---- input
+    if (b.index == 0) {
+      io.in = nullptr; io.in_h = h; io.in_w = w;
+    } else if (b.concat_level >= 0) {
+      io.in = base + cat[b.level]; io.in_planes_total = io.in_planes = b.cin / 8; io.in_plane0 = 0;
+      io.in_h = lh; io.in_w = lw;
+    } else {
+      io.in = prev; io.in_planes_total = io.in_planes = prev_planes; io.in_plane0 = 0;
+      io.in_h = prev_h; io.in_w = prev_w;
+    }
+    // ---- output
+    io.out_h = lh; io.out_w = lw;
+    if (b.role == 4) {
+      io.out = nullptr;
+    } else if (b.role == 0) {
+      if (b.pool_after) {
+        io.out = base + cat[b.level]; io.out_planes_total = 2 * f / 8; io.out_plane0 = f / 8; io.out_planes = f / 8;
+        io.pool = base + pooled[b.level]; io.pool_h = lh / 2; io.pool_w = lw / 2;
+      } else {
+        io.out = base + ((b.conv_j & 1) ? encT1[b.level] : encT0[b.level]);
+        io.out_planes_total = io.out_planes = f / 8; io.out_plane0 = 0;
+      }
+    } else if (b.role == 1) {
+      io.out = base + ((b.conv_j & 1) ? midT1 : midT0);
+      io.out_planes_total = io.out_planes = f / 8; io.out_plane0 = 0;
+    } else if (b.role == 2) {
+      io.out = base + cat[b.level]; io.out_planes_total = 2 * f / 8; io.out_plane0 = 0; io.out_planes = f / 8;
+    } else {
+      io.out = base + ((b.conv_j & 1) ? decT1[b.level] : decT0[b.level]);
+      io.out_planes_total = io.out_planes = f / 8; io.out_plane0 = 0;
+    }
+    // what the next block sees
+    if (io.pool) { prev = io.pool; prev_planes = f / 8; prev_h = io.pool_h; prev_w = io.pool_w; }
+    else { prev = io.out; prev_planes = f / 8; prev_h = lh; prev_w = lw; }
+    // ---- tensor-core plan
+    io.use_tc = false;
+    if (net->precision == OCTSEG_BF16 && !net->disable_tc && b.index > 0 && b.role != 4 &&
+        net->bstate[b.index].geo_ok && tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, io.in_h, io.in_w)) {
+      View<__nv_bfloat16> ov = make_view(reinterpret_cast<__nv_bfloat16 *>(io.out), n, io.out_planes_total,
+                                         io.out_plane0, io.out_planes, io.out_h, io.out_w);
+      if (tc_make_plan(net->bstate[b.index].geo, reinterpret_cast<const __nv_bfloat16 *>(io.in), n, io.in_h,
+                       io.in_w, net->bstate[b.index].wpack, net->bstate[b.index].scale,
+                       net->bstate[b.index].shift, 1, ov, net->d_status, &io.plan))
+        return 1;
+      io.use_tc = true;
+    }
+  }
+  net->ws_n = n; net->ws_h = h; net->ws_w = w;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// forward (inference)
+// ---------------------------------------------------------------------------------
+template <typename T>
+static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h, int w, float *d_probs,
+                     uint8_t *d_labels, cudaStream_t st) {
+  const float *P = net->d_params;
+  for (auto &b : net->blocks) {
+    BlockIO &io = net->io[b.index];
+    BlockState &bs = net->bstate[b.index];
+    if (b.role == 4) {
+      View<const T> in = make_view(reinterpret_cast<const T *>(io.in), n, io.in_planes_total, io.in_plane0,
+                                   io.in_planes, io.in_h, io.in_w);
+      if (launch_head<T>(in, P + net->params[b.p_kernel].offset, P + net->params[b.p_bias].offset, b.cin,
+                         b.cout, d_probs, d_labels, st))
+        return 1;
+      ++net->launches;
+      continue;
+    }
+    View<T> out = make_view(reinterpret_cast<T *>(io.out), n, io.out_planes_total, io.out_plane0,
+                            io.out_planes, io.out_h, io.out_w);
+    if (b.index == 0) {
+      if (launch_conv_first<T>(d_img, dtype, n, h, w, b.cin, P + net->params[b.p_kernel].offset, b.kh, b.kw,
+                               b.cout, bs.scale, bs.shift, 1, out, st))
+        return 1;
+    } else if (io.use_tc) {
+      if (tc_launch(io.plan, st)) return 1;
+    } else {
+      View<const T> in = make_view(reinterpret_cast<const T *>(io.in), n, io.in_planes_total, io.in_plane0,
+                                   io.in_planes, io.in_h, io.in_w);
+      if (launch_conv_direct<T>(in, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout,
+                                b.ups ? 1 : 0, bs.scale, bs.shift, 1, out, st))
+        return 1;
+    }
+    ++net->launches;
+    if (io.pool) {
+      View<const T> pin = make_view(reinterpret_cast<const T *>(io.out), n, io.out_planes_total,
+                                    io.out_plane0, io.out_planes, io.out_h, io.out_w);
+      View<T> pout = make_view(reinterpret_cast<T *>(io.pool), n, io.out_planes, 0, io.out_planes, io.pool_h,
+                               io.pool_w);
+      if (launch_maxpool2<T>(pin, pout, st)) return 1;
+      ++net->launches;
+    }
+  }
+  return 0;
+}
+
+int forward(octseg_net *net, const void *d_img, int dtype, int n, int h, int w, float *d_probs,
+            uint8_t *d_labels, cudaStream_t st) {
+  if (prepare_derived(net)) return 1;
+  if (ensure_workspace(net, n, h, w)) return 1;
+  if (net->precision == OCTSEG_BF16)
+    return forward_t<__nv_bfloat16>(net, d_img, dtype, n, h, w, d_probs, d_labels, st);
+  return forward_t<float>(net, d_img, dtype, n, h, w, d_probs, d_labels, st);
+}
+
+int check_status(octseg_net *net) {
+  OCTSEG_CUDA(cudaMemcpyAsync(net->h_status, net->d_status, sizeof(int), cudaMemcpyDeviceToHost, net->stream));
+  OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+  if (*net->h_status != 0) {
+    set_error("tensor-core conv pipeline timed out (code " + std::to_string(*net->h_status) + ")");
+    OCTSEG_CUDA(cudaMemsetAsync(net->d_status, 0, sizeof(int), net->stream));
+    return 1;
+  }
+  return 0;
+}
+
+static int grow(void **p, size_t *cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p) OCTSEG_CUDA(cudaFree(*p));
+  *p = nullptr;
+  OCTSEG_CUDA(cudaMalloc(p, need));
+  *cap = need;
+  return 0;
+}
+
+static int pick_microbatch(const octseg_net *net, int n, int h, int w) {
+  if (net->microbatch > 0) return std::min(n, net->microbatch);
+  // activation footprint per image (all planned buffers) must stay under ~32 GB
+  const int P = net->cfg.pool_layers, s = net->cfg.start_neurons;
+  double per_img = 0;
+  for (int l = 0; l <= P; ++l) per_img += 7.0 * (s << l) * (double)(h >> l) * (w >> l);
+  per_img *= (net->precision == OCTSEG_BF16 ? 2 : 4);
+  int mb = (int)std::max(1.0, std::min((double)n, 32e9 / per_img));
+  return mb;
+}
+
+}  // namespace octseg
+
+using namespace octseg;
+
+extern "C" void octseg_train_free(octseg_net *net);
+
+// ===================================================================================
+// C ABI
+// ===================================================================================
+extern "C" {
+
+int32_t octseg_version(void) { return 100; }
+const char *octseg_last_error(void) { return g_err.c_str(); }
+
+int32_t octseg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int32_t octseg_param_count(const octseg_config *cfg, int32_t *n_tensors) {
+  std::vector<BlockSpec> b; std::vector<ParamSpec> p; int64_t t;
+  if (!cfg || !n_tensors) { set_error("null argument"); return 1; }
+  if (build_graph(*cfg, &b, &p, &t)) return 1;
+  *n_tensors = (int32_t)p.size();
+  return 0;
+}
+
+int32_t octseg_param_info(const octseg_config *cfg, int32_t index, char *name, int32_t name_cap,
+                          int32_t *ndim, int64_t shape[4], int32_t *trainable) {
+  std::vector<BlockSpec> b; std::vector<ParamSpec> p; int64_t t;
+  if (!cfg) { set_error("null argument"); return 1; }
+  if (build_graph(*cfg, &b, &p, &t)) return 1;
+  if (index < 0 || index >= (int)p.size()) { set_error("param index out of range"); return 1; }
+  const ParamSpec &ps = p[index];
+  if (name && name_cap > 0) { std::strncpy(name, ps.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (ndim) *ndim = ps.ndim;
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = ps.shape[i];
+  if (trainable) *trainable = ps.trainable ? 1 : 0;
+  return 0;
+}
+
+int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precision, octseg_net **out) {
+  if (!cfg || !out) { set_error("null argument"); return 1; }
+  if (precision != OCTSEG_FP32 && precision != OCTSEG_BF16) { set_error("bad precision"); return 1; }
+  int ndev = octseg_device_count();
+  if (ndev <= 0) { set_error("no CUDA device: liboctseg has no CPU fallback"); return 1; }
+  if (device < 0 || device >= ndev) { set_error("device index out of range"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  OCTSEG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) { set_error("liboctseg is built for sm_100a (B200) only"); return 1; }
+  octseg_net *net = new octseg_net();
+  net->cfg = *cfg; net->device = device; net->precision = precision;
+  if (build_graph(*cfg, &net->blocks, &net->params, &net->total_floats) || check_supported(net)) {
+    delete net;
+    return 1;
+  }
+  const char *e = std::getenv("OCTSEG_DISABLE_TC");
+  net->disable_tc = e && e[0] == '1';
+  e = std::getenv("OCTSEG_MICROBATCH");
+  net->microbatch = e ? std::atoi(e) : 0;
+  OCTSEG_CUDA(cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking));
+  OCTSEG_CUDA(cudaMalloc(&net->d_params, net->total_floats * sizeof(float)));
+  OCTSEG_CUDA(cudaMemset(net->d_params, 0, net->total_floats * sizeof(float)));
+  net->h_params.assign(net->total_floats, 0.f);
+  OCTSEG_CUDA(cudaMalloc(&net->d_status, sizeof(int)));
+  OCTSEG_CUDA(cudaMemset(net->d_status, 0, sizeof(int)));
+  OCTSEG_CUDA(cudaMallocHost(&net->h_status, sizeof(int)));
+  if (init_preprocess_lut()) { delete net; return 1; }
+  net->bstate.resize(net->blocks.size());
+  for (auto &b : net->blocks) {
+    BlockState &st = net->bstate[b.index];
+    if (b.has_bn) {
+      OCTSEG_CUDA(cudaMalloc(&st.scale, b.cout * sizeof(float)));
+      OCTSEG_CUDA(cudaMalloc(&st.shift, b.cout * sizeof(float)));
+    }
+    if (precision == OCTSEG_BF16 && b.index > 0 && b.role != 4 && b.cin % 8 == 0 &&
+        tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, kTcTileH, kTcTileW) &&
+        tc_make_geometry(b.kh, b.kw, b.cin, b.cout, b.ups ? 1 : 0, &st.geo) == 0) {
+      st.geo_ok = true;
+      st.wpack_elems = (size_t)st.geo.n_tiles_n * st.geo.cin_chunks * st.geo.ksteps * 2 * st.geo.n_cols * 8;
+      OCTSEG_CUDA(cudaMalloc(&st.wpack, st.wpack_elems * 2));
+    }
+  }
+  *out = net;
+  return 0;
+}
+
+int32_t octseg_destroy(octseg_net *net) {
+  if (!net) return 0;
+  cudaSetDevice(net->device);
+  if (net->stream) cudaStreamSynchronize(net->stream);
+  octseg_train_free(net);
+  for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); }
+  cudaFree(net->d_params); cudaFree(net->ws); cudaFree(net->d_img); cudaFree(net->d_probs);
+  cudaFree(net->d_labels); cudaFree(net->d_status);
+  if (net->h_status) cudaFreeHost(net->h_status);
+  if (net->stream) cudaStreamDestroy(net->stream);
+  delete net;
+  return 0;
+}
+
+int32_t octseg_set_param(octseg_net *net, int32_t index, const float *host, int64_t count) {
+  if (!net || !host) { set_error("null argument"); return 1; }
+  if (index < 0 || index >= (int)net->params.size()) { set_error("param index out of range"); return 1; }
+  const ParamSpec &p = net->params[index];
+  if (count != p.count) { set_error("param " + p.name + ": element count mismatch"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  if (sync_host_mirror(net)) return 1;
+  std::memcpy(net->h_params.data() + p.offset, host, count * sizeof(float));
+  OCTSEG_CUDA(cudaMemcpyAsync(net->d_params + p.offset, net->h_params.data() + p.offset,
+                              count * sizeof(float), cudaMemcpyHostToDevice, net->stream));
+  OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+  net->derived_dirty = true;
+  return 0;
+}
+
+int32_t octseg_get_param(octseg_net *net, int32_t index, float *host, int64_t count) {
+  if (!net || !host) { set_error("null argument"); return 1; }
+  if (index < 0 || index >= (int)net->params.size()) { set_error("param index out of range"); return 1; }
+  const ParamSpec &p = net->params[index];
+  if (count != p.count) { set_error("param " + p.name + ": element count mismatch"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  if (sync_host_mirror(net)) return 1;
+  std::memcpy(host, net->h_params.data() + p.offset, count * sizeof(float));
+  return 0;
+}
+
+int32_t octseg_predict_device(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
+                              int32_t w, float *probs, uint8_t *labels, void *stream) {
+  if (!net || !images) { set_error("null argument"); return 1; }
+  if (n <= 0 || h <= 0 || w <= 0) { set_error("bad image batch shape"); return 1; }
+  if (dtype != OCTSEG_U8 && dtype != OCTSEG_F32) { set_error("bad image dtype"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : net->stream;
+  const int mb = pick_microbatch(net, n, h, w);
+  const size_t img_elem = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)h * w * net->cfg.input_channels;
+  for (int i0 = 0; i0 < n; i0 += mb) {
+    // keep micro-batches equal-sized where possible so the workspace plan is reused
+    const int cur = std::min(mb, n - i0);
+    const uint8_t *img = reinterpret_cast<const uint8_t *>(images) + (size_t)i0 * img_elem;
+    float *pr = probs ? probs + (size_t)i0 * h * w * net->cfg.num_classes : nullptr;
+    uint8_t *lb = labels ? labels + (size_t)i0 * h * w : nullptr;
+    if (forward(net, img, dtype, cur, h, w, pr, lb, st)) return 1;
+  }
+  return 0;
+}
+
+int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
+                            int32_t w, float *probs, uint8_t *labels) {
+  if (!net || !images) { set_error("null argument"); return 1; }
+  if (n <= 0 || h <= 0 || w <= 0) { set_error("bad image batch shape"); return 1; }
+  if (dtype != OCTSEG_U8 && dtype != OCTSEG_F32) { set_error("bad image dtype"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  const size_t img_bytes = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)n * h * w * net->cfg.input_channels;
+  const size_t pr_bytes = (size_t)n * h * w * net->cfg.num_classes * sizeof(float);
+  const size_t lb_bytes = (size_t)n * h * w;
+  if (grow(&net->d_img, &net->d_img_bytes, img_bytes)) return 1;
+  if (probs && grow(reinterpret_cast<void **>(&net->d_probs), &net->d_probs_bytes, pr_bytes)) return 1;
+  if (labels && grow(reinterpret_cast<void **>(&net->d_labels), &net->d_labels_bytes, lb_bytes)) return 1;
+  OCTSEG_CUDA(cudaMemcpyAsync(net->d_img, images, img_bytes, cudaMemcpyHostToDevice, net->stream));
+  if (octseg_predict_device(net, net->d_img, dtype, n, h, w, probs ? net->d_probs : nullptr,
+                            labels ? net->d_labels : nullptr, net->stream))
+    return 1;
+  if (probs) OCTSEG_CUDA(cudaMemcpyAsync(probs, net->d_probs, pr_bytes, cudaMemcpyDeviceToHost, net->stream));
+  if (labels) OCTSEG_CUDA(cudaMemcpyAsync(labels, net->d_labels, lb_bytes, cudaMemcpyDeviceToHost, net->stream));
+  return check_status(net);
+}
+
+int32_t octseg_synchronize(octseg_net *net) {
+  if (!net) { set_error("null argument"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  return check_status(net);
+}
+
+int64_t octseg_launch_count(octseg_net *net) { return net ? net->launches : 0; }
+
+int32_t octseg_layer_uses_tensor_core(octseg_net *net, int32_t conv_index, int32_t h, int32_t w) {
+  if (!net || conv_index < 0 || conv_index >= (int)net->blocks.size()) return 0;
+  const BlockSpec &b = net->blocks[conv_index];
+  if (net->precision != OCTSEG_BF16 || net->disable_tc || b.index == 0 || b.role == 4) return 0;
+  if (!net->bstate[b.index].geo_ok) return 0;
+  int lh = h >> b.level, lw = w >> b.level;
+  if (b.ups) { lh >>= 1; lw >>= 1; }
+  return tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, lh, lw) ? 1 : 0;
+}
+
+// ---- per-block debug entry (tests): NHWC fp32 host in/out ---------------------------
+int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t path, const float *in,
+                                int32_t n, int32_t h, int32_t w, float *out, float *ms_out) {
+  if (!net || !in || !out) { set_error("null argument"); return 1; }
+  if (conv_index <= 0 || conv_index >= (int)net->blocks.size()) { set_error("bad conv index"); return 1; }
+  const BlockSpec &b = net->blocks[conv_index];
+  if (b.role == 4) { set_error("head is not a conv block"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  if (prepare_derived(net)) return 1;
+  const int oh = b.ups ? 2 * h : h, ow = b.ups ? 2 * w : w;
+  const size_t es = elem_size(net);
+  const size_t in_elems = (size_t)n * b.cin * h * w, out_elems = (size_t)n * b.cout * oh * ow;
+  // host re-layout NHWC -> [N][C/8][H][W][8]
+  std::vector<float> blk(in_elems);
+  for (int i = 0; i < n; ++i)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x)
+        for (int c = 0; c < b.cin; ++c)
+          blk[((((size_t)i * (b.cin / 8) + c / 8) * h + y) * w + x) * 8 + (c & 7)] =
+              in[(((size_t)i * h + y) * w + x) * b.cin + c];
+  void *d_in = nullptr, *d_out = nullptr;
+  OCTSEG_CUDA(cudaMalloc(&d_in, in_elems * es));
+  OCTSEG_CUDA(cudaMalloc(&d_out, out_elems * es));
+  OCTSEG_CUDA(cudaMemset(d_out, 0xFF, out_elems * es));   // poison: unwritten outputs show up as NaN
+  std::vector<uint16_t> h16;
+  if (net->precision == OCTSEG_BF16) {
+    h16.resize(in_elems);
+    for (size_t i = 0; i < in_elems; ++i) {
+      __nv_bfloat16 v = __float2bfloat16(blk[i]);
+      std::memcpy(&h16[i], &v, 2);
+    }
+    OCTSEG_CUDA(cudaMemcpy(d_in, h16.data(), in_elems * 2, cudaMemcpyHostToDevice));
+  } else {
+    OCTSEG_CUDA(cudaMemcpy(d_in, blk.data(), in_elems * 4, cudaMemcpyHostToDevice));
+  }
+  const BlockState &bs = net->bstate[b.index];
+  const float *P = net->d_params;
+  cudaEvent_t e0, e1;
+  OCTSEG_CUDA(cudaEventCreate(&e0));
+  OCTSEG_CUDA(cudaEventCreate(&e1));
+  int rc = 0;
+  const int reps = ms_out ? 5 : 1;
+  TcPlan plan;
+  if (path == 1) {
+    if (net->precision != OCTSEG_BF16 || !bs.geo_ok || !tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, h, w)) {
+      set_error("tensor-core path not available for this block/shape");
+      rc = 1;
+    } else {
+      View<__nv_bfloat16> ov = make_view(reinterpret_cast<__nv_bfloat16 *>(d_out), n, b.cout / 8, 0, b.cout / 8, oh, ow);
+      rc = tc_make_plan(bs.geo, reinterpret_cast<const __nv_bfloat16 *>(d_in), n, h, w, bs.wpack, bs.scale,
+                        bs.shift, 1, ov, net->d_status, &plan);
+    }
+  }
+  for (int rep = 0; rc == 0 && rep < reps; ++rep) {
+    if (rep == reps - 1) cudaEventRecord(e0, net->stream);
+    if (path == 1) {
+      rc = tc_launch(plan, net->stream);
+    } else if (net->precision == OCTSEG_BF16) {
+      View<const __nv_bfloat16> iv = make_view(reinterpret_cast<const __nv_bfloat16 *>(d_in), n, b.cin / 8, 0, b.cin / 8, h, w);
+      View<__nv_bfloat16> ov = make_view(reinterpret_cast<__nv_bfloat16 *>(d_out), n, b.cout / 8, 0, b.cout / 8, oh, ow);
+      rc = launch_conv_direct<__nv_bfloat16>(iv, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout,
+                                             b.ups ? 1 : 0, bs.scale, bs.shift, 1, ov, net->stream);
+    } else {
+      View<const float> iv = make_view(reinterpret_cast<const float *>(d_in), n, b.cin / 8, 0, b.cin / 8, h, w);
+      View<float> ov = make_view(reinterpret_cast<float *>(d_out), n, b.cout / 8, 0, b.cout / 8, oh, ow);
+      rc = launch_conv_direct<float>(iv, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout,
+                                     b.ups ? 1 : 0, bs.scale, bs.shift, 1, ov, net->stream);
+    }
+    ++net->launches;
+    if (rep == reps - 1) cudaEventRecord(e1, net->stream);
+  }
+  if (rc == 0) rc = check_status(net);
+  if (rc == 0 && ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc == 0) {
+    std::vector<float> ob(out_elems);
+    if (net->precision == OCTSEG_BF16) {
+      std::vector<uint16_t> o16(out_elems);
+      cudaMemcpy(o16.data(), d_out, out_elems * 2, cudaMemcpyDeviceToHost);
+      for (size_t i = 0; i < out_elems; ++i) {
+        uint32_t u = (uint32_t)o16[i] << 16;
+        std::memcpy(&ob[i], &u, 4);
+      }
+    } else {
+      cudaMemcpy(ob.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost);
+    }
+    for (int i = 0; i < n; ++i)
+      for (int y = 0; y < oh; ++y)
+        for (int x = 0; x < ow; ++x)
+          for (int c = 0; c < b.cout; ++c)
+            out[(((size_t)i * oh + y) * ow + x) * b.cout + c] =
+                ob[((((size_t)i * (b.cout / 8) + c / 8) * oh + y) * ow + x) * 8 + (c & 7)];
+  }
+  cudaFree(d_in);
+  cudaFree(d_out);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// Internal network object behind the C ABI.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/octseg.h"
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace octseg {
+
+struct BlockSpec {
+  int index = 0;
+  int role = 0;  // 0 enc, 1 mid, 2 up, 3 dec, 4 head
+  int level = 0;
+  int kh = 0, kw = 0, cin = 0, cout = 0;
+  bool has_bn = true, pool_after = false, ups = false, dropout_after = false;
+  int concat_level = -1;
+  int conv_j = 0;  // position inside its group of conv_layers
+  // parameter table indices (Keras order): kernel, bias, gamma, beta, mean, var
+  int p_kernel = -1, p_bias = -1, p_gamma = -1, p_beta = -1, p_mean = -1, p_var = -1;
+};
+
+struct ParamSpec {
+  std::string name;
+  int ndim = 0;
+  int64_t shape[4] = {0, 0, 0, 0};
+  int64_t count = 0;
+  int64_t offset = 0;   // floats into the flat buffer (16-float aligned)
+  bool trainable = true;
+  int block = 0;
+};
+
+int build_graph(const octseg_config &cfg, std::vector<BlockSpec> *blocks, std::vector<ParamSpec> *params,
+                int64_t *total_floats);
+
+// Per-block device state
+struct BlockState {
+  float *scale = nullptr, *shift = nullptr;   // folded BN (inference) [cout]
+  bool geo_ok = false;
+  TcGeometry geo{};
+  __nv_bfloat16 *wpack = nullptr;
+  size_t wpack_elems = 0;
+};
+
+// Workspace views for one (n,h,w)
+struct BlockIO {
+  void *in = nullptr;  int in_planes_total = 0, in_plane0 = 0, in_planes = 0, in_h = 0, in_w = 0;
+  void *out = nullptr; int out_planes_total = 0, out_plane0 = 0, out_planes = 0, out_h = 0, out_w = 0;
+  void *pool = nullptr; int pool_h = 0, pool_w = 0;   // pooled copy (encoder last block)
+  bool use_tc = false;
+  TcPlan plan;
+};
+
+}  // namespace octseg
+
+struct octseg_net {
+  octseg_config cfg{};
+  int device = 0;
+  int precision = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<octseg::BlockSpec> blocks;
+  std::vector<octseg::ParamSpec> params;
+  int64_t total_floats = 0;
+  float *d_params = nullptr;          // flat fp32 master weights (Keras order)
+  std::vector<float> h_params;        // host mirror
+  bool host_stale = false;            // device params changed (training) since last mirror
+  bool derived_dirty = true;          // folded BN / packed weights need a rebuild
+  std::vector<octseg::BlockState> bstate;
+  // workspace
+  int ws_n = 0, ws_h = 0, ws_w = 0;
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
+  std::vector<octseg::BlockIO> io;
+  // host-call staging
+  void *d_img = nullptr; size_t d_img_bytes = 0;
+  float *d_probs = nullptr; size_t d_probs_bytes = 0;
+  uint8_t *d_labels = nullptr; size_t d_labels_bytes = 0;
+  int *d_status = nullptr;
+  int *h_status = nullptr;            // pinned
+  int64_t launches = 0;
+  bool disable_tc = false;
+  int microbatch = 0;
+  // training state lives in train.cu
+  void *train = nullptr;
+};

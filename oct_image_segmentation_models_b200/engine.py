@@ -1,0 +1,170 @@
+"""Thin host wrapper around one liboctseg network handle (one per GPU).
+
+numpy in / numpy out; all arithmetic happens in the CUDA library.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as nat
+from .models.unet_spec import unet_param_specs
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class UNetEngine:
+    def __init__(self, *, input_channels: int, num_classes: int, start_neurons: int = 8,
+                 pool_layers: int = 4, conv_layers: int = 2, enc_kernel=(3, 3), dec_kernel=(2, 2),
+                 precision: str = "bf16", device: int = 0):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.spec_kwargs = dict(input_channels=input_channels, num_classes=num_classes,
+                                start_neurons=start_neurons, pool_layers=pool_layers,
+                                conv_layers=conv_layers, enc_kernel=tuple(enc_kernel),
+                                dec_kernel=tuple(dec_kernel))
+        self.precision = precision
+        self.device = device
+        self.input_channels = input_channels
+        self.num_classes = num_classes
+        self._lib = nat.load()
+        self._cfg = nat.make_config(**self.spec_kwargs)
+        self.param_specs = unet_param_specs(**self.spec_kwargs)
+        self._h = C.c_void_p()
+        nat.check(self._lib.octseg_create(C.byref(self._cfg), device,
+                                          nat.BF16 if precision == "bf16" else nat.FP32,
+                                          C.byref(self._h)))
+
+    # ---- lifetime ----------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.octseg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights -----------------------------------------------------------------
+    def set_weights(self, weights: Sequence[np.ndarray]):
+        if len(weights) != len(self.param_specs):
+            raise ValueError(f"expected {len(self.param_specs)} weight tensors, got {len(weights)}")
+        for i, ((name, shape), w) in enumerate(zip(self.param_specs, weights)):
+            a = np.ascontiguousarray(w, dtype=np.float32)
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
+            nat.check(self._lib.octseg_set_param(self._h, i, _ptr(a), a.size))
+
+    def get_weights(self) -> List[np.ndarray]:
+        out = []
+        for i, (name, shape) in enumerate(self.param_specs):
+            a = np.empty(shape, dtype=np.float32)
+            nat.check(self._lib.octseg_get_param(self._h, i, _ptr(a), a.size))
+            out.append(a)
+        return out
+
+    # ---- inference ---------------------------------------------------------------
+    def predict(self, images: np.ndarray, want_probs: bool = True, want_labels: bool = False,
+                probs_out: Optional[np.ndarray] = None, labels_out: Optional[np.ndarray] = None):
+        """images: [N,H,W,C] uint8 (raw) or float32 (raw 0..255 values; x/255 is applied
+        on the device, reference models/unet.py:87-91).  Returns (probs, labels)."""
+        if images.ndim != 4 or images.shape[3] != self.input_channels:
+            raise ValueError(f"images must be [N,H,W,{self.input_channels}]")
+        if images.dtype == np.uint8:
+            dt = nat.U8
+        else:
+            images = np.asarray(images, dtype=np.float32)
+            dt = nat.F32
+        images = np.ascontiguousarray(images)
+        n, h, w, _ = images.shape
+        probs = labels = None
+        if want_probs:
+            probs = probs_out if probs_out is not None else np.empty((n, h, w, self.num_classes), np.float32)
+        if want_labels:
+            labels = labels_out if labels_out is not None else np.empty((n, h, w), np.uint8)
+        nat.check(self._lib.octseg_predict_host(self._h, _ptr(images), dt, n, h, w, _ptr(probs), _ptr(labels)))
+        return probs, labels
+
+    def predict_device(self, images_ptr: int, dtype: int, n: int, h: int, w: int,
+                       probs_ptr: Optional[int], labels_ptr: Optional[int], stream: Optional[int] = None):
+        """Asynchronous variant on device pointers (e.g. torch tensors' data_ptr())."""
+        nat.check(self._lib.octseg_predict_device(self._h, C.c_void_p(images_ptr), dtype, n, h, w,
+                                                  C.c_void_p(probs_ptr) if probs_ptr else None,
+                                                  C.c_void_p(labels_ptr) if labels_ptr else None,
+                                                  C.c_void_p(stream) if stream else None))
+
+    def synchronize(self):
+        nat.check(self._lib.octseg_synchronize(self._h))
+
+    # ---- training ----------------------------------------------------------------
+    def train_begin(self, class_weights: Sequence[float], learning_rate=1e-3, beta_1=0.9, beta_2=0.999,
+                    epsilon=1e-7, dropout_rate=0.5, dropout_seed=0, global_batch=0):
+        cw = np.ascontiguousarray(class_weights, dtype=np.float32)
+        if cw.size != self.num_classes:
+            raise ValueError("class_weights must have num_classes entries")
+        tc = nat.OctsegTrainConfig(learning_rate, beta_1, beta_2, epsilon, dropout_rate, dropout_seed,
+                                   global_batch)
+        nat.check(self._lib.octseg_train_begin(self._h, C.byref(tc), _ptr(cw)))
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        nat.check(self._lib.octseg_comm_init(self._h, buf, rank, world))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        nat.check(nat.load().octseg_comm_unique_id(buf))
+        return bytes(buf)
+
+    def train_step(self, images: np.ndarray, labels: np.ndarray,
+                   dropout_mask: Optional[np.ndarray] = None) -> float:
+        if images.dtype == np.uint8:
+            dt = nat.U8
+        else:
+            images = np.asarray(images, dtype=np.float32)
+            dt = nat.F32
+        images = np.ascontiguousarray(images)
+        n, h, w, _ = images.shape
+        lab = np.ascontiguousarray(labels.reshape(n, h, w), dtype=np.uint8)
+        dm = None if dropout_mask is None else np.ascontiguousarray(dropout_mask, dtype=np.uint8)
+        loss = C.c_float()
+        nat.check(self._lib.octseg_train_step_host(self._h, _ptr(images), dt, _ptr(lab), n, h, w, _ptr(dm),
+                                                   C.byref(loss)))
+        return float(loss.value)
+
+    def get_grads(self) -> List[Optional[np.ndarray]]:
+        out: List[Optional[np.ndarray]] = []
+        for i, (name, shape) in enumerate(self.param_specs):
+            if name.endswith("moving_mean:0") or name.endswith("moving_variance:0"):
+                out.append(None)
+                continue
+            a = np.empty(shape, dtype=np.float32)
+            nat.check(self._lib.octseg_get_grad(self._h, i, _ptr(a), a.size))
+            out.append(a)
+        return out
+
+    # ---- introspection -----------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self._lib.octseg_launch_count(self._h))
+
+    def layer_uses_tensor_core(self, conv_index: int, h: int, w: int) -> bool:
+        return bool(self._lib.octseg_layer_uses_tensor_core(self._h, conv_index, h, w))
+
+    def debug_conv_block(self, conv_index: int, x_nhwc: np.ndarray, path: int = 0, timed: bool = False):
+        """Run one conv block (conv + folded BN + ReLU; x2 upsample first for 'up' blocks)
+        on NHWC float32 input.  path 0 = CUDA-core kernel, 1 = tcgen05 kernel."""
+        from .models.unet_spec import unet_blocks
+        b = unet_blocks(**self.spec_kwargs)[conv_index]
+        x = np.ascontiguousarray(x_nhwc, dtype=np.float32)
+        n, h, w, c = x.shape
+        assert c == b.cin
+        oh, ow = (2 * h, 2 * w) if b.upsample_before else (h, w)
+        out = np.empty((n, oh, ow, b.cout), np.float32)
+        ms = C.c_float(0.0)
+        nat.check(self._lib.octseg_debug_conv_block(self._h, conv_index, path, _ptr(x), n, h, w, _ptr(out),
+                                                    C.byref(ms) if timed else None))
+        return (out, float(ms.value)) if timed else out
