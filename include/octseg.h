@@ -122,6 +122,11 @@ int32_t octseg_get_grad(octseg_net *net, int32_t index, float *host, int64_t cou
 /* ---- introspection for bench / tests -------------------------------------------- */
 /* number of kernels this library launched on the handle since creation */
 int64_t octseg_launch_count(octseg_net *net);
+/* per-block CUDA-event timing of forward passes (bench roofline): when enabled every conv block
+ * (and its pool / the head) is bracketed by events on the launching stream */
+int32_t octseg_set_profiling(octseg_net *net, int32_t enable);
+/* milliseconds per block of the LAST forward micro-batch; n_blocks receives the block count */
+int32_t octseg_get_block_times(octseg_net *net, float *ms, int32_t cap, int32_t *n_blocks);
 /* 1 if conv layer `conv_index` runs on the tcgen05 path at (h,w) in the current mode */
 int32_t octseg_layer_uses_tensor_core(octseg_net *net, int32_t conv_index, int32_t h, int32_t w);
 /* run ONE conv block (index in Keras order) on caller data, for per-layer parity tests:

@@ -245,9 +245,12 @@ template <typename T>
 static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h, int w, float *d_probs,
                      uint8_t *d_labels, cudaStream_t st) {
   const float *P = net->d_params;
+  const bool prof = net->profiling && net->prof_events.size() == net->blocks.size() + 1;
+  if (prof) cudaEventRecord(net->prof_events[0], st);
   for (auto &b : net->blocks) {
     BlockIO &io = net->io[b.index];
     BlockState &bs = net->bstate[b.index];
+    if (b.index > 0 && prof) cudaEventRecord(net->prof_events[b.index], st);
     if (b.role == 4) {
       View<const T> in = make_view(reinterpret_cast<const T *>(io.in), n, io.in_planes_total, io.in_plane0,
                                    io.in_planes, io.in_h, io.in_w);
@@ -255,6 +258,7 @@ static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h
                          b.cout, d_probs, d_labels, st))
         return 1;
       ++net->launches;
+      if (prof) { cudaEventRecord(net->prof_events[net->blocks.size()], st); net->prof_valid = true; }
       continue;
     }
     View<T> out = make_view(reinterpret_cast<T *>(io.out), n, io.out_planes_total, io.out_plane0,
@@ -419,6 +423,7 @@ int32_t octseg_destroy(octseg_net *net) {
   cudaSetDevice(net->device);
   if (net->stream) cudaStreamSynchronize(net->stream);
   octseg_train_free(net);
+  for (auto &e : net->prof_events) cudaEventDestroy(e);
   for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); }
   cudaFree(net->d_params); cudaFree(net->ws); cudaFree(net->d_img); cudaFree(net->d_probs);
   cudaFree(net->d_labels); cudaFree(net->d_status);
@@ -502,6 +507,30 @@ int32_t octseg_synchronize(octseg_net *net) {
 }
 
 int64_t octseg_launch_count(octseg_net *net) { return net ? net->launches : 0; }
+
+int32_t octseg_set_profiling(octseg_net *net, int32_t enable) {
+  if (!net) { set_error("null argument"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  if (enable && net->prof_events.empty()) {
+    net->prof_events.resize(net->blocks.size() + 1);
+    for (auto &e : net->prof_events) OCTSEG_CUDA(cudaEventCreate(&e));
+  }
+  net->profiling = enable != 0;
+  net->prof_valid = false;
+  return 0;
+}
+
+int32_t octseg_get_block_times(octseg_net *net, float *ms, int32_t cap, int32_t *n_blocks) {
+  if (!net || !ms) { set_error("null argument"); return 1; }
+  if (!net->prof_valid) { set_error("no profiled forward pass yet"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  OCTSEG_CUDA(cudaEventSynchronize(net->prof_events.back()));
+  const int nb = (int)net->blocks.size();
+  if (n_blocks) *n_blocks = nb;
+  for (int i = 0; i < nb && i < cap; ++i)
+    OCTSEG_CUDA(cudaEventElapsedTime(&ms[i], net->prof_events[i], net->prof_events[i + 1]));
+  return 0;
+}
 
 int32_t octseg_layer_uses_tensor_core(octseg_net *net, int32_t conv_index, int32_t h, int32_t w) {
   if (!net || conv_index < 0 || conv_index >= (int)net->blocks.size()) return 0;

@@ -82,6 +82,9 @@ struct octseg_net {
   int64_t launches = 0;
   bool disable_tc = false;
   int microbatch = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;   // blocks+1 events
+  bool prof_valid = false;
   // training state lives in train.cu
   void *train = nullptr;
 };

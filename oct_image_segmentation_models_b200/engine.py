@@ -151,6 +151,15 @@ class UNetEngine:
     def launch_count(self) -> int:
         return int(self._lib.octseg_launch_count(self._h))
 
+    def set_profiling(self, enable: bool):
+        nat.check(self._lib.octseg_set_profiling(self._h, 1 if enable else 0))
+
+    def block_times_ms(self) -> List[float]:
+        buf = (C.c_float * 256)()
+        n = C.c_int32()
+        nat.check(self._lib.octseg_get_block_times(self._h, buf, 256, C.byref(n)))
+        return [float(buf[i]) for i in range(n.value)]
+
     def layer_uses_tensor_core(self, conv_index: int, h: int, w: int) -> bool:
         return bool(self._lib.octseg_layer_uses_tensor_core(self._h, conv_index, h, w))
 

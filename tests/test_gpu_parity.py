@@ -1,0 +1,152 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI, against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import postproc
+from oracle.unet_oracle import BN_EPS, OracleUNet
+from oct_image_segmentation_models_b200.common.synthetic import (fast_random_batch, synthetic_batch,
+                                                                  synthetic_weights)
+from oct_image_segmentation_models_b200.models.unet_spec import unet_blocks
+
+pytestmark = pytest.mark.gpu
+CFG = dict(input_channels=1, num_classes=4)
+FP32_REL, BF16_REL, REL_FLOOR = 1e-4, 2e-2, 1e-3   # north_star tolerances; floor per SURVEY section 7
+
+
+def rel_err(p, ref):
+    return np.abs(p - ref) / np.maximum(ref, REL_FLOOR)
+
+
+def bf16_round(a):
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def oracle_block(b, weights, x_nhwc):
+    i = 6 * b.index
+    w, bias, gamma, beta, mean, var = [torch.from_numpy(np.asarray(t, np.float32)).double() for t in weights[i:i + 6]]
+    x = torch.from_numpy(x_nhwc).double().permute(0, 3, 1, 2)
+    if b.upsample_before:
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    pt, pl = (b.kh - 1) // 2, (b.kw - 1) // 2
+    x = F.pad(x, (pl, b.kw - 1 - pl, pt, b.kh - 1 - pt))
+    z = F.conv2d(x, w.permute(3, 2, 0, 1), bias)
+    s = torch.rsqrt(var + BN_EPS) * gamma
+    y = torch.relu((z - mean[None, :, None, None]) * s[None, :, None, None] + beta[None, :, None, None])
+    return y.permute(0, 2, 3, 1).numpy()
+
+
+@pytest.fixture(scope="module")
+def engines():
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    w = synthetic_weights(seed=42, **CFG)
+    e32 = UNetEngine(precision="fp32", **CFG)
+    e16 = UNetEngine(precision="bf16", **CFG)
+    e32.set_weights(w)
+    e16.set_weights(w)
+    yield w, e32, e16
+    e32.close()
+    e16.close()
+
+
+# (block index, n, h, w): every distinct (k, Cin, Cout, upsample) of the default net + ragged tiles
+BLOCK_CASES = [(1, 2, 32, 24), (2, 1, 16, 16), (3, 2, 32, 24), (4, 1, 48, 8), (5, 2, 32, 16), (6, 1, 16, 16),
+               (7, 2, 16, 16), (8, 1, 16, 8), (9, 1, 16, 16), (10, 2, 16, 8), (11, 2, 32, 16), (12, 1, 16, 16),
+               (13, 2, 16, 16), (14, 1, 32, 16), (16, 2, 16, 16), (17, 1, 32, 32), (19, 2, 32, 24),
+               (20, 2, 32, 24), (21, 2, 48, 40), (1, 1, 20, 12), (19, 1, 20, 12)]
+
+
+@pytest.mark.parametrize("idx,n,h,w", BLOCK_CASES)
+def test_conv_block_tcgen05_and_direct_vs_oracle(engines, idx, n, h, w):
+    weights, e32, e16 = engines
+    b = unet_blocks(**CFG)[idx]
+    rng = np.random.default_rng(100 + idx)
+    x = np.maximum(rng.normal(0.3, 1.0, size=(n, h, w, b.cin)), 0).astype(np.float32)
+    ref32 = oracle_block(b, weights, x)
+    got32 = e32.debug_conv_block(idx, x, path=0)
+    scale = np.abs(ref32).max()
+    assert np.abs(got32 - ref32).max() <= 2e-6 * max(scale, 1.0)
+    ref16 = oracle_block(b, weights, bf16_round(x))
+    for path in (0, 1):
+        got = e16.debug_conv_block(idx, x, path=path)
+        assert np.isfinite(got).all()
+        # bf16 operands + bf16 output rounding: 2^-8 relative on the output scale, generously
+        assert np.abs(got - ref16).max() <= 8e-3 * max(scale, 1.0), (path, np.abs(got - ref16).max())
+
+
+def test_default_net_uses_tensor_cores(engines):
+    _, e32, e16 = engines
+    blocks = unet_blocks(**CFG)
+    tc = [i for i in range(len(blocks)) if e16.layer_uses_tensor_core(i, 512, 512)]
+    assert tc == list(range(1, 22)), tc            # every conv block except the Cin=1 stem and the head
+    assert not any(e32.layer_uses_tensor_core(i, 512, 512) for i in range(len(blocks)))
+
+
+@pytest.mark.parametrize("n,h,w", [(4, 256, 256), (2, 64, 64), (3, 32, 48), (1, 16, 16)])
+def test_predict_parity_fp32_and_bf16(engines, n, h, w):
+    weights, e32, e16 = engines
+    imgs, _ = synthetic_batch(10, n, h, w)
+    ref = OracleUNet(weights, **CFG).predict(imgs)
+    p32, l32 = e32.predict(imgs, want_labels=True)
+    assert rel_err(p32, ref).max() <= FP32_REL
+    assert (l32 == ref.argmax(-1)).mean() >= 0.999
+    assert np.array_equal(l32, p32.argmax(-1))      # device argmax == np.argmax on returned probs
+    p16, l16 = e16.predict(imgs, want_labels=True)
+    assert rel_err(p16, ref).max() <= BF16_REL
+    assert np.array_equal(l16, p16.argmax(-1))
+    if n * h * w >= 16384:
+        assert (l16 == ref.argmax(-1)).mean() >= 0.999
+
+
+def test_predict_float_input_equals_uint8_input(engines):
+    _, e32, _ = engines
+    imgs, _ = synthetic_batch(3, 2, 32, 32)
+    a, _ = e32.predict(imgs)
+    b, _ = e32.predict(imgs.astype(np.float32))
+    assert np.array_equal(a, b)
+
+
+def test_predict_batch_equals_per_image_calls(engines):
+    """The reference calls predict() once per image (evaluation.py:129); batching must not
+    change a single bit (inference BN has no cross-image coupling)."""
+    _, e32, e16 = engines
+    imgs, _ = synthetic_batch(20, 3, 64, 32)
+    for e in (e32, e16):
+        full, _ = e.predict(imgs)
+        for i in range(3):
+            one, _ = e.predict(imgs[i:i + 1])
+            assert np.array_equal(one[0], full[i])
+
+
+def test_boundaries_identical_on_trained_weights():
+    """north_star: boundary positions from min_path_processing identical on both outputs."""
+    from pathlib import Path
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    g = np.load(Path(__file__).parent / "golden" / "trained_small_unet.npz")
+    cfg = dict(input_channels=1, num_classes=4, start_neurons=8, pool_layers=2, conv_layers=2)
+    weights = [g[f"w{i:03d}"] for i in range(len([k for k in g.files if k.startswith("w")]))]
+    for prec, tol in (("fp32", FP32_REL), ("bf16", BF16_REL)):
+        eng = UNetEngine(precision=prec, **cfg)
+        eng.set_weights(weights)
+        probs, labels = eng.predict(g["images"], want_labels=True)
+        eng.close()
+        assert rel_err(probs, g["probs"]).max() <= tol
+        assert (labels == g["probs"].argmax(-1)).mean() >= 0.999
+        for i in range(len(g["images"])):
+            segs = postproc.boundaries_from_probs(probs[i:i + 1])
+            assert np.array_equal(segs, g["segs"][i]), (prec, i)
+
+
+def test_full_size_properties_cfg2(engines):
+    """BASELINE cfg2 size (512x512, batch 8 here to bound CPU time): size-independent
+    properties -- probabilities sum to 1, labels == argmax, bf16 and fp32 agree."""
+    _, e32, e16 = engines
+    imgs = fast_random_batch(5, 8, 512, 512)
+    p32, l32 = e32.predict(imgs, want_labels=True)
+    p16, l16 = e16.predict(imgs, want_labels=True)
+    np.testing.assert_allclose(p32.sum(-1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(p16.sum(-1), 1.0, atol=1e-5)
+    assert np.array_equal(l32, p32.argmax(-1)) and np.array_equal(l16, p16.argmax(-1))
+    assert rel_err(p16, p32).max() <= BF16_REL
+    assert e16.launch_count() > 0
