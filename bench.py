@@ -66,11 +66,14 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t_begin = self.t_end = None
 
     def start(self):
+        """Launch the sampler early (nvidia-smi needs ~100 ms to start); samples are kept
+        with their arrival time and only those inside [mark_begin, mark_end] are used."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -78,28 +81,39 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def parse(rows):
+            sm, mx, reasons = [], None, set()
+            for _, ln in rows:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 6:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx = float(f[1])
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, mx, reasons
+        inside = [r for r in self.lines if self.t_begin is not None and self.t_begin <= r[0] <= (self.t_end or 1e30)]
+        sm, mx, reasons = parse(inside if inside else self.lines[-3:])
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "in_timed_region": bool(inside)}
 
 
 def cpu_reference_throughput(n_images, per_call, threads):
@@ -151,8 +165,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
@@ -191,17 +205,22 @@ def main():
     probs_host = torch.empty((n, H, W, K_CLASSES), dtype=torch.float32).pin_memory()
     imgs_dev = imgs_host.cuda(non_blocking=True)
     probs_dev = torch.empty((n, H, W, K_CLASSES), dtype=torch.float32, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: the library launches on it, and torch.cuda.Event times it
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step_device():
         eng.predict_device(imgs_dev.data_ptr(), nat.U8, n, H, W, probs_dev.data_ptr(), None, stream)
 
     # ---------------- device-resident timing ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_begin()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -209,6 +228,7 @@ def main():
         step_device()
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
     clocks = sampler.stop()
@@ -222,13 +242,14 @@ def main():
     # ---------------- per-kernel roofline (instrumented pass, same K steps) ----------------
     eng.set_profiling(True)
     per_block = None
-    for _ in range(args.steps):
+    prof_steps = min(args.steps, 20)
+    for _ in range(prof_steps):
         step_device()
         torch.cuda.synchronize()
         bt = np.asarray(eng.block_times_ms())
         per_block = bt if per_block is None else per_block + bt
     eng.set_profiling(False)
-    per_block /= args.steps
+    per_block /= prof_steps
     elem = 2 if args.precision == "bf16" else 4
     lb = np.asarray(layer_bytes(H, W, elem), dtype=np.float64) * n
     tc_idx = [i for i in range(len(lb)) if eng.layer_uses_tensor_core(i, H, W)]
@@ -268,7 +289,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, secs, done = cpu_reference_throughput(24, 4, threads)
+        v, secs, done = cpu_reference_throughput(480, 4, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{done} synthetic 512x512 B-scans in batches of 4 ({secs:.1f} s), torch-CPU restatement "
                          "of the Keras graph (oracle/unet_oracle.py)"}

@@ -116,12 +116,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
 
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 
 struct __align__(8) TcBarriers {
   uint64_t a_full[kMaxStages], a_empty[kMaxStages];
   uint64_t b_full[kMaxStages], b_empty[kMaxStages];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t w_full;          // resident weights landed
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -136,7 +137,9 @@ __device__ __forceinline__ void decode_tile(const TcConvParams &p, int tile, int
   img = t / p.tiles_y;
 }
 
-__global__ void __launch_bounds__(256, 1)
+constexpr int kTcThreads = 384;   // warps 0..3 control, warps 4..11 epilogue (two warpgroups)
+
+__global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ TcConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -145,14 +148,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint8_t *a_smem = smem;
   uint8_t *b_smem = smem + (size_t)a_stride * p.a_stages;
   TcBarriers *bars = reinterpret_cast<TcBarriers *>(b_smem + (size_t)b_stride * p.b_stages);
+  const int mt = p.mt_x * p.mt_y;                 // M-tiles (128 rows each) per super-tile
+  const uint32_t acc_cols = (uint32_t)(mt * p.n_cols);
 
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * (uint32_t)p.n_cols) tmem_cols <<= 1;
+  while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 8); }
+    mbar_init(smem_u32(&bars->w_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -169,6 +175,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       // ===================== TMA producer =====================
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+      if (p.b_resident) {
+        // whole packed weight image of the layer stays in smem for the kernel's lifetime
+        const uint32_t wfull = smem_u32(&bars->w_full);
+        mbar_expect_tx(wfull, p.b_stage_bytes);
+        uint32_t done = 0;
+        while (done < p.b_stage_bytes) {           // bulk copies are capped well below 1 MB each
+          const uint32_t part = min(p.b_stage_bytes - done, 32768u);
+          bulk_load(smem_u32(b_smem) + done, reinterpret_cast<const uint8_t *>(p.wpack) + done, part, wfull);
+          done += part;
+        }
+      }
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       bool ok = true;
@@ -182,9 +199,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (!ok) break;
           const uint32_t afull = smem_u32(&bars->a_full[as]);
           mbar_expect_tx(afull, p.a_stage_bytes);
+          // tensor map is declared in 8-byte elements: x coordinate = px * 2
           tma_load_4d(smem_u32(a_smem + (size_t)as * a_stride), &tmap_a, afull,
-                      (tx * kTcTileW - p.pad_x) * 8, ty * kTcTileH - p.pad_y, ch * p.planes_per_chunk, img);
+                      (tx * p.mt_x * kTcTileW - p.pad_x) * 2, ty * p.mt_y * kTcTileH - p.pad_y,
+                      ch * p.planes_per_chunk, img);
           if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+          if (p.b_resident) continue;
           for (int g = 0; g < p.ksteps; g += p.bgroup) {
             ok = mbar_wait(smem_u32(&bars->b_empty[bs]), bph ^ 1u, p.status, 2);
             if (!ok) break;
@@ -202,33 +222,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // ===================== MMA issuer =====================
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_cols >> 3) << 17) |
                              ((128u >> 4) << 24);
-      const uint32_t sbo_a = (uint32_t)p.box_w * 16u;
+      const uint32_t pitch = (uint32_t)p.box_w * 16u;
       const uint32_t lbo_b = (uint32_t)p.n_cols * 16u;
+      const uint32_t kstep_b = 32u * (uint32_t)p.n_cols;
       int as = 0, bs = 0, acc = 0;
       uint32_t aph = 0, bph = 0, accph = 0;
       bool ok = true;
+      if (p.b_resident) {
+        ok = mbar_wait(smem_u32(&bars->w_full), 0, p.status, 7);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
         ok = mbar_wait(smem_u32(&bars->acc_empty[acc]), accph ^ 1u, p.status, 3);
         if (!ok) break;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_cols);
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
         for (int ch = 0; ok && ch < p.cin_chunks; ++ch) {
           ok = mbar_wait(smem_u32(&bars->a_full[as]), aph, p.status, 4);
           if (!ok) break;
+          tc_fence_after();
           const uint32_t a_base = smem_u32(a_smem + (size_t)as * a_stride);
           for (int g = 0; g < p.ksteps; g += p.bgroup) {
-            ok = mbar_wait(smem_u32(&bars->b_full[bs]), bph, p.status, 5);
-            if (!ok) break;
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(b_smem + (size_t)bs * b_stride);
+            uint32_t b_base;
+            if (p.b_resident) {
+              b_base = smem_u32(b_smem) + (uint32_t)(ch * p.ksteps + g) * kstep_b;
+            } else {
+              ok = mbar_wait(smem_u32(&bars->b_full[bs]), bph, p.status, 5);
+              if (!ok) break;
+              tc_fence_after();
+              b_base = smem_u32(b_smem + (size_t)bs * b_stride);
+            }
             for (int s = 0; s < p.bgroup; ++s) {
               const int ks = g + s;
-              const uint64_t da = make_desc(a_base + p.a_off[ks], p.a_lbo[ks], sbo_a);
-              const uint64_t db = make_desc(b_base + (uint32_t)s * 32u * p.n_cols, lbo_b, 128u);
-              umma_bf16(d_tmem, da, db, idesc, (ch | ks) != 0 ? 1u : 0u);
+              const uint64_t db = make_desc(b_base + (uint32_t)s * kstep_b, lbo_b, 128u);
+              const uint32_t a_ks = a_base + p.a_off[ks];
+              const uint32_t lbo = p.a_lbo[ks];
+              const uint32_t accum = (ch | ks) != 0 ? 1u : 0u;
+              for (int iy = 0; iy < p.mt_y; ++iy)
+                for (int ix = 0; ix < p.mt_x; ++ix) {
+                  const uint64_t da = make_desc(a_ks + (uint32_t)iy * kTcTileH * pitch + (uint32_t)ix * 128u, lbo, pitch);
+                  umma_bf16(d_tmem + (uint32_t)((iy * p.mt_x + ix) * p.n_cols), da, db, idesc, accum);
+                }
             }
-            umma_commit(smem_u32(&bars->b_empty[bs]));
-            if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+            if (!p.b_resident) {
+              umma_commit(smem_u32(&bars->b_empty[bs]));
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+            }
           }
           umma_commit(smem_u32(&bars->a_empty[as]));
           if (++as == p.a_stages) { as = 0; aph ^= 1u; }
@@ -238,10 +277,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue (2 warpgroups, M-tiles interleaved) =====================
     const int q = warp & 3;                 // TMEM lane quarter
+    const int wg = (warp - 4) >> 2;         // 0 or 1
     const int m = q * 32 + lane;            // GEMM row == TMEM lane
-    const int r = m >> 3, px = m & 7;       // tile row / px
+    const int r = m >> 3, px = m & 7;       // row / px inside the 8x16 M-tile
     int acc = 0;
     uint32_t accph = 0;
     bool ok = true;
@@ -251,19 +291,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ok = mbar_wait(smem_u32(&bars->acc_full[acc]), accph, p.status, 6);
       if (!ok) break;
       tc_fence_after();
-      const int y = ty * kTcTileH + r, x = tx * kTcTileW + px;
-      const bool inside = (y < p.h) && (x < p.w);
-      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_cols);
-      for (int j = 0; j < p.n_cols; j += 8) {
-        const int col = n_tile * p.n_cols + j;   // warp-uniform
-        if (col >= p.cols_valid) break;
-        uint32_t v[8];
-        tmem_ld8(t_base + (uint32_t)j, v);
-        tmem_ld_wait();
-        if (inside) {
-          int co0, oy, ox;
-          if (p.mode == 0) { co0 = col; oy = y; ox = x; }
-          else {
+      for (int t = wg; t < mt; t += 2) {
+        const int iy = t / p.mt_x, ix = t - iy * p.mt_x;
+        const int y = (ty * p.mt_y + iy) * kTcTileH + r, x = (tx * p.mt_x + ix) * kTcTileW + px;
+        const bool inside = (y < p.h) && (x < p.w);
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols +
+                                (uint32_t)(t * p.n_cols);
+        float z[kTcMaxClasses];
+        if (p.mode == 2) {
+#pragma unroll
+          for (int k = 0; k < kTcMaxClasses; ++k) z[k] = (k < p.head_k) ? __ldg(p.head_b + k) : 0.f;
+        }
+        for (int j = 0; j < p.n_cols; j += 8) {
+          const int col = n_tile * p.n_cols + j;   // warp-uniform
+          if (col >= p.cols_valid) break;
+          uint32_t v[8];
+          tmem_ld8(t_base + (uint32_t)j, v);
+          tmem_ld_wait();
+          int co0 = col, oy = y, ox = x;
+          if (p.mode == 1) {
             const int par = col / p.cout;
             co0 = col - par * p.cout;
             oy = 2 * y + (par >> 1);
@@ -275,9 +321,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             float f = fmaf(__uint_as_float(v[k]), __ldg(p.scale + co0 + k), __ldg(p.shift + co0 + k));
             o.v[k] = p.relu ? fmaxf(f, 0.f) : f;
           }
-          __nv_bfloat16 *dst = p.out + (long long)img * p.out_img_stride +
-                               (((long long)(co0 >> 3) * p.out_h + oy) * p.out_w + ox) * 8;
-          store8(dst, o);
+          if (p.mode == 2) {
+            // fused 1x1 conv head: logits accumulate over the channel chunks (fp32 activations)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float *wr = p.head_w + (size_t)(co0 + c) * p.head_k;
+#pragma unroll
+              for (int k = 0; k < kTcMaxClasses; ++k)
+                if (k < p.head_k) z[k] = fmaf(o.v[c], __ldg(wr + k), z[k]);
+            }
+            continue;
+          }
+          if (inside) {
+            __nv_bfloat16 *dst = p.out + (long long)img * p.out_img_stride +
+                                 (((long long)(co0 >> 3) * p.out_h + oy) * p.out_w + ox) * 8;
+            store8(dst, o);
+          }
+          if (p.pool_out) {
+            // 2x2 max over (px^1, row^1): partners are lanes ^1 and ^8 of this warp
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              float a = fmaxf(o.v[k], __shfl_xor_sync(0xffffffffu, o.v[k], 1));
+              o.v[k] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 8));
+            }
+            if (inside && !(px & 1) && !(r & 1)) {
+              __nv_bfloat16 *dst = p.pool_out + (long long)img * p.pool_img_stride +
+                                   (((long long)(co0 >> 3) * (p.out_h >> 1) + (y >> 1)) * (p.out_w >> 1) + (x >> 1)) * 8;
+              store8(dst, o);
+            }
+          }
+        }
+        if (p.mode == 2 && inside) {
+          // softmax over classes + first-max argmax on the float32 probabilities
+          float mx = z[0];
+#pragma unroll
+          for (int k = 1; k < kTcMaxClasses; ++k)
+            if (k < p.head_k) mx = fmaxf(mx, z[k]);
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < kTcMaxClasses; ++k)
+            if (k < p.head_k) { z[k] = expf(z[k] - mx); s += z[k]; }
+          const float inv = 1.f / s;
+          const long long pix = ((long long)img * p.h + y) * p.w + x;
+          float pm = -1.f;
+          int pa = 0;
+#pragma unroll
+          for (int k = 0; k < kTcMaxClasses; ++k)
+            if (k < p.head_k) {
+              z[k] *= inv;
+              if (z[k] > pm) { pm = z[k]; pa = k; }
+            }
+          if (p.probs) {
+            float *dst = p.probs + pix * p.head_k;
+            if (p.head_k == 4) *reinterpret_cast<float4 *>(dst) = make_float4(z[0], z[1], z[2], z[3]);
+            else {
+#pragma unroll
+              for (int k = 0; k < kTcMaxClasses; ++k)
+                if (k < p.head_k) dst[k] = z[k];
+            }
+          }
+          if (p.labels) p.labels[pix] = (uint8_t)pa;
         }
       }
       tc_fence_before();
@@ -324,8 +427,8 @@ int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g) 
     g->dx_min = floordiv2(0 - pl); g->dx_max = floordiv2(1 + kw - 1 - pl);
   }
   const int nty = g->dy_max - g->dy_min + 1, ntx = g->dx_max - g->dx_min + 1;
-  g->box_h = kTcTileH + nty - 1;
-  g->box_w = kTcTileW + ntx - 1;
+  g->box_h = nty - 1;   // halo rows / px added to the super-tile
+  g->box_w = ntx - 1;
   const int cg = cin / 8;
   g->planes_per_chunk = std::min(cg, 8);
   g->cin_chunks = cg / g->planes_per_chunk;
@@ -445,22 +548,53 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
   TcConvParams &p = *pp;
   std::memset(&p, 0, sizeof(p));
   p.n = n; p.h = h; p.w = w;
-  p.tiles_x = (w + kTcTileW - 1) / kTcTileW;
-  p.tiles_y = (h + kTcTileH - 1) / kTcTileH;
   p.n_tiles_n = g.n_tiles_n;
-  p.num_tiles = n * p.tiles_x * p.tiles_y * p.n_tiles_n;
   p.cin_chunks = g.cin_chunks;
   p.planes_per_chunk = g.planes_per_chunk;
   p.ksteps = g.ksteps;
-  p.bgroup = g.bgroup;
   p.n_cols = g.n_cols;
   p.cols_valid = g.cols_valid;
   p.pad_y = -g.dy_min; p.pad_x = -g.dx_min;
-  p.box_w = g.box_w; p.box_h = g.box_h;
-  const uint32_t pitch = (uint32_t)g.box_w * 16u;
-  const uint32_t plane = pitch * (uint32_t)g.box_h;
+  // ---- weights: resident in smem when the whole packed image of the layer is small
+  const size_t w_total = (size_t)g.cin_chunks * g.ksteps * 32u * g.n_cols;
+  p.b_resident = (g.n_tiles_n == 1 && w_total <= 80 * 1024) ? 1 : 0;
+  size_t b_bytes_total;
+  if (p.b_resident) {
+    p.bgroup = g.ksteps; p.b_stages = 1; p.b_stage_bytes = (uint32_t)w_total;
+    b_bytes_total = (w_total + 127) & ~(size_t)127;
+  } else {
+    p.bgroup = g.bgroup;
+    p.b_stage_bytes = (uint32_t)g.bgroup * 32u * (uint32_t)g.n_cols;
+    p.b_stages = 4;
+    while (p.b_stages > 2 && (size_t)p.b_stages * p.b_stage_bytes > 96 * 1024) --p.b_stages;
+    b_bytes_total = (size_t)p.b_stages * ((p.b_stage_bytes + 127u) & ~127u);
+  }
+  // ---- super-tile: mt_x x mt_y M-tiles of 8 px x 16 rows share one TMA halo box
+  const size_t budget = 208 * 1024 - b_bytes_total - sizeof(TcBarriers) - 1024;
+  const int max_mt = std::max(1, 256 / g.n_cols);          // 2 accumulator stages in 512 TMEM columns
+  static const int cand[][2] = {{8, 2}, {4, 2}, {8, 1}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
+  int best_x = 1, best_y = 1;
+  for (auto &c : cand) {
+    const int mx = c[0], my = c[1];
+    if (mx * my > max_mt) continue;
+    if (mx * kTcTileW > std::max(w, kTcTileW) || my * kTcTileH > std::max(h, kTcTileH)) continue;
+    const size_t stage = (size_t)g.planes_per_chunk * (mx * kTcTileW + g.box_w) * (my * kTcTileH + g.box_h) * 16;
+    if (stage > 48 * 1024 || 3 * stage > budget) continue;
+    const long long tiles = (long long)n * ((w + mx * kTcTileW - 1) / (mx * kTcTileW)) *
+                            ((h + my * kTcTileH - 1) / (my * kTcTileH)) * g.n_tiles_n;
+    if (tiles < 2 * 148 && mx * my > 1) continue;            // keep every SM busy
+    best_x = mx; best_y = my;
+    break;
+  }
+  p.mt_x = best_x; p.mt_y = best_y;
+  p.box_w = best_x * kTcTileW + g.box_w;
+  p.box_h = best_y * kTcTileH + g.box_h;
+  p.tiles_x = (w + best_x * kTcTileW - 1) / (best_x * kTcTileW);
+  p.tiles_y = (h + best_y * kTcTileH - 1) / (best_y * kTcTileH);
+  p.num_tiles = n * p.tiles_x * p.tiles_y * p.n_tiles_n;
+  const uint32_t pitch = (uint32_t)p.box_w * 16u;
+  const uint32_t plane = pitch * (uint32_t)p.box_h;
   p.a_stage_bytes = plane * (uint32_t)g.planes_per_chunk;
-  p.b_stage_bytes = (uint32_t)g.bgroup * 32u * (uint32_t)g.n_cols;
   for (int s = 0; s < g.ksteps; ++s) {
     uint32_t off[2];
     for (int hf = 0; hf < 2; ++hf) {
@@ -471,16 +605,14 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
     if (off[1] <= off[0]) { set_error("tc plan: non-positive LBO"); return 1; }
     p.a_off[s] = off[0];
     p.a_lbo[s] = off[1] - off[0];
+    if (p.a_lbo[s] >= (1u << 18) || pitch >= (1u << 18)) { set_error("tc plan: descriptor stride overflow"); return 1; }
   }
-  const uint32_t a_stride = (p.a_stage_bytes + 127u) & ~127u, b_stride = (p.b_stage_bytes + 127u) & ~127u;
-  const size_t budget = 200 * 1024;
-  p.b_stages = 4;
-  p.a_stages = 4;
-  while (p.b_stages > 2 && (size_t)p.b_stages * b_stride > budget / 2) --p.b_stages;
-  while (p.a_stages > 1 &&
-         (size_t)p.a_stages * a_stride + (size_t)p.b_stages * b_stride + sizeof(TcBarriers) + 1024 > budget)
-    --p.a_stages;
-  *smem_bytes = (size_t)p.a_stages * a_stride + (size_t)p.b_stages * b_stride + sizeof(TcBarriers) + 1024;
+  const uint32_t a_stride = (p.a_stage_bytes + 127u) & ~127u;
+  p.a_stages = (int)std::min<size_t>(kMaxStages, budget / a_stride);
+  if (p.a_stages < 1) { set_error("tc plan: smem budget exceeded"); return 1; }
+  // beyond ~96 KB in flight per SM more stages buy nothing
+  while (p.a_stages > 3 && (size_t)(p.a_stages - 1) * a_stride >= 96 * 1024) --p.a_stages;
+  *smem_bytes = (size_t)p.a_stages * a_stride + b_bytes_total + sizeof(TcBarriers) + 1024;
   if (*smem_bytes > 227 * 1024) { set_error("tc plan: smem budget exceeded"); return 1; }
   p.mode = g.ups ? 1 : 0;
   p.cout = g.cout;
@@ -488,24 +620,33 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
 }
 
 int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int w,
-                 const __nv_bfloat16 *wpack_dev, const float *scale, const float *shift, int relu,
-                 View<__nv_bfloat16> out, int *status_dev, TcPlan *plan) {
+                 const __nv_bfloat16 *wpack_dev, const TcEpilogue &epi, int *status_dev, TcPlan *plan) {
   TcConvParams &p = plan->p;
   if (tc_fill_params(g, n, h, w, &p, &plan->smem_bytes)) return 1;
-  p.relu = relu;
-  p.scale = scale; p.shift = shift;
-  p.out = out.ptr; p.out_img_stride = out.img_stride; p.out_h = out.h; p.out_w = out.w;
+  p.relu = epi.relu;
+  p.scale = epi.scale; p.shift = epi.shift;
+  p.out = epi.out.ptr; p.out_img_stride = epi.out.img_stride; p.out_h = epi.out.h; p.out_w = epi.out.w;
+  p.pool_out = epi.pool_out; p.pool_img_stride = epi.pool_img_stride;
+  if (epi.head_w) {
+    if (g.ups || g.n_tiles_n != 1 || epi.head_k > kTcMaxClasses) { set_error("tc plan: head fusion not applicable"); return 1; }
+    p.mode = 2;
+    p.head_w = epi.head_w; p.head_b = epi.head_b; p.head_k = epi.head_k;
+    p.probs = epi.probs; p.labels = epi.labels;
+    p.out_h = h; p.out_w = w;
+  }
+  if (epi.pool_out && (g.ups || (h & 1) || (w & 1))) { set_error("tc plan: pool fusion not applicable"); return 1; }
   p.wpack = wpack_dev;
   p.status = status_dev;
 
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return 1; }
   const int cg = g.cin / 8;
-  cuuint64_t dims[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)cg, (cuuint64_t)n};
+  // declared as 8-byte elements (2 per pixel-plane vector) so that one box row may span up to 128 px
+  cuuint64_t dims[4] = {(cuuint64_t)w * 2, (cuuint64_t)h, (cuuint64_t)cg, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)cg * h * w * 16};
-  cuuint32_t box[4] = {(cuuint32_t)g.box_w * 8, (cuuint32_t)g.box_h, (cuuint32_t)g.planes_per_chunk, 1};
+  cuuint32_t box[4] = {(cuuint32_t)p.box_w * 2, (cuuint32_t)p.box_h, (cuuint32_t)g.planes_per_chunk, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&plan->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16 *>(in), dims,
+  CUresult r = enc(&plan->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<__nv_bfloat16 *>(in), dims,
                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return 1; }
@@ -523,7 +664,7 @@ int tc_launch(const TcPlan &plan, cudaStream_t st) {
     OCTSEG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<<<plan.grid, 256, plan.smem_bytes, st>>>(plan.tmap, plan.p);
+  conv_tc_kernel<<<plan.grid, kTcThreads, plan.smem_bytes, st>>>(plan.tmap, plan.p);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }

@@ -9,6 +9,7 @@ namespace octseg {
 constexpr int kTcMaxKSteps = 40;   // k-steps (K=16 each) per input-channel chunk
 constexpr int kTcTileW = 8;        // output tile: 8 px wide x 16 rows = 128 GEMM rows
 constexpr int kTcTileH = 16;
+constexpr int kTcMaxClasses = 16;
 
 // Kernel parameters (passed by value as __grid_constant__).
 struct TcConvParams {
@@ -18,6 +19,8 @@ struct TcConvParams {
   int planes_per_chunk;        // 8-channel planes per chunk
   int ksteps;                  // MMA k-steps per chunk
   int bgroup;                  // k-steps per weight stage
+  int mt_x, mt_y;              // M-tiles per super-tile (one TMA halo box, mt_x*mt_y accumulators)
+  int b_resident;              // 1: whole packed weight image stays in smem
   int n_cols;                  // MMA N per n-tile (multiple of 16, <= 256)
   int cols_valid;              // total valid GEMM columns over all n-tiles
   int pad_y, pad_x;            // halo before (rows / px)
@@ -27,13 +30,20 @@ struct TcConvParams {
   uint32_t a_off[kTcMaxKSteps];   // byte offset of the k-step's first 8-channel half
   uint32_t a_lbo[kTcMaxKSteps];   // byte distance to its second half
   // epilogue
-  int mode;                    // 0: plain NHWC-blocked store, 1: 2x2 pixel-shuffle store (up-conv)
+  int mode;                    // 0: plain blocked store, 1: 2x2 pixel-shuffle store (up-conv),
+                               // 2: fused 1x1-conv + softmax head (activation never stored)
   int cout;                    // channels per parity (mode 1) or total (mode 0)
   int relu;
   const float *scale, *shift;  // [cout]
   __nv_bfloat16 *out;          // plane 0 of image 0 of the destination view
   long long out_img_stride;    // elements
   int out_h, out_w;
+  __nv_bfloat16 *pool_out;     // mode 0: also write the 2x2 max-pooled tensor (NULL = off)
+  long long pool_img_stride;
+  const float *head_w, *head_b; // mode 2: [cout][K] and [K]
+  int head_k;
+  float *probs;                // mode 2 outputs (NHWC fp32 / u8), either may be NULL
+  uint8_t *labels;
   const __nv_bfloat16 *wpack;  // packed weights [n_tile][chunk][kstep][2][n_cols][8]
   int *status;                 // device word: non-zero = pipeline timeout code
 };
@@ -53,7 +63,7 @@ struct TcGeometry {
   int kh, kw, cin, cout, ups;          // conv block
   int dy_min, dy_max, dx_min, dx_max;  // low-res tap range
   int planes_per_chunk, cin_chunks, ksteps, n_cols, n_tiles_n, cols_valid, bgroup;
-  int box_w, box_h;
+  int box_w, box_h;                    // halo px / rows added around a super-tile
   // per k-step, per half: tap (dy,dx relative to dy_min/dx_min) and plane within chunk; tap -1 = zero
   int half_ty[kTcMaxKSteps][2], half_tx[kTcMaxKSteps][2], half_pl[kTcMaxKSteps][2];
 };
@@ -64,9 +74,19 @@ int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g);
 void tc_pack_weights(const TcGeometry &g, const float *w_hwio, std::vector<uint16_t> *out);
 // pure host part of the plan (no CUDA driver needed): tiling, stage sizes, A-descriptor table
 int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *p, size_t *smem_bytes);
+struct TcEpilogue {
+  int relu = 1;
+  const float *scale = nullptr, *shift = nullptr;
+  View<__nv_bfloat16> out{};                 // unused when the head is fused
+  __nv_bfloat16 *pool_out = nullptr;         // fused 2x2 max-pool (encoder-final blocks)
+  long long pool_img_stride = 0;
+  const float *head_w = nullptr, *head_b = nullptr;   // fused 1x1 conv + softmax head
+  int head_k = 0;
+  float *probs = nullptr;
+  uint8_t *labels = nullptr;
+};
 int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int w,
-                 const __nv_bfloat16 *wpack_dev, const float *scale, const float *shift, int relu,
-                 View<__nv_bfloat16> out, int *status_dev, TcPlan *plan);
+                 const __nv_bfloat16 *wpack_dev, const TcEpilogue &epi, int *status_dev, TcPlan *plan);
 int tc_launch(const TcPlan &plan, cudaStream_t st);
 
 }  // namespace octseg

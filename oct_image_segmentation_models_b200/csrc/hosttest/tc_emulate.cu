@@ -50,31 +50,35 @@ static int run(int kh, int kw, int cin, int cout, int ups, int n, int h, int w) 
   for (int tile = 0; tile < p.num_tiles; ++tile) {
     int n_tile = tile % p.n_tiles_n, t = tile / p.n_tiles_n;
     int tx = t % p.tiles_x; t /= p.tiles_x; int ty = t % p.tiles_y; int img = t / p.tiles_y;
-    std::vector<double> D((size_t)128 * p.n_cols, 0.0);
+    const int MT = p.mt_x * p.mt_y;
+    std::vector<double> D((size_t)MT * 128 * p.n_cols, 0.0);
     for (int ch = 0; ch < p.cin_chunks; ++ch) {
       // TMA box: dims (W*8, H, CG, N), start ((tx*8-pad_x)*8, ty*16-pad_y, ch*CGC, img)
       uint16_t *s16 = reinterpret_cast<uint16_t *>(stage.data());
       for (int pc = 0; pc < p.planes_per_chunk; ++pc) for (int r = 0; r < p.box_h; ++r) for (int e = 0; e < p.box_w * 8; ++e) {
-        int gx = (tx * kTcTileW - p.pad_x) * 8 + e, gy = ty * kTcTileH - p.pad_y + r, gp = ch * p.planes_per_chunk + pc;
+        int gx = (tx * p.mt_x * kTcTileW - p.pad_x) * 8 + e, gy = ty * p.mt_y * kTcTileH - p.pad_y + r, gp = ch * p.planes_per_chunk + pc;
         uint16_t v = 0;
         if (gx >= 0 && gx < w * 8 && gy >= 0 && gy < h) v = x[(((size_t)img * cg + gp) * h + gy) * w * 8 + gx];
         s16[((size_t)pc * p.box_h + r) * p.box_w * 8 + e] = v;
       }
       for (int ks = 0; ks < p.ksteps; ++ks) {
         const uint16_t *bbase = wp.data() + ((size_t)(n_tile * p.cin_chunks + ch) * p.ksteps + ks) * 2 * p.n_cols * 8;
-        for (int m = 0; m < 128; ++m) for (int k = 0; k < 16; ++k) {
-          size_t aoff = p.a_off[ks] + (size_t)(k / 8) * p.a_lbo[ks] + (size_t)(m / 8) * p.box_w * 16 + (m % 8) * 16 + (k % 8) * 2;
+        for (int t = 0; t < MT; ++t) for (int m = 0; m < 128; ++m) for (int k = 0; k < 16; ++k) {
+          const int iy = t / p.mt_x, ix = t % p.mt_x;
+          size_t aoff = p.a_off[ks] + (size_t)iy * kTcTileH * p.box_w * 16 + (size_t)ix * 128 +
+                        (size_t)(k / 8) * p.a_lbo[ks] + (size_t)(m / 8) * p.box_w * 16 + (m % 8) * 16 + (k % 8) * 2;
           if (aoff + 2 > p.a_stage_bytes) { printf("A read out of stage: ks %d m %d k %d off %zu\n", ks, m, k, aoff); return 1; }
           float av = bf2f(*reinterpret_cast<uint16_t *>(stage.data() + aoff));
           for (int nn = 0; nn < p.n_cols; ++nn) {
             size_t boff = (size_t)(k / 8) * p.n_cols * 16 + (size_t)(nn / 8) * 128 + (nn % 8) * 16 + (k % 8) * 2;
-            D[(size_t)m * p.n_cols + nn] += (double)av * bf2f(bbase[boff / 2]);
+            D[((size_t)t * 128 + m) * p.n_cols + nn] += (double)av * bf2f(bbase[boff / 2]);
           }
         }
       }
     }
-    for (int m = 0; m < 128; ++m) {
-      int r = m >> 3, px = m & 7, y = ty * kTcTileH + r, xx = tx * kTcTileW + px;
+    for (int t = 0; t < MT; ++t) for (int m = 0; m < 128; ++m) {
+      const int iy = t / p.mt_x, ix = t % p.mt_x;
+      int r = m >> 3, px = m & 7, y = (ty * p.mt_y + iy) * kTcTileH + r, xx = (tx * p.mt_x + ix) * kTcTileW + px;
       if (y >= h || xx >= w) continue;
       for (int j = 0; j < p.n_cols; ++j) {
         int col = n_tile * p.n_cols + j;
@@ -82,14 +86,14 @@ static int run(int kh, int kw, int cin, int cout, int ups, int n, int h, int w) 
         int co, oy, ox;
         if (p.mode == 0) { co = col; oy = y; ox = xx; }
         else { int par = col / p.cout; co = col - par * p.cout; oy = 2 * y + (par >> 1); ox = 2 * xx + (par & 1); }
-        out[(((size_t)img * oh + oy) * ow + ox) * cout + co] = D[(size_t)m * p.n_cols + j];
+        out[(((size_t)img * oh + oy) * ow + ox) * cout + co] = D[((size_t)t * 128 + m) * p.n_cols + j];
       }
     }
   }
   double maxerr = 0, maxref = 0;
   for (size_t i = 0; i < ref.size(); ++i) { maxerr = std::max(maxerr, std::fabs(out[i] - ref[i])); maxref = std::max(maxref, std::fabs(ref[i])); }
-  printf("k%dx%d cin %d cout %d ups %d %dx%dx%d: ksteps %d bgroup %d n_cols %d n_tiles %d chunks %d a_st %d b_st %d smem %zu | max err %.4g (ref max %.3g) %s\n",
-         kh, kw, cin, cout, ups, n, h, w, p.ksteps, p.bgroup, p.n_cols, p.n_tiles_n, p.cin_chunks, p.a_stages, p.b_stages, smem,
+  printf("k%dx%d cin %d cout %d ups %d %dx%dx%d: mt %dx%d res %d ksteps %d bgroup %d n_cols %d n_tiles %d chunks %d a_st %d b_st %d smem %zu | max err %.4g (ref max %.3g) %s\n",
+         kh, kw, cin, cout, ups, n, h, w, p.mt_x, p.mt_y, p.b_resident, p.ksteps, p.bgroup, p.n_cols, p.n_tiles_n, p.cin_chunks, p.a_stages, p.b_stages, smem,
          maxerr, maxref, maxerr < 0.02 * maxref ? "OK" : "MISMATCH");
   return maxerr < 0.02 * maxref ? 0 : 1;
 }
@@ -105,6 +109,10 @@ int main() {
   bad += run(2, 2, 128, 64, 1, 1, 16, 8);
   bad += run(2, 2, 16, 8, 1, 2, 32, 24);
   bad += run(3, 3, 16, 8, 0, 1, 20, 12);   // ragged tiles
+  bad += run(3, 3, 8, 8, 0, 40, 64, 64);    // super-tiles 8x2
+  bad += run(3, 3, 16, 8, 0, 80, 32, 64);   // super-tiles
+  bad += run(2, 2, 16, 8, 1, 80, 32, 32);   // up-conv super-tiles
+  bad += run(3, 3, 64, 64, 0, 40, 32, 32);
   bad += run(3, 3, 512, 512, 0, 1, 16, 8); // wide net: n-tiles + chunks
   bad += run(2, 2, 256, 128, 1, 1, 16, 8); // wide up-conv: 512 columns
   printf(bad ? "FAILED %d\n" : "ALL OK\n", bad);

@@ -6,29 +6,27 @@
 
 namespace octseg {
 
-__constant__ float c_lut255[256];
-
-int init_preprocess_lut() {
-  float h[256];
-  for (int i = 0; i < 256; ++i) h[i] = (float)((double)i / 255.0);
-  OCTSEG_CUDA(cudaMemcpyToSymbol(c_lut255, h, sizeof(h)));
-  return 0;
-}
+int init_preprocess_lut() { return 0; }   // x/255 is computed in-kernel (see conv_first_kernel)
 
 // ---------------------------------------------------------------------------------
-// first conv: thread = (pixel, output plane)
+// first conv: thread = pixel; the kh*kw*cin (<= 27) preprocessed inputs are loaded once
+// into registers and reused for every output plane.  x/255: for u8 inputs
+// float32(u)/255f is bit-identical to float32(float64(u)/255) for all 256 values
+// (checked in tests/test_oracle.py), so no table and no fp64 is needed.
 // ---------------------------------------------------------------------------------
+constexpr int kFirstMaxTaps = 27;
+
 template <typename T, typename IMG>
 __global__ void __launch_bounds__(256) conv_first_kernel(
     const IMG *__restrict__ img, int n, int h, int w, int cin, const float *__restrict__ wgt, int kh,
     int kw, int cout, const float *__restrict__ scale, const float *__restrict__ shift, int relu,
     View<T> out) {
-  extern __shared__ float wsm[];  // [kh*kw*cin][8] for this output plane
-  const int cog = blockIdx.y;
+  extern __shared__ float wsm[];  // [kh*kw*cin][cout] + scale[cout] + shift[cout]
   const int taps = kh * kw * cin;
-  for (int i = threadIdx.x; i < taps * 8; i += blockDim.x) {
-    int t = i >> 3, co = i & 7;
-    wsm[i] = wgt[(long long)t * cout + cog * 8 + co];
+  for (int i = threadIdx.x; i < taps * cout; i += blockDim.x) wsm[i] = wgt[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) {
+    wsm[taps * cout + i] = scale[i];
+    wsm[taps * cout + cout + i] = shift[i];
   }
   __syncthreads();
   const long long total = (long long)n * h * w;
@@ -38,31 +36,42 @@ __global__ void __launch_bounds__(256) conv_first_kernel(
     const int x = (int)(pix % w);
     const int y = (int)((pix / w) % h);
     const int b = (int)(pix / ((long long)w * h));
-    Vec8f acc = zero8();
-    for (int dy = 0; dy < kh; ++dy) {
-      const int iy = y + dy - pt;
-      if (iy < 0 || iy >= h) continue;
-      for (int dx = 0; dx < kw; ++dx) {
-        const int ix = x + dx - pl;
-        if (ix < 0 || ix >= w) continue;
-        const IMG *px = img + (((long long)b * h + iy) * w + ix) * cin;
-        for (int ci = 0; ci < cin; ++ci) {
-          float v;
-          if constexpr (sizeof(IMG) == 1) v = c_lut255[px[ci]];
-          else v = (float)((double)px[ci] / 255.0);
-          const float *wr = wsm + ((dy * kw + dx) * cin + ci) * 8;
+    float in[kFirstMaxTaps];
 #pragma unroll
-          for (int co = 0; co < 8; ++co) acc.v[co] = fmaf(v, wr[co], acc.v[co]);
+    for (int t = 0; t < kFirstMaxTaps; ++t) {
+      float v = 0.f;
+      if (t < taps) {
+        const int ci = t % cin, dx = (t / cin) % kw, dy = t / (cin * kw);
+        const int iy = y + dy - pt, ix = x + dx - pl;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+          const IMG raw = img[(((long long)b * h + iy) * w + ix) * cin + ci];
+          if constexpr (sizeof(IMG) == 1) v = __fdiv_rn((float)raw, 255.0f);
+          else v = (float)((double)raw / 255.0);
         }
       }
+      in[t] = v;
     }
+    for (int cog = 0; cog < cout / 8; ++cog) {
+      Vec8f acc = zero8();
 #pragma unroll
-    for (int co = 0; co < 8; ++co) {
-      float v = fmaf(acc.v[co], scale[cog * 8 + co], shift[cog * 8 + co]);
-      acc.v[co] = relu ? fmaxf(v, 0.f) : v;
+      for (int t = 0; t < kFirstMaxTaps; ++t) {
+        if (t < taps) {
+          const float4 wa = *reinterpret_cast<const float4 *>(wsm + t * cout + cog * 8);
+          const float4 wb = *reinterpret_cast<const float4 *>(wsm + t * cout + cog * 8 + 4);
+          acc.v[0] = fmaf(in[t], wa.x, acc.v[0]); acc.v[1] = fmaf(in[t], wa.y, acc.v[1]);
+          acc.v[2] = fmaf(in[t], wa.z, acc.v[2]); acc.v[3] = fmaf(in[t], wa.w, acc.v[3]);
+          acc.v[4] = fmaf(in[t], wb.x, acc.v[4]); acc.v[5] = fmaf(in[t], wb.y, acc.v[5]);
+          acc.v[6] = fmaf(in[t], wb.z, acc.v[6]); acc.v[7] = fmaf(in[t], wb.w, acc.v[7]);
+        }
+      }
+#pragma unroll
+      for (int co = 0; co < 8; ++co) {
+        float v = fmaf(acc.v[co], wsm[taps * cout + cog * 8 + co], wsm[taps * cout + cout + cog * 8 + co]);
+        acc.v[co] = relu ? fmaxf(v, 0.f) : v;
+      }
+      T *dst = out.ptr + b * out.img_stride + (((long long)cog * h + y) * w + x) * 8;
+      store8(dst, acc);
     }
-    T *dst = out.ptr + b * out.img_stride + (((long long)cog * h + y) * w + x) * 8;
-    store8(dst, acc);
   }
 }
 
@@ -70,9 +79,10 @@ template <typename T>
 int launch_conv_first(const void *img, int img_dtype, int n, int h, int w, int cin_img,
                       const float *wgt, int kh, int kw, int cout, const float *scale,
                       const float *shift, int relu, View<T> out, cudaStream_t st) {
+  if (kh * kw * cin_img > kFirstMaxTaps) { set_error("first conv: kh*kw*input_channels > 27 not supported"); return 1; }
   const long long total = (long long)n * h * w;
-  dim3 grid((unsigned)std::min<long long>((total + 255) / 256, 148 * 16), cout / 8);
-  size_t smem = (size_t)kh * kw * cin_img * 8 * sizeof(float);
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  size_t smem = ((size_t)kh * kw * cin_img * cout + 2 * cout) * sizeof(float);
   if (img_dtype == 0)
     conv_first_kernel<T, uint8_t><<<grid, 256, smem, st>>>((const uint8_t *)img, n, h, w, cin_img, wgt,
                                                            kh, kw, cout, scale, shift, relu, out);
@@ -212,11 +222,10 @@ int launch_maxpool2(View<const T> in, View<T> out, cudaStream_t st) {
 // ---------------------------------------------------------------------------------
 // head: 1x1 conv + softmax (+ first-max argmax).  thread = pixel.
 // ---------------------------------------------------------------------------------
-constexpr int kMaxClasses = 16;
 
-template <typename T>
+template <typename T, int K>
 __global__ void __launch_bounds__(256) head_kernel(View<const T> in, const float *__restrict__ wgt,
-                                                   const float *__restrict__ bias, int cin, int K,
+                                                   const float *__restrict__ bias, int cin,
                                                    float *__restrict__ probs,
                                                    uint8_t *__restrict__ labels) {
   extern __shared__ float wsm[];  // [cin][K] + [K]
@@ -229,63 +238,67 @@ __global__ void __launch_bounds__(256) head_kernel(View<const T> in, const float
        pix += (long long)gridDim.x * blockDim.x) {
     const long long hw = pix % ((long long)H * W);
     const int b = (int)(pix / ((long long)H * W));
-    float z[kMaxClasses];
+    float z[K];
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) z[k] = (k < K) ? wsm[cin * K + k] : 0.f;
+    for (int k = 0; k < K; ++k) z[k] = wsm[cin * K + k];
     for (int pl = 0; pl < cin / 8; ++pl) {
       Vec8f v = load8(in.ptr + b * in.img_stride + ((long long)pl * H * W + hw) * 8);
 #pragma unroll
       for (int ci = 0; ci < 8; ++ci) {
         const float *wr = wsm + (pl * 8 + ci) * K;
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k)
-          if (k < K) z[k] = fmaf(v.v[ci], wr[k], z[k]);
+        for (int k = 0; k < K; ++k) z[k] = fmaf(v.v[ci], wr[k], z[k]);
       }
     }
     float m = z[0];
-    int am = 0;
 #pragma unroll
-    for (int k = 1; k < kMaxClasses; ++k)
-      if (k < K && z[k] > m) { m = z[k]; am = k; }
+    for (int k = 1; k < K; ++k) m = fmaxf(m, z[k]);
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k)
-      if (k < K) { z[k] = expf(z[k] - m); s += z[k]; }
+    for (int k = 0; k < K; ++k) { z[k] = expf(z[k] - m); s += z[k]; }
     const float inv = 1.f / s;
+    // np.argmax runs on the float32 probabilities (reference common/utils.py:104): take the
+    // first max of p itself so ties created by rounding resolve as they would on the host
+    float pm = -1.f;
+    int pa = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      z[k] *= inv;
+      if (z[k] > pm) { pm = z[k]; pa = k; }
+    }
     if (probs) {
       float *dst = probs + pix * K;
-      if (K == 4) {
-        *reinterpret_cast<float4 *>(dst) = make_float4(z[0] * inv, z[1] * inv, z[2] * inv, z[3] * inv);
-      } else {
+      if constexpr (K == 4) *reinterpret_cast<float4 *>(dst) = make_float4(z[0], z[1], z[2], z[3]);
+      else {
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k)
-          if (k < K) dst[k] = z[k] * inv;
+        for (int k = 0; k < K; ++k) dst[k] = z[k];
       }
     }
-    if (labels) {
-      // np.argmax runs on the float32 probabilities: recompute on p so that ties created
-      // by rounding resolve exactly as they would on the returned array
-      float pm = z[0] * inv;
-      int pa = 0;
-#pragma unroll
-      for (int k = 1; k < kMaxClasses; ++k)
-        if (k < K && z[k] * inv > pm) { pm = z[k] * inv; pa = k; }
-      labels[pix] = (uint8_t)pa;
-      (void)am;
-    }
+    if (labels) labels[pix] = (uint8_t)pa;
   }
+}
+
+template <typename T, int K>
+static int launch_head_k(View<const T> in, const float *wgt, const float *bias, int cin, float *probs,
+                         uint8_t *labels, cudaStream_t st) {
+  const long long total = (long long)in.n * in.h * in.w;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  size_t smem = (size_t)(cin * K + K) * sizeof(float);
+  head_kernel<T, K><<<grid, 256, smem, st>>>(in, wgt, bias, cin, probs, labels);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <typename T>
 int launch_head(View<const T> in, const float *wgt, const float *bias, int cin, int K, float *probs,
                 uint8_t *labels, cudaStream_t st) {
-  if (K > kMaxClasses) { set_error("num_classes > 16 not supported"); return 1; }
-  const long long total = (long long)in.n * in.h * in.w;
-  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
-  size_t smem = (size_t)(cin * K + K) * sizeof(float);
-  head_kernel<T><<<grid, 256, smem, st>>>(in, wgt, bias, cin, K, probs, labels);
-  OCTSEG_CUDA(cudaGetLastError());
-  return 0;
+  switch (K) {
+#define HK(k) case k: return launch_head_k<T, k>(in, wgt, bias, cin, probs, labels, st);
+    HK(1) HK(2) HK(3) HK(4) HK(5) HK(6) HK(7) HK(8) HK(9) HK(10) HK(11) HK(12) HK(13) HK(14) HK(15) HK(16)
+#undef HK
+  }
+  set_error("num_classes must be 1..16");
+  return 1;
 }
 
 // ---------------------------------------------------------------------------------

@@ -225,11 +225,25 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
     io.use_tc = false;
     if (net->precision == OCTSEG_BF16 && !net->disable_tc && b.index > 0 && b.role != 4 &&
         net->bstate[b.index].geo_ok && tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, io.in_h, io.in_w)) {
-      View<__nv_bfloat16> ov = make_view(reinterpret_cast<__nv_bfloat16 *>(io.out), n, io.out_planes_total,
-                                         io.out_plane0, io.out_planes, io.out_h, io.out_w);
+      TcEpilogue epi;
+      epi.scale = net->bstate[b.index].scale; epi.shift = net->bstate[b.index].shift;
+      epi.out = make_view(reinterpret_cast<__nv_bfloat16 *>(io.out), n, io.out_planes_total, io.out_plane0,
+                          io.out_planes, io.out_h, io.out_w);
+      if (io.pool && !net->disable_fusion) {
+        epi.pool_out = reinterpret_cast<__nv_bfloat16 *>(io.pool);
+        epi.pool_img_stride = (long long)io.out_planes * io.pool_h * io.pool_w * 8;
+        io.pool_fused = true;
+      }
+      const BlockSpec &last = net->blocks.back();
+      if (!net->disable_fusion && b.index == last.index - 1 && last.role == 4 &&
+          net->bstate[b.index].geo.n_tiles_n == 1) {
+        epi.head_w = net->d_params + net->params[last.p_kernel].offset;
+        epi.head_b = net->d_params + net->params[last.p_bias].offset;
+        epi.head_k = last.cout;
+        io.head_fused = true;
+      }
       if (tc_make_plan(net->bstate[b.index].geo, reinterpret_cast<const __nv_bfloat16 *>(io.in), n, io.in_h,
-                       io.in_w, net->bstate[b.index].wpack, net->bstate[b.index].scale,
-                       net->bstate[b.index].shift, 1, ov, net->d_status, &io.plan))
+                       io.in_w, net->bstate[b.index].wpack, epi, net->d_status, &io.plan))
         return 1;
       io.use_tc = true;
     }
@@ -252,6 +266,10 @@ static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h
     BlockState &bs = net->bstate[b.index];
     if (b.index > 0 && prof) cudaEventRecord(net->prof_events[b.index], st);
     if (b.role == 4) {
+      if (net->io[b.index - 1].head_fused) {   // already produced by the last conv's epilogue
+        if (prof) { cudaEventRecord(net->prof_events[net->blocks.size()], st); net->prof_valid = true; }
+        continue;
+      }
       View<const T> in = make_view(reinterpret_cast<const T *>(io.in), n, io.in_planes_total, io.in_plane0,
                                    io.in_planes, io.in_h, io.in_w);
       if (launch_head<T>(in, P + net->params[b.p_kernel].offset, P + net->params[b.p_bias].offset, b.cin,
@@ -268,7 +286,11 @@ static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h
                                b.cout, bs.scale, bs.shift, 1, out, st))
         return 1;
     } else if (io.use_tc) {
-      if (tc_launch(io.plan, st)) return 1;
+      if (io.head_fused) {
+        TcPlan pl = io.plan;
+        pl.p.probs = d_probs; pl.p.labels = d_labels;
+        if (tc_launch(pl, st)) return 1;
+      } else if (tc_launch(io.plan, st)) return 1;
     } else {
       View<const T> in = make_view(reinterpret_cast<const T *>(io.in), n, io.in_planes_total, io.in_plane0,
                                    io.in_planes, io.in_h, io.in_w);
@@ -277,7 +299,7 @@ static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h
         return 1;
     }
     ++net->launches;
-    if (io.pool) {
+    if (io.pool && !io.pool_fused) {
       View<const T> pin = make_view(reinterpret_cast<const T *>(io.out), n, io.out_planes_total,
                                     io.out_plane0, io.out_planes, io.out_h, io.out_w);
       View<T> pout = make_view(reinterpret_cast<T *>(io.pool), n, io.out_planes, 0, io.out_planes, io.pool_h,
@@ -389,6 +411,8 @@ int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precisio
   }
   const char *e = std::getenv("OCTSEG_DISABLE_TC");
   net->disable_tc = e && e[0] == '1';
+  e = std::getenv("OCTSEG_DISABLE_FUSION");
+  net->disable_fusion = e && e[0] == '1';
   e = std::getenv("OCTSEG_MICROBATCH");
   net->microbatch = e ? std::atoi(e) : 0;
   OCTSEG_CUDA(cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking));
@@ -590,9 +614,11 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
       set_error("tensor-core path not available for this block/shape");
       rc = 1;
     } else {
-      View<__nv_bfloat16> ov = make_view(reinterpret_cast<__nv_bfloat16 *>(d_out), n, b.cout / 8, 0, b.cout / 8, oh, ow);
-      rc = tc_make_plan(bs.geo, reinterpret_cast<const __nv_bfloat16 *>(d_in), n, h, w, bs.wpack, bs.scale,
-                        bs.shift, 1, ov, net->d_status, &plan);
+      TcEpilogue epi;
+      epi.scale = bs.scale; epi.shift = bs.shift;
+      epi.out = make_view(reinterpret_cast<__nv_bfloat16 *>(d_out), n, b.cout / 8, 0, b.cout / 8, oh, ow);
+      rc = tc_make_plan(bs.geo, reinterpret_cast<const __nv_bfloat16 *>(d_in), n, h, w, bs.wpack, epi,
+                        net->d_status, &plan);
     }
   }
   for (int rep = 0; rc == 0 && rep < reps; ++rep) {

@@ -50,6 +50,8 @@ struct BlockIO {
   void *out = nullptr; int out_planes_total = 0, out_plane0 = 0, out_planes = 0, out_h = 0, out_w = 0;
   void *pool = nullptr; int pool_h = 0, pool_w = 0;   // pooled copy (encoder last block)
   bool use_tc = false;
+  bool pool_fused = false;   // 2x2 max-pool written by the conv epilogue
+  bool head_fused = false;   // 1x1 conv + softmax computed in this block's epilogue
   TcPlan plan;
 };
 
@@ -81,6 +83,7 @@ struct octseg_net {
   int *h_status = nullptr;            // pinned
   int64_t launches = 0;
   bool disable_tc = false;
+  bool disable_fusion = false;
   int microbatch = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;   // blocks+1 events
