@@ -22,11 +22,10 @@
 //   * accumulators sit in TMEM (double buffered), the epilogue applies the folded
 //     BatchNorm scale/shift + ReLU and stores one 16 B vector per pixel per plane.
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0 lane 0 : TMA producer (A halo tiles + packed weight stages)
-//   warp 1 lane 0 : MMA issuer (tcgen05.mma, commits to mbarriers)
-//   warp 2        : TMEM allocator
-//   warps 4..7    : epilogue (TMEM lane quarter = warp % 4)
+// Warp roles (384 threads, 1 CTA/SM, persistent over super-tiles):
+//   warp 0        : TMEM allocator; lane 0 = TMA producer (A halo tiles + packed weights)
+//   warps 1..3    : lane 0 of each = MMA issuer for a third of the super-tile's M-tiles
+//   warps 4..11   : epilogue, two warpgroups (TMEM lane quarter = warp % 4)
 #include "conv_tc.cuh"
 
 #include <algorithm>
@@ -137,8 +136,11 @@ __device__ __forceinline__ void decode_tile(const TcConvParams &p, int tile, int
   img = t / p.tiles_y;
 }
 
+constexpr int kTcIssuers = 3;    // MMA-issuing threads (warps 1..3)
 constexpr int kTcThreads = 384;   // warps 0..3 control, warps 4..11 epilogue (two warpgroups)
 
+// HK: compile-time class count of the fused 1x1-conv + softmax head (0 = no head fusion)
+template <int HK>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ TcConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -155,14 +157,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.a_stages; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
-    for (int i = 0; i < p.b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 8); }
+    // every one of the kTcIssuers MMA-issuing threads commits to the "consumed" barriers
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), kTcIssuers); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), kTcIssuers); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), kTcIssuers); mbar_init(smem_u32(&bars->acc_empty[i]), 8); }
     mbar_init(smem_u32(&bars->w_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -217,14 +220,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp <= kTcIssuers) {
     if (lane == 0) {
-      // ===================== MMA issuer =====================
+      // ===================== MMA issuers (warps 1..kTcIssuers, one thread each) =====================
+      // One thread sustains only ~1 tcgen05.mma per 108 clk (measured, tools/mma_bench.cu) while
+      // the tensor pipe accepts one M128xN16xK16 MMA per ~39 clk, so the M-tiles of a super-tile
+      // are dealt round-robin to kTcIssuers threads, each with its own commits.
+      const int issuer = warp - 1;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_cols >> 3) << 17) |
                              ((128u >> 4) << 24);
       const uint32_t pitch = (uint32_t)p.box_w * 16u;
       const uint32_t lbo_b = (uint32_t)p.n_cols * 16u;
       const uint32_t kstep_b = 32u * (uint32_t)p.n_cols;
+      // this issuer's M-tiles: descriptor start-address deltas (16 B units) and TMEM column offsets
+      constexpr int kMaxMine = (16 + kTcIssuers - 1) / kTcIssuers;
+      uint32_t t_desc[kMaxMine], t_col[kMaxMine];
+      int n_mine = 0;
+#pragma unroll
+      for (int j = 0; j < kMaxMine; ++j) {
+        const int t = issuer + j * kTcIssuers;
+        t_desc[j] = 0; t_col[j] = 0;
+        if (t < mt) {
+          const int iy = t / p.mt_x, ix = t - iy * p.mt_x;
+          t_desc[j] = ((uint32_t)iy * kTcTileH * pitch + (uint32_t)ix * 128u) >> 4;
+          t_col[j] = (uint32_t)(t * p.n_cols);
+          n_mine = j + 1;
+        }
+      }
       int as = 0, bs = 0, acc = 0;
       uint32_t aph = 0, bph = 0, accph = 0;
       bool ok = true;
@@ -255,14 +277,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int s = 0; s < p.bgroup; ++s) {
               const int ks = g + s;
               const uint64_t db = make_desc(b_base + (uint32_t)s * kstep_b, lbo_b, 128u);
-              const uint32_t a_ks = a_base + p.a_off[ks];
-              const uint32_t lbo = p.a_lbo[ks];
+              // descriptors of the M-tiles differ only in the 14-bit start-address field
+              const uint64_t da0 = make_desc(a_base + p.a_off[ks], p.a_lbo[ks], pitch);
               const uint32_t accum = (ch | ks) != 0 ? 1u : 0u;
-              for (int iy = 0; iy < p.mt_y; ++iy)
-                for (int ix = 0; ix < p.mt_x; ++ix) {
-                  const uint64_t da = make_desc(a_ks + (uint32_t)iy * kTcTileH * pitch + (uint32_t)ix * 128u, lbo, pitch);
-                  umma_bf16(d_tmem + (uint32_t)((iy * p.mt_x + ix) * p.n_cols), da, db, idesc, accum);
-                }
+#pragma unroll
+              for (int j = 0; j < kMaxMine; ++j)
+                if (j < n_mine) umma_bf16(d_tmem + t_col[j], da0 + t_desc[j], db, idesc, accum);
             }
             if (!p.b_resident) {
               umma_commit(smem_u32(&bars->b_empty[bs]));
@@ -297,10 +317,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool inside = (y < p.h) && (x < p.w);
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols +
                                 (uint32_t)(t * p.n_cols);
-        float z[kTcMaxClasses];
-        if (p.mode == 2) {
+        float z[HK > 0 ? HK : 1];
+        if constexpr (HK > 0) {
 #pragma unroll
-          for (int k = 0; k < kTcMaxClasses; ++k) z[k] = (k < p.head_k) ? __ldg(p.head_b + k) : 0.f;
+          for (int k = 0; k < HK; ++k) z[k] = __ldg(p.head_b + k);
         }
         for (int j = 0; j < p.n_cols; j += 8) {
           const int col = n_tile * p.n_cols + j;   // warp-uniform
@@ -321,14 +341,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             float f = fmaf(__uint_as_float(v[k]), __ldg(p.scale + co0 + k), __ldg(p.shift + co0 + k));
             o.v[k] = p.relu ? fmaxf(f, 0.f) : f;
           }
-          if (p.mode == 2) {
+          if constexpr (HK > 0) {
             // fused 1x1 conv head: logits accumulate over the channel chunks (fp32 activations)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float *wr = p.head_w + (size_t)(co0 + c) * p.head_k;
+              const float *wr = p.head_w + (size_t)(co0 + c) * HK;
 #pragma unroll
-              for (int k = 0; k < kTcMaxClasses; ++k)
-                if (k < p.head_k) z[k] = fmaf(o.v[c], __ldg(wr + k), z[k]);
+              for (int k = 0; k < HK; ++k) z[k] = fmaf(o.v[c], __ldg(wr + k), z[k]);
             }
             continue;
           }
@@ -351,36 +370,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         }
-        if (p.mode == 2 && inside) {
-          // softmax over classes + first-max argmax on the float32 probabilities
-          float mx = z[0];
+        if constexpr (HK > 0) {
+          if (inside) {
+            // softmax over classes + first-max argmax on the float32 probabilities
+            float mx = z[0];
 #pragma unroll
-          for (int k = 1; k < kTcMaxClasses; ++k)
-            if (k < p.head_k) mx = fmaxf(mx, z[k]);
-          float s = 0.f;
+            for (int k = 1; k < HK; ++k) mx = fmaxf(mx, z[k]);
+            float s = 0.f;
 #pragma unroll
-          for (int k = 0; k < kTcMaxClasses; ++k)
-            if (k < p.head_k) { z[k] = expf(z[k] - mx); s += z[k]; }
-          const float inv = 1.f / s;
-          const long long pix = ((long long)img * p.h + y) * p.w + x;
-          float pm = -1.f;
-          int pa = 0;
+            for (int k = 0; k < HK; ++k) { z[k] = expf(z[k] - mx); s += z[k]; }
+            const float inv = 1.f / s;
+            const long long pix = ((long long)img * p.h + y) * p.w + x;
+            float pm = -1.f;
+            int pa = 0;
 #pragma unroll
-          for (int k = 0; k < kTcMaxClasses; ++k)
-            if (k < p.head_k) {
+            for (int k = 0; k < HK; ++k) {
               z[k] *= inv;
               if (z[k] > pm) { pm = z[k]; pa = k; }
             }
-          if (p.probs) {
-            float *dst = p.probs + pix * p.head_k;
-            if (p.head_k == 4) *reinterpret_cast<float4 *>(dst) = make_float4(z[0], z[1], z[2], z[3]);
-            else {
+            if (p.probs) {
+              float *dst = p.probs + pix * HK;
+              if constexpr (HK == 4) *reinterpret_cast<float4 *>(dst) = make_float4(z[0], z[1], z[2], z[3]);
+              else {
 #pragma unroll
-              for (int k = 0; k < kTcMaxClasses; ++k)
-                if (k < p.head_k) dst[k] = z[k];
+                for (int k = 0; k < HK; ++k) dst[k] = z[k];
+              }
             }
+            if (p.labels) p.labels[pix] = (uint8_t)pa;
           }
-          if (p.labels) p.labels[pix] = (uint8_t)pa;
         }
       }
       tc_fence_before();
@@ -392,7 +409,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -401,6 +418,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // ----------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------
+bool tc_head_fusable(int num_classes);
 static inline int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
 bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w) {
@@ -628,7 +646,7 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
   p.out = epi.out.ptr; p.out_img_stride = epi.out.img_stride; p.out_h = epi.out.h; p.out_w = epi.out.w;
   p.pool_out = epi.pool_out; p.pool_img_stride = epi.pool_img_stride;
   if (epi.head_w) {
-    if (g.ups || g.n_tiles_n != 1 || epi.head_k > kTcMaxClasses) { set_error("tc plan: head fusion not applicable"); return 1; }
+    if (g.ups || g.n_tiles_n != 1 || !tc_head_fusable(epi.head_k)) { set_error("tc plan: head fusion not applicable"); return 1; }
     p.mode = 2;
     p.head_w = epi.head_w; p.head_b = epi.head_b; p.head_k = epi.head_k;
     p.probs = epi.probs; p.labels = epi.labels;
@@ -658,15 +676,33 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
   return 0;
 }
 
-int tc_launch(const TcPlan &plan, cudaStream_t st) {
+template <int HK>
+static int tc_launch_k(const TcPlan &plan, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    OCTSEG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OCTSEG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<HK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<<<plan.grid, kTcThreads, plan.smem_bytes, st>>>(plan.tmap, plan.p);
+  conv_tc_kernel<HK><<<plan.grid, kTcThreads, plan.smem_bytes, st>>>(plan.tmap, plan.p);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
+}
+
+bool tc_head_fusable(int num_classes) { return num_classes >= 2 && num_classes <= 8; }
+
+int tc_launch(const TcPlan &plan, cudaStream_t st) {
+  if (plan.p.mode != 2) return tc_launch_k<0>(plan, st);
+  switch (plan.p.head_k) {
+    case 2: return tc_launch_k<2>(plan, st);
+    case 3: return tc_launch_k<3>(plan, st);
+    case 4: return tc_launch_k<4>(plan, st);
+    case 5: return tc_launch_k<5>(plan, st);
+    case 6: return tc_launch_k<6>(plan, st);
+    case 7: return tc_launch_k<7>(plan, st);
+    case 8: return tc_launch_k<8>(plan, st);
+  }
+  set_error("tc launch: fused head supports 2..8 classes");
+  return 1;
 }
 
 }  // namespace octseg

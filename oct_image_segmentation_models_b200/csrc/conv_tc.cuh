@@ -88,5 +88,6 @@ struct TcEpilogue {
 int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int w,
                  const __nv_bfloat16 *wpack_dev, const TcEpilogue &epi, int *status_dev, TcPlan *plan);
 int tc_launch(const TcPlan &plan, cudaStream_t st);
+bool tc_head_fusable(int num_classes);
 
 }  // namespace octseg

@@ -16,12 +16,14 @@ int init_preprocess_lut() { return 0; }   // x/255 is computed in-kernel (see co
 // ---------------------------------------------------------------------------------
 constexpr int kFirstMaxTaps = 27;
 
-template <typename T, typename IMG>
+// KH/KW/CIN > 0: compile-time filter geometry (the 3x3x1 stem of every OCT model); 0 = runtime
+template <typename T, typename IMG, int KH, int KW, int CIN>
 __global__ void __launch_bounds__(256) conv_first_kernel(
     const IMG *__restrict__ img, int n, int h, int w, int cin, const float *__restrict__ wgt, int kh,
     int kw, int cout, const float *__restrict__ scale, const float *__restrict__ shift, int relu,
     View<T> out) {
   extern __shared__ float wsm[];  // [kh*kw*cin][cout] + scale[cout] + shift[cout]
+  if constexpr (KH > 0) { kh = KH; kw = KW; cin = CIN; }
   const int taps = kh * kw * cin;
   for (int i = threadIdx.x; i < taps * cout; i += blockDim.x) wsm[i] = wgt[i];
   for (int i = threadIdx.x; i < cout; i += blockDim.x) {
@@ -75,6 +77,87 @@ __global__ void __launch_bounds__(256) conv_first_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------
+// 3x3 / 1-channel stem, the first conv of every OCT U-Net: thread = 4 consecutive pixels
+// of a row.  3 rows x 6 raw pixels are fetched once (one aligned 4-byte word + two edge
+// bytes per row), preprocessed once, and reused for 4 px x all output planes; stores are
+// 64 contiguous bytes per thread per plane.
+// ---------------------------------------------------------------------------------
+template <typename T, typename IMG>
+__global__ void __launch_bounds__(256) conv_stem3x3_kernel(
+    const IMG *__restrict__ img, int n, int h, int w, const float *__restrict__ wgt, int cout,
+    const float *__restrict__ scale, const float *__restrict__ shift, int relu, View<T> out) {
+  extern __shared__ float wsm[];  // [9][cout] + scale[cout] + shift[cout]
+  for (int i = threadIdx.x; i < 9 * cout; i += blockDim.x) wsm[i] = wgt[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) {
+    wsm[9 * cout + i] = scale[i];
+    wsm[10 * cout + i] = shift[i];
+  }
+  __syncthreads();
+  const int w4 = w >> 2;                       // launcher guarantees w % 4 == 0
+  const long long total = (long long)n * h * w4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total;
+       q += (long long)gridDim.x * blockDim.x) {
+    const int x0 = (int)(q % w4) * 4;
+    const int y = (int)((q / w4) % h);
+    const int b = (int)(q / ((long long)w4 * h));
+    float in[3][6];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = y + dy - 1;
+      const bool rowok = (iy >= 0 && iy < h);
+      const IMG *row = img + ((long long)b * h + (rowok ? iy : 0)) * w;
+      IMG raw[6];
+      if constexpr (sizeof(IMG) == 1) {
+        const uint32_t word = rowok ? *reinterpret_cast<const uint32_t *>(row + x0) : 0u;
+        raw[1] = (IMG)(word & 0xFF); raw[2] = (IMG)((word >> 8) & 0xFF);
+        raw[3] = (IMG)((word >> 16) & 0xFF); raw[4] = (IMG)(word >> 24);
+      } else {
+        const float4 word = rowok ? *reinterpret_cast<const float4 *>(row + x0) : make_float4(0, 0, 0, 0);
+        raw[1] = word.x; raw[2] = word.y; raw[3] = word.z; raw[4] = word.w;
+      }
+      raw[0] = (rowok && x0 > 0) ? row[x0 - 1] : (IMG)0;
+      raw[5] = (rowok && x0 + 4 < w) ? row[x0 + 4] : (IMG)0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if constexpr (sizeof(IMG) == 1) in[dy][i] = __fdiv_rn((float)raw[i], 255.0f);
+        else in[dy][i] = (float)((double)raw[i] / 255.0);
+      }
+    }
+    for (int cog = 0; cog < cout / 8; ++cog) {
+      Vec8f acc[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[p] = zero8();
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float *wr = wsm + (dy * 3 + dx) * cout + cog * 8;
+          const float4 wa = *reinterpret_cast<const float4 *>(wr);
+          const float4 wb = *reinterpret_cast<const float4 *>(wr + 4);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float v = in[dy][p + dx];
+            acc[p].v[0] = fmaf(v, wa.x, acc[p].v[0]); acc[p].v[1] = fmaf(v, wa.y, acc[p].v[1]);
+            acc[p].v[2] = fmaf(v, wa.z, acc[p].v[2]); acc[p].v[3] = fmaf(v, wa.w, acc[p].v[3]);
+            acc[p].v[4] = fmaf(v, wb.x, acc[p].v[4]); acc[p].v[5] = fmaf(v, wb.y, acc[p].v[5]);
+            acc[p].v[6] = fmaf(v, wb.z, acc[p].v[6]); acc[p].v[7] = fmaf(v, wb.w, acc[p].v[7]);
+          }
+        }
+      T *dst = out.ptr + b * out.img_stride + (((long long)cog * h + y) * w + x0) * 8;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+#pragma unroll
+        for (int co = 0; co < 8; ++co) {
+          float v = fmaf(acc[p].v[co], wsm[9 * cout + cog * 8 + co], wsm[10 * cout + cog * 8 + co]);
+          acc[p].v[co] = relu ? fmaxf(v, 0.f) : v;
+        }
+        store8(dst + p * 8, acc[p]);
+      }
+    }
+  }
+}
+
 template <typename T>
 int launch_conv_first(const void *img, int img_dtype, int n, int h, int w, int cin_img,
                       const float *wgt, int kh, int kw, int cout, const float *scale,
@@ -83,12 +166,35 @@ int launch_conv_first(const void *img, int img_dtype, int n, int h, int w, int c
   const long long total = (long long)n * h * w;
   unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
   size_t smem = ((size_t)kh * kw * cin_img * cout + 2 * cout) * sizeof(float);
-  if (img_dtype == 0)
-    conv_first_kernel<T, uint8_t><<<grid, 256, smem, st>>>((const uint8_t *)img, n, h, w, cin_img, wgt,
-                                                           kh, kw, cout, scale, shift, relu, out);
-  else
-    conv_first_kernel<T, float><<<grid, 256, smem, st>>>((const float *)img, n, h, w, cin_img, wgt, kh,
-                                                         kw, cout, scale, shift, relu, out);
+  if (kh == 3 && kw == 3 && cin_img == 1 && (w % 4) == 0 && ((uintptr_t)img % 16) == 0) {
+    const long long quads = total / 4;
+    unsigned g4 = (unsigned)std::min<long long>((quads + 255) / 256, 148 * 16);
+    size_t sm4 = (size_t)11 * cout * sizeof(float);
+    if (img_dtype == 0)
+      conv_stem3x3_kernel<T, uint8_t><<<g4, 256, sm4, st>>>((const uint8_t *)img, n, h, w, wgt, cout, scale,
+                                                            shift, relu, out);
+    else
+      conv_stem3x3_kernel<T, float><<<g4, 256, sm4, st>>>((const float *)img, n, h, w, wgt, cout, scale, shift,
+                                                          relu, out);
+    OCTSEG_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const bool stem331 = (kh == 3 && kw == 3 && cin_img == 1);
+  if (img_dtype == 0) {
+    if (stem331)
+      conv_first_kernel<T, uint8_t, 3, 3, 1><<<grid, 256, smem, st>>>((const uint8_t *)img, n, h, w, cin_img,
+                                                                      wgt, kh, kw, cout, scale, shift, relu, out);
+    else
+      conv_first_kernel<T, uint8_t, 0, 0, 0><<<grid, 256, smem, st>>>((const uint8_t *)img, n, h, w, cin_img,
+                                                                      wgt, kh, kw, cout, scale, shift, relu, out);
+  } else {
+    if (stem331)
+      conv_first_kernel<T, float, 3, 3, 1><<<grid, 256, smem, st>>>((const float *)img, n, h, w, cin_img, wgt,
+                                                                    kh, kw, cout, scale, shift, relu, out);
+    else
+      conv_first_kernel<T, float, 0, 0, 0><<<grid, 256, smem, st>>>((const float *)img, n, h, w, cin_img, wgt,
+                                                                    kh, kw, cout, scale, shift, relu, out);
+  }
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }

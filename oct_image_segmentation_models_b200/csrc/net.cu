@@ -236,7 +236,7 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
       }
       const BlockSpec &last = net->blocks.back();
       if (!net->disable_fusion && b.index == last.index - 1 && last.role == 4 &&
-          net->bstate[b.index].geo.n_tiles_n == 1) {
+          net->bstate[b.index].geo.n_tiles_n == 1 && tc_head_fusable(last.cout)) {
         epi.head_w = net->d_params + net->params[last.p_kernel].offset;
         epi.head_b = net->d_params + net->params[last.p_bias].offset;
         epi.head_k = last.cout;
