@@ -50,7 +50,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Bounded wait: a broken pipeline must end in an error code, never in a hung GPU.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int *status, int code) {
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int *status, int code,
+                                          long long *waited = nullptr) {
   const long long t0 = clock64();
   for (uint32_t it = 1;; ++it) {
     uint32_t done;
@@ -61,7 +62,10 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int *st
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (done) return true;
+    if (done) {
+      if (waited) *waited += clock64() - t0;
+      return true;
+    }
     if ((it & 0x3FFu) == 0) {
       // ~2 s at 2 GHz, or another role already gave up
       if (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int *>(status) != 0) break;
@@ -84,18 +88,37 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+// One lane of a fully converged warp.  tcgen05.mma / TMA take their operands in UNIFORM registers:
+// the issuing code must stay warp-uniform (all 32 lanes compute the same descriptors) and only the
+// instruction itself is predicated on the elected lane -- issuing from inside an `if (lane == 0)`
+// region makes the compiler wrap every MMA in a VOTEU/ELECT/R2UR waterfall loop (~20 extra
+// instructions, measured 220 clk per MMA instead of 39).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                           uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (elect_one_sync()) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
+  if (elect_one_sync()) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -144,12 +167,23 @@ template <int HK>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ TcConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const uint32_t a_stride = (p.a_stage_bytes + 127u) & ~127u;
   const uint32_t b_stride = (p.b_stage_bytes + 127u) & ~127u;
   uint8_t *a_smem = smem;
   uint8_t *b_smem = smem + (size_t)a_stride * p.a_stages;
   TcBarriers *bars = reinterpret_cast<TcBarriers *>(b_smem + (size_t)b_stride * p.b_stages);
+  float *s_scale = reinterpret_cast<float *>(bars + 1);     // [cout] folded BN scale
+  float *s_shift = s_scale + p.cout;                        // [cout] folded BN shift
+  float *s_head = s_shift + p.cout;                         // [cout][HK] + [HK] fused-head weights
+  for (int i = threadIdx.x; i < p.cout; i += blockDim.x) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+  if constexpr (HK > 0) {
+    for (int i = threadIdx.x; i < p.cout * HK; i += blockDim.x) s_head[i] = p.head_w[i];
+    for (int i = threadIdx.x; i < HK; i += blockDim.x) s_head[p.cout * HK + i] = p.head_b[i];
+  } else {
+    (void)s_head;
+  }
   const int mt = p.mt_x * p.mt_y;                 // M-tiles (128 rows each) per super-tile
   const uint32_t acc_cols = (uint32_t)(mt * p.n_cols);
 
@@ -175,10 +209,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-      if (p.b_resident) {
+    {
+      // ===================== TMA producer (warp-uniform; elected lane issues) =====================
+      const bool leader = elect_one_sync() != 0;
+      if (leader) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+      if (p.b_resident && leader) {
         // whole packed weight image of the layer stays in smem for the kernel's lifetime
         const uint32_t wfull = smem_u32(&bars->w_full);
         mbar_expect_tx(wfull, p.b_stage_bytes);
@@ -192,37 +227,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       bool ok = true;
+      long long w_prod = 0;
+      const long long t_start = clock64();
       for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
         int n_tile, tx, ty, img;
         decode_tile(p, tile, n_tile, tx, ty, img);
         const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.wpack) +
                               (size_t)n_tile * p.cin_chunks * p.ksteps * 32u * p.n_cols;
         for (int ch = 0; ok && ch < p.cin_chunks; ++ch) {
-          ok = mbar_wait(smem_u32(&bars->a_empty[as]), aph ^ 1u, p.status, 1);
+          ok = mbar_wait(smem_u32(&bars->a_empty[as]), aph ^ 1u, p.status, 1, &w_prod);
           if (!ok) break;
           const uint32_t afull = smem_u32(&bars->a_full[as]);
-          mbar_expect_tx(afull, p.a_stage_bytes);
-          // tensor map is declared in 8-byte elements: x coordinate = px * 2
-          tma_load_4d(smem_u32(a_smem + (size_t)as * a_stride), &tmap_a, afull,
-                      (tx * p.mt_x * kTcTileW - p.pad_x) * 2, ty * p.mt_y * kTcTileH - p.pad_y,
-                      ch * p.planes_per_chunk, img);
+          if (leader) {
+            mbar_expect_tx(afull, p.a_stage_bytes);
+            // tensor map is declared in 8-byte elements: x coordinate = px * 2
+            tma_load_4d(smem_u32(a_smem + (size_t)as * a_stride), &tmap_a, afull,
+                        (tx * p.mt_x * kTcTileW - p.pad_x) * 2, ty * p.mt_y * kTcTileH - p.pad_y,
+                        ch * p.planes_per_chunk, img);
+          }
           if (++as == p.a_stages) { as = 0; aph ^= 1u; }
           if (p.b_resident) continue;
           for (int g = 0; g < p.ksteps; g += p.bgroup) {
             ok = mbar_wait(smem_u32(&bars->b_empty[bs]), bph ^ 1u, p.status, 2);
             if (!ok) break;
             const uint32_t bfull = smem_u32(&bars->b_full[bs]);
-            mbar_expect_tx(bfull, p.b_stage_bytes);
-            bulk_load(smem_u32(b_smem + (size_t)bs * b_stride),
-                      wsrc + ((size_t)ch * p.ksteps + g) * 32u * p.n_cols, p.b_stage_bytes, bfull);
+            if (leader) {
+              mbar_expect_tx(bfull, p.b_stage_bytes);
+              bulk_load(smem_u32(b_smem + (size_t)bs * b_stride),
+                        wsrc + ((size_t)ch * p.ksteps + g) * 32u * p.n_cols, p.b_stage_bytes, bfull);
+            }
             if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
           }
         }
       }
+      if (p.dbg && blockIdx.x == 0 && leader) { p.dbg[0] = w_prod; p.dbg[1] = clock64() - t_start; }
     }
   } else if (warp <= kTcIssuers) {
-    if (lane == 0) {
-      // ===================== MMA issuers (warps 1..kTcIssuers, one thread each) =====================
+    {
+      // ===================== MMA issuers (warps 1..kTcIssuers; warp-uniform code, elected lane issues) ====
       // One thread sustains only ~1 tcgen05.mma per 108 clk (measured, tools/mma_bench.cu) while
       // the tensor pipe accepts one M128xN16xK16 MMA per ~39 clk, so the M-tiles of a super-tile
       // are dealt round-robin to kTcIssuers threads, each with its own commits.
@@ -250,17 +292,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int as = 0, bs = 0, acc = 0;
       uint32_t aph = 0, bph = 0, accph = 0;
       bool ok = true;
+      long long w_acc = 0, w_a = 0, w_b = 0;
+      const long long t_start = clock64();
       if (p.b_resident) {
         ok = mbar_wait(smem_u32(&bars->w_full), 0, p.status, 7);
         tc_fence_after();
       }
       for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
-        ok = mbar_wait(smem_u32(&bars->acc_empty[acc]), accph ^ 1u, p.status, 3);
+        ok = mbar_wait(smem_u32(&bars->acc_empty[acc]), accph ^ 1u, p.status, 3, &w_acc);
         if (!ok) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
         for (int ch = 0; ok && ch < p.cin_chunks; ++ch) {
-          ok = mbar_wait(smem_u32(&bars->a_full[as]), aph, p.status, 4);
+          ok = mbar_wait(smem_u32(&bars->a_full[as]), aph, p.status, 4, &w_a);
           if (!ok) break;
           tc_fence_after();
           const uint32_t a_base = smem_u32(a_smem + (size_t)as * a_stride);
@@ -269,7 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (p.b_resident) {
               b_base = smem_u32(b_smem) + (uint32_t)(ch * p.ksteps + g) * kstep_b;
             } else {
-              ok = mbar_wait(smem_u32(&bars->b_full[bs]), bph, p.status, 5);
+              ok = mbar_wait(smem_u32(&bars->b_full[bs]), bph, p.status, 5, &w_b);
               if (!ok) break;
               tc_fence_after();
               b_base = smem_u32(b_smem + (size_t)bs * b_stride);
@@ -295,98 +339,83 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         umma_commit(smem_u32(&bars->acc_full[acc]));
         if (++acc == 2) { acc = 0; accph ^= 1u; }
       }
+      if (p.dbg && blockIdx.x == 0 && issuer == 0 && lane == 0) {
+        p.dbg[2] = w_acc; p.dbg[3] = w_a; p.dbg[4] = w_b; p.dbg[5] = clock64() - t_start;
+      }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (2 warpgroups, M-tiles interleaved) =====================
+    // Each thread owns one GEMM row (= pixel) of an M-tile: TMEM lane m, columns = channels.
+    // Work is done on 8-column chunks (one 16 B output vector), two chunks per TMEM-load batch.
     const int q = warp & 3;                 // TMEM lane quarter
     const int wg = (warp - 4) >> 2;         // 0 or 1
     const int m = q * 32 + lane;            // GEMM row == TMEM lane
     const int r = m >> 3, px = m & 7;       // row / px inside the 8x16 M-tile
+    const float relu_floor = p.relu ? 0.f : -3.0e38f;
+    const int nch = (min(p.cols_valid, p.n_cols)) >> 3;      // chunks per n-tile holding valid columns
+    const long long plane_elems = (long long)p.out_h * p.out_w * 8;
     int acc = 0;
     uint32_t accph = 0;
     bool ok = true;
+    long long w_epi = 0;
+    const long long t_start = clock64();
     for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
       int n_tile, tx, ty, img;
       decode_tile(p, tile, n_tile, tx, ty, img);
-      ok = mbar_wait(smem_u32(&bars->acc_full[acc]), accph, p.status, 6);
+      ok = mbar_wait(smem_u32(&bars->acc_full[acc]), accph, p.status, 6, &w_epi);
       if (!ok) break;
       tc_fence_after();
+      const int col_base = n_tile * p.n_cols;
+      const int my_nch = min(nch, (p.cols_valid - col_base) >> 3);
       for (int t = wg; t < mt; t += 2) {
-        const int iy = t / p.mt_x, ix = t - iy * p.mt_x;
+        const int iy = t >> p.mt_x_log2, ix = t & (p.mt_x - 1);
         const int y = (ty * p.mt_y + iy) * kTcTileH + r, x = (tx * p.mt_x + ix) * kTcTileW + px;
         const bool inside = (y < p.h) && (x < p.w);
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols +
                                 (uint32_t)(t * p.n_cols);
-        float z[HK > 0 ? HK : 1];
         if constexpr (HK > 0) {
+          // ---- fused 1x1 conv + softmax head (fp32 activations never leave registers)
+          float z[HK];
 #pragma unroll
-          for (int k = 0; k < HK; ++k) z[k] = __ldg(p.head_b + k);
-        }
-        for (int j = 0; j < p.n_cols; j += 8) {
-          const int col = n_tile * p.n_cols + j;   // warp-uniform
-          if (col >= p.cols_valid) break;
-          uint32_t v[8];
-          tmem_ld8(t_base + (uint32_t)j, v);
-          tmem_ld_wait();
-          int co0 = col, oy = y, ox = x;
-          if (p.mode == 1) {
-            const int par = col / p.cout;
-            co0 = col - par * p.cout;
-            oy = 2 * y + (par >> 1);
-            ox = 2 * x + (par & 1);
-          }
-          Vec8f o;
+          for (int k = 0; k < HK; ++k) z[k] = s_head[p.cout * HK + k];
+          for (int j = 0; j < my_nch; j += 2) {
+            uint32_t v[2][8];
+            const bool two = (j + 1 < my_nch);
+            tmem_ld8(t_base + (uint32_t)(j * 8), v[0]);
+            if (two) tmem_ld8(t_base + (uint32_t)(j * 8 + 8), v[1]);
+            tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float f = fmaf(__uint_as_float(v[k]), __ldg(p.scale + co0 + k), __ldg(p.shift + co0 + k));
-            o.v[k] = p.relu ? fmaxf(f, 0.f) : f;
-          }
-          if constexpr (HK > 0) {
-            // fused 1x1 conv head: logits accumulate over the channel chunks (fp32 activations)
+            for (int u = 0; u < 2; ++u) {
+              if (u == 1 && !two) break;
+              const int co0 = col_base + (j + u) * 8;
+              const float4 sa = *reinterpret_cast<const float4 *>(s_scale + co0), sb = *reinterpret_cast<const float4 *>(s_scale + co0 + 4);
+              const float4 ha = *reinterpret_cast<const float4 *>(s_shift + co0), hb = *reinterpret_cast<const float4 *>(s_shift + co0 + 4);
+              const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+              const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float *wr = p.head_w + (size_t)(co0 + c) * HK;
+              for (int c = 0; c < 8; ++c) {
+                const float o = fmaxf(fmaf(__uint_as_float(v[u][c]), sc[c], sh[c]), relu_floor);
+                const float *wr = s_head + (co0 + c) * HK;
 #pragma unroll
-              for (int k = 0; k < HK; ++k) z[k] = fmaf(o.v[c], __ldg(wr + k), z[k]);
+                for (int k = 0; k < HK; ++k) z[k] = fmaf(o, wr[k], z[k]);
+              }
             }
-            continue;
           }
           if (inside) {
-            __nv_bfloat16 *dst = p.out + (long long)img * p.out_img_stride +
-                                 (((long long)(co0 >> 3) * p.out_h + oy) * p.out_w + ox) * 8;
-            store8(dst, o);
-          }
-          if (p.pool_out) {
-            // 2x2 max over (px^1, row^1): partners are lanes ^1 and ^8 of this warp
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              float a = fmaxf(o.v[k], __shfl_xor_sync(0xffffffffu, o.v[k], 1));
-              o.v[k] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 8));
-            }
-            if (inside && !(px & 1) && !(r & 1)) {
-              __nv_bfloat16 *dst = p.pool_out + (long long)img * p.pool_img_stride +
-                                   (((long long)(co0 >> 3) * (p.out_h >> 1) + (y >> 1)) * (p.out_w >> 1) + (x >> 1)) * 8;
-              store8(dst, o);
-            }
-          }
-        }
-        if constexpr (HK > 0) {
-          if (inside) {
-            // softmax over classes + first-max argmax on the float32 probabilities
             float mx = z[0];
 #pragma unroll
             for (int k = 1; k < HK; ++k) mx = fmaxf(mx, z[k]);
-            float s = 0.f;
+            float ssum = 0.f;
 #pragma unroll
-            for (int k = 0; k < HK; ++k) { z[k] = expf(z[k] - mx); s += z[k]; }
-            const float inv = 1.f / s;
+            for (int k = 0; k < HK; ++k) { z[k] = expf(z[k] - mx); ssum += z[k]; }
+            const float inv = 1.f / ssum;
             const long long pix = ((long long)img * p.h + y) * p.w + x;
             float pm = -1.f;
             int pa = 0;
 #pragma unroll
             for (int k = 0; k < HK; ++k) {
               z[k] *= inv;
-              if (z[k] > pm) { pm = z[k]; pa = k; }
+              if (z[k] > pm) { pm = z[k]; pa = k; }   // first max, computed on the float32 probabilities
             }
             if (p.probs) {
               float *dst = p.probs + pix * HK;
@@ -398,6 +427,93 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             if (p.labels) p.labels[pix] = (uint8_t)pa;
           }
+        } else if (p.mode == 1 && p.shuffle_pairs) {
+          // ---- up-conv pixel shuffle: the two x-parities of one (y-parity, plane) are loaded
+          //      together so each thread stores 32 contiguous bytes (2 output pixels)
+          const int planes_per_par = p.cout >> 3;
+          const int first = col_base / p.cout;                   // first parity in this n-tile (even)
+          const int npar = (my_nch << 3) / p.cout;               // parities in this n-tile (2 or 4)
+          for (int pp = 0; pp < npar; pp += 2) {
+            const int py = (first + pp) >> 1;
+            for (int c8 = 0; c8 < planes_per_par; ++c8) {
+              uint32_t v[2][8];
+              tmem_ld8(t_base + (uint32_t)(pp * p.cout + c8 * 8), v[0]);
+              tmem_ld8(t_base + (uint32_t)((pp + 1) * p.cout + c8 * 8), v[1]);
+              tmem_ld_wait();
+              const int co0 = c8 * 8;
+              const float4 sa = *reinterpret_cast<const float4 *>(s_scale + co0), sb = *reinterpret_cast<const float4 *>(s_scale + co0 + 4);
+              const float4 ha = *reinterpret_cast<const float4 *>(s_shift + co0), hb = *reinterpret_cast<const float4 *>(s_shift + co0 + 4);
+              const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+              const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+              uint4 pk[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&pk[u]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  h2[k] = __floats2bfloat162_rn(fmaxf(fmaf(__uint_as_float(v[u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
+                                                fmaxf(fmaf(__uint_as_float(v[u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor));
+              }
+              if (inside) {
+                __nv_bfloat16 *dst = p.out + (long long)img * p.out_img_stride + (long long)c8 * plane_elems +
+                                     ((long long)(2 * y + py) * p.out_w + 2 * x) * 8;
+                *reinterpret_cast<uint4 *>(dst) = pk[0];
+                *reinterpret_cast<uint4 *>(dst + 8) = pk[1];
+              }
+            }
+          }
+        } else {
+          // ---- plain store (+ optional fused 2x2 max-pool); generic pixel shuffle falls back here
+          const long long px_off = ((long long)y * p.out_w + x) * 8;
+          for (int j = 0; j < my_nch; j += 2) {
+            uint32_t v[2][8];
+            const bool two = (j + 1 < my_nch);
+            tmem_ld8(t_base + (uint32_t)(j * 8), v[0]);
+            if (two) tmem_ld8(t_base + (uint32_t)(j * 8 + 8), v[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (u == 1 && !two) break;
+              const int col = col_base + (j + u) * 8;
+              int co0 = col;
+              long long off = px_off;
+              if (p.mode == 1) {
+                const int par = col / p.cout;
+                co0 = col - par * p.cout;
+                off = ((long long)(2 * y + (par >> 1)) * p.out_w + 2 * x + (par & 1)) * 8;
+              }
+              const float4 sa = *reinterpret_cast<const float4 *>(s_scale + co0), sb = *reinterpret_cast<const float4 *>(s_scale + co0 + 4);
+              const float4 ha = *reinterpret_cast<const float4 *>(s_shift + co0), hb = *reinterpret_cast<const float4 *>(s_shift + co0 + 4);
+              const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+              const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+              uint4 pk;
+              __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                h2[k] = __floats2bfloat162_rn(fmaxf(fmaf(__uint_as_float(v[u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
+                                              fmaxf(fmaf(__uint_as_float(v[u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor));
+              if (inside)
+                *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)(co0 >> 3) * plane_elems + off) = pk;
+              if (p.pool_out) {
+                // 2x2 max on the packed bf16 pairs (max commutes with the monotonic rounding):
+                // partners are lanes ^1 (x) and ^8 (row) of this warp
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  uint32_t w0 = reinterpret_cast<uint32_t *>(&pk)[k];
+                  uint32_t w1 = __shfl_xor_sync(0xffffffffu, w0, 1);
+                  __nv_bfloat162 a = __hmax2(*reinterpret_cast<__nv_bfloat162 *>(&w0), *reinterpret_cast<__nv_bfloat162 *>(&w1));
+                  w0 = *reinterpret_cast<uint32_t *>(&a);
+                  w1 = __shfl_xor_sync(0xffffffffu, w0, 8);
+                  a = __hmax2(a, *reinterpret_cast<__nv_bfloat162 *>(&w1));
+                  h2[k] = a;
+                }
+                if (inside && !(px & 1) && !(r & 1))
+                  *reinterpret_cast<uint4 *>(p.pool_out + (long long)img * p.pool_img_stride +
+                                             (long long)(co0 >> 3) * (plane_elems >> 2) +
+                                             ((long long)(y >> 1) * (p.out_w >> 1) + (x >> 1)) * 8) = pk;
+              }
+            }
+          }
         }
       }
       tc_fence_before();
@@ -405,6 +521,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
       if (++acc == 2) { acc = 0; accph ^= 1u; }
     }
+    if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) { p.dbg[6] = w_epi; p.dbg[7] = clock64() - t_start; }
   }
 
   tc_fence_before();
@@ -588,7 +705,8 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
     b_bytes_total = (size_t)p.b_stages * ((p.b_stage_bytes + 127u) & ~127u);
   }
   // ---- super-tile: mt_x x mt_y M-tiles of 8 px x 16 rows share one TMA halo box
-  const size_t budget = 208 * 1024 - b_bytes_total - sizeof(TcBarriers) - 1024;
+  const size_t epi_bytes = ((size_t)g.cout * (2 + kTcMaxClasses) + kTcMaxClasses) * sizeof(float);
+  const size_t budget = 208 * 1024 - b_bytes_total - sizeof(TcBarriers) - epi_bytes - 1024;
   const int max_mt = std::max(1, 256 / g.n_cols);          // 2 accumulator stages in 512 TMEM columns
   static const int cand[][2] = {{8, 2}, {4, 2}, {8, 1}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
   int best_x = 1, best_y = 1;
@@ -605,6 +723,8 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
     break;
   }
   p.mt_x = best_x; p.mt_y = best_y;
+  p.mt_x_log2 = best_x == 8 ? 3 : best_x == 4 ? 2 : best_x == 2 ? 1 : 0;
+  p.shuffle_pairs = (g.ups && (g.n_cols % (2 * g.cout)) == 0 && (g.cols_valid % (2 * g.cout)) == 0) ? 1 : 0;
   p.box_w = best_x * kTcTileW + g.box_w;
   p.box_h = best_y * kTcTileH + g.box_h;
   p.tiles_x = (w + best_x * kTcTileW - 1) / (best_x * kTcTileW);
@@ -630,7 +750,7 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
   if (p.a_stages < 1) { set_error("tc plan: smem budget exceeded"); return 1; }
   // beyond ~96 KB in flight per SM more stages buy nothing
   while (p.a_stages > 3 && (size_t)(p.a_stages - 1) * a_stride >= 96 * 1024) --p.a_stages;
-  *smem_bytes = (size_t)p.a_stages * a_stride + b_bytes_total + sizeof(TcBarriers) + 1024;
+  *smem_bytes = (size_t)p.a_stages * a_stride + b_bytes_total + sizeof(TcBarriers) + epi_bytes + 1024;
   if (*smem_bytes > 227 * 1024) { set_error("tc plan: smem budget exceeded"); return 1; }
   p.mode = g.ups ? 1 : 0;
   p.cout = g.cout;

@@ -20,6 +20,8 @@ struct TcConvParams {
   int ksteps;                  // MMA k-steps per chunk
   int bgroup;                  // k-steps per weight stage
   int mt_x, mt_y;              // M-tiles per super-tile (one TMA halo box, mt_x*mt_y accumulators)
+  int mt_x_log2;               // mt_x is a power of two
+  int shuffle_pairs;           // mode 1: both x-parities of a plane live in the same n-tile
   int b_resident;              // 1: whole packed weight image stays in smem
   int n_cols;                  // MMA N per n-tile (multiple of 16, <= 256)
   int cols_valid;              // total valid GEMM columns over all n-tiles
@@ -46,6 +48,7 @@ struct TcConvParams {
   uint8_t *labels;
   const __nv_bfloat16 *wpack;  // packed weights [n_tile][chunk][kstep][2][n_cols][8]
   int *status;                 // device word: non-zero = pipeline timeout code
+  long long *dbg;              // optional [8] cycle counters of block 0 (NULL = off)
 };
 
 // Host-side plan for one conv block at one (n,h,w).

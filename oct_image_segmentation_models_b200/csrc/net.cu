@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 
 #include "kernels.cuh"
 
@@ -621,6 +622,16 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
                         net->d_status, &plan);
     }
   }
+  long long *d_dbg = nullptr;
+  if (path == 1 && rc == 0 && std::getenv("OCTSEG_TC_DEBUG")) {
+    cudaMalloc(&d_dbg, 64);
+    cudaMemset(d_dbg, 0, 64);
+    plan.p.dbg = d_dbg;
+    fprintf(stderr, "[tc] block %d: mt %dx%d tiles %d grid %d a_stages %d (%u B) b_res %d b_stages %d (%u B) n_cols %d ksteps %d chunks %d smem %zu\n",
+            conv_index, plan.p.mt_x, plan.p.mt_y, plan.p.num_tiles, plan.grid, plan.p.a_stages, plan.p.a_stage_bytes,
+            plan.p.b_resident, plan.p.b_stages, plan.p.b_stage_bytes, plan.p.n_cols, plan.p.ksteps, plan.p.cin_chunks,
+            plan.smem_bytes);
+  }
   for (int rep = 0; rc == 0 && rep < reps; ++rep) {
     if (rep == reps - 1) cudaEventRecord(e0, net->stream);
     if (path == 1) {
@@ -641,6 +652,13 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
   }
   if (rc == 0) rc = check_status(net);
   if (rc == 0 && ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+  if (d_dbg) {
+    long long h[8];
+    cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc] block0 cycles: producer wait_a_empty %lld of %lld | issuer0 wait_acc_empty %lld wait_a_full %lld wait_b_full %lld of %lld | epilogue wait_acc_full %lld of %lld\n",
+            h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+    cudaFree(d_dbg);
+  }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (rc == 0) {
