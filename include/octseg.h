@@ -44,7 +44,9 @@ typedef struct octseg_config {
 } octseg_config;
 
 enum { OCTSEG_FP32 = 0, OCTSEG_BF16 = 1 };          /* precision modes            */
-enum { OCTSEG_U8 = 0, OCTSEG_F32 = 1 };             /* host/device image dtypes   */
+/* image dtypes: raw uint8, raw float32 (0..255, x/255 applied on the device), or float32 that the
+ * caller already preprocessed with the reference's x/255.0 (models/unet.py:87-91) */
+enum { OCTSEG_U8 = 0, OCTSEG_F32 = 1, OCTSEG_F32_PRE = 2 };
 
 /* ---- library / device ---------------------------------------------------------- */
 int32_t     octseg_version(void);
@@ -73,7 +75,7 @@ int32_t octseg_get_param(octseg_net *net, int32_t index, float *host, int64_t co
  * Replaces `loaded_model.predict(preprocess(x))`
  * (reference prediction/prediction.py:75-81, evaluation/evaluation.py:129-135, with
  * the x/255 preprocessing of models/unet.py:87-91 applied on the device).
- *   images : [n,h,w,input_channels], dtype OCTSEG_U8 or OCTSEG_F32 (raw 0..255 values)
+ *   images : [n,h,w,input_channels], dtype OCTSEG_U8 / OCTSEG_F32 (raw 0..255) / OCTSEG_F32_PRE
  *   probs  : [n,h,w,num_classes] float32 softmax output, may be NULL
  *   labels : [n,h,w] uint8 argmax (first max on ties, as np.argmax), may be NULL
  * *_host: pageable or pinned host pointers, copies are part of the call.

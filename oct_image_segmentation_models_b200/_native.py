@@ -27,7 +27,7 @@ class OctsegTrainConfig(C.Structure):
 
 
 FP32, BF16 = 0, 1
-U8, F32 = 0, 1
+U8, F32, F32_PRE = 0, 1, 2
 
 # name -> (restype, argtypes); mirrors include/octseg.h one to one
 _PROTOS = {

@@ -22,10 +22,10 @@
 //   * accumulators sit in TMEM (double buffered), the epilogue applies the folded
 //     BatchNorm scale/shift + ReLU and stores one 16 B vector per pixel per plane.
 //
-// Warp roles (384 threads, 1 CTA/SM, persistent over super-tiles):
+// Warp roles (512 threads, 1 CTA/SM, persistent over super-tiles):
 //   warp 0        : TMEM allocator; lane 0 = TMA producer (A halo tiles + packed weights)
 //   warps 1..3    : lane 0 of each = MMA issuer for a third of the super-tile's M-tiles
-//   warps 4..11   : epilogue, two warpgroups (TMEM lane quarter = warp % 4)
+//   warps 4..15   : epilogue, three warpgroups (TMEM lane quarter = warp % 4)
 #include "conv_tc.cuh"
 
 #include <algorithm>
@@ -160,7 +160,8 @@ __device__ __forceinline__ void decode_tile(const TcConvParams &p, int tile, int
 }
 
 constexpr int kTcIssuers = 3;    // MMA-issuing threads (warps 1..3)
-constexpr int kTcThreads = 384;   // warps 0..3 control, warps 4..11 epilogue (two warpgroups)
+constexpr int kTcEpiWarps = 12;   // epilogue warps 4..15 (three warpgroups)
+constexpr int kTcThreads = (4 + kTcEpiWarps) * 32;
 
 // HK: compile-time class count of the fused 1x1-conv + softmax head (0 = no head fusion)
 template <int HK>
@@ -194,7 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // every one of the kTcIssuers MMA-issuing threads commits to the "consumed" barriers
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), kTcIssuers); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), kTcIssuers); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), kTcIssuers); mbar_init(smem_u32(&bars->acc_empty[i]), 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), kTcIssuers); mbar_init(smem_u32(&bars->acc_empty[i]), kTcEpiWarps); }
     mbar_init(smem_u32(&bars->w_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -348,7 +349,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // Each thread owns one GEMM row (= pixel) of an M-tile: TMEM lane m, columns = channels.
     // Work is done on 8-column chunks (one 16 B output vector), two chunks per TMEM-load batch.
     const int q = warp & 3;                 // TMEM lane quarter
-    const int wg = (warp - 4) >> 2;         // 0 or 1
+    const int wg = (warp - 4) >> 2;         // epilogue warpgroup 0..kTcEpiWarps/4-1
     const int m = q * 32 + lane;            // GEMM row == TMEM lane
     const int r = m >> 3, px = m & 7;       // row / px inside the 8x16 M-tile
     const float relu_floor = p.relu ? 0.f : -3.0e38f;
@@ -367,7 +368,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const int col_base = n_tile * p.n_cols;
       const int my_nch = min(nch, (p.cols_valid - col_base) >> 3);
-      for (int t = wg; t < mt; t += 2) {
+      for (int t = wg; t < mt; t += kTcEpiWarps / 4) {
         const int iy = t >> p.mt_x_log2, ix = t & (p.mt_x - 1);
         const int y = (ty * p.mt_y + iy) * kTcTileH + r, x = (tx * p.mt_x + ix) * kTcTileW + px;
         const bool inside = (y < p.h) && (x < p.w);

@@ -22,6 +22,14 @@ int launch_conv_direct(View<const T> in, const float *wgt, int kh, int kw, int c
                        int ups, const float *scale, const float *shift, int relu, View<T> out,
                        cudaStream_t st);
 
+// Same kernel with explicit geometry: output pixel (y,x) reads input (y*stride+dy-pad_top,
+// x*stride+dx-pad_left).  Used by the backward pass (dgrad = conv with transformed weights;
+// the up-conv's dgrad is a stride-2 3x3 conv over dz).
+template <typename T>
+int launch_conv_direct_ex(View<const T> in, const float *wgt, int kh, int kw, int cin, int cout,
+                          int ups, int stride, int pad_top, int pad_left, const float *scale,
+                          const float *shift, int relu, View<T> out, cudaStream_t st);
+
 // 2x2/stride-2 max pool (reference models/unet.py:37)
 template <typename T>
 int launch_maxpool2(View<const T> in, View<T> out, cudaStream_t st);

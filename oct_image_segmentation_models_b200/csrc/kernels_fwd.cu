@@ -21,7 +21,7 @@ template <typename T, typename IMG, int KH, int KW, int CIN>
 __global__ void __launch_bounds__(256) conv_first_kernel(
     const IMG *__restrict__ img, int n, int h, int w, int cin, const float *__restrict__ wgt, int kh,
     int kw, int cout, const float *__restrict__ scale, const float *__restrict__ shift, int relu,
-    View<T> out) {
+    View<T> out, int pre) {
   extern __shared__ float wsm[];  // [kh*kw*cin][cout] + scale[cout] + shift[cout]
   if constexpr (KH > 0) { kh = KH; kw = KW; cin = CIN; }
   const int taps = kh * kw * cin;
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(
         if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
           const IMG raw = img[(((long long)b * h + iy) * w + ix) * cin + ci];
           if constexpr (sizeof(IMG) == 1) v = __fdiv_rn((float)raw, 255.0f);
-          else v = (float)((double)raw / 255.0);
+          else v = pre ? (float)raw : (float)((double)raw / 255.0);
         }
       }
       in[t] = v;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(
 template <typename T, typename IMG>
 __global__ void __launch_bounds__(256) conv_stem3x3_kernel(
     const IMG *__restrict__ img, int n, int h, int w, const float *__restrict__ wgt, int cout,
-    const float *__restrict__ scale, const float *__restrict__ shift, int relu, View<T> out) {
+    const float *__restrict__ scale, const float *__restrict__ shift, int relu, View<T> out, int pre) {
   extern __shared__ float wsm[];  // [9][cout] + scale[cout] + shift[cout]
   for (int i = threadIdx.x; i < 9 * cout; i += blockDim.x) wsm[i] = wgt[i];
   for (int i = threadIdx.x; i < cout; i += blockDim.x) {
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) conv_stem3x3_kernel(
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         if constexpr (sizeof(IMG) == 1) in[dy][i] = __fdiv_rn((float)raw[i], 255.0f);
-        else in[dy][i] = (float)((double)raw[i] / 255.0);
+        else in[dy][i] = pre ? (float)raw[i] : (float)((double)raw[i] / 255.0);
       }
     }
     for (int cog = 0; cog < cout / 8; ++cog) {
@@ -162,6 +162,7 @@ template <typename T>
 int launch_conv_first(const void *img, int img_dtype, int n, int h, int w, int cin_img,
                       const float *wgt, int kh, int kw, int cout, const float *scale,
                       const float *shift, int relu, View<T> out, cudaStream_t st) {
+  const int pre = (img_dtype == 2) ? 1 : 0;   // 2 = float32 already divided by 255 on the host
   if (kh * kw * cin_img > kFirstMaxTaps) { set_error("first conv: kh*kw*input_channels > 27 not supported"); return 1; }
   const long long total = (long long)n * h * w;
   unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
@@ -172,10 +173,10 @@ int launch_conv_first(const void *img, int img_dtype, int n, int h, int w, int c
     size_t sm4 = (size_t)11 * cout * sizeof(float);
     if (img_dtype == 0)
       conv_stem3x3_kernel<T, uint8_t><<<g4, 256, sm4, st>>>((const uint8_t *)img, n, h, w, wgt, cout, scale,
-                                                            shift, relu, out);
+                                                            shift, relu, out, 0);
     else
       conv_stem3x3_kernel<T, float><<<g4, 256, sm4, st>>>((const float *)img, n, h, w, wgt, cout, scale, shift,
-                                                          relu, out);
+                                                          relu, out, pre);
     OCTSEG_CUDA(cudaGetLastError());
     return 0;
   }
@@ -183,17 +184,17 @@ int launch_conv_first(const void *img, int img_dtype, int n, int h, int w, int c
   if (img_dtype == 0) {
     if (stem331)
       conv_first_kernel<T, uint8_t, 3, 3, 1><<<grid, 256, smem, st>>>((const uint8_t *)img, n, h, w, cin_img,
-                                                                      wgt, kh, kw, cout, scale, shift, relu, out);
+                                                                      wgt, kh, kw, cout, scale, shift, relu, out, pre);
     else
       conv_first_kernel<T, uint8_t, 0, 0, 0><<<grid, 256, smem, st>>>((const uint8_t *)img, n, h, w, cin_img,
-                                                                      wgt, kh, kw, cout, scale, shift, relu, out);
+                                                                      wgt, kh, kw, cout, scale, shift, relu, out, pre);
   } else {
     if (stem331)
       conv_first_kernel<T, float, 3, 3, 1><<<grid, 256, smem, st>>>((const float *)img, n, h, w, cin_img, wgt,
-                                                                    kh, kw, cout, scale, shift, relu, out);
+                                                                    kh, kw, cout, scale, shift, relu, out, pre);
     else
       conv_first_kernel<T, float, 0, 0, 0><<<grid, 256, smem, st>>>((const float *)img, n, h, w, cin_img, wgt,
-                                                                    kh, kw, cout, scale, shift, relu, out);
+                                                                    kh, kw, cout, scale, shift, relu, out, pre);
   }
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
@@ -210,7 +211,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) conv_direct_kernel(
     View<const T> in, const float *__restrict__ wgt, int kh, int kw, int cin, int cout, int ups,
     const float *__restrict__ scale, const float *__restrict__ shift, int relu, View<T> out,
-    int tiles_x) {
+    int tiles_x, int stride, int pt, int pl) {
   extern __shared__ float wsm[];  // [kh*kw][chunk][8]
   const int cog = blockIdx.y;
   const int b = blockIdx.z;
@@ -219,8 +220,8 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(
   const int x0 = tile_x * 64 + tx * 2;
   const int y = tile_y * 4 + ty;
   const int H = out.h, W = out.w;           // output grid
-  const int Hin = in.h, Win = in.w;         // input grid (H/2 when ups)
-  const int pt = (kh - 1) / 2, pl = (kw - 1) / 2;
+  const int Hin = in.h, Win = in.w;         // input grid (H/2 when ups, H*stride when strided)
+  const int Hv = ups ? H : Hin, Wv = ups ? W : Win;   // extent of the (virtual) input the taps index
   const int ntap = kh * kw;
   const bool active = (y < H) && (x0 < W);
   Vec8f acc0 = zero8(), acc1 = zero8();
@@ -239,13 +240,13 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(
     for (int cgl = 0; cgl < chunk / 8; ++cgl) {
       const T *plane = in.ptr + b * in.img_stride + (long long)(c0 / 8 + cgl) * Hin * Win * 8;
       for (int dy = 0; dy < kh; ++dy) {
-        int iy = y + dy - pt;
-        if (iy < 0 || iy >= H) continue;
+        int iy = y * stride + dy - pt;
+        if (iy < 0 || iy >= Hv) continue;
         if (ups) iy >>= 1;
         for (int dx = 0; dx < kw; ++dx) {
-          int ix0 = x0 + dx - pl, ix1 = ix0 + 1;
-          const bool v0ok = (ix0 >= 0 && ix0 < W);
-          const bool v1ok = (ix1 >= 0 && ix1 < W) && (x0 + 1 < W);
+          int ix0 = x0 * stride + dx - pl, ix1 = ix0 + stride;
+          const bool v0ok = (ix0 >= 0 && ix0 < Wv);
+          const bool v1ok = (ix1 >= 0 && ix1 < Wv) && (x0 + 1 < W);
           if (ups) { ix0 >>= 1; ix1 >>= 1; }
           Vec8f v0 = v0ok ? load8(plane + ((long long)iy * Win + ix0) * 8) : zero8();
           Vec8f v1 = v1ok ? load8(plane + ((long long)iy * Win + ix1) * 8) : zero8();
@@ -282,16 +283,24 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(
 }
 
 template <typename T>
-int launch_conv_direct(View<const T> in, const float *wgt, int kh, int kw, int cin, int cout,
-                       int ups, const float *scale, const float *shift, int relu, View<T> out,
-                       cudaStream_t st) {
+int launch_conv_direct_ex(View<const T> in, const float *wgt, int kh, int kw, int cin, int cout,
+                          int ups, int stride, int pad_top, int pad_left, const float *scale,
+                          const float *shift, int relu, View<T> out, cudaStream_t st) {
   const int tiles_x = (out.w + 63) / 64, tiles_y = (out.h + 3) / 4;
   dim3 grid(tiles_x * tiles_y, cout / 8, out.n);
   size_t smem = (size_t)kh * kw * std::min(cin, kDirectChunk) * 8 * sizeof(float);
   conv_direct_kernel<T><<<grid, 128, smem, st>>>(in, wgt, kh, kw, cin, cout, ups, scale, shift, relu, out,
-                                               tiles_x);
+                                               tiles_x, stride, pad_top, pad_left);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <typename T>
+int launch_conv_direct(View<const T> in, const float *wgt, int kh, int kw, int cin, int cout,
+                       int ups, const float *scale, const float *shift, int relu, View<T> out,
+                       cudaStream_t st) {
+  return launch_conv_direct_ex<T>(in, wgt, kh, kw, cin, cout, ups, 1, (kh - 1) / 2, (kw - 1) / 2, scale, shift,
+                                  relu, out, st);
 }
 
 // ---------------------------------------------------------------------------------
@@ -432,6 +441,9 @@ int launch_bn_fold(const float *bias, const float *gamma, const float *beta, con
                                     int, const float *, const float *, int, View<T>, cudaStream_t);    \
   template int launch_conv_direct<T>(View<const T>, const float *, int, int, int, int, int,            \
                                      const float *, const float *, int, View<T>, cudaStream_t);        \
+  template int launch_conv_direct_ex<T>(View<const T>, const float *, int, int, int, int, int, int,    \
+                                        int, int, const float *, const float *, int, View<T>,          \
+                                        cudaStream_t);                                                 \
   template int launch_maxpool2<T>(View<const T>, View<T>, cudaStream_t);                               \
   template int launch_head<T>(View<const T>, const float *, const float *, int, int, float *,          \
                               uint8_t *, cudaStream_t);

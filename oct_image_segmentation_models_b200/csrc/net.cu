@@ -110,7 +110,7 @@ static int check_supported(const octseg_net *net) {
 // ---------------------------------------------------------------------------------
 // derived state: folded BN + packed tensor-core weights
 // ---------------------------------------------------------------------------------
-static int sync_host_mirror(octseg_net *net) {
+int sync_host_mirror(octseg_net *net) {
   if (!net->host_stale) return 0;
   OCTSEG_CUDA(cudaMemcpyAsync(net->h_params.data(), net->d_params, net->total_floats * sizeof(float),
                               cudaMemcpyDeviceToHost, net->stream));
@@ -488,7 +488,7 @@ int32_t octseg_predict_device(octseg_net *net, const void *images, int32_t dtype
                               int32_t w, float *probs, uint8_t *labels, void *stream) {
   if (!net || !images) { set_error("null argument"); return 1; }
   if (n <= 0 || h <= 0 || w <= 0) { set_error("bad image batch shape"); return 1; }
-  if (dtype != OCTSEG_U8 && dtype != OCTSEG_F32) { set_error("bad image dtype"); return 1; }
+  if (dtype != OCTSEG_U8 && dtype != OCTSEG_F32 && dtype != OCTSEG_F32_PRE) { set_error("bad image dtype"); return 1; }
   OCTSEG_CUDA(cudaSetDevice(net->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : net->stream;
   const int mb = pick_microbatch(net, n, h, w);
@@ -508,7 +508,7 @@ int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, 
                             int32_t w, float *probs, uint8_t *labels) {
   if (!net || !images) { set_error("null argument"); return 1; }
   if (n <= 0 || h <= 0 || w <= 0) { set_error("bad image batch shape"); return 1; }
-  if (dtype != OCTSEG_U8 && dtype != OCTSEG_F32) { set_error("bad image dtype"); return 1; }
+  if (dtype != OCTSEG_U8 && dtype != OCTSEG_F32 && dtype != OCTSEG_F32_PRE) { set_error("bad image dtype"); return 1; }
   OCTSEG_CUDA(cudaSetDevice(net->device));
   const size_t img_bytes = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)n * h * w * net->cfg.input_channels;
   const size_t pr_bytes = (size_t)n * h * w * net->cfg.num_classes * sizeof(float);

@@ -1,34 +1,492 @@
-// Training half of the C ABI (forward with batch-stat BN + dropout, weighted CE, backward,
-// NCCL gradient all-reduce, Keras-Adam).  Filled in after the inference path is parity-green.
+// Training half of the C ABI: one synchronous data-parallel step
+//   forward (batch-statistics BN, dropout) -> weighted CE -> backward -> NCCL all-reduce ->
+//   Keras-Adam, mirroring model.fit under MirroredStrategy (reference training/training.py:185,
+//   262-266, 401-407; loss math common/custom_losses.py:27-35).
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels.cuh"
 #include "net.cuh"
+#include "train_kernels.cuh"
 
 using namespace octseg;
 
+namespace octseg {
+int ensure_workspace(octseg_net *net, int n, int h, int w);
+int check_status(octseg_net *net);
+
+// ---- NCCL, resolved at run time from the process' libnccl (torch ships one) ------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.lib) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) { set_error(std::string("cannot dlopen libnccl.so.2: ") + dlerror()); return 1; }
+  g_nccl.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    set_error("libnccl is missing required symbols");
+    return 1;
+  }
+  return 0;
+}
+#define OCTSEG_NCCL(expr)                                                                  \
+  do {                                                                                     \
+    int _r = (expr);                                                                       \
+    if (_r != 0) {                                                                         \
+      set_error(std::string(#expr) + ": " +                                               \
+                (g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "nccl error"));      \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+// ---- per-block training tensors ------------------------------------------------------------------
+struct TrainBlock {
+  void *z = nullptr;        // pre-BN conv output [n][cout/8][h][w][8]
+  void *a = nullptr;        // post BN+ReLU(+dropout) activation (may alias a concat-buffer slice)
+  int a_planes_total = 0, a_plane0 = 0;
+  void *pooled = nullptr;   // 2x2 max-pooled activation
+  void *dz = nullptr;       // gradient wrt z
+  float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr;   // [cout]
+  float *w_t = nullptr;     // transformed weights for the data gradient
+  int h = 0, w = 0;         // output grid
+};
+
+struct TrainState {
+  octseg_train_config tc{};
+  float *d_class_w = nullptr;
+  float *d_grads = nullptr, *d_m = nullptr, *d_v = nullptr;
+  float *d_ones = nullptr;          // [max cout] of 1.0f: conv epilogue scale in training
+  float *d_zeros = nullptr;         // [max cout] of 0.0f: conv epilogue shift of the data gradient
+  double *d_sums = nullptr;         // [2 * max cout]
+  double *d_loss = nullptr;
+  double *h_loss = nullptr;         // pinned
+  float *d_stem_tmp = nullptr;      // [taps][8][cout] stem wgrad scratch
+  long long step = 0;
+  int max_cout = 0;
+  // workspace
+  int n = 0, h = 0, w = 0;
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
+  std::vector<TrainBlock> tb;
+  std::vector<void *> dcat;         // gradient wrt each level's concat buffer [n][2f/8][h][w][8]
+  std::vector<void *> gA, gB;       // ping-pong gradient buffers per level (f channels... sized 2f)
+  void *img_blocked = nullptr;      // stem input as a 1-plane blocked tensor
+  void *mask = nullptr;             // dropout multiplier tensor at the bottleneck
+  void *d_img = nullptr; size_t d_img_bytes = 0;
+  uint8_t *d_labels = nullptr; size_t d_labels_bytes = 0;
+  uint8_t *d_mask_in = nullptr; size_t d_mask_bytes = 0;
+  // communicator
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+static TrainState *ts(octseg_net *net) { return reinterpret_cast<TrainState *>(net->train); }
+static size_t esz(const octseg_net *net) { return net->precision == OCTSEG_BF16 ? 2 : 4; }
+
+struct Bump2 {
+  size_t off = 0;
+  size_t take(size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; }
+};
+
+static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
+  TrainState *S = ts(net);
+  if (S->ws && S->n == n && S->h == h && S->w == w) return 0;
+  const int P = net->cfg.pool_layers, s = net->cfg.start_neurons;
+  if ((h % (1 << P)) || (w % (1 << P))) { set_error("image height/width must be multiples of 2^pool_layers"); return 1; }
+  const size_t es = esz(net);
+  auto bytes = [&](int ch, int lvl) { return (size_t)n * ch * (h >> lvl) * (w >> lvl) * es; };
+  Bump2 bump;
+  const size_t nb = net->blocks.size();
+  std::vector<size_t> o_z(nb), o_a(nb), o_pool(nb), o_dz(nb);
+  std::vector<size_t> o_cat(P), o_dcat(P), o_gA(P + 1), o_gB(P + 1);
+  for (int l = 0; l < P; ++l) { o_cat[l] = bump.take(bytes(2 * (s << l), l)); o_dcat[l] = bump.take(bytes(2 * (s << l), l)); }
+  for (int l = 0; l <= P; ++l) { o_gA[l] = bump.take(bytes(2 * (s << l), l)); o_gB[l] = bump.take(bytes(2 * (s << l), l)); }
+  for (auto &b : net->blocks) {
+    if (b.role == 4) continue;
+    o_z[b.index] = bump.take(bytes(b.cout, b.level));
+    o_dz[b.index] = bump.take(bytes(b.cout, b.level));
+    const bool in_cat = (b.role == 0 && b.pool_after) || b.role == 2;
+    o_a[b.index] = in_cat ? (size_t)-1 : bump.take(bytes(b.cout, b.level));
+    o_pool[b.index] = b.pool_after ? bump.take(bytes(b.cout, b.level + 1)) : (size_t)-1;
+  }
+  const size_t o_img = bump.take((size_t)n * h * w * 8 * es);
+  const size_t o_mask = bump.take(bytes(s << P, P));
+  if (bump.off > S->ws_bytes) {
+    if (S->ws) OCTSEG_CUDA(cudaFree(S->ws));
+    S->ws = nullptr;
+    OCTSEG_CUDA(cudaMalloc(&S->ws, bump.off));
+    S->ws_bytes = bump.off;
+  }
+  uint8_t *base = reinterpret_cast<uint8_t *>(S->ws);
+  S->dcat.resize(P); S->gA.resize(P + 1); S->gB.resize(P + 1);
+  for (int l = 0; l < P; ++l) S->dcat[l] = base + o_dcat[l];
+  for (int l = 0; l <= P; ++l) { S->gA[l] = base + o_gA[l]; S->gB[l] = base + o_gB[l]; }
+  for (auto &b : net->blocks) {
+    if (b.role == 4) continue;
+    TrainBlock &t = S->tb[b.index];
+    t.h = h >> b.level; t.w = w >> b.level;
+    t.z = base + o_z[b.index];
+    t.dz = base + o_dz[b.index];
+    const int f8 = b.cout / 8;
+    if (b.role == 0 && b.pool_after) { t.a = base + o_cat[b.level]; t.a_planes_total = 2 * f8; t.a_plane0 = f8; }
+    else if (b.role == 2) { t.a = base + o_cat[b.level]; t.a_planes_total = 2 * f8; t.a_plane0 = 0; }
+    else { t.a = base + o_a[b.index]; t.a_planes_total = f8; t.a_plane0 = 0; }
+    t.pooled = b.pool_after ? base + o_pool[b.index] : nullptr;
+  }
+  S->img_blocked = base + o_img;
+  S->mask = base + o_mask;
+  S->n = n; S->h = h; S->w = w;
+  return 0;
+}
+
+// Input activation of block b (as a view) during training
+template <typename T>
+static View<const T> block_input(octseg_net *net, const BlockSpec &b, int n) {
+  TrainState *S = ts(net);
+  if (b.index == 0) return make_view((const T *)S->img_blocked, n, 1, 0, 1, S->h, S->w);
+  const BlockSpec &pb = net->blocks[b.index - 1];
+  const TrainBlock &pt = S->tb[pb.index];
+  if (b.concat_level >= 0) {   // concat([up, skip]) buffer of this level == where the up block wrote
+    return make_view((const T *)pt.a, n, pt.a_planes_total, 0, pt.a_planes_total, pt.h, pt.w);
+  }
+  if (pb.pool_after) return make_view((const T *)pt.pooled, n, pb.cout / 8, 0, pb.cout / 8, pt.h / 2, pt.w / 2);
+  return make_view((const T *)pt.a, n, pt.a_planes_total, pt.a_plane0, pb.cout / 8, pt.h, pt.w);
+}
+
+template <typename T>
+static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uint8_t *d_labels, int n, int h,
+                        int w, const uint8_t *d_mask_in, cudaStream_t st) {
+  TrainState *S = ts(net);
+  const float *P = net->d_params;
+  float *G = S->d_grads;
+  const int nblk = (int)net->blocks.size();
+  const BlockSpec &head = net->blocks.back();
+  OCTSEG_CUDA(cudaMemsetAsync(G, 0, net->total_floats * sizeof(float), st));
+  OCTSEG_CUDA(cudaMemsetAsync(S->d_loss, 0, sizeof(double), st));
+  if (launch_image_to_blocked<T>(d_img, dtype, n, h, w, net->cfg.input_channels, (T *)S->img_blocked, st)) return 1;
+  ++net->launches;
+  const BlockSpec *mid_last = nullptr;
+  for (auto &b : net->blocks) if (b.dropout_after) mid_last = &b;
+  const bool use_dropout = mid_last && (d_mask_in || S->tc.dropout_rate > 0.f);
+  if (use_dropout) {
+    const TrainBlock &t = S->tb[mid_last->index];
+    if (launch_dropout_mask<T>(d_mask_in, S->tc.dropout_seed + (unsigned long long)S->step * 0x51ED27ULL,
+                               S->tc.dropout_rate > 0.f ? S->tc.dropout_rate : 0.5f, n, mid_last->cout, t.h, t.w,
+                               (T *)S->mask, st))
+      return 1;
+    ++net->launches;
+  }
+  // ------------------------------- forward -------------------------------
+  for (auto &b : net->blocks) {
+    if (b.role == 4) break;
+    TrainBlock &t = S->tb[b.index];
+    View<const T> in = block_input<T>(net, b, n);
+    View<T> z = make_view((T *)t.z, n, b.cout / 8, 0, b.cout / 8, t.h, t.w);
+    // z = conv(in) + bias  (epilogue scale = 1, shift = bias, no ReLU)
+    if (b.index == 0) {
+      if (launch_conv_first<T>(d_img, dtype, n, h, w, b.cin, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cout,
+                               S->d_ones, P + net->params[b.p_bias].offset, 0, z, st))
+        return 1;
+    } else if (launch_conv_direct<T>(in, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout,
+                                     b.ups ? 1 : 0, S->d_ones, P + net->params[b.p_bias].offset, 0, z, st))
+      return 1;
+    View<const T> zc = make_view((const T *)t.z, n, b.cout / 8, 0, b.cout / 8, t.h, t.w);
+    if (launch_bn_stats<T>(zc, S->d_sums, st)) return 1;
+    if (launch_bn_finalize(S->d_sums, (long long)n * t.h * t.w, b.cout, 1e-3f, 0.99f, P + net->params[b.p_gamma].offset,
+                           P + net->params[b.p_beta].offset, net->d_params + net->params[b.p_mean].offset,
+                           net->d_params + net->params[b.p_var].offset, t.mean, t.invstd, t.scale, t.shift, st))
+      return 1;
+    View<T> a = make_view((T *)t.a, n, t.a_planes_total, t.a_plane0, b.cout / 8, t.h, t.w);
+    const T *mask = (use_dropout && b.dropout_after) ? (const T *)S->mask : nullptr;
+    if (launch_bn_apply_relu<T>(zc, t.scale, t.shift, mask, a, st)) return 1;
+    net->launches += 4;
+    if (b.pool_after) {
+      View<const T> ac = make_view((const T *)t.a, n, t.a_planes_total, t.a_plane0, b.cout / 8, t.h, t.w);
+      View<T> po = make_view((T *)t.pooled, n, b.cout / 8, 0, b.cout / 8, t.h / 2, t.w / 2);
+      if (launch_maxpool2<T>(ac, po, st)) return 1;
+      ++net->launches;
+    }
+  }
+  // ------------------------------- loss + head backward -------------------------------
+  const BlockSpec &last = net->blocks[nblk - 2];
+  const TrainBlock &tl = S->tb[last.index];
+  {
+    View<const T> a = make_view((const T *)tl.a, n, tl.a_planes_total, tl.a_plane0, last.cout / 8, tl.h, tl.w);
+    View<T> da = make_view((T *)S->gA[0], n, last.cout / 8, 0, last.cout / 8, tl.h, tl.w);
+    const float inv_den = 1.0f / ((float)S->tc.global_batch * (float)h * (float)w);
+    if (launch_head_loss<T>(a, P + net->params[head.p_kernel].offset, P + net->params[head.p_bias].offset, head.cin,
+                            head.cout, d_labels, S->d_class_w, inv_den, da, G + net->params[head.p_kernel].offset,
+                            G + net->params[head.p_bias].offset, S->d_loss, st))
+      return 1;
+    ++net->launches;
+  }
+  // ------------------------------- backward -------------------------------
+  // `g` = gradient wrt the output activation of the block being processed
+  const void *g_ptr = S->gA[0];
+  int g_planes_total = last.cout / 8, g_plane0 = 0;
+  for (int bi = nblk - 2; bi >= 0; --bi) {
+    const BlockSpec &b = net->blocks[bi];
+    TrainBlock &t = S->tb[bi];
+    const int f8 = b.cout / 8;
+    View<const T> zc = make_view((const T *)t.z, n, f8, 0, f8, t.h, t.w);
+    View<const T> da = make_view((const T *)g_ptr, n, g_planes_total, g_plane0, f8, t.h, t.w);
+    if (b.pool_after) {
+      // da = d(skip half of the concat gradient) + scatter(d pooled); g currently holds d pooled
+      View<const T> ac = make_view((const T *)t.a, n, t.a_planes_total, t.a_plane0, f8, t.h, t.w);
+      View<const T> dpool = make_view((const T *)g_ptr, n, g_planes_total, g_plane0, f8, t.h / 2, t.w / 2);
+      View<const T> dskip = make_view((const T *)S->dcat[b.level], n, 2 * f8, f8, f8, t.h, t.w);
+      View<T> tot = make_view((T *)S->gB[b.level], n, f8, 0, f8, t.h, t.w);
+      if (launch_pool_bwd_add<T>(ac, dpool, dskip, tot, st)) return 1;
+      ++net->launches;
+      da = make_view((const T *)S->gB[b.level], n, f8, 0, f8, t.h, t.w);
+    }
+    const T *mask = (use_dropout && b.dropout_after) ? (const T *)S->mask : nullptr;
+    const float *gamma = P + net->params[b.p_gamma].offset, *beta = P + net->params[b.p_beta].offset;
+    if (launch_bn_bwd_reduce<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, S->d_sums, st)) return 1;
+    View<T> dz = make_view((T *)t.dz, n, f8, 0, f8, t.h, t.w);
+    if (launch_bn_bwd_apply<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, S->d_sums, (long long)n * t.h * t.w, dz,
+                               G + net->params[b.p_gamma].offset, G + net->params[b.p_beta].offset, st))
+      return 1;
+    View<const T> dzc = make_view((const T *)t.dz, n, f8, 0, f8, t.h, t.w);
+    View<const T> in = block_input<T>(net, b, n);
+    const int pt = (b.kh - 1) / 2, pl = (b.kw - 1) / 2;
+    if (b.index == 0) {
+      const int taps = b.kh * b.kw;
+      OCTSEG_CUDA(cudaMemsetAsync(S->d_stem_tmp, 0, (size_t)taps * 8 * b.cout * sizeof(float), st));
+      if (launch_wgrad<T>(in, dzc, b.kh, b.kw, pt, pl, 0, 8, b.cout, S->d_stem_tmp, G + net->params[b.p_bias].offset, st))
+        return 1;
+      if (launch_stem_wgrad_extract(S->d_stem_tmp, taps, b.cin, b.cout, G + net->params[b.p_kernel].offset, st)) return 1;
+      net->launches += 4;
+      break;
+    }
+    if (launch_wgrad<T>(in, dzc, b.kh, b.kw, pt, pl, b.ups ? 1 : 0, b.cin, b.cout, G + net->params[b.p_kernel].offset,
+                        G + net->params[b.p_bias].offset, st))
+      return 1;
+    // ---- data gradient wrt this block's input
+    const BlockSpec &pb = net->blocks[bi - 1];
+    if (!b.ups) {
+      if (launch_flip_transpose(P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout, t.w_t, st)) return 1;
+      void *dst;
+      int dst_total;
+      if (b.concat_level >= 0) { dst = S->dcat[b.level]; dst_total = b.cin / 8; }
+      else { dst = (g_ptr == S->gA[b.level]) ? S->gB[b.level] : S->gA[b.level]; dst_total = b.cin / 8; }
+      // destination grid = this block's input grid (pooled input has the same h,w as the output here)
+      View<T> din = make_view((T *)dst, n, dst_total, 0, b.cin / 8, t.h, t.w);
+      if (launch_conv_direct_ex<T>(dzc, t.w_t, b.kh, b.kw, b.cout, b.cin, 0, 1, b.kh - 1 - pt, b.kw - 1 - pl, S->d_ones,
+                                   S->d_zeros, 0, din, st))
+        return 1;
+      g_ptr = dst;
+      if (b.concat_level >= 0) { g_planes_total = b.cin / 8; g_plane0 = 0; }   // next: the up block (planes [0,f/8))
+      else { g_planes_total = b.cin / 8; g_plane0 = 0; }
+    } else {
+      // up-conv: d(prev) on the low-res grid = stride-2 (kh+1)x(kw+1) conv over dz
+      if (launch_upconv_dgrad_weights(P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout, t.w_t, st)) return 1;
+      void *dst = S->gA[b.level + 1];
+      View<T> din = make_view((T *)dst, n, b.cin / 8, 0, b.cin / 8, t.h / 2, t.w / 2);
+      if (launch_conv_direct_ex<T>(dzc, t.w_t, b.kh + 1, b.kw + 1, b.cout, b.cin, 0, 2, b.kh - 1 - pt, b.kw - 1 - pl,
+                                   S->d_ones, S->d_zeros, 0, din, st))
+        return 1;
+      g_ptr = dst;
+      g_planes_total = b.cin / 8; g_plane0 = 0;
+    }
+    (void)pb;
+    net->launches += 5;
+  }
+  // ------------------------------- all-reduce + optimizer -------------------------------
+  if (S->comm && S->world > 1)
+    OCTSEG_NCCL(g_nccl.AllReduce(G, G, (size_t)net->total_floats, /*ncclFloat*/ 7, /*ncclSum*/ 0, S->comm, st));
+  ++S->step;
+  const double b1 = S->tc.beta_1, b2 = S->tc.beta_2;
+  const float lr_t = (float)(S->tc.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)S->step)) /
+                             (1.0 - std::pow(b1, (double)S->step)));
+  if (launch_adam(net->d_params, G, S->d_m, S->d_v, net->total_floats, lr_t, S->tc.beta_1, S->tc.beta_2, S->tc.epsilon, st))
+    return 1;
+  ++net->launches;
+  net->host_stale = true;
+  net->derived_dirty = true;
+  return 0;
+}
+
+__global__ void store_loss_kernel(const double *src, float *dst) { *dst = (float)*src; }
+
+}  // namespace octseg
+
 extern "C" {
 
-void octseg_train_free(octseg_net *net) { (void)net; }
+void octseg_train_free(octseg_net *net) {
+  TrainState *S = ts(net);
+  if (!S) return;
+  if (S->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S->comm);
+  for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); }
+  cudaFree(S->d_class_w); cudaFree(S->d_grads); cudaFree(S->d_m); cudaFree(S->d_v); cudaFree(S->d_ones); cudaFree(S->d_zeros);
+  cudaFree(S->d_sums); cudaFree(S->d_loss); cudaFree(S->d_stem_tmp); cudaFree(S->ws); cudaFree(S->d_img);
+  cudaFree(S->d_labels); cudaFree(S->d_mask_in);
+  if (S->h_loss) cudaFreeHost(S->h_loss);
+  delete S;
+  net->train = nullptr;
+}
 
-int32_t octseg_train_begin(octseg_net *, const octseg_train_config *, const float *) {
-  set_error("training path not built yet");
-  return 1;
+int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc, const float *class_weights) {
+  if (!net || !tc || !class_weights) { set_error("null argument"); return 1; }
+  if (tc->global_batch <= 0) { set_error("global_batch must be positive"); return 1; }
+  if (tc->dropout_rate < 0.f || tc->dropout_rate >= 1.f) { set_error("dropout_rate must be in [0,1)"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  TrainState *S = ts(net);
+  if (!S) {
+    S = new TrainState();
+    net->train = S;
+    const size_t fb = net->total_floats * sizeof(float);
+    OCTSEG_CUDA(cudaMalloc(&S->d_grads, fb));
+    OCTSEG_CUDA(cudaMalloc(&S->d_m, fb));
+    OCTSEG_CUDA(cudaMalloc(&S->d_v, fb));
+    OCTSEG_CUDA(cudaMalloc(&S->d_class_w, net->cfg.num_classes * sizeof(float)));
+    int maxc = 8;
+    for (auto &b : net->blocks) maxc = std::max(maxc, std::max(b.cin, b.cout));
+    S->max_cout = maxc;
+    std::vector<float> ones(maxc, 1.0f);
+    OCTSEG_CUDA(cudaMalloc(&S->d_ones, maxc * sizeof(float)));
+    OCTSEG_CUDA(cudaMemcpy(S->d_ones, ones.data(), maxc * sizeof(float), cudaMemcpyHostToDevice));
+    OCTSEG_CUDA(cudaMalloc(&S->d_zeros, maxc * sizeof(float)));
+    OCTSEG_CUDA(cudaMemset(S->d_zeros, 0, maxc * sizeof(float)));
+    OCTSEG_CUDA(cudaMalloc(&S->d_sums, 2 * maxc * sizeof(double)));
+    OCTSEG_CUDA(cudaMalloc(&S->d_loss, sizeof(double)));
+    OCTSEG_CUDA(cudaMallocHost(&S->h_loss, sizeof(double)));
+    const BlockSpec &b0 = net->blocks[0];
+    OCTSEG_CUDA(cudaMalloc(&S->d_stem_tmp, (size_t)b0.kh * b0.kw * 8 * b0.cout * sizeof(float)));
+    S->tb.resize(net->blocks.size());
+    for (auto &b : net->blocks) {
+      if (b.role == 4) continue;
+      TrainBlock &t = S->tb[b.index];
+      OCTSEG_CUDA(cudaMalloc(&t.mean, b.cout * sizeof(float)));
+      OCTSEG_CUDA(cudaMalloc(&t.invstd, b.cout * sizeof(float)));
+      OCTSEG_CUDA(cudaMalloc(&t.scale, b.cout * sizeof(float)));
+      OCTSEG_CUDA(cudaMalloc(&t.shift, b.cout * sizeof(float)));
+      OCTSEG_CUDA(cudaMalloc(&t.w_t, (size_t)(b.kh + 1) * (b.kw + 1) * b.cin * b.cout * sizeof(float)));
+    }
+  }
+  S->tc = *tc;
+  S->step = 0;
+  OCTSEG_CUDA(cudaMemset(S->d_m, 0, net->total_floats * sizeof(float)));
+  OCTSEG_CUDA(cudaMemset(S->d_v, 0, net->total_floats * sizeof(float)));
+  OCTSEG_CUDA(cudaMemset(S->d_grads, 0, net->total_floats * sizeof(float)));
+  OCTSEG_CUDA(cudaMemcpy(S->d_class_w, class_weights, net->cfg.num_classes * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
 }
-int32_t octseg_comm_unique_id(uint8_t *) { set_error("training path not built yet"); return 1; }
-int32_t octseg_comm_init(octseg_net *, const uint8_t *, int32_t, int32_t) {
-  set_error("training path not built yet");
-  return 1;
+
+int32_t octseg_comm_unique_id(uint8_t *id_out) {
+  if (!id_out) { set_error("null argument"); return 1; }
+  if (load_nccl()) return 1;
+  ncclUniqueId id;
+  OCTSEG_NCCL(g_nccl.GetUniqueId(&id));
+  std::memcpy(id_out, &id, 128);
+  return 0;
 }
-int32_t octseg_train_step_host(octseg_net *, const void *, int32_t, const uint8_t *, int32_t, int32_t,
-                               int32_t, const uint8_t *, float *) {
-  set_error("training path not built yet");
-  return 1;
+
+int32_t octseg_comm_init(octseg_net *net, const uint8_t *unique_id, int32_t rank, int32_t world) {
+  if (!net || !unique_id) { set_error("null argument"); return 1; }
+  TrainState *S = ts(net);
+  if (!S) { set_error("call octseg_train_begin first"); return 1; }
+  if (world < 1 || rank < 0 || rank >= world) { set_error("bad rank/world"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  S->rank = rank; S->world = world;
+  if (world == 1) return 0;
+  if (load_nccl()) return 1;
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id, 128);
+  OCTSEG_NCCL(g_nccl.CommInitRank(&S->comm, world, id, rank));
+  return 0;
 }
-int32_t octseg_train_step_device(octseg_net *, const void *, int32_t, const uint8_t *, int32_t, int32_t,
-                                 int32_t, const uint8_t *, float *, void *) {
-  set_error("training path not built yet");
-  return 1;
+
+int32_t octseg_train_step_device(octseg_net *net, const void *images, int32_t dtype, const uint8_t *labels,
+                                 int32_t n, int32_t h, int32_t w, const uint8_t *dropout_mask,
+                                 float *loss_out_device, void *stream) {
+  if (!net || !images || !labels) { set_error("null argument"); return 1; }
+  TrainState *S = ts(net);
+  if (!S) { set_error("call octseg_train_begin first"); return 1; }
+  if (n <= 0 || h <= 0 || w <= 0) { set_error("bad batch shape"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : net->stream;
+  if (ensure_train_workspace(net, n, h, w)) return 1;
+  int rc = net->precision == OCTSEG_BF16
+               ? train_step_t<__nv_bfloat16>(net, images, dtype, labels, n, h, w, dropout_mask, st)
+               : train_step_t<float>(net, images, dtype, labels, n, h, w, dropout_mask, st);
+  if (rc) return 1;
+  // loss is accumulated in double on the device; pinned host copy for the host API,
+  // float copy into the caller's device word for the device API
+  OCTSEG_CUDA(cudaMemcpyAsync(S->h_loss, S->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (loss_out_device) {
+    store_loss_kernel<<<1, 1, 0, st>>>(S->d_loss, loss_out_device);
+    OCTSEG_CUDA(cudaGetLastError());
+  }
+  return 0;
 }
-int32_t octseg_get_grad(octseg_net *, int32_t, float *, int64_t) {
-  set_error("training path not built yet");
-  return 1;
+
+int32_t octseg_train_step_host(octseg_net *net, const void *images, int32_t dtype, const uint8_t *labels,
+                               int32_t n, int32_t h, int32_t w, const uint8_t *dropout_mask, float *loss_out) {
+  if (!net || !images || !labels) { set_error("null argument"); return 1; }
+  TrainState *S = ts(net);
+  if (!S) { set_error("call octseg_train_begin first"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  const size_t img_bytes = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)n * h * w * net->cfg.input_channels;
+  const size_t lab_bytes = (size_t)n * h * w;
+  auto grow = [&](void **p, size_t *cap, size_t need) -> int {
+    if (need <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    if (cudaMalloc(p, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+    *cap = need;
+    return 0;
+  };
+  if (grow(&S->d_img, &S->d_img_bytes, img_bytes)) return 1;
+  if (grow((void **)&S->d_labels, &S->d_labels_bytes, lab_bytes)) return 1;
+  OCTSEG_CUDA(cudaMemcpyAsync(S->d_img, images, img_bytes, cudaMemcpyHostToDevice, net->stream));
+  OCTSEG_CUDA(cudaMemcpyAsync(S->d_labels, labels, lab_bytes, cudaMemcpyHostToDevice, net->stream));
+  const uint8_t *d_mask = nullptr;
+  if (dropout_mask) {
+    const int P = net->cfg.pool_layers;
+    const size_t mb = (size_t)n * (h >> P) * (w >> P) * (net->cfg.start_neurons << P);
+    if (grow((void **)&S->d_mask_in, &S->d_mask_bytes, mb)) return 1;
+    OCTSEG_CUDA(cudaMemcpyAsync(S->d_mask_in, dropout_mask, mb, cudaMemcpyHostToDevice, net->stream));
+    d_mask = S->d_mask_in;
+  }
+  if (octseg_train_step_device(net, S->d_img, dtype, S->d_labels, n, h, w, d_mask, nullptr, net->stream)) return 1;
+  OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+  if (loss_out) *loss_out = (float)*S->h_loss;
+  return check_status(net);
 }
+
+int32_t octseg_get_grad(octseg_net *net, int32_t index, float *host, int64_t count) {
+  if (!net || !host) { set_error("null argument"); return 1; }
+  TrainState *S = ts(net);
+  if (!S) { set_error("call octseg_train_begin first"); return 1; }
+  if (index < 0 || index >= (int)net->params.size()) { set_error("param index out of range"); return 1; }
+  const ParamSpec &p = net->params[index];
+  if (count != p.count) { set_error("param " + p.name + ": element count mismatch"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+  OCTSEG_CUDA(cudaMemcpy(host, S->d_grads + p.offset, count * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
 }
+
+}  // extern "C"

@@ -1,0 +1,679 @@
+// Training kernels: batch-statistics BatchNorm (fwd/bwd), fused head + weighted CE,
+// pool backward, weight gradient, weight transforms, Adam.  Memory-bound ops are vectorised
+// over the blocked [N][C/8][H][W][8] layout (one 16/32 B vector per thread access),
+// reductions are warp-shuffle -> shared -> one double/float atomic per block.
+#include "train_kernels.cuh"
+
+namespace octseg {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// address of vector `v` (0 .. n*h*w-1) of plane `pl` in a view
+template <typename T>
+__device__ __forceinline__ const T *vec_ptr(const View<const T> &t, int pl, long long v) {
+  const long long hw = (long long)t.h * t.w;
+  const long long img = v / hw, off = v - img * hw;
+  return t.ptr + img * t.img_stride + ((long long)pl * hw + off) * 8;
+}
+template <typename T>
+__device__ __forceinline__ T *vec_ptr_w(const View<T> &t, int pl, long long v) {
+  const long long hw = (long long)t.h * t.w;
+  const long long img = v / hw, off = v - img * hw;
+  return t.ptr + img * t.img_stride + ((long long)pl * hw + off) * 8;
+}
+
+// ---------------------------------------------------------------------------------
+// per-channel reductions: grid = (chunks, planes); each block reduces 16 values
+// ---------------------------------------------------------------------------------
+constexpr int kRedThreads = 256;
+constexpr int kRedPerThread = 32;   // vectors per thread -> bounded fp32 partial sums
+
+__device__ __forceinline__ void block_reduce16_to_double(float (&acc)[16], double *dst_lo, double *dst_hi, int c0) {
+  __shared__ float red[kRedThreads / 32][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) red[warp][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double s = 0;
+    for (int w = 0; w < kRedThreads / 32; ++w) s += (double)red[w][threadIdx.x];
+    if (threadIdx.x < 8) atomicAdd(dst_lo + c0 + threadIdx.x, s);
+    else atomicAdd(dst_hi + c0 + threadIdx.x - 8, s);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads) bn_stats_kernel(View<const T> z, double *sums, int c) {
+  const int pl = blockIdx.y;
+  const long long total = (long long)z.n * z.h * z.w;
+  const long long v0 = (long long)blockIdx.x * kRedThreads * kRedPerThread;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int k = 0; k < kRedPerThread; ++k) {
+    const long long v = v0 + (long long)k * kRedThreads + threadIdx.x;
+    if (v >= total) break;
+    const Vec8f x = load8(vec_ptr(z, pl, v));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] += x.v[i]; acc[8 + i] = fmaf(x.v[i], x.v[i], acc[8 + i]); }
+  }
+  block_reduce16_to_double(acc, sums, sums + c, pl * 8);
+}
+
+template <typename T>
+int launch_bn_stats(View<const T> z, double *sums, cudaStream_t st) {
+  const int c = z.planes * 8;
+  OCTSEG_CUDA(cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st));
+  const long long total = (long long)z.n * z.h * z.w;
+  dim3 grid((unsigned)((total + kRedThreads * kRedPerThread - 1) / (kRedThreads * kRedPerThread)), z.planes);
+  bn_stats_kernel<T><<<grid, kRedThreads, 0, st>>>(z, sums, c);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void bn_finalize_kernel(const double *sums, long long count, int c, float eps, float momentum,
+                                   const float *gamma, const float *beta, float *moving_mean,
+                                   float *moving_var, float *mean, float *invstd, float *scale, float *shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const double m = sums[i] / (double)count;
+  double var = sums[c + i] / (double)count - m * m;
+  if (var < 0) var = 0;
+  const float mf = (float)m, vf = (float)var;
+  const float inv = 1.0f / sqrtf(vf + eps);
+  mean[i] = mf;
+  invstd[i] = inv;
+  const float s = inv * gamma[i];
+  scale[i] = s;
+  shift[i] = beta[i] - mf * s;
+  // Keras fused BN: moving <- moving*momentum + batch*(1-momentum); Bessel-corrected variance
+  const float unbiased = (float)(var * ((double)count / (double)(count > 1 ? count - 1 : 1)));
+  moving_mean[i] = moving_mean[i] * momentum + mf * (1.f - momentum);
+  moving_var[i] = moving_var[i] * momentum + unbiased * (1.f - momentum);
+}
+
+int launch_bn_finalize(const double *sums, long long count, int c, float eps, float momentum,
+                       const float *gamma, const float *beta, float *moving_mean, float *moving_var,
+                       float *mean, float *invstd, float *scale, float *shift, cudaStream_t st) {
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, count, c, eps, momentum, gamma, beta, moving_mean,
+                                                      moving_var, mean, invstd, scale, shift);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_relu_kernel(View<const T> z, const float *__restrict__ scale,
+                                                            const float *__restrict__ shift,
+                                                            const T *__restrict__ mask, View<T> a) {
+  const long long per_plane = (long long)z.n * z.h * z.w;
+  const long long total = per_plane * z.planes;
+  const long long hw = (long long)z.h * z.w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int pl = (int)(i / per_plane);
+    const long long v = i - (long long)pl * per_plane;
+    Vec8f x = load8(vec_ptr(z, pl, v));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x.v[k] = fmaxf(fmaf(x.v[k], scale[pl * 8 + k], shift[pl * 8 + k]), 0.f);
+    if (mask) {
+      const long long img = v / hw, off = v - img * hw;
+      const Vec8f mk = load8(mask + ((img * z.planes + pl) * hw + off) * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x.v[k] *= mk.v[k];
+    }
+    store8(vec_ptr_w(a, pl, v), x);
+  }
+}
+
+template <typename T>
+int launch_bn_apply_relu(View<const T> z, const float *scale, const float *shift, const T *mask,
+                         View<T> a, cudaStream_t st) {
+  const long long total = (long long)z.n * z.h * z.w * z.planes;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  bn_apply_relu_kernel<T><<<grid, 256, 0, st>>>(z, scale, shift, mask, a);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_u64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return (uint32_t)x;
+}
+
+template <typename T>
+__global__ void dropout_mask_kernel(const uint8_t *__restrict__ mask_nhwc, unsigned long long seed, float rate,
+                                    int n, int c, int h, int w, T *__restrict__ out) {
+  const long long total = (long long)n * c * h * w;
+  const float keep_scale = 1.f / (1.f - rate);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i indexes the blocked layout [n][c/8][h][w][8]
+    const int c8 = (int)(i & 7);
+    long long t = i >> 3;
+    const int x = (int)(t % w); t /= w;
+    const int y = (int)(t % h); t /= h;
+    const int cg = (int)(t % (c / 8));
+    const int b = (int)(t / (c / 8));
+    const int ch = cg * 8 + c8;
+    bool keep;
+    if (mask_nhwc) keep = mask_nhwc[(((long long)b * h + y) * w + x) * c + ch] != 0;
+    else keep = (hash_u64(seed + (unsigned long long)i * 0x9E3779B97F4A7C15ULL) * 2.3283064365386963e-10f) >= rate;
+    out[i] = (T)(keep ? keep_scale : 0.f);
+  }
+}
+
+template <typename T>
+int launch_dropout_mask(const uint8_t *mask_nhwc, unsigned long long seed, float rate, int n, int c,
+                        int h, int w, T *out, cudaStream_t st) {
+  const long long total = (long long)n * c * h * w;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
+  dropout_mask_kernel<T><<<grid, 256, 0, st>>>(mask_nhwc, seed, rate, n, c, h, w, out);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// fused head: logits -> softmax -> weighted CE (reference common/custom_losses.py:27-35)
+//   p /= sum(p); p = clip(p, 1e-7, 1-1e-7); loss = -w_t*log(p_t)
+//   dlogit_j = w_t*(p_j - [j==t]) * inv_denominator, zero where the clip is active
+// ---------------------------------------------------------------------------------
+constexpr int kHeadMaxK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) head_loss_kernel(View<const T> a, const float *__restrict__ wgt,
+                                                        const float *__restrict__ bias, int cin, int K,
+                                                        const uint8_t *__restrict__ labels,
+                                                        const float *__restrict__ class_w, float inv_den,
+                                                        View<T> da, float *__restrict__ d_wgt,
+                                                        float *__restrict__ d_bias, double *loss_acc) {
+  extern __shared__ float sm[];   // w[cin*K] | b[K] | cw[K] | acc_dw[cin*K] | acc_db[K] | acc_loss[1]
+  float *s_w = sm, *s_b = s_w + cin * K, *s_cw = s_b + K, *s_dw = s_cw + K, *s_db = s_dw + cin * K,
+        *s_loss = s_db + K;
+  for (int i = threadIdx.x; i < cin * K; i += blockDim.x) { s_w[i] = wgt[i]; s_dw[i] = 0.f; }
+  for (int i = threadIdx.x; i < K; i += blockDim.x) { s_b[i] = bias[i]; s_cw[i] = class_w[i]; s_db[i] = 0.f; }
+  if (threadIdx.x == 0) *s_loss = 0.f;
+  __syncthreads();
+  const int H = a.h, W = a.w, lane = threadIdx.x & 31;
+  const long long hw = (long long)H * W, total = (long long)a.n * hw;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long iters = (total + stride - 1) / stride;
+  for (long long it = 0; it < iters; ++it) {
+    const long long pix = it * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = pix < total;
+    float dl[kHeadMaxK];
+    float loss = 0.f;
+    const long long off = valid ? pix % hw : 0;
+    const int b = valid ? (int)(pix / hw) : 0;
+    if (valid) {
+      float z[kHeadMaxK];
+#pragma unroll
+      for (int k = 0; k < kHeadMaxK; ++k) z[k] = k < K ? s_b[k] : -3.0e38f;
+      for (int pl = 0; pl < cin / 8; ++pl) {
+        const Vec8f v = load8(a.ptr + b * a.img_stride + ((long long)pl * hw + off) * 8);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int k = 0; k < kHeadMaxK; ++k)
+            if (k < K) z[k] = fmaf(v.v[c], s_w[(pl * 8 + c) * K + k], z[k]);
+      }
+      float mx = z[0];
+#pragma unroll
+      for (int k = 1; k < kHeadMaxK; ++k) if (k < K) mx = fmaxf(mx, z[k]);
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < kHeadMaxK; ++k) if (k < K) { z[k] = expf(z[k] - mx); s += z[k]; }
+      const float inv = 1.f / s;
+      float S = 0.f;
+#pragma unroll
+      for (int k = 0; k < kHeadMaxK; ++k) if (k < K) { z[k] *= inv; S += z[k]; }
+      const int t = labels[pix];
+      float pt = 0.f;
+#pragma unroll
+      for (int k = 0; k < kHeadMaxK; ++k) if (k < K) { z[k] = z[k] / S; if (k == t) pt = z[k]; }
+      const float wt = (t < K) ? s_cw[t] : 0.f;
+      const bool active = (pt >= 1e-7f) && (pt <= 1.f - 1e-7f);
+      loss = -wt * logf(fminf(fmaxf(pt, 1e-7f), 1.f - 1e-7f)) * inv_den;
+#pragma unroll
+      for (int k = 0; k < kHeadMaxK; ++k)
+        dl[k] = (k < K && active) ? wt * (z[k] - (k == t ? 1.f : 0.f)) * inv_den : 0.f;
+    } else {
+#pragma unroll
+      for (int k = 0; k < kHeadMaxK; ++k) dl[k] = 0.f;
+    }
+    // d(input) and d(weights): per plane
+    for (int pl = 0; pl < cin / 8; ++pl) {
+      Vec8f v = zero8(), g = zero8();
+      if (valid) v = load8(a.ptr + b * a.img_stride + ((long long)pl * hw + off) * 8);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < kHeadMaxK; ++k)
+          if (k < K) {
+            acc = fmaf(dl[k], s_w[(pl * 8 + c) * K + k], acc);
+            const float p = warp_sum(v.v[c] * dl[k]);
+            if (lane == 0) atomicAdd(&s_dw[(pl * 8 + c) * K + k], p);
+          }
+        g.v[c] = acc;
+      }
+      if (valid) store8(da.ptr + b * da.img_stride + ((long long)pl * hw + off) * 8, g);
+    }
+#pragma unroll
+    for (int k = 0; k < kHeadMaxK; ++k)
+      if (k < K) {
+        const float p = warp_sum(dl[k]);
+        if (lane == 0) atomicAdd(&s_db[k], p);
+      }
+    loss = warp_sum(loss);
+    if (lane == 0) atomicAdd(s_loss, loss);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cin * K; i += blockDim.x) atomicAdd(&d_wgt[i], s_dw[i]);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) atomicAdd(&d_bias[i], s_db[i]);
+  if (threadIdx.x == 0) atomicAdd(loss_acc, (double)*s_loss);
+}
+
+template <typename T>
+int launch_head_loss(View<const T> a, const float *wgt, const float *bias, int cin, int K,
+                     const uint8_t *labels, const float *class_w, float inv_denominator, View<T> da,
+                     float *d_wgt, float *d_bias, double *loss_acc, cudaStream_t st) {
+  if (K > kHeadMaxK) { set_error("num_classes > 16 not supported"); return 1; }
+  const long long total = (long long)a.n * a.h * a.w;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
+  size_t smem = (size_t)(2 * cin * K + 3 * K + 1) * sizeof(float);
+  head_loss_kernel<T><<<grid, 256, smem, st>>>(a, wgt, bias, cin, K, labels, class_w, inv_denominator, da,
+                                               d_wgt, d_bias, loss_acc);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// BN + ReLU (+dropout multiplier) backward
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
+    View<const T> da, View<const T> z, const float *__restrict__ mean, const float *__restrict__ invstd,
+    const float *__restrict__ gamma, const float *__restrict__ beta, const T *__restrict__ mask, double *sums,
+    int c) {
+  const int pl = blockIdx.y;
+  const long long hw = (long long)z.h * z.w;
+  const long long total = (long long)z.n * hw;
+  const long long v0 = (long long)blockIdx.x * kRedThreads * kRedPerThread;
+  float mu[8], is[8], ga[8], be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mu[i] = mean[pl * 8 + i]; is[i] = invstd[pl * 8 + i]; ga[i] = gamma[pl * 8 + i]; be[i] = beta[pl * 8 + i]; }
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int k = 0; k < kRedPerThread; ++k) {
+    const long long v = v0 + (long long)k * kRedThreads + threadIdx.x;
+    if (v >= total) break;
+    const Vec8f zz = load8(vec_ptr(z, pl, v));
+    Vec8f g = load8(vec_ptr(da, pl, v));
+    if (mask) {
+      const long long img = v / hw, off = v - img * hw;
+      const Vec8f mk = load8(mask + ((img * z.planes + pl) * hw + off) * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g.v[i] *= mk.v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float zh = (zz.v[i] - mu[i]) * is[i];
+      const float dy = (fmaf(ga[i], zh, be[i]) > 0.f) ? g.v[i] : 0.f;
+      acc[i] += dy;
+      acc[8 + i] = fmaf(dy, zh, acc[8 + i]);
+    }
+  }
+  block_reduce16_to_double(acc, sums, sums + c, pl * 8);
+}
+
+template <typename T>
+int launch_bn_bwd_reduce(View<const T> da, View<const T> z, const float *mean, const float *invstd,
+                         const float *gamma, const float *beta, const T *mask, double *sums,
+                         cudaStream_t st) {
+  const int c = z.planes * 8;
+  OCTSEG_CUDA(cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st));
+  const long long total = (long long)z.n * z.h * z.w;
+  dim3 grid((unsigned)((total + kRedThreads * kRedPerThread - 1) / (kRedThreads * kRedPerThread)), z.planes);
+  bn_bwd_reduce_kernel<T><<<grid, kRedThreads, 0, st>>>(da, z, mean, invstd, gamma, beta, mask, sums, c);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+    View<const T> da, View<const T> z, const float *__restrict__ mean, const float *__restrict__ invstd,
+    const float *__restrict__ gamma, const float *__restrict__ beta, const T *__restrict__ mask,
+    const double *__restrict__ sums, long long count, View<T> dz, float *d_gamma, float *d_beta, int c) {
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < c; i += blockDim.x) { d_beta[i] = (float)sums[i]; d_gamma[i] = (float)sums[c + i]; }
+  const long long hw = (long long)z.h * z.w;
+  const long long per_plane = (long long)z.n * hw;
+  const long long total = per_plane * z.planes;
+  const float inv_m = 1.f / (float)count;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int pl = (int)(i / per_plane);
+    const long long v = i - (long long)pl * per_plane;
+    const Vec8f zz = load8(vec_ptr(z, pl, v));
+    Vec8f g = load8(vec_ptr(da, pl, v));
+    if (mask) {
+      const long long img = v / hw, off = v - img * hw;
+      const Vec8f mk = load8(mask + ((img * z.planes + pl) * hw + off) * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g.v[k] *= mk.v[k];
+    }
+    Vec8f o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = pl * 8 + k;
+      const float is = invstd[ch], ga = gamma[ch];
+      const float zh = (zz.v[k] - mean[ch]) * is;
+      const float dy = (fmaf(ga, zh, beta[ch]) > 0.f) ? g.v[k] : 0.f;
+      const float sdy = (float)sums[ch] * inv_m, sdyz = (float)sums[c + ch] * inv_m;
+      o.v[k] = ga * is * (dy - sdy - zh * sdyz);
+    }
+    store8(vec_ptr_w(dz, pl, v), o);
+  }
+}
+
+template <typename T>
+int launch_bn_bwd_apply(View<const T> da, View<const T> z, const float *mean, const float *invstd,
+                        const float *gamma, const float *beta, const T *mask, const double *sums,
+                        long long count, View<T> dz, float *d_gamma, float *d_beta, cudaStream_t st) {
+  const long long total = (long long)z.n * z.h * z.w * z.planes;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  bn_bwd_apply_kernel<T><<<grid, 256, 0, st>>>(da, z, mean, invstd, gamma, beta, mask, sums, count, dz, d_gamma,
+                                               d_beta, z.planes * 8);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// max-pool backward + skip add: first max in window scan order gets the pooled gradient
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) pool_bwd_add_kernel(View<const T> a, View<const T> d_pooled,
+                                                           View<const T> d_skip, View<T> out, int has_skip) {
+  const int Ho = d_pooled.h, Wo = d_pooled.w;
+  const long long total = (long long)d_pooled.n * d_pooled.planes * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wo);
+    const int y = (int)((i / Wo) % Ho);
+    const int pl = (int)((i / ((long long)Wo * Ho)) % d_pooled.planes);
+    const int b = (int)(i / ((long long)Wo * Ho * d_pooled.planes));
+    const long long base = (((long long)pl * a.h + 2 * y) * a.w + 2 * x) * 8;
+    const long long row = (long long)a.w * 8;
+    const T *ap = a.ptr + b * a.img_stride + base;
+    const Vec8f a00 = load8(ap), a01 = load8(ap + 8), a10 = load8(ap + row), a11 = load8(ap + row + 8);
+    const Vec8f g = load8(d_pooled.ptr + b * d_pooled.img_stride + (((long long)pl * Ho + y) * Wo + x) * 8);
+    Vec8f o00 = zero8(), o01 = zero8(), o10 = zero8(), o11 = zero8();
+    if (has_skip) {
+      const T *sp = d_skip.ptr + b * d_skip.img_stride + base;
+      o00 = load8(sp); o01 = load8(sp + 8); o10 = load8(sp + row); o11 = load8(sp + row + 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float m = a00.v[k];
+      int am = 0;
+      if (a01.v[k] > m) { m = a01.v[k]; am = 1; }
+      if (a10.v[k] > m) { m = a10.v[k]; am = 2; }
+      if (a11.v[k] > m) { m = a11.v[k]; am = 3; }
+      if (am == 0) o00.v[k] += g.v[k];
+      else if (am == 1) o01.v[k] += g.v[k];
+      else if (am == 2) o10.v[k] += g.v[k];
+      else o11.v[k] += g.v[k];
+    }
+    T *op = out.ptr + b * out.img_stride + base;
+    store8(op, o00); store8(op + 8, o01); store8(op + row, o10); store8(op + row + 8, o11);
+  }
+}
+
+template <typename T>
+int launch_pool_bwd_add(View<const T> a, View<const T> d_pooled, View<const T> d_skip, View<T> da_total,
+                        cudaStream_t st) {
+  const long long total = (long long)d_pooled.n * d_pooled.planes * d_pooled.h * d_pooled.w;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  pool_bwd_add_kernel<T><<<grid, 256, 0, st>>>(a, d_pooled, d_skip, da_total, d_skip.ptr != nullptr);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// weight gradient (CUDA cores): block = one (ci-plane, co-plane) pair x one 32x8 pixel tile
+//   thread (co8, ci8, q): 9 tap accumulators over a quarter of the tile's pixels
+// ---------------------------------------------------------------------------------
+constexpr int kWgTW = 32, kWgTH = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_kernel(View<const T> a_in, View<const T> dz, int kh, int kw, int pt,
+                                                    int pl_, int ups, int cin, int cout, float *__restrict__ dW,
+                                                    float *__restrict__ db, int tiles_x) {
+  extern __shared__ float sm[];
+  const int aw = kWgTW + kw - 1, ah = kWgTH + kh - 1;
+  float *s_a = sm;                       // [ah][aw][8]
+  float *s_d = s_a + ah * aw * 8;        // [TH][TW][8]
+  float *s_red = s_d + kWgTH * kWgTW * 8;   // [4][64][9]
+  const int co_planes = cout / 8;
+  const int cgi = blockIdx.y / co_planes, cgo = blockIdx.y % co_planes;
+  const int b = blockIdx.z;
+  const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+  const int H = dz.h, W = dz.w;          // output grid of the conv
+  const int x0 = tile_x * kWgTW, y0 = tile_y * kWgTH;
+  // stage the (virtual) input tile with halo; ups: virtual coords index the x2-upsampled input
+  for (int i = threadIdx.x; i < ah * aw; i += blockDim.x) {
+    const int ty = i / aw, tx = i % aw;
+    int vy = y0 + ty - pt, vx = x0 + tx - pl_;
+    Vec8f v = zero8();
+    if (vy >= 0 && vy < H && vx >= 0 && vx < W) {
+      if (ups) { vy >>= 1; vx >>= 1; }
+      v = load8(a_in.ptr + b * a_in.img_stride + (((long long)cgi * a_in.h + vy) * a_in.w + vx) * 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_a[i * 8 + k] = v.v[k];
+  }
+  for (int i = threadIdx.x; i < kWgTH * kWgTW; i += blockDim.x) {
+    const int ty = i / kWgTW, tx = i % kWgTW;
+    const int y = y0 + ty, x = x0 + tx;
+    Vec8f v = zero8();
+    if (y < H && x < W) v = load8(dz.ptr + b * dz.img_stride + (((long long)cgo * H + y) * W + x) * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_d[i * 8 + k] = v.v[k];
+  }
+  __syncthreads();
+  const int co8 = threadIdx.x & 7, ci8 = (threadIdx.x >> 3) & 7, q = threadIdx.x >> 6;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  float dsum = 0.f;
+  for (int p = q * (kWgTH * kWgTW / 4); p < (q + 1) * (kWgTH * kWgTW / 4); ++p) {
+    const int ty = p / kWgTW, tx = p % kWgTW;
+    const float d = s_d[p * 8 + co8];
+    dsum += d;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx)
+        if (dy < kh && dx < kw) acc[dy * 3 + dx] = fmaf(s_a[((ty + dy) * aw + tx + dx) * 8 + ci8], d, acc[dy * 3 + dx]);
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) s_red[(q * 64 + (threadIdx.x & 63)) * 9 + t] = acc[t];
+  __syncthreads();
+  if (q == 0) {
+    for (int dy = 0; dy < kh; ++dy)
+      for (int dx = 0; dx < kw; ++dx) {
+        const int t = dy * 3 + dx;
+        const float s = s_red[(0 * 64 + threadIdx.x) * 9 + t] + s_red[(1 * 64 + threadIdx.x) * 9 + t] +
+                        s_red[(2 * 64 + threadIdx.x) * 9 + t] + s_red[(3 * 64 + threadIdx.x) * 9 + t];
+        atomicAdd(&dW[(((long long)dy * kw + dx) * cin + cgi * 8 + ci8) * cout + cgo * 8 + co8], s);
+      }
+  }
+  if (db && cgi == 0 && ci8 == 0) {
+    // bias gradient: sum of dz over pixels (4 quarter-partials per co8)
+    atomicAdd(&db[cgo * 8 + co8], dsum);
+  }
+}
+
+template <typename T>
+int launch_wgrad(View<const T> a_in, View<const T> dz, int kh, int kw, int pad_top, int pad_left,
+                 int ups, int cin, int cout, float *dW, float *db, cudaStream_t st) {
+  if (kh > 3 || kw > 3) { set_error("wgrad: kernel larger than 3x3 not supported"); return 1; }
+  const int tiles_x = (dz.w + kWgTW - 1) / kWgTW, tiles_y = (dz.h + kWgTH - 1) / kWgTH;
+  dim3 grid(tiles_x * tiles_y, (cin / 8) * (cout / 8), dz.n);
+  const int aw = kWgTW + kw - 1, ah = kWgTH + kh - 1;
+  size_t smem = (size_t)(ah * aw * 8 + kWgTH * kWgTW * 8 + 4 * 64 * 9) * sizeof(float);
+  wgrad_kernel<T><<<grid, 256, smem, st>>>(a_in, dz, kh, kw, pad_top, pad_left, ups, cin, cout, dW, db, tiles_x);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+template <typename T, typename IMG>
+__global__ void image_to_blocked_kernel(const IMG *__restrict__ img, int n, int h, int w, int cin, int pre,
+                                        T *__restrict__ out) {
+  const long long total = (long long)n * h * w;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    Vec8f v = zero8();
+    for (int c = 0; c < cin && c < 8; ++c) {
+      const IMG raw = img[p * cin + c];
+      if constexpr (sizeof(IMG) == 1) v.v[c] = __fdiv_rn((float)raw, 255.0f);
+      else v.v[c] = pre ? (float)raw : (float)((double)raw / 255.0);
+    }
+    store8(out + p * 8, v);   // single plane: [n][1][h][w][8]
+  }
+}
+
+template <typename T>
+int launch_image_to_blocked(const void *img, int img_dtype, int n, int h, int w, int cin, T *out,
+                            cudaStream_t st) {
+  if (cin > 8) { set_error("training supports input_channels <= 8"); return 1; }
+  const long long total = (long long)n * h * w;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+  if (img_dtype == 0)
+    image_to_blocked_kernel<T, uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)img, n, h, w, cin, 0, out);
+  else
+    image_to_blocked_kernel<T, float><<<grid, 256, 0, st>>>((const float *)img, n, h, w, cin, img_dtype == 2, out);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+__global__ void flip_transpose_kernel(const float *__restrict__ w, int kh, int kw, int cin, int cout,
+                                      float *__restrict__ out) {
+  const int total = kh * kw * cin * cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % cout;
+    const int ci = (i / cout) % cin;
+    const int b = (i / (cout * cin)) % kw;
+    const int a = i / (cout * cin * kw);
+    out[(((kh - 1 - a) * kw + (kw - 1 - b)) * cout + co) * cin + ci] = w[i];
+  }
+}
+int launch_flip_transpose(const float *w, int kh, int kw, int cin, int cout, float *out, cudaStream_t st) {
+  flip_transpose_kernel<<<64, 256, 0, st>>>(w, kh, kw, cin, cout, out);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Wd[r][c][co][ci] = sum_{py,a: py-a+kh-1 == r} sum_{px,b: px-b+kw-1 == c} w[a][b][ci][co]
+__global__ void upconv_dgrad_weights_kernel(const float *__restrict__ w, int kh, int kw, int cin, int cout,
+                                            float *__restrict__ out) {
+  const int R = kh + 1, C = kw + 1;
+  const int total = R * C * cout * cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % cin;
+    const int co = (i / cin) % cout;
+    const int c = (i / (cin * cout)) % C;
+    const int r = i / (cin * cout * C);
+    float s = 0.f;
+    for (int py = 0; py < 2; ++py) {
+      const int a = py + kh - 1 - r;
+      if (a < 0 || a >= kh) continue;
+      for (int px = 0; px < 2; ++px) {
+        const int b = px + kw - 1 - c;
+        if (b < 0 || b >= kw) continue;
+        s += w[((a * kw + b) * cin + ci) * cout + co];
+      }
+    }
+    out[i] = s;
+  }
+}
+int launch_upconv_dgrad_weights(const float *w, int kh, int kw, int cin, int cout, float *out,
+                                cudaStream_t st) {
+  upconv_dgrad_weights_kernel<<<64, 256, 0, st>>>(w, kh, kw, cin, cout, out);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void stem_wgrad_extract_kernel(const float *__restrict__ tmp, int taps, int cin, int cout,
+                                          float *__restrict__ dW) {
+  const int total = taps * cin * cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % cout, ci = (i / cout) % cin, t = i / (cout * cin);
+    dW[i] = tmp[(t * 8 + ci) * cout + co];
+  }
+}
+int launch_stem_wgrad_extract(const float *tmp, int taps, int cin, int cout, float *dW, cudaStream_t st) {
+  stem_wgrad_extract_kernel<<<8, 256, 0, st>>>(tmp, taps, cin, cout, dW);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float4 *__restrict__ p, const float4 *__restrict__ g,
+                                                   float4 *__restrict__ m, float4 *__restrict__ v, long long n4,
+                                                   float lr_t, float b1, float b2, float eps) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+#define ADAM1(f)                                            \
+  mm.f = b1 * mm.f + (1.f - b1) * gg.f;                     \
+  vv.f = b2 * vv.f + (1.f - b2) * gg.f * gg.f;              \
+  pp.f -= lr_t * mm.f / (sqrtf(vv.f) + eps);
+    ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+int launch_adam(float *p, const float *g, float *m, float *v, long long n, float lr_t, float b1, float b2,
+                float eps, cudaStream_t st) {
+  const long long n4 = n / 4;   // flat buffers are padded to 16 floats per tensor
+  unsigned grid = (unsigned)std::min<long long>((n4 + 255) / 256, 148 * 8);
+  adam_kernel<<<grid, 256, 0, st>>>((float4 *)p, (const float4 *)g, (float4 *)m, (float4 *)v, n4, lr_t, b1, b2, eps);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+#define INST(T)                                                                                             \
+  template int launch_bn_stats<T>(View<const T>, double *, cudaStream_t);                                   \
+  template int launch_bn_apply_relu<T>(View<const T>, const float *, const float *, const T *, View<T>,     \
+                                       cudaStream_t);                                                       \
+  template int launch_dropout_mask<T>(const uint8_t *, unsigned long long, float, int, int, int, int, T *,  \
+                                      cudaStream_t);                                                        \
+  template int launch_head_loss<T>(View<const T>, const float *, const float *, int, int, const uint8_t *,  \
+                                   const float *, float, View<T>, float *, float *, double *, cudaStream_t); \
+  template int launch_bn_bwd_reduce<T>(View<const T>, View<const T>, const float *, const float *,          \
+                                       const float *, const float *, const T *, double *, cudaStream_t);    \
+  template int launch_bn_bwd_apply<T>(View<const T>, View<const T>, const float *, const float *,           \
+                                      const float *, const float *, const T *, const double *, long long,   \
+                                      View<T>, float *, float *, cudaStream_t);                             \
+  template int launch_pool_bwd_add<T>(View<const T>, View<const T>, View<const T>, View<T>, cudaStream_t);  \
+  template int launch_wgrad<T>(View<const T>, View<const T>, int, int, int, int, int, int, int, float *,    \
+                               float *, cudaStream_t);                                                      \
+  template int launch_image_to_blocked<T>(const void *, int, int, int, int, int, T *, cudaStream_t);
+INST(float)
+INST(__nv_bfloat16)
+
+}  // namespace octseg

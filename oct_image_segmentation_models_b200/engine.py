@@ -89,6 +89,17 @@ class UNetEngine:
         nat.check(self._lib.octseg_predict_host(self._h, _ptr(images), dt, n, h, w, _ptr(probs), _ptr(labels)))
         return probs, labels
 
+    def predict_preprocessed(self, x32: np.ndarray) -> np.ndarray:
+        """x32: float32 [N,H,W,C] already divided by 255 on the host (the reference's
+        preprocess_input_fn output after Keras' float32 cast)."""
+        if x32.ndim != 4 or x32.shape[3] != self.input_channels or x32.dtype != np.float32:
+            raise ValueError(f"x must be float32 [N,H,W,{self.input_channels}]")
+        x32 = np.ascontiguousarray(x32)
+        n, h, w, _ = x32.shape
+        probs = np.empty((n, h, w, self.num_classes), np.float32)
+        nat.check(self._lib.octseg_predict_host(self._h, _ptr(x32), nat.F32_PRE, n, h, w, _ptr(probs), None))
+        return probs
+
     def predict_device(self, images_ptr: int, dtype: int, n: int, h: int, w: int,
                        probs_ptr: Optional[int], labels_ptr: Optional[int], stream: Optional[int] = None):
         """Asynchronous variant on device pointers (e.g. torch tensors' data_ptr())."""
@@ -135,6 +146,15 @@ class UNetEngine:
         nat.check(self._lib.octseg_train_step_host(self._h, _ptr(images), dt, _ptr(lab), n, h, w, _ptr(dm),
                                                    C.byref(loss)))
         return float(loss.value)
+
+    def train_step_device(self, images_ptr: int, dtype: int, labels_ptr: int, n: int, h: int, w: int,
+                          loss_ptr: Optional[int] = None, stream: Optional[int] = None,
+                          mask_ptr: Optional[int] = None):
+        """Asynchronous train step on device pointers (this rank's shard)."""
+        nat.check(self._lib.octseg_train_step_device(
+            self._h, C.c_void_p(images_ptr), dtype, C.c_void_p(labels_ptr), n, h, w,
+            C.c_void_p(mask_ptr) if mask_ptr else None, C.c_void_p(loss_ptr) if loss_ptr else None,
+            C.c_void_p(stream) if stream else None))
 
     def get_grads(self) -> List[Optional[np.ndarray]]:
         out: List[Optional[np.ndarray]] = []

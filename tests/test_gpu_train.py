@@ -1,0 +1,122 @@
+"""GPU training parity (B200): one train step through the C ABI against the CPU oracle
+(torch autograd + Keras-Adam restatement): loss, every gradient tensor, updated weights and
+BN moving statistics; then a short loss curve."""
+import numpy as np
+import pytest
+
+from oracle.unet_oracle import KerasAdam, OracleUNet
+from oct_image_segmentation_models_b200.common.synthetic import synthetic_batch, synthetic_weights
+from oct_image_segmentation_models_b200.models.unet_spec import unet_param_specs
+
+pytestmark = pytest.mark.gpu
+CW = [0.5, 1.0, 2.0, 1.0]
+
+
+def _setup(cfg, n, h, w, seed=3):
+    weights = synthetic_weights(seed=seed, random_bn_stats=True, **cfg)
+    imgs, labs = synthetic_batch(40, n, h, w, cfg["num_classes"])
+    P = cfg.get("pool_layers", 4)
+    cmid = cfg.get("start_neurons", 8) << P
+    rng = np.random.default_rng(9)
+    mask = (rng.random((n, h >> P, w >> P, cmid)) < 0.5).astype(np.uint8)
+    return weights, imgs, labs, mask
+
+
+def _grad_check(names, got, ref, rel_tol, what):
+    worst = 0.0
+    for name, g, r in zip(names, got, ref):
+        if r is None:
+            assert g is None or "moving" in name
+            continue
+        r = r.numpy()
+        scale = max(np.abs(r).max(), 1e-7)
+        if name.endswith("bias:0") and name != names[-1]:
+            # conv bias in front of BatchNorm: mathematically zero gradient, both sides hold rounding noise
+            assert np.abs(r).max() < 1e-4 and np.abs(g).max() < 1e-4, (name, np.abs(g).max(), np.abs(r).max())
+            continue
+        err = np.abs(g - r).max() / scale
+        worst = max(worst, err)
+        assert err <= rel_tol, (what, name, err, scale)
+    return worst
+
+
+@pytest.mark.parametrize("cfg,n,h,w", [
+    (dict(input_channels=1, num_classes=4, start_neurons=8, pool_layers=2, conv_layers=2), 4, 32, 32),
+    (dict(input_channels=1, num_classes=4), 2, 64, 48),
+    (dict(input_channels=1, num_classes=3, start_neurons=8, pool_layers=1, conv_layers=1), 3, 16, 24),
+])
+def test_train_step_fp32_matches_oracle(cfg, n, h, w):
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    weights, imgs, labs, mask = _setup(cfg, n, h, w)
+    cw = CW[:cfg["num_classes"]]
+    names = [nm for nm, _ in unet_param_specs(**cfg)]
+    ora = OracleUNet(weights, **cfg)
+    loss_ref, grads_ref, stats, _ = ora.loss_and_grads(imgs, labs, cw, dropout_mask=mask)
+    eng = UNetEngine(precision="fp32", **cfg)
+    eng.set_weights(weights)
+    eng.train_begin(cw, learning_rate=1e-3, global_batch=n)
+    loss = eng.train_step(imgs, labs, dropout_mask=mask)
+    assert abs(loss - loss_ref) <= 1e-4 * max(1.0, abs(loss_ref)), (loss, loss_ref)
+    worst = _grad_check(names, eng.get_grads(), grads_ref, 1e-2, "fp32")   # ReLU-mask / pool-argmax flips of near-zero values are discrete
+    # optimizer + BN moving statistics
+    opt = KerasAdam(lr=1e-3)
+    opt.step(ora.params, grads_ref)
+    ora.apply_bn_moving_update(stats)
+    new_w = eng.get_weights()
+    for name, a, b, g in zip(names, new_w, ora.get_weights(), grads_ref):
+        if name.endswith("bias:0") and name != names[-1]:
+            continue   # Adam normalises the pure-noise bias gradient: direction is arbitrary on both sides
+        d = np.abs(a - b)
+        if g is None:       # BN moving statistics
+            assert d.max() <= 1e-5 * max(1.0, np.abs(b).max()), (name, d.max())
+            continue
+        # the first Adam step moves every weight by ~lr*sign(g): elements whose gradient is
+        # rounding noise may legitimately differ by 2*lr, the others must agree closely
+        g = np.abs(g.numpy())
+        solid = g > 1e-2 * g.max()
+        assert d[solid].max() <= 2e-4, (name, d[solid].max())
+        assert d.max() <= 2.1e-3, (name, d.max())
+    eng.close()
+    print("worst relative gradient error", worst)
+
+
+def test_train_step_bf16_close_to_oracle():
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    cfg = dict(input_channels=1, num_classes=4, start_neurons=8, pool_layers=2, conv_layers=2)
+    weights, imgs, labs, mask = _setup(cfg, 4, 32, 32)
+    names = [nm for nm, _ in unet_param_specs(**cfg)]
+    ora = OracleUNet(weights, **cfg)
+    loss_ref, grads_ref, _, _ = ora.loss_and_grads(imgs, labs, CW, dropout_mask=mask)
+    eng = UNetEngine(precision="bf16", **cfg)
+    eng.set_weights(weights)
+    eng.train_begin(CW, global_batch=4)
+    loss = eng.train_step(imgs, labs, dropout_mask=mask)
+    assert abs(loss - loss_ref) <= 2e-2 * max(1.0, abs(loss_ref))
+    _grad_check(names, eng.get_grads(), grads_ref, 0.35, "bf16")   # bf16 storage of z/a/dz: noise accumulates towards the stem (tools/bf16_grad_noise.py)
+    eng.close()
+
+
+def test_loss_decreases_and_tracks_oracle_curve():
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    cfg = dict(input_channels=1, num_classes=4, start_neurons=8, pool_layers=2, conv_layers=2)
+    weights = synthetic_weights(seed=7, random_bn_stats=False, **cfg)
+    imgs, labs = synthetic_batch(100, 8, 32, 32)
+    ora = OracleUNet(weights, **cfg)
+    opt = KerasAdam(lr=2e-3)
+    eng = UNetEngine(precision="fp32", **cfg)
+    eng.set_weights(weights)
+    eng.train_begin(CW, learning_rate=2e-3, dropout_rate=0.0, global_batch=8)
+    ref_curve, got_curve = [], []
+    for _ in range(12):
+        l, g, st, _ = ora.loss_and_grads(imgs, labs, CW)
+        opt.step(ora.params, g)
+        ora.apply_bn_moving_update(st)
+        ref_curve.append(l)
+        got_curve.append(eng.train_step(imgs, labs))
+    assert got_curve[-1] < got_curve[0] * 0.8
+    np.testing.assert_allclose(got_curve, ref_curve, rtol=2e-2)
+    # inference after training uses the updated weights and moving statistics
+    p_eng, _ = eng.predict(imgs[:2])
+    p_ora = ora.predict(imgs[:2])
+    assert np.abs(p_eng - p_ora).max() <= 5e-3
+    eng.close()
