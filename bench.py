@@ -162,6 +162,59 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+TRAIN_H, TRAIN_W, TRAIN_GLOBAL_BATCH = 512, 256, 256
+
+
+def bench_train(args, eng_cfg, rank, local_rank, world, torch, dist, stream):
+    """BASELINE configs[2]: fwd + bwd + Adam, weighted CE, 512x256x1 B-scans, GLOBAL batch 256
+    split over the ranks (strong scaling), gradients all-reduced with NCCL inside the library."""
+    from oct_image_segmentation_models_b200 import _native as nat
+    from oct_image_segmentation_models_b200 import parallel
+    from oct_image_segmentation_models_b200.common.synthetic import fast_random_batch, synthetic_weights
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    per = parallel.split_global_batch(TRAIN_GLOBAL_BATCH, world)
+    eng = UNetEngine(precision=args.precision, device=local_rank, **eng_cfg)
+    eng.set_weights(synthetic_weights(seed=7, random_bn_stats=False, **eng_cfg))
+    eng.train_begin([0.5, 1.0, 2.0, 1.0], learning_rate=1e-3, dropout_rate=0.5, dropout_seed=1234 + rank,
+                    global_batch=TRAIN_GLOBAL_BATCH)
+    parallel.init_training_comm(eng, dist)
+    imgs = torch.from_numpy(fast_random_batch(77 + rank, per, TRAIN_H, TRAIN_W)).cuda()
+    rng = np.random.default_rng(5 + rank)
+    labs = torch.from_numpy(rng.integers(0, K_CLASSES, size=(per, TRAIN_H, TRAIN_W), dtype=np.uint8)).cuda()
+    loss = torch.zeros(1, dtype=torch.float32, device="cuda")
+
+    def step():
+        eng.train_step_device(imgs.data_ptr(), nat.U8, labs.data_ptr(), per, TRAIN_H, TRAIN_W, loss.data_ptr(), stream)
+
+    for _ in range(3):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.train_steps
+    eng.synchronize()
+    out = {"metric": "unet_train_samples_per_sec", "value": TRAIN_GLOBAL_BATCH / (ms / 1e3), "unit": "samples/s",
+           "ms_per_step": ms, "steps": args.train_steps, "scaling": "strong", "dtype": args.precision,
+           "config": {"workload": "BASELINE configs[2]: U-Net train step (fwd+bwd+Adam, weighted CE, dropout), "
+                                  "512x256x1, global batch 256", "per_gpu_batch": per,
+                      "collective": "NCCL sum all-reduce of the flat fp32 gradient (1.95 MB)" if world > 1 else "none"},
+           "gpu_launches": int(eng.launch_count() - l0), "final_loss": float(loss.item())}
+    eng.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,6 +224,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -285,6 +340,15 @@ def main():
     e2e_val = world * n * e2e_steps / float(dt.item())
     checksum = float(p_np[0, :4, :4].sum())
 
+    # ---------------- training step (BASELINE configs[2]) ----------------
+    train = None
+    if not args.no_train:
+        try:
+            train = bench_train(args, eng_cfg=CFG, rank=rank, local_rank=local_rank, world=world, torch=torch,
+                                dist=dist, stream=stream)
+        except Exception as ex:  # noqa: BLE001  -- the predict line must still be printed
+            train = {"error": str(ex)[:300]}
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -304,7 +368,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_np.nbytes),
                         "d2h_bytes_per_step": int(p_np.nbytes), "steps": e2e_steps, "checksum": checksum},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "roofline_step": roofline_step, "cpu_baseline": cpu,
+                "roofline_step": roofline_step, "cpu_baseline": cpu, "train": train,
                 "block_ms": [round(float(x), 4) for x in per_block]}
         print(json.dumps(line))
     eng.close()

@@ -663,6 +663,54 @@ void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> 
         }
 }
 
+// Device-side twin of tc_pack_weights (training: the weights change every step).
+// transposed=1 packs the data-gradient operator: W'[a][b][ci'][co'] = w[kh-1-a][kw-1-b][co'][ci']
+// where w is the forward kernel [kh][kw][g.cout][g.cin] (g describes the dgrad conv).
+__global__ void tc_pack_kernel(TcGeometry g, const float *__restrict__ w, int transposed,
+                               __nv_bfloat16 *__restrict__ out, long long total) {
+  const int pt = (g.kh - 1) / 2, pl = (g.kw - 1) / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i & 7);
+    long long t = i >> 3;
+    const int n = (int)(t % g.n_cols); t /= g.n_cols;
+    const int hf = (int)(t & 1); t >>= 1;
+    const int s = (int)(t % g.ksteps); t /= g.ksteps;
+    const int ch = (int)(t % g.cin_chunks);
+    const int nt = (int)(t / g.cin_chunks);
+    float val = 0.f;
+    const int col = nt * g.n_cols + n;
+    if (g.half_ty[s][hf] >= 0 && col < g.cols_valid) {
+      const int dy = g.half_ty[s][hf] + g.dy_min, dx = g.half_tx[s][hf] + g.dx_min;
+      const int ci = (ch * g.planes_per_chunk + g.half_pl[s][hf]) * 8 + kk;
+      if (!g.ups) {
+        const int a = dy + pt, b = dx + pl;
+        if (!transposed) val = w[(((long long)a * g.kw + b) * g.cin + ci) * g.cout + col];
+        else val = w[(((long long)(g.kh - 1 - a) * g.kw + (g.kw - 1 - b)) * g.cout + col) * g.cin + ci];
+      } else {
+        const int par = col / g.cout, co = col % g.cout;
+        const int py = par >> 1, px = par & 1;
+        for (int a = 0; a < g.kh; ++a)
+          for (int b = 0; b < g.kw; ++b) {
+            const int ya = py + a - pt, xb = px + b - pl;
+            const int fy = ya >= 0 ? ya / 2 : -((-ya + 1) / 2), fx = xb >= 0 ? xb / 2 : -((-xb + 1) / 2);
+            if (fy == dy && fx == dx) val += w[(((long long)a * g.kw + b) * g.cin + ci) * g.cout + co];
+          }
+      }
+    }
+    out[i] = __float2bfloat16(val);
+  }
+}
+
+int tc_pack_weights_device(const TcGeometry &g, const float *w_dev, int transposed, __nv_bfloat16 *out,
+                           cudaStream_t st) {
+  const long long total = (long long)g.n_tiles_n * g.cin_chunks * g.ksteps * 2 * g.n_cols * 8;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 4);
+  tc_pack_kernel<<<grid, 256, 0, st>>>(g, w_dev, transposed, out, total);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,

@@ -75,6 +75,9 @@ bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w);
 int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g);
 // packs fp32 HWIO weights into the bf16 smem image the kernel streams (host memory)
 void tc_pack_weights(const TcGeometry &g, const float *w_hwio, std::vector<uint16_t> *out);
+// same packing on the device, from fp32 weights in device memory (training)
+int tc_pack_weights_device(const TcGeometry &g, const float *w_dev, int transposed, __nv_bfloat16 *out,
+                           cudaStream_t st);
 // pure host part of the plan (no CUDA driver needed): tiling, stage sizes, A-descriptor table
 int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *p, size_t *smem_bytes);
 struct TcEpilogue {

@@ -7,7 +7,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 
+#include "conv_tc.cuh"
 #include "kernels.cuh"
 #include "net.cuh"
 #include "train_kernels.cuh"
@@ -70,6 +72,12 @@ struct TrainBlock {
   float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr;   // [cout]
   float *w_t = nullptr;     // transformed weights for the data gradient
   int h = 0, w = 0;         // output grid
+  // tensor-core path (bf16 mode): forward z-conv and data-gradient conv through conv_tc_kernel
+  bool tc_fwd = false, tc_dgrad = false;
+  TcGeometry geo_dgrad{};
+  bool geo_dgrad_ok = false;
+  __nv_bfloat16 *wpack_dgrad = nullptr;
+  TcPlan plan_fwd, plan_dgrad;
 };
 
 struct TrainState {
@@ -100,6 +108,52 @@ struct TrainState {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
 };
+
+// optional per-phase CUDA-event profile of one train step (env OCTSEG_TRAIN_PROFILE=1)
+struct PhaseProf {
+  bool on = false;
+  cudaStream_t st = nullptr;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+  int cur = -1;
+  cudaEvent_t cur_start = nullptr;
+  void begin(int phase) {
+    if (!on) return;
+    end();
+    cur = phase;
+    cudaEventCreate(&cur_start);
+    cudaEventRecord(cur_start, st);
+  }
+  void end() {
+    if (!on || cur < 0) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    spans.push_back({cur, {cur_start, e}});
+    cur = -1;
+  }
+  void report() {
+    if (!on) return;
+    end();
+    cudaStreamSynchronize(st);
+    static const char *names[] = {"conv_fwd", "bn_fwd", "pool_fwd", "head_loss", "pool_bwd", "bn_bwd", "wgrad", "dgrad",
+                                  "allreduce", "adam", "misc"};
+    double tot[11] = {0};
+    for (auto &s : spans) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, s.second.first, s.second.second);
+      tot[s.first] += ms;
+      cudaEventDestroy(s.second.first);
+      cudaEventDestroy(s.second.second);
+    }
+    double sum = 0;
+    for (double t : tot) sum += t;
+    fprintf(stderr, "[train profile] total %.2f ms:", sum);
+    for (int i = 0; i < 11; ++i) fprintf(stderr, " %s %.2f", names[i], tot[i]);
+    fprintf(stderr, "\n");
+    spans.clear();
+  }
+};
+enum { PH_CONV = 0, PH_BNF, PH_POOLF, PH_HEAD, PH_POOLB, PH_BNB, PH_WGRAD, PH_DGRAD, PH_AR, PH_ADAM, PH_MISC };
 
 static TrainState *ts(octseg_net *net) { return reinterpret_cast<TrainState *>(net->train); }
 static size_t esz(const octseg_net *net) { return net->precision == OCTSEG_BF16 ? 2 : 4; }
@@ -157,6 +211,33 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
   S->img_blocked = base + o_img;
   S->mask = base + o_mask;
   S->n = n; S->h = h; S->w = w;
+  // ---- tensor-core plans (bf16): z = conv(in)+bias and d(in) = conv(dz, W^T flipped)
+  for (auto &b : net->blocks) {
+    if (b.role == 4) continue;
+    TrainBlock &t = S->tb[b.index];
+    t.tc_fwd = t.tc_dgrad = false;
+    if (net->precision != OCTSEG_BF16 || net->disable_tc || b.index == 0) continue;
+    const BlockState &bs = net->bstate[b.index];
+    // input view of this block (same rules as block_input)
+    const BlockSpec &pb = net->blocks[b.index - 1];
+    const TrainBlock &pt = S->tb[pb.index];
+    const __nv_bfloat16 *in_ptr;
+    int in_h, in_w;
+    bool dense_in = true;
+    if (b.concat_level >= 0) { in_ptr = (const __nv_bfloat16 *)pt.a; in_h = pt.h; in_w = pt.w; }
+    else if (pb.pool_after) { in_ptr = (const __nv_bfloat16 *)pt.pooled; in_h = pt.h / 2; in_w = pt.w / 2; }
+    else { in_ptr = (const __nv_bfloat16 *)pt.a; in_h = pt.h; in_w = pt.w; dense_in = (pt.a_planes_total == pb.cout / 8); }
+    if (bs.geo_ok && dense_in && tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, in_h, in_w)) {
+      TcEpilogue epi;
+      epi.relu = 0;
+      epi.scale = S->d_ones;
+      epi.shift = net->d_params + net->params[b.p_bias].offset;
+      epi.out = make_view((__nv_bfloat16 *)t.z, n, b.cout / 8, 0, b.cout / 8, t.h, t.w);
+      if (tc_make_plan(bs.geo, in_ptr, n, in_h, in_w, bs.wpack, epi, net->d_status, &t.plan_fwd)) return 1;
+      t.tc_fwd = true;
+    }
+    if (t.geo_dgrad_ok && !b.ups && tc_supported(b.kh, b.kw, b.cout, b.cin, 0, t.h, t.w)) t.tc_dgrad = true;
+  }
   return 0;
 }
 
@@ -182,6 +263,10 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   float *G = S->d_grads;
   const int nblk = (int)net->blocks.size();
   const BlockSpec &head = net->blocks.back();
+  PhaseProf prof;
+  prof.on = std::getenv("OCTSEG_TRAIN_PROFILE") != nullptr;
+  prof.st = st;
+  prof.begin(PH_MISC);
   OCTSEG_CUDA(cudaMemsetAsync(G, 0, net->total_floats * sizeof(float), st));
   OCTSEG_CUDA(cudaMemsetAsync(S->d_loss, 0, sizeof(double), st));
   if (launch_image_to_blocked<T>(d_img, dtype, n, h, w, net->cfg.input_channels, (T *)S->img_blocked, st)) return 1;
@@ -204,14 +289,22 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     View<const T> in = block_input<T>(net, b, n);
     View<T> z = make_view((T *)t.z, n, b.cout / 8, 0, b.cout / 8, t.h, t.w);
     // z = conv(in) + bias  (epilogue scale = 1, shift = bias, no ReLU)
+    prof.begin(PH_CONV);
     if (b.index == 0) {
       if (launch_conv_first<T>(d_img, dtype, n, h, w, b.cin, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cout,
                                S->d_ones, P + net->params[b.p_bias].offset, 0, z, st))
         return 1;
+    } else if (t.tc_fwd) {
+      if (tc_pack_weights_device(net->bstate[b.index].geo, P + net->params[b.p_kernel].offset, 0,
+                                 net->bstate[b.index].wpack, st))
+        return 1;
+      if (tc_launch(t.plan_fwd, st)) return 1;
+      ++net->launches;
     } else if (launch_conv_direct<T>(in, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout,
                                      b.ups ? 1 : 0, S->d_ones, P + net->params[b.p_bias].offset, 0, z, st))
       return 1;
     View<const T> zc = make_view((const T *)t.z, n, b.cout / 8, 0, b.cout / 8, t.h, t.w);
+    prof.begin(PH_BNF);
     if (launch_bn_stats<T>(zc, S->d_sums, st)) return 1;
     if (launch_bn_finalize(S->d_sums, (long long)n * t.h * t.w, b.cout, 1e-3f, 0.99f, P + net->params[b.p_gamma].offset,
                            P + net->params[b.p_beta].offset, net->d_params + net->params[b.p_mean].offset,
@@ -222,6 +315,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     if (launch_bn_apply_relu<T>(zc, t.scale, t.shift, mask, a, st)) return 1;
     net->launches += 4;
     if (b.pool_after) {
+      prof.begin(PH_POOLF);
       View<const T> ac = make_view((const T *)t.a, n, t.a_planes_total, t.a_plane0, b.cout / 8, t.h, t.w);
       View<T> po = make_view((T *)t.pooled, n, b.cout / 8, 0, b.cout / 8, t.h / 2, t.w / 2);
       if (launch_maxpool2<T>(ac, po, st)) return 1;
@@ -231,6 +325,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   // ------------------------------- loss + head backward -------------------------------
   const BlockSpec &last = net->blocks[nblk - 2];
   const TrainBlock &tl = S->tb[last.index];
+  prof.begin(PH_HEAD);
   {
     View<const T> a = make_view((const T *)tl.a, n, tl.a_planes_total, tl.a_plane0, last.cout / 8, tl.h, tl.w);
     View<T> da = make_view((T *)S->gA[0], n, last.cout / 8, 0, last.cout / 8, tl.h, tl.w);
@@ -252,6 +347,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     View<const T> zc = make_view((const T *)t.z, n, f8, 0, f8, t.h, t.w);
     View<const T> da = make_view((const T *)g_ptr, n, g_planes_total, g_plane0, f8, t.h, t.w);
     if (b.pool_after) {
+      prof.begin(PH_POOLB);
       // da = d(skip half of the concat gradient) + scatter(d pooled); g currently holds d pooled
       View<const T> ac = make_view((const T *)t.a, n, t.a_planes_total, t.a_plane0, f8, t.h, t.w);
       View<const T> dpool = make_view((const T *)g_ptr, n, g_planes_total, g_plane0, f8, t.h / 2, t.w / 2);
@@ -263,6 +359,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     }
     const T *mask = (use_dropout && b.dropout_after) ? (const T *)S->mask : nullptr;
     const float *gamma = P + net->params[b.p_gamma].offset, *beta = P + net->params[b.p_beta].offset;
+    prof.begin(PH_BNB);
     if (launch_bn_bwd_reduce<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, S->d_sums, st)) return 1;
     View<T> dz = make_view((T *)t.dz, n, f8, 0, f8, t.h, t.w);
     if (launch_bn_bwd_apply<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, S->d_sums, (long long)n * t.h * t.w, dz,
@@ -271,6 +368,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     View<const T> dzc = make_view((const T *)t.dz, n, f8, 0, f8, t.h, t.w);
     View<const T> in = block_input<T>(net, b, n);
     const int pt = (b.kh - 1) / 2, pl = (b.kw - 1) / 2;
+    prof.begin(PH_WGRAD);
     if (b.index == 0) {
       const int taps = b.kh * b.kw;
       OCTSEG_CUDA(cudaMemsetAsync(S->d_stem_tmp, 0, (size_t)taps * 8 * b.cout * sizeof(float), st));
@@ -284,6 +382,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
                         G + net->params[b.p_bias].offset, st))
       return 1;
     // ---- data gradient wrt this block's input
+    prof.begin(PH_DGRAD);
     const BlockSpec &pb = net->blocks[bi - 1];
     if (!b.ups) {
       if (launch_flip_transpose(P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout, t.w_t, st)) return 1;
@@ -293,8 +392,17 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
       else { dst = (g_ptr == S->gA[b.level]) ? S->gB[b.level] : S->gA[b.level]; dst_total = b.cin / 8; }
       // destination grid = this block's input grid (pooled input has the same h,w as the output here)
       View<T> din = make_view((T *)dst, n, dst_total, 0, b.cin / 8, t.h, t.w);
-      if (launch_conv_direct_ex<T>(dzc, t.w_t, b.kh, b.kw, b.cout, b.cin, 0, 1, b.kh - 1 - pt, b.kw - 1 - pl, S->d_ones,
-                                   S->d_zeros, 0, din, st))
+      if (t.tc_dgrad) {
+        if (tc_pack_weights_device(t.geo_dgrad, P + net->params[b.p_kernel].offset, 1, t.wpack_dgrad, st)) return 1;
+        TcEpilogue epi;
+        epi.relu = 0; epi.scale = S->d_ones; epi.shift = S->d_zeros;
+        epi.out = make_view((__nv_bfloat16 *)dst, n, dst_total, 0, b.cin / 8, t.h, t.w);
+        if (tc_make_plan(t.geo_dgrad, (const __nv_bfloat16 *)t.dz, n, t.h, t.w, t.wpack_dgrad, epi, net->d_status,
+                         &t.plan_dgrad))
+          return 1;
+        if (tc_launch(t.plan_dgrad, st)) return 1;
+      } else if (launch_conv_direct_ex<T>(dzc, t.w_t, b.kh, b.kw, b.cout, b.cin, 0, 1, b.kh - 1 - pt, b.kw - 1 - pl,
+                                          S->d_ones, S->d_zeros, 0, din, st))
         return 1;
       g_ptr = dst;
       if (b.concat_level >= 0) { g_planes_total = b.cin / 8; g_plane0 = 0; }   // next: the up block (planes [0,f/8))
@@ -314,8 +422,10 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     net->launches += 5;
   }
   // ------------------------------- all-reduce + optimizer -------------------------------
+  prof.begin(PH_AR);
   if (S->comm && S->world > 1)
     OCTSEG_NCCL(g_nccl.AllReduce(G, G, (size_t)net->total_floats, /*ncclFloat*/ 7, /*ncclSum*/ 0, S->comm, st));
+  prof.begin(PH_ADAM);
   ++S->step;
   const double b1 = S->tc.beta_1, b2 = S->tc.beta_2;
   const float lr_t = (float)(S->tc.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)S->step)) /
@@ -323,6 +433,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   if (launch_adam(net->d_params, G, S->d_m, S->d_v, net->total_floats, lr_t, S->tc.beta_1, S->tc.beta_2, S->tc.epsilon, st))
     return 1;
   ++net->launches;
+  prof.report();
   net->host_stale = true;
   net->derived_dirty = true;
   return 0;
@@ -338,7 +449,7 @@ void octseg_train_free(octseg_net *net) {
   TrainState *S = ts(net);
   if (!S) return;
   if (S->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S->comm);
-  for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); }
+  for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); cudaFree(t.wpack_dgrad); }
   cudaFree(S->d_class_w); cudaFree(S->d_grads); cudaFree(S->d_m); cudaFree(S->d_v); cudaFree(S->d_ones); cudaFree(S->d_zeros);
   cudaFree(S->d_sums); cudaFree(S->d_loss); cudaFree(S->d_stem_tmp); cudaFree(S->ws); cudaFree(S->d_img);
   cudaFree(S->d_labels); cudaFree(S->d_mask_in);
@@ -383,6 +494,14 @@ int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc, const
       OCTSEG_CUDA(cudaMalloc(&t.scale, b.cout * sizeof(float)));
       OCTSEG_CUDA(cudaMalloc(&t.shift, b.cout * sizeof(float)));
       OCTSEG_CUDA(cudaMalloc(&t.w_t, (size_t)(b.kh + 1) * (b.kw + 1) * b.cin * b.cout * sizeof(float)));
+      if (net->precision == OCTSEG_BF16 && !net->disable_tc && b.index > 0 && !b.ups &&
+          tc_supported(b.kh, b.kw, b.cout, b.cin, 0, kTcTileH, kTcTileW) &&
+          tc_make_geometry(b.kh, b.kw, b.cout, b.cin, 0, &t.geo_dgrad) == 0) {
+        t.geo_dgrad_ok = true;
+        const size_t elems = (size_t)t.geo_dgrad.n_tiles_n * t.geo_dgrad.cin_chunks * t.geo_dgrad.ksteps * 2 *
+                             t.geo_dgrad.n_cols * 8;
+        OCTSEG_CUDA(cudaMalloc(&t.wpack_dgrad, elems * 2));
+      }
     }
   }
   S->tc = *tc;
