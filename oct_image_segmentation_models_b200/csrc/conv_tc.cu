@@ -806,6 +806,23 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
   return 0;
 }
 
+// 4-D tensor map over a dense blocked bf16 tensor [n][planes][h][w][8], declared in 8-byte elements
+// (2 per pixel-plane vector); box = box_w px x box_h rows x box_planes planes of one image.
+int tc_encode_map_4d(const void *base, int w, int h, int planes, int n, int box_w, int box_h, int box_planes,
+                     CUtensorMap *out) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return 1; }
+  cuuint64_t dims[4] = {(cuuint64_t)w * 2, (cuuint64_t)h, (cuuint64_t)planes, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)planes * h * w * 16};
+  cuuint32_t box[4] = {(cuuint32_t)box_w * 2, (cuuint32_t)box_h, (cuuint32_t)box_planes, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return 1; }
+  return 0;
+}
+
 int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int w,
                  const __nv_bfloat16 *wpack_dev, const TcEpilogue &epi, int *status_dev, TcPlan *plan) {
   TcConvParams &p = plan->p;

