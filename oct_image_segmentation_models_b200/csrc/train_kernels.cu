@@ -189,112 +189,140 @@ int launch_dropout_mask(const uint8_t *mask_nhwc, unsigned long long seed, float
 // ---------------------------------------------------------------------------------
 constexpr int kHeadMaxK = 16;
 
-template <typename T>
+// K and the number of input planes are compile-time so that every per-thread partial
+// (d_wgt[cin][K], d_bias[K], loss) lives in registers for the whole grid-stride loop and is
+// reduced ONCE per block (warp shuffles -> smem -> one global atomic per value per block).
+template <typename T, int K, int PL>
 __global__ void __launch_bounds__(256) head_loss_kernel(View<const T> a, const float *__restrict__ wgt,
-                                                        const float *__restrict__ bias, int cin, int K,
+                                                        const float *__restrict__ bias,
                                                         const uint8_t *__restrict__ labels,
                                                         const float *__restrict__ class_w, float inv_den,
                                                         View<T> da, float *__restrict__ d_wgt,
                                                         float *__restrict__ d_bias, double *loss_acc) {
-  extern __shared__ float sm[];   // w[cin*K] | b[K] | cw[K] | acc_dw[cin*K] | acc_db[K] | acc_loss[1]
-  float *s_w = sm, *s_b = s_w + cin * K, *s_cw = s_b + K, *s_dw = s_cw + K, *s_db = s_dw + cin * K,
-        *s_loss = s_db + K;
-  for (int i = threadIdx.x; i < cin * K; i += blockDim.x) { s_w[i] = wgt[i]; s_dw[i] = 0.f; }
-  for (int i = threadIdx.x; i < K; i += blockDim.x) { s_b[i] = bias[i]; s_cw[i] = class_w[i]; s_db[i] = 0.f; }
-  if (threadIdx.x == 0) *s_loss = 0.f;
+  constexpr int CIN = PL * 8;
+  __shared__ float s_w[CIN * K], s_b[K], s_cw[K];
+  __shared__ float s_red[8][CIN * K + K + 1];
+  for (int i = threadIdx.x; i < CIN * K; i += blockDim.x) s_w[i] = wgt[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) { s_b[i] = bias[i]; s_cw[i] = class_w[i]; }
   __syncthreads();
-  const int H = a.h, W = a.w, lane = threadIdx.x & 31;
-  const long long hw = (long long)H * W, total = (long long)a.n * hw;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long iters = (total + stride - 1) / stride;
-  for (long long it = 0; it < iters; ++it) {
-    const long long pix = it * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = pix < total;
-    float dl[kHeadMaxK];
-    float loss = 0.f;
-    const long long off = valid ? pix % hw : 0;
-    const int b = valid ? (int)(pix / hw) : 0;
-    if (valid) {
-      float z[kHeadMaxK];
+  const long long hw = (long long)a.h * a.w, total = (long long)a.n * hw;
+  float p_dw[CIN * K], p_db[K], p_loss = 0.f;
 #pragma unroll
-      for (int k = 0; k < kHeadMaxK; ++k) z[k] = k < K ? s_b[k] : -3.0e38f;
-      for (int pl = 0; pl < cin / 8; ++pl) {
-        const Vec8f v = load8(a.ptr + b * a.img_stride + ((long long)pl * hw + off) * 8);
+  for (int i = 0; i < CIN * K; ++i) p_dw[i] = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+  for (int k = 0; k < K; ++k) p_db[k] = 0.f;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const long long off = pix % hw;
+    const int b = (int)(pix / hw);
+    Vec8f v[PL];
+    float z[K];
 #pragma unroll
-          for (int k = 0; k < kHeadMaxK; ++k)
-            if (k < K) z[k] = fmaf(v.v[c], s_w[(pl * 8 + c) * K + k], z[k]);
-      }
-      float mx = z[0];
+    for (int k = 0; k < K; ++k) z[k] = s_b[k];
 #pragma unroll
-      for (int k = 1; k < kHeadMaxK; ++k) if (k < K) mx = fmaxf(mx, z[k]);
-      float s = 0.f;
+    for (int pl = 0; pl < PL; ++pl) {
+      v[pl] = load8(a.ptr + b * a.img_stride + ((long long)pl * hw + off) * 8);
 #pragma unroll
-      for (int k = 0; k < kHeadMaxK; ++k) if (k < K) { z[k] = expf(z[k] - mx); s += z[k]; }
-      const float inv = 1.f / s;
-      float S = 0.f;
+      for (int c = 0; c < 8; ++c)
 #pragma unroll
-      for (int k = 0; k < kHeadMaxK; ++k) if (k < K) { z[k] *= inv; S += z[k]; }
-      const int t = labels[pix];
-      float pt = 0.f;
-#pragma unroll
-      for (int k = 0; k < kHeadMaxK; ++k) if (k < K) { z[k] = z[k] / S; if (k == t) pt = z[k]; }
-      const float wt = (t < K) ? s_cw[t] : 0.f;
-      const bool active = (pt >= 1e-7f) && (pt <= 1.f - 1e-7f);
-      loss = -wt * logf(fminf(fmaxf(pt, 1e-7f), 1.f - 1e-7f)) * inv_den;
-#pragma unroll
-      for (int k = 0; k < kHeadMaxK; ++k)
-        dl[k] = (k < K && active) ? wt * (z[k] - (k == t ? 1.f : 0.f)) * inv_den : 0.f;
-    } else {
-#pragma unroll
-      for (int k = 0; k < kHeadMaxK; ++k) dl[k] = 0.f;
+        for (int k = 0; k < K; ++k) z[k] = fmaf(v[pl].v[c], s_w[(pl * 8 + c) * K + k], z[k]);
     }
-    // d(input) and d(weights): per plane
-    for (int pl = 0; pl < cin / 8; ++pl) {
-      Vec8f v = zero8(), g = zero8();
-      if (valid) v = load8(a.ptr + b * a.img_stride + ((long long)pl * hw + off) * 8);
+    float mx = z[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) mx = fmaxf(mx, z[k]);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { z[k] = expf(z[k] - mx); s += z[k]; }
+    const float inv = 1.f / s;
+    float S = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { z[k] *= inv; S += z[k]; }
+    const int t = labels[pix];
+    float pt = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { z[k] = z[k] / S; if (k == t) pt = z[k]; }
+    const float wt = (t < K) ? s_cw[t] : 0.f;
+    const bool active = (pt >= 1e-7f) && (pt <= 1.f - 1e-7f);
+    p_loss += -wt * logf(fminf(fmaxf(pt, 1e-7f), 1.f - 1e-7f)) * inv_den;
+    float dl[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      dl[k] = active ? wt * (z[k] - (k == t ? 1.f : 0.f)) * inv_den : 0.f;
+      p_db[k] += dl[k];
+    }
+#pragma unroll
+    for (int pl = 0; pl < PL; ++pl) {
+      Vec8f g;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < kHeadMaxK; ++k)
-          if (k < K) {
-            acc = fmaf(dl[k], s_w[(pl * 8 + c) * K + k], acc);
-            const float p = warp_sum(v.v[c] * dl[k]);
-            if (lane == 0) atomicAdd(&s_dw[(pl * 8 + c) * K + k], p);
-          }
+        for (int k = 0; k < K; ++k) {
+          acc = fmaf(dl[k], s_w[(pl * 8 + c) * K + k], acc);
+          p_dw[(pl * 8 + c) * K + k] = fmaf(v[pl].v[c], dl[k], p_dw[(pl * 8 + c) * K + k]);
+        }
         g.v[c] = acc;
       }
-      if (valid) store8(da.ptr + b * da.img_stride + ((long long)pl * hw + off) * 8, g);
+      store8(da.ptr + b * da.img_stride + ((long long)pl * hw + off) * 8, g);
     }
-#pragma unroll
-    for (int k = 0; k < kHeadMaxK; ++k)
-      if (k < K) {
-        const float p = warp_sum(dl[k]);
-        if (lane == 0) atomicAdd(&s_db[k], p);
-      }
-    loss = warp_sum(loss);
-    if (lane == 0) atomicAdd(s_loss, loss);
   }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < CIN * K; ++i) {
+    const float r = warp_sum(p_dw[i]);
+    if (lane == 0) s_red[warp][i] = r;
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float r = warp_sum(p_db[k]);
+    if (lane == 0) s_red[warp][CIN * K + k] = r;
+  }
+  p_loss = warp_sum(p_loss);
+  if (lane == 0) s_red[warp][CIN * K + K] = p_loss;
   __syncthreads();
-  for (int i = threadIdx.x; i < cin * K; i += blockDim.x) atomicAdd(&d_wgt[i], s_dw[i]);
-  for (int i = threadIdx.x; i < K; i += blockDim.x) atomicAdd(&d_bias[i], s_db[i]);
-  if (threadIdx.x == 0) atomicAdd(loss_acc, (double)*s_loss);
+  for (int i = threadIdx.x; i < CIN * K + K + 1; i += blockDim.x) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += s_red[w][i];
+    if (i < CIN * K) atomicAdd(&d_wgt[i], r);
+    else if (i < CIN * K + K) atomicAdd(&d_bias[i - CIN * K], r);
+    else atomicAdd(loss_acc, (double)r);
+  }
+}
+
+template <typename T, int K, int PL>
+static int launch_head_loss_kp(View<const T> a, const float *wgt, const float *bias, const uint8_t *labels,
+                               const float *class_w, float inv_den, View<T> da, float *d_wgt, float *d_bias,
+                               double *loss_acc, cudaStream_t st) {
+  const long long total = (long long)a.n * a.h * a.w;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 4);
+  head_loss_kernel<T, K, PL><<<grid, 256, 0, st>>>(a, wgt, bias, labels, class_w, inv_den, da, d_wgt, d_bias,
+                                                   loss_acc);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T, int K>
+static int launch_head_loss_k(View<const T> a, const float *wgt, const float *bias, int cin, const uint8_t *labels,
+                              const float *class_w, float inv_den, View<T> da, float *d_wgt, float *d_bias,
+                              double *loss_acc, cudaStream_t st) {
+  if (cin == 8) return launch_head_loss_kp<T, K, 1>(a, wgt, bias, labels, class_w, inv_den, da, d_wgt, d_bias, loss_acc, st);
+  if (cin == 16 && K <= 8) return launch_head_loss_kp<T, K, 2>(a, wgt, bias, labels, class_w, inv_den, da, d_wgt, d_bias, loss_acc, st);
+  set_error("training head supports start_neurons 8 (any K<=16) or 16 (K<=8); wider heads: not built yet");
+  return 1;
 }
 
 template <typename T>
 int launch_head_loss(View<const T> a, const float *wgt, const float *bias, int cin, int K,
                      const uint8_t *labels, const float *class_w, float inv_denominator, View<T> da,
                      float *d_wgt, float *d_bias, double *loss_acc, cudaStream_t st) {
-  if (K > kHeadMaxK) { set_error("num_classes > 16 not supported"); return 1; }
-  const long long total = (long long)a.n * a.h * a.w;
-  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
-  size_t smem = (size_t)(2 * cin * K + 3 * K + 1) * sizeof(float);
-  head_loss_kernel<T><<<grid, 256, smem, st>>>(a, wgt, bias, cin, K, labels, class_w, inv_denominator, da,
-                                               d_wgt, d_bias, loss_acc);
-  OCTSEG_CUDA(cudaGetLastError());
-  return 0;
+  switch (K) {
+#define HK(k) case k: return launch_head_loss_k<T, k>(a, wgt, bias, cin, labels, class_w, inv_denominator, da, d_wgt, d_bias, loss_acc, st);
+    HK(2) HK(3) HK(4) HK(5) HK(6) HK(7) HK(8)
+#undef HK
+  }
+  set_error("training supports 2..8 classes");
+  return 1;
 }
 
 // ---------------------------------------------------------------------------------

@@ -211,6 +211,7 @@ __device__ __forceinline__ bool wm_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+template <int NB>
 __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_d,
                                                             const WgParams p, int th, int *status) {
@@ -230,8 +231,8 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
   const int ones_group = want_db ? ng : -1;
   const int ng_all = ng + (want_db ? 1 : 0);
   const int n_mt = (ng_all + 1) / 2;
-  const int nb0 = nchunk * kWmNB;
-  const int nb_cur = min(kWmNB, p.cout_planes - nb0);
+  const int nb0 = nchunk * NB;
+  const int nb_cur = min(NB, p.cout_planes - nb0);
 
   const uint32_t a_bytes = (uint32_t)p.pc * ah * aw * 16, d_bytes = (uint32_t)p.d_planes * th * kWmTW * 16;
   const uint32_t stage_bytes = ((a_bytes + 127u) & ~127u) + ((d_bytes + 127u) & ~127u);
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
   __nv_bfloat16 *s_ones = reinterpret_cast<__nv_bfloat16 *>(bars + 2 * kWmStages);
   float *s_acc = reinterpret_cast<float *>(s_ones + 64);
   for (int i = threadIdx.x; i < 64; i += blockDim.x) s_ones[i] = __float2bfloat16(1.0f);
-  for (int i = threadIdx.x; i < (kWmMaxGroups + 2) * 8 * kWmNB * 8; i += blockDim.x) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < (kWmMaxGroups + 2) * 8 * NB * 8; i += blockDim.x) s_acc[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWmStages; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[i])), "r"(1) : "memory");
@@ -299,11 +300,11 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
       }
     }
     const uint32_t so_base = wm_smem_u32(s_ones);
-    float acc[kWmMaxMT][kWmNB][4];
+    float acc[kWmMaxMT][NB][4];
 #pragma unroll
     for (int mt = 0; mt < kWmMaxMT; ++mt)
 #pragma unroll
-      for (int nb = 0; nb < kWmNB; ++nb)
+      for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[mt][nb][k] = 0.f;
     int st = 0;
@@ -317,9 +318,9 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
       for (int y = cw; y < th; y += 8) {
 #pragma unroll
         for (int ks = 0; ks < kWmTW / 16; ++ks) {
-          uint32_t bfrag[kWmNB][2];
+          uint32_t bfrag[NB][2];
 #pragma unroll
-          for (int nb = 0; nb < kWmNB; ++nb) {
+          for (int nb = 0; nb < NB; ++nb) {
             if (nb < nb_cur) {
               const int i = (lane >> 3) & 1, r = lane & 7;
               ldmatrix_x2_trans(sd_base + (uint32_t)((((nb * th + y) * kWmTW) + ks * 16 + i * 8 + r) * 16), bfrag[nb]);
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
               const uint32_t addr = (o & 0x80000000u) ? so_base + (o & 0x7FFFFFFFu) : sa_base + o + row_off;
               ldmatrix_x4_trans(addr, afrag);
 #pragma unroll
-              for (int nb = 0; nb < kWmNB; ++nb) mma_bf16_16816(acc[mt][nb], afrag, bfrag[nb]);
+              for (int nb = 0; nb < NB; ++nb) mma_bf16_16816(acc[mt][nb], afrag, bfrag[nb]);
             }
           }
         }
@@ -347,12 +348,12 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
     for (int mt = 0; mt < kWmMaxMT; ++mt) {
       if (mt < n_mt) {
 #pragma unroll
-        for (int nb = 0; nb < kWmNB; ++nb) {
+        for (int nb = 0; nb < NB; ++nb) {
           const int ci = lane >> 2, co = nb * 8 + (lane & 3) * 2;
-          atomicAdd(&s_acc[((2 * mt) * 8 + ci) * (kWmNB * 8) + co], acc[mt][nb][0]);
-          atomicAdd(&s_acc[((2 * mt) * 8 + ci) * (kWmNB * 8) + co + 1], acc[mt][nb][1]);
-          atomicAdd(&s_acc[((2 * mt + 1) * 8 + ci) * (kWmNB * 8) + co], acc[mt][nb][2]);
-          atomicAdd(&s_acc[((2 * mt + 1) * 8 + ci) * (kWmNB * 8) + co + 1], acc[mt][nb][3]);
+          atomicAdd(&s_acc[((2 * mt) * 8 + ci) * (NB * 8) + co], acc[mt][nb][0]);
+          atomicAdd(&s_acc[((2 * mt) * 8 + ci) * (NB * 8) + co + 1], acc[mt][nb][1]);
+          atomicAdd(&s_acc[((2 * mt + 1) * 8 + ci) * (NB * 8) + co], acc[mt][nb][2]);
+          atomicAdd(&s_acc[((2 * mt + 1) * 8 + ci) * (NB * 8) + co + 1], acc[mt][nb][3]);
         }
       }
     }
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
     const int co = i % (nb_cur * 8);
     const int ci = (i / (nb_cur * 8)) % 8;
     const int g = i / (nb_cur * 8 * 8);
-    const float v = s_acc[(g * 8 + ci) * (kWmNB * 8) + co];
+    const float v = s_acc[(g * 8 + ci) * (NB * 8) + co];
     if (g == ones_group) {
       if (ci == 0) atomicAdd(&p.db[nb0 * 8 + co], v);
     } else {
@@ -407,14 +408,16 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
                          (size_t)(kWmMaxGroups + 2) * 8 * kWmNB * 8 * sizeof(float) + 1024;
     static bool attr2 = false;
     if (!attr2) {
-      OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_mma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_mma_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_mma_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       attr2 = true;
     }
     if (smem2 <= 220 * 1024) {
       const int blocks_y2 = p.n_pchunks * p.n_gblocks * p.n_nchunks;
       int gx2 = std::max(1, std::min(p.num_tiles, (148 + blocks_y2 - 1) / blocks_y2));
       dim3 grid2(gx2, blocks_y2);
-      wgrad_mma_tma_kernel<<<grid2, 288, smem2, st>>>(map_a, map_d, p, th, status);
+      if (p.d_planes == 1) wgrad_mma_tma_kernel<1><<<grid2, 288, smem2, st>>>(map_a, map_d, p, th, status);
+      else wgrad_mma_tma_kernel<2><<<grid2, 288, smem2, st>>>(map_a, map_d, p, th, status);
       OCTSEG_CUDA(cudaGetLastError());
       return 0;
     }

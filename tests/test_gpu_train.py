@@ -81,18 +81,28 @@ def test_train_step_fp32_matches_oracle(cfg, n, h, w):
 
 
 def test_train_step_bf16_close_to_oracle():
+    """bf16 mode stores z / a / dz in bf16 and runs every conv (fwd, dgrad, wgrad) on tensor cores:
+    the gradient is that of a slightly different (rounded) network, so the check is statistical --
+    direction of the whole gradient and a loose per-tensor bound (noise grows towards the stem,
+    tools/bf16_grad_noise.py)."""
     from oct_image_segmentation_models_b200.engine import UNetEngine
     cfg = dict(input_channels=1, num_classes=4, start_neurons=8, pool_layers=2, conv_layers=2)
-    weights, imgs, labs, mask = _setup(cfg, 4, 32, 32)
+    weights, imgs, labs, mask = _setup(cfg, 8, 64, 64)
     names = [nm for nm, _ in unet_param_specs(**cfg)]
     ora = OracleUNet(weights, **cfg)
     loss_ref, grads_ref, _, _ = ora.loss_and_grads(imgs, labs, CW, dropout_mask=mask)
     eng = UNetEngine(precision="bf16", **cfg)
     eng.set_weights(weights)
-    eng.train_begin(CW, global_batch=4)
+    eng.train_begin(CW, global_batch=8)
     loss = eng.train_step(imgs, labs, dropout_mask=mask)
     assert abs(loss - loss_ref) <= 2e-2 * max(1.0, abs(loss_ref))
-    _grad_check(names, eng.get_grads(), grads_ref, 0.35, "bf16", bias_noise=2e-2)   # bf16 storage of z/a/dz: noise accumulates towards the stem (tools/bf16_grad_noise.py)
+    got = eng.get_grads()
+    _grad_check(names, got, grads_ref, 0.5, "bf16", bias_noise=2e-2)
+    keep = [i for i, nm in enumerate(names) if grads_ref[i] is not None and not (nm.endswith("bias:0") and nm != names[-1])]
+    a = np.concatenate([got[i].ravel() for i in keep])
+    b = np.concatenate([grads_ref[i].numpy().ravel() for i in keep])
+    cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+    assert cos >= 0.97, cos
     eng.close()
 
 
