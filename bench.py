@@ -162,7 +162,8 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-TRAIN_H, TRAIN_W, TRAIN_GLOBAL_BATCH = 512, 256, 256
+TRAIN_H, TRAIN_W = 512, 256
+TRAIN_GLOBAL_BATCH = int(os.environ.get("OCTSEG_BENCH_TRAIN_BATCH", "256"))   # BASELINE configs[2]: 256
 
 
 def bench_train(args, eng_cfg, rank, local_rank, world, torch, dist, stream):

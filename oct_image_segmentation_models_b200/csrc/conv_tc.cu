@@ -552,10 +552,11 @@ bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w) {
   return true;
 }
 
-int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g) {
+int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, int pad_top, int pad_left) {
   std::memset(g, 0, sizeof(*g));
   g->kh = kh; g->kw = kw; g->cin = cin; g->cout = cout; g->ups = ups;
-  const int pt = (kh - 1) / 2, pl = (kw - 1) / 2;
+  const int pt = pad_top >= 0 ? pad_top : (kh - 1) / 2, pl = pad_left >= 0 ? pad_left : (kw - 1) / 2;
+  g->pt = pt; g->pl = pl;
   if (!ups) {
     g->dy_min = -pt; g->dy_max = kh - 1 - pt; g->dx_min = -pl; g->dx_max = kw - 1 - pl;
   } else {
@@ -630,7 +631,7 @@ static inline uint16_t f2bf(float f) {
 }
 
 void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> *out) {
-  const int pt = (g.kh - 1) / 2, pl = (g.kw - 1) / 2;
+  const int pt = g.pt, pl = g.pl;
   const size_t per_step = (size_t)2 * g.n_cols * 8;
   out->assign((size_t)g.n_tiles_n * g.cin_chunks * g.ksteps * per_step, 0);
   for (int nt = 0; nt < g.n_tiles_n; ++nt)
@@ -668,7 +669,7 @@ void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> 
 // where w is the forward kernel [kh][kw][g.cout][g.cin] (g describes the dgrad conv).
 __global__ void tc_pack_kernel(TcGeometry g, const float *__restrict__ w, int transposed,
                                __nv_bfloat16 *__restrict__ out, long long total) {
-  const int pt = (g.kh - 1) / 2, pl = (g.kw - 1) / 2;
+  const int pt = g.pt, pl = g.pl;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int kk = (int)(i & 7);

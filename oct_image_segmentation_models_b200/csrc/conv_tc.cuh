@@ -64,6 +64,7 @@ struct TcPlan {
 // the kernel's A-descriptor table.
 struct TcGeometry {
   int kh, kw, cin, cout, ups;          // conv block
+  int pt, pl;                          // padding before (rows / px); Keras "same": (k-1)/2
   int dy_min, dy_max, dx_min, dx_max;  // low-res tap range
   int planes_per_chunk, cin_chunks, ksteps, n_cols, n_tiles_n, cols_valid, bgroup;
   int box_w, box_h;                    // halo px / rows added around a super-tile
@@ -72,7 +73,8 @@ struct TcGeometry {
 };
 
 bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w);
-int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g);
+// pad_top/pad_left < 0: Keras "same" padding ((k-1)/2 before); otherwise explicit (data-gradient convs)
+int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, int pad_top = -1, int pad_left = -1);
 // packs fp32 HWIO weights into the bf16 smem image the kernel streams (host memory)
 void tc_pack_weights(const TcGeometry &g, const float *w_hwio, std::vector<uint16_t> *out);
 // same packing on the device, from fp32 weights in device memory (training)

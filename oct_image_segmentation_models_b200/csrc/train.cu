@@ -100,10 +100,16 @@ struct TrainState {
   std::vector<void *> dcat;         // gradient wrt each level's concat buffer [n][2f/8][h][w][8]
   std::vector<void *> gA, gB;       // ping-pong gradient buffers per level (f channels... sized 2f)
   void *img_blocked = nullptr;      // stem input as a 1-plane blocked tensor
+  void *up_scratch = nullptr;       // materialised x2-upsampled input of an up-conv (weight-gradient stream)
+  void *dup_scratch = nullptr;      // gradient wrt the upsampled tensor (main stream), then 2x2 sum-pooled
   void *mask = nullptr;             // dropout multiplier tensor at the bottleneck
   void *d_img = nullptr; size_t d_img_bytes = 0;
   uint8_t *d_labels = nullptr; size_t d_labels_bytes = 0;
   uint8_t *d_mask_in = nullptr; size_t d_mask_bytes = 0;
+  // weight gradients run on a second stream, concurrently with the rest of the backward chain
+  cudaStream_t wg_stream = nullptr;
+  std::vector<cudaEvent_t> ev_dz;   // per block: dz ready
+  cudaEvent_t ev_wg_done = nullptr, ev_step_start = nullptr;
   // communicator
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -198,6 +204,9 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
     o_a[b.index] = in_cat ? (size_t)-1 : bump.take(bytes(b.cout, b.level));
     o_pool[b.index] = b.pool_after ? bump.take(bytes(b.cout, b.level + 1)) : (size_t)-1;
   }
+  size_t up_bytes = 1024;
+  for (auto &b : net->blocks) if (b.ups) up_bytes = std::max(up_bytes, bytes(b.cin, b.level));
+  const size_t o_up = bump.take(up_bytes), o_dup = bump.take(up_bytes);
   const size_t o_img = bump.take((size_t)n * h * w * 8 * es);
   const size_t o_mask = bump.take(bytes(s << P, P));
   if (bump.off > S->ws_bytes) {
@@ -223,6 +232,8 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
     t.pooled = b.pool_after ? base + o_pool[b.index] : nullptr;
   }
   S->img_blocked = base + o_img;
+  S->up_scratch = base + o_up;
+  S->dup_scratch = base + o_dup;
   S->mask = base + o_mask;
   S->n = n; S->h = h; S->w = w;
   // ---- tensor-core plans (bf16): z = conv(in)+bias and d(in) = conv(dz, W^T flipped)
@@ -250,8 +261,12 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
       if (tc_make_plan(bs.geo, in_ptr, n, in_h, in_w, bs.wpack, epi, net->d_status, &t.plan_fwd)) return 1;
       t.tc_fwd = true;
     }
-    if (t.geo_dgrad_ok && !b.ups && tc_supported(b.kh, b.kw, b.cout, b.cin, 0, t.h, t.w)) t.tc_dgrad = true;
+    if (t.geo_dgrad_ok && tc_supported(b.kh, b.kw, b.cout, b.cin, 0, t.h, t.w)) {
+      // destination of the data gradient: fixed per block (see the buffer walk in train_step_t)
+      t.tc_dgrad = true;
+    }
   }
+  for (auto &b : net->blocks) S->tb[b.index].plan_dgrad.valid = false;
   return 0;
 }
 
@@ -284,6 +299,8 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   prof.begin(PH_MISC);
   OCTSEG_CUDA(cudaMemsetAsync(G, 0, net->total_floats * sizeof(float), st));
   OCTSEG_CUDA(cudaMemsetAsync(S->d_loss, 0, sizeof(double), st));
+  const bool dual = !prof.on && std::getenv("OCTSEG_NO_DUAL_STREAM") == nullptr;
+  cudaStream_t wst = dual ? S->wg_stream : st;
   if (launch_image_to_blocked<T>(d_img, dtype, n, h, w, net->cfg.input_channels, (T *)S->img_blocked, st)) return 1;
   ++net->launches;
   const BlockSpec *mid_last = nullptr;
@@ -386,18 +403,31 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     View<const T> in = block_input<T>(net, b, n);
     const int pt = (b.kh - 1) / 2, pl = (b.kw - 1) / 2;
     prof.begin(PH_WGRAD);
+    if (dual) {   // dW needs only dz and the saved input: run it beside the remaining backward chain
+      OCTSEG_CUDA(cudaEventRecord(S->ev_dz[bi], st));
+      OCTSEG_CUDA(cudaStreamWaitEvent(wst, S->ev_dz[bi], 0));
+    }
     if (b.index == 0) {
       const int taps = b.kh * b.kw;
-      OCTSEG_CUDA(cudaMemsetAsync(S->d_stem_tmp, 0, (size_t)taps * 8 * b.cout * sizeof(float), st));
+      OCTSEG_CUDA(cudaMemsetAsync(S->d_stem_tmp, 0, (size_t)taps * 8 * b.cout * sizeof(float), wst));
       if (wgrad_dispatch<T>(net, in, dzc, b.kh, b.kw, pt, pl, 0, 8, b.cout, S->d_stem_tmp,
-                            G + net->params[b.p_bias].offset, st))
+                            G + net->params[b.p_bias].offset, wst))
         return 1;
-      if (launch_stem_wgrad_extract(S->d_stem_tmp, taps, b.cin, b.cout, G + net->params[b.p_kernel].offset, st)) return 1;
+      if (launch_stem_wgrad_extract(S->d_stem_tmp, taps, b.cin, b.cout, G + net->params[b.p_kernel].offset, wst)) return 1;
       net->launches += 4;
       break;
     }
-    if (wgrad_dispatch<T>(net, in, dzc, b.kh, b.kw, pt, pl, b.ups ? 1 : 0, b.cin, b.cout,
-                          G + net->params[b.p_kernel].offset, G + net->params[b.p_bias].offset, st))
+    if (b.ups && sizeof(T) == 2 && !net->disable_tc) {
+      // tensor-core path wants a real tensor: materialise the x2-upsampled input once (1 write + 1 read
+      // of a tensor the forward pass never stores) and run the plain 2x2 weight gradient on it
+      View<T> up = make_view((T *)S->up_scratch, n, b.cin / 8, 0, b.cin / 8, t.h, t.w);
+      if (launch_upsample2x<T>(in, up, wst)) return 1;
+      View<const T> upc = make_view((const T *)S->up_scratch, n, b.cin / 8, 0, b.cin / 8, t.h, t.w);
+      if (wgrad_dispatch<T>(net, upc, dzc, b.kh, b.kw, pt, pl, 0, b.cin, b.cout, G + net->params[b.p_kernel].offset,
+                            G + net->params[b.p_bias].offset, wst))
+        return 1;
+    } else if (wgrad_dispatch<T>(net, in, dzc, b.kh, b.kw, pt, pl, b.ups ? 1 : 0, b.cin, b.cout,
+                                 G + net->params[b.p_kernel].offset, G + net->params[b.p_bias].offset, wst))
       return 1;
     // ---- data gradient wrt this block's input
     prof.begin(PH_DGRAD);
@@ -415,9 +445,12 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
         TcEpilogue epi;
         epi.relu = 0; epi.scale = S->d_ones; epi.shift = S->d_zeros;
         epi.out = make_view((__nv_bfloat16 *)dst, n, dst_total, 0, b.cin / 8, t.h, t.w);
-        if (tc_make_plan(t.geo_dgrad, (const __nv_bfloat16 *)t.dz, n, t.h, t.w, t.wpack_dgrad, epi, net->d_status,
-                         &t.plan_dgrad))
-          return 1;
+        // the destination buffer of a block never changes between steps: build the plan once
+        if (!t.plan_dgrad.valid || t.plan_dgrad.p.out != epi.out.ptr) {
+          if (tc_make_plan(t.geo_dgrad, (const __nv_bfloat16 *)t.dz, n, t.h, t.w, t.wpack_dgrad, epi, net->d_status,
+                           &t.plan_dgrad))
+            return 1;
+        }
         if (tc_launch(t.plan_dgrad, st)) return 1;
       } else if (launch_conv_direct_ex<T>(dzc, t.w_t, b.kh, b.kw, b.cout, b.cin, 0, 1, b.kh - 1 - pt, b.kw - 1 - pl,
                                           S->d_ones, S->d_zeros, 0, din, st))
@@ -426,13 +459,29 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
       if (b.concat_level >= 0) { g_planes_total = b.cin / 8; g_plane0 = 0; }   // next: the up block (planes [0,f/8))
       else { g_planes_total = b.cin / 8; g_plane0 = 0; }
     } else {
-      // up-conv: d(prev) on the low-res grid = stride-2 (kh+1)x(kw+1) conv over dz
-      if (launch_upconv_dgrad_weights(P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout, t.w_t, st)) return 1;
       void *dst = S->gA[b.level + 1];
       View<T> din = make_view((T *)dst, n, b.cin / 8, 0, b.cin / 8, t.h / 2, t.w / 2);
-      if (launch_conv_direct_ex<T>(dzc, t.w_t, b.kh + 1, b.kw + 1, b.cout, b.cin, 0, 2, b.kh - 1 - pt, b.kw - 1 - pl,
-                                   S->d_ones, S->d_zeros, 0, din, st))
-        return 1;
+      if (t.tc_dgrad) {
+        // d(upsampled input) on the high-res grid with the flipped kernel, then its 2x2 sum-pool
+        if (tc_pack_weights_device(t.geo_dgrad, P + net->params[b.p_kernel].offset, 1, t.wpack_dgrad, st)) return 1;
+        TcEpilogue epi;
+        epi.relu = 0; epi.scale = S->d_ones; epi.shift = S->d_zeros;
+        epi.out = make_view((__nv_bfloat16 *)S->dup_scratch, n, b.cin / 8, 0, b.cin / 8, t.h, t.w);
+        if (!t.plan_dgrad.valid || t.plan_dgrad.p.out != epi.out.ptr) {
+          if (tc_make_plan(t.geo_dgrad, (const __nv_bfloat16 *)t.dz, n, t.h, t.w, t.wpack_dgrad, epi, net->d_status,
+                           &t.plan_dgrad))
+            return 1;
+        }
+        if (tc_launch(t.plan_dgrad, st)) return 1;
+        View<const T> dup = make_view((const T *)S->dup_scratch, n, b.cin / 8, 0, b.cin / 8, t.h, t.w);
+        if (launch_sumpool2x<T>(dup, din, st)) return 1;
+      } else {
+        // up-conv: d(prev) on the low-res grid = stride-2 (kh+1)x(kw+1) conv over dz
+        if (launch_upconv_dgrad_weights(P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout, t.w_t, st)) return 1;
+        if (launch_conv_direct_ex<T>(dzc, t.w_t, b.kh + 1, b.kw + 1, b.cout, b.cin, 0, 2, b.kh - 1 - pt, b.kw - 1 - pl,
+                                     S->d_ones, S->d_zeros, 0, din, st))
+          return 1;
+      }
       g_ptr = dst;
       g_planes_total = b.cin / 8; g_plane0 = 0;
     }
@@ -440,6 +489,10 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     net->launches += 5;
   }
   // ------------------------------- all-reduce + optimizer -------------------------------
+  if (dual) {
+    OCTSEG_CUDA(cudaEventRecord(S->ev_wg_done, wst));
+    OCTSEG_CUDA(cudaStreamWaitEvent(st, S->ev_wg_done, 0));
+  }
   prof.begin(PH_AR);
   if (S->comm && S->world > 1)
     OCTSEG_NCCL(g_nccl.AllReduce(G, G, (size_t)net->total_floats, /*ncclFloat*/ 7, /*ncclSum*/ 0, S->comm, st));
@@ -467,6 +520,10 @@ void octseg_train_free(octseg_net *net) {
   TrainState *S = ts(net);
   if (!S) return;
   if (S->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S->comm);
+  for (auto &e : S->ev_dz) cudaEventDestroy(e);
+  if (S->ev_wg_done) cudaEventDestroy(S->ev_wg_done);
+  if (S->ev_step_start) cudaEventDestroy(S->ev_step_start);
+  if (S->wg_stream) cudaStreamDestroy(S->wg_stream);
   for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); cudaFree(t.wpack_dgrad); }
   cudaFree(S->d_class_w); cudaFree(S->d_grads); cudaFree(S->d_m); cudaFree(S->d_v); cudaFree(S->d_ones); cudaFree(S->d_zeros);
   cudaFree(S->d_sums); cudaFree(S->d_loss); cudaFree(S->d_stem_tmp); cudaFree(S->ws); cudaFree(S->d_img);
@@ -504,6 +561,11 @@ int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc, const
     const BlockSpec &b0 = net->blocks[0];
     OCTSEG_CUDA(cudaMalloc(&S->d_stem_tmp, (size_t)b0.kh * b0.kw * 8 * b0.cout * sizeof(float)));
     S->tb.resize(net->blocks.size());
+    OCTSEG_CUDA(cudaStreamCreateWithFlags(&S->wg_stream, cudaStreamNonBlocking));
+    S->ev_dz.resize(net->blocks.size());
+    for (auto &e : S->ev_dz) OCTSEG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    OCTSEG_CUDA(cudaEventCreateWithFlags(&S->ev_wg_done, cudaEventDisableTiming));
+    OCTSEG_CUDA(cudaEventCreateWithFlags(&S->ev_step_start, cudaEventDisableTiming));
     for (auto &b : net->blocks) {
       if (b.role == 4) continue;
       TrainBlock &t = S->tb[b.index];
@@ -512,9 +574,10 @@ int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc, const
       OCTSEG_CUDA(cudaMalloc(&t.scale, b.cout * sizeof(float)));
       OCTSEG_CUDA(cudaMalloc(&t.shift, b.cout * sizeof(float)));
       OCTSEG_CUDA(cudaMalloc(&t.w_t, (size_t)(b.kh + 1) * (b.kw + 1) * b.cin * b.cout * sizeof(float)));
-      if (net->precision == OCTSEG_BF16 && !net->disable_tc && b.index > 0 && !b.ups &&
+      if (net->precision == OCTSEG_BF16 && !net->disable_tc && b.index > 0 &&
           tc_supported(b.kh, b.kw, b.cout, b.cin, 0, kTcTileH, kTcTileW) &&
-          tc_make_geometry(b.kh, b.kw, b.cout, b.cin, 0, &t.geo_dgrad) == 0) {
+          tc_make_geometry(b.kh, b.kw, b.cout, b.cin, 0, &t.geo_dgrad, b.kh - 1 - (b.kh - 1) / 2,
+                           b.kw - 1 - (b.kw - 1) / 2) == 0) {
         t.geo_dgrad_ok = true;
         const size_t elems = (size_t)t.geo_dgrad.n_tiles_n * t.geo_dgrad.cin_chunks * t.geo_dgrad.ksteps * 2 *
                              t.geo_dgrad.n_cols * 8;

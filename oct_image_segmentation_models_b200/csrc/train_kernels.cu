@@ -50,18 +50,21 @@ __device__ __forceinline__ void block_reduce16_to_double(float (&acc)[16], doubl
   }
 }
 
+// grid = (chunks, planes, images): every block walks a contiguous span of one (image, plane), so
+// the address is base + linear offset (no 64-bit divisions in the loop)
+constexpr int kSpanVecs = 8192;   // vectors per block span
+
 template <typename T>
 __global__ void __launch_bounds__(kRedThreads) bn_stats_kernel(View<const T> z, double *sums, int c) {
-  const int pl = blockIdx.y;
-  const long long total = (long long)z.n * z.h * z.w;
-  const long long v0 = (long long)blockIdx.x * kRedThreads * kRedPerThread;
+  const int pl = blockIdx.y, img = blockIdx.z;
+  const int hw = z.h * z.w;
+  const T *base = z.ptr + (long long)img * z.img_stride + (long long)pl * hw * 8;
+  const int v_end = min(hw, (int)(blockIdx.x + 1) * kSpanVecs);
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int k = 0; k < kRedPerThread; ++k) {
-    const long long v = v0 + (long long)k * kRedThreads + threadIdx.x;
-    if (v >= total) break;
-    const Vec8f x = load8(vec_ptr(z, pl, v));
+  for (int v = blockIdx.x * kSpanVecs + threadIdx.x; v < v_end; v += kRedThreads) {
+    const Vec8f x = load8(base + (long long)v * 8);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { acc[i] += x.v[i]; acc[8 + i] = fmaf(x.v[i], x.v[i], acc[8 + i]); }
   }
@@ -72,8 +75,8 @@ template <typename T>
 int launch_bn_stats(View<const T> z, double *sums, cudaStream_t st) {
   const int c = z.planes * 8;
   OCTSEG_CUDA(cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st));
-  const long long total = (long long)z.n * z.h * z.w;
-  dim3 grid((unsigned)((total + kRedThreads * kRedPerThread - 1) / (kRedThreads * kRedPerThread)), z.planes);
+  const int hw = z.h * z.w;
+  dim3 grid((hw + kSpanVecs - 1) / kSpanVecs, z.planes, z.n);
   bn_stats_kernel<T><<<grid, kRedThreads, 0, st>>>(z, sums, c);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
@@ -114,31 +117,32 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_relu_kernel(View<const T> z, const float *__restrict__ scale,
                                                             const float *__restrict__ shift,
                                                             const T *__restrict__ mask, View<T> a) {
-  const long long per_plane = (long long)z.n * z.h * z.w;
-  const long long total = per_plane * z.planes;
-  const long long hw = (long long)z.h * z.w;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int pl = (int)(i / per_plane);
-    const long long v = i - (long long)pl * per_plane;
-    Vec8f x = load8(vec_ptr(z, pl, v));
+  const int pl = blockIdx.y, img = blockIdx.z;
+  const int hw = z.h * z.w;
+  const T *zb = z.ptr + (long long)img * z.img_stride + (long long)pl * hw * 8;
+  T *ab = a.ptr + (long long)img * a.img_stride + (long long)pl * hw * 8;
+  const T *mb = mask ? mask + ((long long)img * z.planes + pl) * hw * 8 : nullptr;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x.v[k] = fmaxf(fmaf(x.v[k], scale[pl * 8 + k], shift[pl * 8 + k]), 0.f);
-    if (mask) {
-      const long long img = v / hw, off = v - img * hw;
-      const Vec8f mk = load8(mask + ((img * z.planes + pl) * hw + off) * 8);
+  for (int k = 0; k < 8; ++k) { sc[k] = scale[pl * 8 + k]; sh[k] = shift[pl * 8 + k]; }
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < hw; v += gridDim.x * blockDim.x) {
+    Vec8f x = load8(zb + (long long)v * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x.v[k] = fmaxf(fmaf(x.v[k], sc[k], sh[k]), 0.f);
+    if (mb) {
+      const Vec8f mk = load8(mb + (long long)v * 8);
 #pragma unroll
       for (int k = 0; k < 8; ++k) x.v[k] *= mk.v[k];
     }
-    store8(vec_ptr_w(a, pl, v), x);
+    store8(ab + (long long)v * 8, x);
   }
 }
 
 template <typename T>
 int launch_bn_apply_relu(View<const T> z, const float *scale, const float *shift, const T *mask,
                          View<T> a, cudaStream_t st) {
-  const long long total = (long long)z.n * z.h * z.w * z.planes;
-  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  const int hw = z.h * z.w;
+  dim3 grid(std::max(1, std::min((hw + 1023) / 1024, 64)), z.planes, z.n);
   bn_apply_relu_kernel<T><<<grid, 256, 0, st>>>(z, scale, shift, mask, a);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
@@ -333,24 +337,23 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
     View<const T> da, View<const T> z, const float *__restrict__ mean, const float *__restrict__ invstd,
     const float *__restrict__ gamma, const float *__restrict__ beta, const T *__restrict__ mask, double *sums,
     int c) {
-  const int pl = blockIdx.y;
-  const long long hw = (long long)z.h * z.w;
-  const long long total = (long long)z.n * hw;
-  const long long v0 = (long long)blockIdx.x * kRedThreads * kRedPerThread;
+  const int pl = blockIdx.y, img = blockIdx.z;
+  const int hw = z.h * z.w;
+  const T *zb = z.ptr + (long long)img * z.img_stride + (long long)pl * hw * 8;
+  const T *gb = da.ptr + (long long)img * da.img_stride + (long long)pl * hw * 8;
+  const T *mb = mask ? mask + ((long long)img * z.planes + pl) * hw * 8 : nullptr;
+  const int v_end = min(hw, (int)(blockIdx.x + 1) * kSpanVecs);
   float mu[8], is[8], ga[8], be[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { mu[i] = mean[pl * 8 + i]; is[i] = invstd[pl * 8 + i]; ga[i] = gamma[pl * 8 + i]; be[i] = beta[pl * 8 + i]; }
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int k = 0; k < kRedPerThread; ++k) {
-    const long long v = v0 + (long long)k * kRedThreads + threadIdx.x;
-    if (v >= total) break;
-    const Vec8f zz = load8(vec_ptr(z, pl, v));
-    Vec8f g = load8(vec_ptr(da, pl, v));
-    if (mask) {
-      const long long img = v / hw, off = v - img * hw;
-      const Vec8f mk = load8(mask + ((img * z.planes + pl) * hw + off) * 8);
+  for (int v = blockIdx.x * kSpanVecs + threadIdx.x; v < v_end; v += kRedThreads) {
+    const Vec8f zz = load8(zb + (long long)v * 8);
+    Vec8f g = load8(gb + (long long)v * 8);
+    if (mb) {
+      const Vec8f mk = load8(mb + (long long)v * 8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g.v[i] *= mk.v[i];
     }
@@ -371,8 +374,8 @@ int launch_bn_bwd_reduce(View<const T> da, View<const T> z, const float *mean, c
                          cudaStream_t st) {
   const int c = z.planes * 8;
   OCTSEG_CUDA(cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st));
-  const long long total = (long long)z.n * z.h * z.w;
-  dim3 grid((unsigned)((total + kRedThreads * kRedPerThread - 1) / (kRedThreads * kRedPerThread)), z.planes);
+  const int hw = z.h * z.w;
+  dim3 grid((hw + kSpanVecs - 1) / kSpanVecs, z.planes, z.n);
   bn_bwd_reduce_kernel<T><<<grid, kRedThreads, 0, st>>>(da, z, mean, invstd, gamma, beta, mask, sums, c);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
@@ -383,35 +386,38 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     View<const T> da, View<const T> z, const float *__restrict__ mean, const float *__restrict__ invstd,
     const float *__restrict__ gamma, const float *__restrict__ beta, const T *__restrict__ mask,
     const double *__restrict__ sums, long long count, View<T> dz, float *d_gamma, float *d_beta, int c) {
-  if (blockIdx.x == 0)
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
     for (int i = threadIdx.x; i < c; i += blockDim.x) { d_beta[i] = (float)sums[i]; d_gamma[i] = (float)sums[c + i]; }
-  const long long hw = (long long)z.h * z.w;
-  const long long per_plane = (long long)z.n * hw;
-  const long long total = per_plane * z.planes;
+  const int pl = blockIdx.y, img = blockIdx.z;
+  const int hw = z.h * z.w;
+  const T *zb = z.ptr + (long long)img * z.img_stride + (long long)pl * hw * 8;
+  const T *gb = da.ptr + (long long)img * da.img_stride + (long long)pl * hw * 8;
+  T *ob = dz.ptr + (long long)img * dz.img_stride + (long long)pl * hw * 8;
+  const T *mb = mask ? mask + ((long long)img * z.planes + pl) * hw * 8 : nullptr;
   const float inv_m = 1.f / (float)count;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int pl = (int)(i / per_plane);
-    const long long v = i - (long long)pl * per_plane;
-    const Vec8f zz = load8(vec_ptr(z, pl, v));
-    Vec8f g = load8(vec_ptr(da, pl, v));
-    if (mask) {
-      const long long img = v / hw, off = v - img * hw;
-      const Vec8f mk = load8(mask + ((img * z.planes + pl) * hw + off) * 8);
+  float mu[8], is[8], ga[8], be[8], sdy[8], sdyz[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = pl * 8 + k;
+    mu[k] = mean[ch]; is[k] = invstd[ch]; ga[k] = gamma[ch]; be[k] = beta[ch];
+    sdy[k] = (float)sums[ch] * inv_m; sdyz[k] = (float)sums[c + ch] * inv_m;
+  }
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < hw; v += gridDim.x * blockDim.x) {
+    const Vec8f zz = load8(zb + (long long)v * 8);
+    Vec8f g = load8(gb + (long long)v * 8);
+    if (mb) {
+      const Vec8f mk = load8(mb + (long long)v * 8);
 #pragma unroll
       for (int k = 0; k < 8; ++k) g.v[k] *= mk.v[k];
     }
     Vec8f o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int ch = pl * 8 + k;
-      const float is = invstd[ch], ga = gamma[ch];
-      const float zh = (zz.v[k] - mean[ch]) * is;
-      const float dy = (fmaf(ga, zh, beta[ch]) > 0.f) ? g.v[k] : 0.f;
-      const float sdy = (float)sums[ch] * inv_m, sdyz = (float)sums[c + ch] * inv_m;
-      o.v[k] = ga * is * (dy - sdy - zh * sdyz);
+      const float zh = (zz.v[k] - mu[k]) * is[k];
+      const float dy = (fmaf(ga[k], zh, be[k]) > 0.f) ? g.v[k] : 0.f;
+      o.v[k] = ga[k] * is[k] * (dy - sdy[k] - zh * sdyz[k]);
     }
-    store8(vec_ptr_w(dz, pl, v), o);
+    store8(ob + (long long)v * 8, o);
   }
 }
 
@@ -419,8 +425,8 @@ template <typename T>
 int launch_bn_bwd_apply(View<const T> da, View<const T> z, const float *mean, const float *invstd,
                         const float *gamma, const float *beta, const T *mask, const double *sums,
                         long long count, View<T> dz, float *d_gamma, float *d_beta, cudaStream_t st) {
-  const long long total = (long long)z.n * z.h * z.w * z.planes;
-  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  const int hw = z.h * z.w;
+  dim3 grid(std::max(1, std::min((hw + 1023) / 1024, 64)), z.planes, z.n);
   bn_bwd_apply_kernel<T><<<grid, 256, 0, st>>>(da, z, mean, invstd, gamma, beta, mask, sums, count, dz, d_gamma,
                                                d_beta, z.planes * 8);
   OCTSEG_CUDA(cudaGetLastError());
@@ -434,13 +440,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) pool_bwd_add_kernel(View<const T> a, View<const T> d_pooled,
                                                            View<const T> d_skip, View<T> out, int has_skip) {
   const int Ho = d_pooled.h, Wo = d_pooled.w;
-  const long long total = (long long)d_pooled.n * d_pooled.planes * Ho * Wo;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % Wo);
-    const int y = (int)((i / Wo) % Ho);
-    const int pl = (int)((i / ((long long)Wo * Ho)) % d_pooled.planes);
-    const int b = (int)(i / ((long long)Wo * Ho * d_pooled.planes));
+  const int pl = blockIdx.y, b = blockIdx.z;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Ho * Wo; i += gridDim.x * blockDim.x) {
+    const int x = i % Wo, y = i / Wo;
     const long long base = (((long long)pl * a.h + 2 * y) * a.w + 2 * x) * 8;
     const long long row = (long long)a.w * 8;
     const T *ap = a.ptr + b * a.img_stride + base;
@@ -471,9 +473,64 @@ __global__ void __launch_bounds__(256) pool_bwd_add_kernel(View<const T> a, View
 template <typename T>
 int launch_pool_bwd_add(View<const T> a, View<const T> d_pooled, View<const T> d_skip, View<T> da_total,
                         cudaStream_t st) {
-  const long long total = (long long)d_pooled.n * d_pooled.planes * d_pooled.h * d_pooled.w;
-  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  const int hw = d_pooled.h * d_pooled.w;
+  dim3 grid(std::max(1, std::min((hw + 255) / 256, 64)), d_pooled.planes, d_pooled.n);
   pool_bwd_add_kernel<T><<<grid, 256, 0, st>>>(a, d_pooled, d_skip, da_total, d_skip.ptr != nullptr);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// nearest x2 up-sampling (materialised only for the up-conv's weight gradient) and its adjoint,
+// the 2x2 sum-pool (gradient of the up-sampling in front of the decoder's 2x2 conv)
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_kernel(View<const T> in, View<T> out) {
+  const int pl = blockIdx.y, b = blockIdx.z;
+  const int h = in.h, w = in.w;
+  const T *ib = in.ptr + b * in.img_stride + (long long)pl * h * w * 8;
+  T *ob = out.ptr + b * out.img_stride + (long long)pl * (4LL * h * w) * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h * w; i += gridDim.x * blockDim.x) {
+    const int x = i % w, y = i / w;
+    const uint4 v = *reinterpret_cast<const uint4 *>(ib + (long long)i * 8);
+    T *o = ob + ((long long)(2 * y) * (2 * w) + 2 * x) * 8;
+    if constexpr (sizeof(T) == 2) {
+      *reinterpret_cast<uint4 *>(o) = v; *reinterpret_cast<uint4 *>(o + 8) = v;
+      *reinterpret_cast<uint4 *>(o + (long long)2 * w * 8) = v; *reinterpret_cast<uint4 *>(o + (long long)2 * w * 8 + 8) = v;
+    } else {
+      const Vec8f f = load8(ib + (long long)i * 8);
+      store8(o, f); store8(o + 8, f); store8(o + (long long)2 * w * 8, f); store8(o + (long long)2 * w * 8 + 8, f);
+    }
+  }
+}
+template <typename T>
+int launch_upsample2x(View<const T> in, View<T> out, cudaStream_t st) {
+  dim3 grid(std::max(1, std::min((in.h * in.w + 255) / 256, 64)), in.planes, in.n);
+  upsample2x_kernel<T><<<grid, 256, 0, st>>>(in, out);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sumpool2x_kernel(View<const T> in, View<T> out) {
+  const int pl = blockIdx.y, b = blockIdx.z;
+  const int h = out.h, w = out.w;
+  const T *ib = in.ptr + b * in.img_stride + (long long)pl * (4LL * h * w) * 8;
+  T *ob = out.ptr + b * out.img_stride + (long long)pl * h * w * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h * w; i += gridDim.x * blockDim.x) {
+    const int x = i % w, y = i / w;
+    const T *p = ib + ((long long)(2 * y) * (2 * w) + 2 * x) * 8;
+    const Vec8f a = load8(p), c = load8(p + 8), d = load8(p + (long long)2 * w * 8), e = load8(p + (long long)2 * w * 8 + 8);
+    Vec8f o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = (a.v[k] + c.v[k]) + (d.v[k] + e.v[k]);
+    store8(ob + (long long)i * 8, o);
+  }
+}
+template <typename T>
+int launch_sumpool2x(View<const T> in, View<T> out, cudaStream_t st) {
+  dim3 grid(std::max(1, std::min((out.h * out.w + 255) / 256, 64)), out.planes, out.n);
+  sumpool2x_kernel<T><<<grid, 256, 0, st>>>(in, out);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -700,7 +757,9 @@ int launch_adam(float *p, const float *g, float *m, float *v, long long n, float
   template int launch_pool_bwd_add<T>(View<const T>, View<const T>, View<const T>, View<T>, cudaStream_t);  \
   template int launch_wgrad<T>(View<const T>, View<const T>, int, int, int, int, int, int, int, float *,    \
                                float *, cudaStream_t);                                                      \
-  template int launch_image_to_blocked<T>(const void *, int, int, int, int, int, T *, cudaStream_t);
+  template int launch_image_to_blocked<T>(const void *, int, int, int, int, int, T *, cudaStream_t);         \
+  template int launch_upsample2x<T>(View<const T>, View<T>, cudaStream_t);                                  \
+  template int launch_sumpool2x<T>(View<const T>, View<T>, cudaStream_t);
 INST(float)
 INST(__nv_bfloat16)
 

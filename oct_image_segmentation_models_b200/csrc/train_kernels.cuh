@@ -47,6 +47,12 @@ template <typename T>
 int launch_pool_bwd_add(View<const T> a, View<const T> d_pooled, View<const T> d_skip, View<T> da_total,
                         cudaStream_t st);
 
+// nearest x2 up-sampling into a dense tensor, and its adjoint (2x2 sum-pool)
+template <typename T>
+int launch_upsample2x(View<const T> in, View<T> out, cudaStream_t st);
+template <typename T>
+int launch_sumpool2x(View<const T> in, View<T> out, cudaStream_t st);
+
 // weight gradient (accumulates with atomics into zero-initialised dW [kh][kw][cin][cout], db [cout])
 template <typename T>
 int launch_wgrad(View<const T> a_in, View<const T> dz, int kh, int kw, int pad_top, int pad_left,

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgParams p) {
 // TMA-pipelined variant (non-upsampled inputs): warp 0 streams (input halo tile, dz tile)
 // pairs through an mbarrier ring, warps 1..8 run the MMAs; no staging instructions at all.
 // ----------------------------------------------------------------------------------
-constexpr int kWmStages = 3;
+constexpr int kWmMaxStages = 8;   // ring depth is chosen per launch: small tiles need many loads in flight
 
 __device__ __forceinline__ uint32_t wm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ bool wm_wait(uint32_t bar, uint32_t parity) {
@@ -214,7 +214,7 @@ __device__ __forceinline__ bool wm_wait(uint32_t bar, uint32_t parity) {
 template <int NB>
 __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_d,
-                                                            const WgParams p, int th, int *status) {
+                                                            const WgParams p, int th, int n_stages, int *status) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int aw = kWmTW + p.kw - 1, ah = th + p.kh - 1;
   int by = blockIdx.y;
@@ -237,15 +237,15 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
   const uint32_t a_bytes = (uint32_t)p.pc * ah * aw * 16, d_bytes = (uint32_t)p.d_planes * th * kWmTW * 16;
   const uint32_t stage_bytes = ((a_bytes + 127u) & ~127u) + ((d_bytes + 127u) & ~127u);
   uint8_t *s_stage = smem_raw;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kWmStages * stage_bytes);   // full[S], empty[S]
-  __nv_bfloat16 *s_ones = reinterpret_cast<__nv_bfloat16 *>(bars + 2 * kWmStages);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes);   // full[S], empty[S]
+  __nv_bfloat16 *s_ones = reinterpret_cast<__nv_bfloat16 *>(bars + 2 * n_stages);
   float *s_acc = reinterpret_cast<float *>(s_ones + 64);
   for (int i = threadIdx.x; i < 64; i += blockDim.x) s_ones[i] = __float2bfloat16(1.0f);
   for (int i = threadIdx.x; i < (kWmMaxGroups + 2) * 8 * NB * 8; i += blockDim.x) s_acc[i] = 0.f;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kWmStages; ++i) {
+    for (int i = 0; i < n_stages; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[i])), "r"(1) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[kWmStages + i])), "r"(8) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[n_stages + i])), "r"(8) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
       const int txi = tile % p.tiles_x;
       const int tyi = (tile / p.tiles_x) % p.tiles_y;
       const int img = tile / (p.tiles_x * p.tiles_y);
-      if (!wm_wait(wm_smem_u32(&bars[kWmStages + st]), ph ^ 1u)) { if (pred) atomicCAS(status, 0, 21); break; }
+      if (!wm_wait(wm_smem_u32(&bars[n_stages + st]), ph ^ 1u)) { if (pred) atomicCAS(status, 0, 21); break; }
       if (pred) {
         const uint32_t full = wm_smem_u32(&bars[st]);
         const uint32_t dst_a = wm_smem_u32(s_stage + (size_t)st * stage_bytes);
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
         asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                      ::"r"(dst_d), "l"(&map_d), "r"(full), "r"(txi * kWmTW * 2), "r"(tyi * th), "r"(nb0), "r"(img) : "memory");
       }
-      if (++st == kWmStages) { st = 0; ph ^= 1u; }
+      if (++st == n_stages) { st = 0; ph ^= 1u; }
     }
   } else {
     // ---------------- consumers: warp w-1 owns rows (w-1), (w-1)+8, ... of every tile ----------------
@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
         }
       }
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wm_smem_u32(&bars[kWmStages + st])) : "memory");
-      if (++st == kWmStages) { st = 0; ph ^= 1u; }
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wm_smem_u32(&bars[n_stages + st])) : "memory");
+      if (++st == n_stages) { st = 0; ph ^= 1u; }
     }
 #pragma unroll
     for (int mt = 0; mt < kWmMaxMT; ++mt) {
@@ -394,7 +394,7 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
   const bool dense = a_in.img_stride == (long long)a_in.planes * a_in.h * a_in.w * 8 &&
                      dz.img_stride == (long long)dz.planes * dz.h * dz.w * 8 && a_in.planes == p.cin_planes;
   if (!ups && dense && status) {
-    const int th = p.pc <= 2 ? 16 : 8;
+    const int th = p.pc == 1 ? 32 : (p.pc == 2 ? 16 : 8);
     p.tiles_y = (dz.h + th - 1) / th;
     p.num_tiles = dz.n * p.tiles_x * p.tiles_y;
     const int aw2 = kWmTW + kw - 1, ah2 = th + kh - 1;
@@ -404,8 +404,10 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
     if (tc_encode_map_4d(dz.ptr, dz.w, dz.h, p.cout_planes, dz.n, kWmTW, th, p.d_planes, &map_d)) return 1;
     const size_t a_bytes = (size_t)p.pc * ah2 * aw2 * 16, d_bytes = (size_t)p.d_planes * th * kWmTW * 16;
     const size_t stage = ((a_bytes + 127) & ~(size_t)127) + ((d_bytes + 127) & ~(size_t)127);
-    const size_t smem2 = kWmStages * stage + 2 * kWmStages * 8 + 128 +
-                         (size_t)(kWmMaxGroups + 2) * 8 * kWmNB * 8 * sizeof(float) + 1024;
+    const size_t fixed = 2 * kWmMaxStages * 8 + 128 + (size_t)(kWmMaxGroups + 2) * 8 * kWmNB * 8 * sizeof(float) + 1024;
+    int n_stages = (int)std::min<size_t>(kWmMaxStages, (200 * 1024 - fixed) / stage);
+    if (n_stages < 2) n_stages = 2;
+    const size_t smem2 = n_stages * stage + fixed;
     static bool attr2 = false;
     if (!attr2) {
       OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_mma_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -416,8 +418,8 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
       const int blocks_y2 = p.n_pchunks * p.n_gblocks * p.n_nchunks;
       int gx2 = std::max(1, std::min(p.num_tiles, (148 + blocks_y2 - 1) / blocks_y2));
       dim3 grid2(gx2, blocks_y2);
-      if (p.d_planes == 1) wgrad_mma_tma_kernel<1><<<grid2, 288, smem2, st>>>(map_a, map_d, p, th, status);
-      else wgrad_mma_tma_kernel<2><<<grid2, 288, smem2, st>>>(map_a, map_d, p, th, status);
+      if (p.d_planes == 1) wgrad_mma_tma_kernel<1><<<grid2, 288, smem2, st>>>(map_a, map_d, p, th, n_stages, status);
+      else wgrad_mma_tma_kernel<2><<<grid2, 288, smem2, st>>>(map_a, map_d, p, th, n_stages, status);
       OCTSEG_CUDA(cudaGetLastError());
       return 0;
     }
