@@ -703,6 +703,52 @@ __global__ void tc_pack_kernel(TcGeometry g, const float *__restrict__ w, int tr
   }
 }
 
+// One launch packs every tensor-core weight image of the net (training: after each optimizer step)
+__global__ void tc_pack_all_kernel(const TcPackJob *__restrict__ jobs) {
+  const TcPackJob &j = jobs[blockIdx.y];
+  const TcGeometry &g = j.g;
+  const int pt = g.pt, pl = g.pl;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < j.total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i & 7);
+    long long t = i >> 3;
+    const int n = (int)(t % g.n_cols); t /= g.n_cols;
+    const int hf = (int)(t & 1); t >>= 1;
+    const int s = (int)(t % g.ksteps); t /= g.ksteps;
+    const int ch = (int)(t % g.cin_chunks);
+    const int nt = (int)(t / g.cin_chunks);
+    float val = 0.f;
+    const int col = nt * g.n_cols + n;
+    if (g.half_ty[s][hf] >= 0 && col < g.cols_valid) {
+      const int dy = g.half_ty[s][hf] + g.dy_min, dx = g.half_tx[s][hf] + g.dx_min;
+      const int ci = (ch * g.planes_per_chunk + g.half_pl[s][hf]) * 8 + kk;
+      if (!g.ups) {
+        const int a = dy + pt, b = dx + pl;
+        if (!j.transposed) val = j.w[(((long long)a * g.kw + b) * g.cin + ci) * g.cout + col];
+        else val = j.w[(((long long)(g.kh - 1 - a) * g.kw + (g.kw - 1 - b)) * g.cout + col) * g.cin + ci];
+      } else {
+        const int par = col / g.cout, co = col % g.cout;
+        const int py = par >> 1, px = par & 1;
+        for (int a = 0; a < g.kh; ++a)
+          for (int b = 0; b < g.kw; ++b) {
+            const int ya = py + a - pt, xb = px + b - pl;
+            const int fy = ya >= 0 ? ya / 2 : -((-ya + 1) / 2), fx = xb >= 0 ? xb / 2 : -((-xb + 1) / 2);
+            if (fy == dy && fx == dx) val += j.w[(((long long)a * g.kw + b) * g.cin + ci) * g.cout + co];
+          }
+      }
+    }
+    j.out[i] = __float2bfloat16(val);
+  }
+}
+
+int tc_pack_all_device(const TcPackJob *jobs_dev, int n_jobs, cudaStream_t st) {
+  if (n_jobs <= 0) return 0;
+  dim3 grid(32, n_jobs);
+  tc_pack_all_kernel<<<grid, 256, 0, st>>>(jobs_dev);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int tc_pack_weights_device(const TcGeometry &g, const float *w_dev, int transposed, __nv_bfloat16 *out,
                            cudaStream_t st) {
   const long long total = (long long)g.n_tiles_n * g.cin_chunks * g.ksteps * 2 * g.n_cols * 8;

@@ -80,6 +80,14 @@ void tc_pack_weights(const TcGeometry &g, const float *w_hwio, std::vector<uint1
 // same packing on the device, from fp32 weights in device memory (training)
 int tc_pack_weights_device(const TcGeometry &g, const float *w_dev, int transposed, __nv_bfloat16 *out,
                            cudaStream_t st);
+struct TcPackJob {
+  TcGeometry g;
+  const float *w;
+  __nv_bfloat16 *out;
+  long long total;
+  int transposed;
+};
+int tc_pack_all_device(const TcPackJob *jobs_dev, int n_jobs, cudaStream_t st);
 // pure host part of the plan (no CUDA driver needed): tiling, stage sizes, A-descriptor table
 int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *p, size_t *smem_bytes);
 struct TcEpilogue {

@@ -86,7 +86,7 @@ struct TrainState {
   float *d_grads = nullptr, *d_m = nullptr, *d_v = nullptr;
   float *d_ones = nullptr;          // [max cout] of 1.0f: conv epilogue scale in training
   float *d_zeros = nullptr;         // [max cout] of 0.0f: conv epilogue shift of the data gradient
-  double *d_sums = nullptr;         // [2 * max cout]
+  double *d_sums = nullptr;         // [blocks][2 phases][2 * max cout]: all zeroed by one memset per step
   double *d_loss = nullptr;
   double *h_loss = nullptr;         // pinned
   float *d_stem_tmp = nullptr;      // [taps][8][cout] stem wgrad scratch
@@ -99,6 +99,8 @@ struct TrainState {
   std::vector<TrainBlock> tb;
   std::vector<void *> dcat;         // gradient wrt each level's concat buffer [n][2f/8][h][w][8]
   std::vector<void *> gA, gB;       // ping-pong gradient buffers per level (f channels... sized 2f)
+  TcPackJob *d_pack_jobs = nullptr; // all tensor-core weight images of the net, packed in one launch per step
+  int n_pack_jobs = 0;
   void *img_blocked = nullptr;      // stem input as a 1-plane blocked tensor
   void *up_scratch = nullptr;       // materialised x2-upsampled input of an up-conv (weight-gradient stream)
   void *dup_scratch = nullptr;      // gradient wrt the upsampled tensor (main stream), then 2x2 sum-pooled
@@ -267,6 +269,31 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
     }
   }
   for (auto &b : net->blocks) S->tb[b.index].plan_dgrad.valid = false;
+  std::vector<TcPackJob> jobs;
+  for (auto &b : net->blocks) {
+    if (b.role == 4) continue;
+    TrainBlock &t = S->tb[b.index];
+    if (t.tc_fwd) {
+      TcPackJob j;
+      j.g = net->bstate[b.index].geo; j.w = net->d_params + net->params[b.p_kernel].offset;
+      j.out = net->bstate[b.index].wpack; j.total = (long long)net->bstate[b.index].wpack_elems; j.transposed = 0;
+      jobs.push_back(j);
+    }
+    if (t.tc_dgrad) {
+      TcPackJob j;
+      j.g = t.geo_dgrad; j.w = net->d_params + net->params[b.p_kernel].offset; j.out = t.wpack_dgrad;
+      j.total = (long long)t.geo_dgrad.n_tiles_n * t.geo_dgrad.cin_chunks * t.geo_dgrad.ksteps * 2 * t.geo_dgrad.n_cols * 8;
+      j.transposed = 1;
+      jobs.push_back(j);
+    }
+  }
+  if (S->d_pack_jobs) OCTSEG_CUDA(cudaFree(S->d_pack_jobs));
+  S->d_pack_jobs = nullptr;
+  S->n_pack_jobs = (int)jobs.size();
+  if (!jobs.empty()) {
+    OCTSEG_CUDA(cudaMalloc(&S->d_pack_jobs, jobs.size() * sizeof(TcPackJob)));
+    OCTSEG_CUDA(cudaMemcpy(S->d_pack_jobs, jobs.data(), jobs.size() * sizeof(TcPackJob), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
@@ -299,6 +326,10 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   prof.begin(PH_MISC);
   OCTSEG_CUDA(cudaMemsetAsync(G, 0, net->total_floats * sizeof(float), st));
   OCTSEG_CUDA(cudaMemsetAsync(S->d_loss, 0, sizeof(double), st));
+  OCTSEG_CUDA(cudaMemsetAsync(S->d_sums, 0, net->blocks.size() * 2 * 2 * S->max_cout * sizeof(double), st));
+  auto sums_of = [&](int block, int phase) { return S->d_sums + ((size_t)block * 2 + phase) * 2 * S->max_cout; };
+  if (tc_pack_all_device(S->d_pack_jobs, S->n_pack_jobs, st)) return 1;
+  ++net->launches;
   const bool dual = !prof.on && std::getenv("OCTSEG_NO_DUAL_STREAM") == nullptr;
   cudaStream_t wst = dual ? S->wg_stream : st;
   if (launch_image_to_blocked<T>(d_img, dtype, n, h, w, net->cfg.input_channels, (T *)S->img_blocked, st)) return 1;
@@ -328,9 +359,6 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
                                S->d_ones, P + net->params[b.p_bias].offset, 0, z, st))
         return 1;
     } else if (t.tc_fwd) {
-      if (tc_pack_weights_device(net->bstate[b.index].geo, P + net->params[b.p_kernel].offset, 0,
-                                 net->bstate[b.index].wpack, st))
-        return 1;
       if (tc_launch(t.plan_fwd, st)) return 1;
       ++net->launches;
     } else if (launch_conv_direct<T>(in, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout,
@@ -338,8 +366,8 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
       return 1;
     View<const T> zc = make_view((const T *)t.z, n, b.cout / 8, 0, b.cout / 8, t.h, t.w);
     prof.begin(PH_BNF);
-    if (launch_bn_stats<T>(zc, S->d_sums, st)) return 1;
-    if (launch_bn_finalize(S->d_sums, (long long)n * t.h * t.w, b.cout, 1e-3f, 0.99f, P + net->params[b.p_gamma].offset,
+    if (launch_bn_stats<T>(zc, sums_of(b.index, 0), st)) return 1;
+    if (launch_bn_finalize(sums_of(b.index, 0), (long long)n * t.h * t.w, b.cout, 1e-3f, 0.99f, P + net->params[b.p_gamma].offset,
                            P + net->params[b.p_beta].offset, net->d_params + net->params[b.p_mean].offset,
                            net->d_params + net->params[b.p_var].offset, t.mean, t.invstd, t.scale, t.shift, st))
       return 1;
@@ -394,9 +422,9 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     const T *mask = (use_dropout && b.dropout_after) ? (const T *)S->mask : nullptr;
     const float *gamma = P + net->params[b.p_gamma].offset, *beta = P + net->params[b.p_beta].offset;
     prof.begin(PH_BNB);
-    if (launch_bn_bwd_reduce<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, S->d_sums, st)) return 1;
+    if (launch_bn_bwd_reduce<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, sums_of(bi, 1), st)) return 1;
     View<T> dz = make_view((T *)t.dz, n, f8, 0, f8, t.h, t.w);
-    if (launch_bn_bwd_apply<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, S->d_sums, (long long)n * t.h * t.w, dz,
+    if (launch_bn_bwd_apply<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, sums_of(bi, 1), (long long)n * t.h * t.w, dz,
                                G + net->params[b.p_gamma].offset, G + net->params[b.p_beta].offset, st))
       return 1;
     View<const T> dzc = make_view((const T *)t.dz, n, f8, 0, f8, t.h, t.w);
@@ -433,7 +461,8 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     prof.begin(PH_DGRAD);
     const BlockSpec &pb = net->blocks[bi - 1];
     if (!b.ups) {
-      if (launch_flip_transpose(P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout, t.w_t, st)) return 1;
+      if (!t.tc_dgrad && launch_flip_transpose(P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout, t.w_t, st))
+        return 1;
       void *dst;
       int dst_total;
       if (b.concat_level >= 0) { dst = S->dcat[b.level]; dst_total = b.cin / 8; }
@@ -441,7 +470,6 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
       // destination grid = this block's input grid (pooled input has the same h,w as the output here)
       View<T> din = make_view((T *)dst, n, dst_total, 0, b.cin / 8, t.h, t.w);
       if (t.tc_dgrad) {
-        if (tc_pack_weights_device(t.geo_dgrad, P + net->params[b.p_kernel].offset, 1, t.wpack_dgrad, st)) return 1;
         TcEpilogue epi;
         epi.relu = 0; epi.scale = S->d_ones; epi.shift = S->d_zeros;
         epi.out = make_view((__nv_bfloat16 *)dst, n, dst_total, 0, b.cin / 8, t.h, t.w);
@@ -463,7 +491,6 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
       View<T> din = make_view((T *)dst, n, b.cin / 8, 0, b.cin / 8, t.h / 2, t.w / 2);
       if (t.tc_dgrad) {
         // d(upsampled input) on the high-res grid with the flipped kernel, then its 2x2 sum-pool
-        if (tc_pack_weights_device(t.geo_dgrad, P + net->params[b.p_kernel].offset, 1, t.wpack_dgrad, st)) return 1;
         TcEpilogue epi;
         epi.relu = 0; epi.scale = S->d_ones; epi.shift = S->d_zeros;
         epi.out = make_view((__nv_bfloat16 *)S->dup_scratch, n, b.cin / 8, 0, b.cin / 8, t.h, t.w);
@@ -527,7 +554,7 @@ void octseg_train_free(octseg_net *net) {
   for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); cudaFree(t.wpack_dgrad); }
   cudaFree(S->d_class_w); cudaFree(S->d_grads); cudaFree(S->d_m); cudaFree(S->d_v); cudaFree(S->d_ones); cudaFree(S->d_zeros);
   cudaFree(S->d_sums); cudaFree(S->d_loss); cudaFree(S->d_stem_tmp); cudaFree(S->ws); cudaFree(S->d_img);
-  cudaFree(S->d_labels); cudaFree(S->d_mask_in);
+  cudaFree(S->d_labels); cudaFree(S->d_mask_in); cudaFree(S->d_pack_jobs);
   if (S->h_loss) cudaFreeHost(S->h_loss);
   delete S;
   net->train = nullptr;
@@ -555,7 +582,7 @@ int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc, const
     OCTSEG_CUDA(cudaMemcpy(S->d_ones, ones.data(), maxc * sizeof(float), cudaMemcpyHostToDevice));
     OCTSEG_CUDA(cudaMalloc(&S->d_zeros, maxc * sizeof(float)));
     OCTSEG_CUDA(cudaMemset(S->d_zeros, 0, maxc * sizeof(float)));
-    OCTSEG_CUDA(cudaMalloc(&S->d_sums, 2 * maxc * sizeof(double)));
+    OCTSEG_CUDA(cudaMalloc(&S->d_sums, net->blocks.size() * 2 * 2 * maxc * sizeof(double)));
     OCTSEG_CUDA(cudaMalloc(&S->d_loss, sizeof(double)));
     OCTSEG_CUDA(cudaMallocHost(&S->h_loss, sizeof(double)));
     const BlockSpec &b0 = net->blocks[0];

@@ -73,8 +73,7 @@ __global__ void __launch_bounds__(kRedThreads) bn_stats_kernel(View<const T> z, 
 
 template <typename T>
 int launch_bn_stats(View<const T> z, double *sums, cudaStream_t st) {
-  const int c = z.planes * 8;
-  OCTSEG_CUDA(cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st));
+  const int c = z.planes * 8;   // `sums` is zeroed by the caller (one memset per train step)
   const int hw = z.h * z.w;
   dim3 grid((hw + kSpanVecs - 1) / kSpanVecs, z.planes, z.n);
   bn_stats_kernel<T><<<grid, kRedThreads, 0, st>>>(z, sums, c);
@@ -372,8 +371,7 @@ template <typename T>
 int launch_bn_bwd_reduce(View<const T> da, View<const T> z, const float *mean, const float *invstd,
                          const float *gamma, const float *beta, const T *mask, double *sums,
                          cudaStream_t st) {
-  const int c = z.planes * 8;
-  OCTSEG_CUDA(cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st));
+  const int c = z.planes * 8;   // `sums` is zeroed by the caller
   const int hw = z.h * z.w;
   dim3 grid((hw + kSpanVecs - 1) / kSpanVecs, z.planes, z.n);
   bn_bwd_reduce_kernel<T><<<grid, kRedThreads, 0, st>>>(da, z, mean, invstd, gamma, beta, mask, sums, c);
