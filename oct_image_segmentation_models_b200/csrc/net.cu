@@ -449,6 +449,9 @@ int32_t octseg_destroy(octseg_net *net) {
   if (net->stream) cudaStreamSynchronize(net->stream);
   octseg_train_free(net);
   for (auto &e : net->prof_events) cudaEventDestroy(e);
+  for (auto &e : net->pipe_events) cudaEventDestroy(e);
+  if (net->copy_in) cudaStreamDestroy(net->copy_in);
+  if (net->copy_out) cudaStreamDestroy(net->copy_out);
   for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); }
   cudaFree(net->d_params); cudaFree(net->ws); cudaFree(net->d_img); cudaFree(net->d_probs);
   cudaFree(net->d_labels); cudaFree(net->d_status);
@@ -516,12 +519,48 @@ int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, 
   if (grow(&net->d_img, &net->d_img_bytes, img_bytes)) return 1;
   if (probs && grow(reinterpret_cast<void **>(&net->d_probs), &net->d_probs_bytes, pr_bytes)) return 1;
   if (labels && grow(reinterpret_cast<void **>(&net->d_labels), &net->d_labels_bytes, lb_bytes)) return 1;
-  OCTSEG_CUDA(cudaMemcpyAsync(net->d_img, images, img_bytes, cudaMemcpyHostToDevice, net->stream));
-  if (octseg_predict_device(net, net->d_img, dtype, n, h, w, probs ? net->d_probs : nullptr,
-                            labels ? net->d_labels : nullptr, net->stream))
-    return 1;
-  if (probs) OCTSEG_CUDA(cudaMemcpyAsync(probs, net->d_probs, pr_bytes, cudaMemcpyDeviceToHost, net->stream));
-  if (labels) OCTSEG_CUDA(cudaMemcpyAsync(labels, net->d_labels, lb_bytes, cudaMemcpyDeviceToHost, net->stream));
+  // Chunked three-stage pipeline: H2D of chunk i+1, forward of chunk i and D2H of chunk i-1 overlap
+  // on three streams (PCIe is full duplex; the fp32 probabilities going back dominate the bytes).
+  const int chunk = std::max(1, std::min(n, (net->microbatch > 0 ? net->microbatch : 16)));
+  if (!net->copy_in) {
+    OCTSEG_CUDA(cudaStreamCreateWithFlags(&net->copy_in, cudaStreamNonBlocking));
+    OCTSEG_CUDA(cudaStreamCreateWithFlags(&net->copy_out, cudaStreamNonBlocking));
+  }
+  const int n_chunks = (n + chunk - 1) / chunk;
+  if ((int)net->pipe_events.size() < 3 * n_chunks) {
+    const size_t old = net->pipe_events.size();
+    net->pipe_events.resize(3 * n_chunks);
+    for (size_t i = old; i < net->pipe_events.size(); ++i)
+      OCTSEG_CUDA(cudaEventCreateWithFlags(&net->pipe_events[i], cudaEventDisableTiming));
+  }
+  const size_t img_per = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)h * w * net->cfg.input_channels;
+  const size_t pr_per = (size_t)h * w * net->cfg.num_classes * sizeof(float), lb_per = (size_t)h * w;
+  // the pipeline streams must not start before earlier work on the handle's stream is done
+  OCTSEG_CUDA(cudaEventRecord(net->pipe_events[0], net->stream));
+  OCTSEG_CUDA(cudaStreamWaitEvent(net->copy_in, net->pipe_events[0], 0));
+  OCTSEG_CUDA(cudaStreamWaitEvent(net->copy_out, net->pipe_events[0], 0));
+  for (int c = 0; c < n_chunks; ++c) {
+    const int i0 = c * chunk, cur = std::min(chunk, n - i0);
+    cudaEvent_t ev_in = net->pipe_events[3 * c], ev_fw = net->pipe_events[3 * c + 1];
+    uint8_t *dimg = reinterpret_cast<uint8_t *>(net->d_img) + (size_t)i0 * img_per;
+    OCTSEG_CUDA(cudaMemcpyAsync(dimg, reinterpret_cast<const uint8_t *>(images) + (size_t)i0 * img_per,
+                                (size_t)cur * img_per, cudaMemcpyHostToDevice, net->copy_in));
+    OCTSEG_CUDA(cudaEventRecord(ev_in, net->copy_in));
+    OCTSEG_CUDA(cudaStreamWaitEvent(net->stream, ev_in, 0));
+    float *dpr = probs ? net->d_probs + (size_t)i0 * h * w * net->cfg.num_classes : nullptr;
+    uint8_t *dlb = labels ? net->d_labels + (size_t)i0 * lb_per : nullptr;
+    if (forward(net, dimg, dtype, cur, h, w, dpr, dlb, net->stream)) return 1;
+    OCTSEG_CUDA(cudaEventRecord(ev_fw, net->stream));
+    OCTSEG_CUDA(cudaStreamWaitEvent(net->copy_out, ev_fw, 0));
+    if (probs)
+      OCTSEG_CUDA(cudaMemcpyAsync(probs + (size_t)i0 * h * w * net->cfg.num_classes, dpr, (size_t)cur * pr_per,
+                                  cudaMemcpyDeviceToHost, net->copy_out));
+    if (labels)
+      OCTSEG_CUDA(cudaMemcpyAsync(labels + (size_t)i0 * lb_per, dlb, (size_t)cur * lb_per, cudaMemcpyDeviceToHost,
+                                  net->copy_out));
+  }
+  OCTSEG_CUDA(cudaEventRecord(net->pipe_events[2], net->copy_out));
+  OCTSEG_CUDA(cudaStreamWaitEvent(net->stream, net->pipe_events[2], 0));
   return check_status(net);
 }
 

@@ -85,6 +85,8 @@ struct octseg_net {
   bool disable_tc = false;
   bool disable_fusion = false;
   int microbatch = 0;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host-API pipeline: H2D / D2H beside the compute stream
+  std::vector<cudaEvent_t> pipe_events;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;   // blocks+1 events
   bool prof_valid = false;
