@@ -23,7 +23,8 @@ class _Output:
 class B200Model:
     """`model = UNet(**config).build_model()`; weights live on the GPU."""
 
-    def __init__(self, name: str, spec_kwargs: dict, precision: Optional[str] = None, device: int = 0):
+    def __init__(self, name: str, spec_kwargs: dict, precision: Optional[str] = None, device: int = 0,
+                 init_seed: Optional[int] = None):
         import os
         self.name = name
         self.spec_kwargs = dict(spec_kwargs)
@@ -32,6 +33,11 @@ class B200Model:
         self.output = _Output(spec_kwargs["num_classes"])
         self.input_channels = spec_kwargs["input_channels"]
         self._compiled = None
+        # Keras initialises a freshly built model: glorot_uniform kernels, zero biases,
+        # BatchNormalization (gamma, beta, moving_mean, moving_variance) = (1, 0, 0, 1)
+        from ..common.synthetic import synthetic_weights
+        seed = int(np.random.SeedSequence().entropy % (2 ** 31)) if init_seed is None else init_seed
+        self.engine.set_weights(synthetic_weights(seed=seed, random_bn_stats=False, **spec_kwargs))
 
     # ---- Keras-compatible inference --------------------------------------------
     def predict(self, x, verbose=0, batch_size=None, **_):
