@@ -368,6 +368,100 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const int col_base = n_tile * p.n_cols;
       const int my_nch = min(nch, (p.cols_valid - col_base) >> 3);
+      if (my_nch == 1 && p.mode != 1) {
+        // ---- 8-channel layers (the full-resolution layers that carry most of the bytes): one
+        //      chunk per M-tile, so batch the TMEM loads of up to kEpiBatch M-tiles behind ONE
+        //      tcgen05.wait::ld and process them back to back (hides the TMEM/LDS/shuffle latency
+        //      that otherwise serialises per M-tile)
+        constexpr int kEpiBatch = 3;
+        constexpr int kWG = kTcEpiWarps / 4;
+        const float4 sa = *reinterpret_cast<const float4 *>(s_scale + col_base), sb = *reinterpret_cast<const float4 *>(s_scale + col_base + 4);
+        const float4 ha = *reinterpret_cast<const float4 *>(s_shift + col_base), hb = *reinterpret_cast<const float4 *>(s_shift + col_base + 4);
+        const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+        const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+        for (int t0 = wg; t0 < mt; t0 += kEpiBatch * kWG) {
+          uint32_t v[kEpiBatch][8];
+#pragma unroll
+          for (int bb = 0; bb < kEpiBatch; ++bb) {
+            const int t = t0 + bb * kWG;
+            if (t < mt)
+              tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * p.n_cols), v[bb]);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int bb = 0; bb < kEpiBatch; ++bb) {
+            const int t = t0 + bb * kWG;
+            if (t >= mt) break;
+            const int iy = t >> p.mt_x_log2, ix = t & (p.mt_x - 1);
+            const int y = (ty * p.mt_y + iy) * kTcTileH + r, x = (tx * p.mt_x + ix) * kTcTileW + px;
+            const bool inside = (y < p.h) && (x < p.w);
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fmaxf(fmaf(__uint_as_float(v[bb][k]), sc[k], sh[k]), relu_floor);
+            if constexpr (HK > 0) {
+              float z[HK];
+#pragma unroll
+              for (int k = 0; k < HK; ++k) z[k] = s_head[p.cout * HK + k];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float *wr = s_head + (col_base + c) * HK;
+#pragma unroll
+                for (int k = 0; k < HK; ++k) z[k] = fmaf(o[c], wr[k], z[k]);
+              }
+              if (inside) {
+                float mx = z[0];
+#pragma unroll
+                for (int k = 1; k < HK; ++k) mx = fmaxf(mx, z[k]);
+                float ssum = 0.f;
+#pragma unroll
+                for (int k = 0; k < HK; ++k) { z[k] = __expf(z[k] - mx); ssum += z[k]; }
+                const float inv = __frcp_rn(ssum);
+                const long long pix = ((long long)img * p.h + y) * p.w + x;
+                float pm = -1.f;
+                int pa = 0;
+#pragma unroll
+                for (int k = 0; k < HK; ++k) {
+                  z[k] *= inv;
+                  if (z[k] > pm) { pm = z[k]; pa = k; }
+                }
+                if (p.probs) {
+                  float *dst = p.probs + pix * HK;
+                  if constexpr (HK == 4) *reinterpret_cast<float4 *>(dst) = make_float4(z[0], z[1], z[2], z[3]);
+                  else {
+#pragma unroll
+                    for (int k = 0; k < HK; ++k) dst[k] = z[k];
+                  }
+                }
+                if (p.labels) p.labels[pix] = (uint8_t)pa;
+              }
+            } else {
+              uint4 pk;
+              __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+              if (inside)
+                *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)(col_base >> 3) * plane_elems +
+                                           ((long long)y * p.out_w + x) * 8) = pk;
+              if (p.pool_out) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  uint32_t w0 = reinterpret_cast<uint32_t *>(&pk)[k];
+                  uint32_t w1 = __shfl_xor_sync(0xffffffffu, w0, 1);
+                  __nv_bfloat162 a = __hmax2(*reinterpret_cast<__nv_bfloat162 *>(&w0), *reinterpret_cast<__nv_bfloat162 *>(&w1));
+                  w0 = *reinterpret_cast<uint32_t *>(&a);
+                  w1 = __shfl_xor_sync(0xffffffffu, w0, 8);
+                  a = __hmax2(a, *reinterpret_cast<__nv_bfloat162 *>(&w1));
+                  h2[k] = a;
+                }
+                if (inside && !(px & 1) && !(r & 1))
+                  *reinterpret_cast<uint4 *>(p.pool_out + (long long)img * p.pool_img_stride +
+                                             (long long)(col_base >> 3) * (plane_elems >> 2) +
+                                             ((long long)(y >> 1) * (p.out_w >> 1) + (x >> 1)) * 8) = pk;
+              }
+            }
+          }
+        }
+      } else
       for (int t = wg; t < mt; t += kTcEpiWarps / 4) {
         const int iy = t >> p.mt_x_log2, ix = t & (p.mt_x - 1);
         const int y = (ty * p.mt_y + iy) * kTcTileH + r, x = (tx * p.mt_x + ix) * kTcTileW + px;
