@@ -216,6 +216,59 @@ def bench_train(args, eng_cfg, rank, local_rank, world, torch, dist, stream):
     return out
 
 
+def bench_wide(args, rank, local_rank, world, torch, dist, stream):
+    """BASELINE configs[3]: wide U-Net (start_neurons 64, 64..1024 channels) inference on 1024x512x1
+    B-scans, micro-batch 8 per GPU, B-scans sharded across ranks -- the tensor-core-bound case."""
+    from oct_image_segmentation_models_b200 import _native as nat
+    from oct_image_segmentation_models_b200.common.synthetic import fast_random_batch, synthetic_weights
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    from oct_image_segmentation_models_b200.models.unet_spec import unet_blocks
+    cfg = dict(input_channels=1, num_classes=K_CLASSES, start_neurons=64)
+    n, h, w = 8, 1024, 512
+    eng = UNetEngine(precision="bf16", device=local_rank, **cfg)
+    eng.set_weights(synthetic_weights(seed=4, **cfg))
+    x = torch.from_numpy(fast_random_batch(9 + rank, n, h, w)).cuda()
+    out = torch.empty((n, h, w, K_CLASSES), dtype=torch.float32, device="cuda")
+    for _ in range(3):
+        eng.predict_device(x.data_ptr(), nat.U8, n, h, w, out.data_ptr(), None, stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.predict_device(x.data_ptr(), nat.U8, n, h, w, out.data_ptr(), None, stream)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    eng.set_profiling(True)
+    eng.predict_device(x.data_ptr(), nat.U8, n, h, w, out.data_ptr(), None, stream)
+    torch.cuda.synchronize()
+    bt = eng.block_times_ms()
+    eng.set_profiling(False)
+    blocks = unet_blocks(**cfg)
+    flops = [2.0 * n * (h >> b.level) * (w >> b.level) * b.cin * b.cout * b.kh * b.kw for b in blocks]
+    c3 = [i for i, b in enumerate(blocks) if b.kh == 3 and b.cin >= 64]
+    tf_c3 = sum(flops[i] for i in c3) / (sum(bt[i] for i in c3) / 1e3) / 1e12
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    res = {"metric": "wide_unet_predict_bscans_per_sec", "value": world * n / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+           "config": {"workload": "BASELINE configs[3]: wide U-Net (base 64 filters, 5 levels) predict, 1024x512x1, "
+                                  "micro-batch 8 per GPU", "scaling": "weak"},
+           "tflops_whole_net": sum(flops) / (ms / 1e3) / 1e12,
+           "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (Conv3x3 layers with Cin >= 64)", "achieved": tf_c3,
+                        "peak": peak, "unit": "TFLOP/s", "frac": tf_c3 / peak,
+                        "peak_source": "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)" if peaks else "fallback"}}
+    eng.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,6 +279,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-wide", action="store_true")
     ap.add_argument("--train-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -350,6 +404,14 @@ def main():
         except Exception as ex:  # noqa: BLE001  -- the predict line must still be printed
             train = {"error": str(ex)[:300]}
 
+    # ---------------- wide U-Net (BASELINE configs[3]): tensor-core-bound layers ----------------
+    wide = None
+    if not args.no_wide:
+        try:
+            wide = bench_wide(args, rank, local_rank, world, torch, dist, stream)
+        except Exception as ex:  # noqa: BLE001
+            wide = {"error": str(ex)[:300]}
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -369,7 +431,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_np.nbytes),
                         "d2h_bytes_per_step": int(p_np.nbytes), "steps": e2e_steps, "checksum": checksum},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "roofline_step": roofline_step, "cpu_baseline": cpu, "train": train,
+                "roofline_step": roofline_step, "cpu_baseline": cpu, "train": train, "wide_net": wide,
                 "block_ms": [round(float(x), 4) for x in per_block]}
         print(json.dumps(line))
     eng.close()

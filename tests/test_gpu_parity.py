@@ -165,3 +165,20 @@ def test_full_size_properties_cfg2(engines):
     assert np.array_equal(l32, p32.argmax(-1)) and np.array_equal(l16, p16.argmax(-1))
     assert rel_err(p16, p32).max() <= BF16_REL
     assert e16.launch_count() > 0
+
+
+def test_wide_net_parity_bf16():
+    """BASELINE configs[3] network (start_neurons 64: 64..1024 channels; exercises input-channel
+    chunking, streamed weights and N-tiling of the tensor-core kernel) at a CPU-checkable size."""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    cfg = dict(input_channels=1, num_classes=4, start_neurons=64)
+    w = synthetic_weights(seed=4, **cfg)
+    imgs, _ = synthetic_batch(0, 2, 64, 32)
+    ref = OracleUNet(w, **cfg).predict(imgs)
+    eng = UNetEngine(precision="bf16", **cfg)
+    eng.set_weights(w)
+    p, l = eng.predict(imgs, want_labels=True)
+    assert all(eng.layer_uses_tensor_core(i, 1024, 512) for i in range(1, 22))
+    eng.close()
+    assert rel_err(p, ref).max() <= BF16_REL
+    assert (l == ref.argmax(-1)).mean() >= 0.999
