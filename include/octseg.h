@@ -121,6 +121,16 @@ int32_t octseg_train_step_device(octseg_net *net, const void *images, int32_t dt
 /* flat float32 gradient of the last step, Keras trainable-weight order (tests) */
 int32_t octseg_get_grad(octseg_net *net, int32_t index, float *host, int64_t count);
 
+/* ---- boundary extraction (host code) ------------------------------ *
+ * Replaces graph_search.segment_maps (reference min_path_processing/graph_search.py:519-572 and
+ * the Dijkstra at :5-105, graph at :108-225) with identical tie-breaking.
+ *   maps_t  : [n_maps][width][height] uint8 boundary maps, transposed as the reference callers do
+ *             (prediction/prediction.py:134-135)
+ *   rows_out: [n_maps][width] uint16 boundary row per column
+ *   n_threads: maps are independent; <=1 = serial */
+int32_t octseg_min_path_segment(const uint8_t *maps_t, int32_t n_maps, int32_t width, int32_t height,
+                                uint16_t *rows_out, int32_t n_threads);
+
 /* ---- introspection for bench / tests -------------------------------------------- */
 /* number of kernels this library launched on the handle since creation */
 int64_t octseg_launch_count(octseg_net *net);

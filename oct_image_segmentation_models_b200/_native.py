@@ -54,6 +54,7 @@ _PROTOS = {
     "octseg_train_step_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                              C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "octseg_get_grad": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+    "octseg_min_path_segment": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "octseg_launch_count": (C.c_int64, [C.c_void_p]),
     "octseg_set_profiling": (C.c_int32, [C.c_void_p, C.c_int32]),
     "octseg_get_block_times": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]),

@@ -60,3 +60,22 @@ def test_minpath_matches_live_reference():
         gw, gh = shape[1] + 2, shape[2]
         for node in range(gw * gh):
             assert min_path.neighbours(node, gw, gh) == G[node]
+
+
+def test_native_min_path_matches_reference_golden_and_oracle():
+    """csrc/min_path.cpp (host code inside liboctseg.so, runs without a GPU) reproduces the
+    reference's boundaries bit for bit, including noise / exact-tie maps."""
+    from oct_image_segmentation_models_b200.min_path_processing import graph_search
+    g = np.load(GOLD / "minpath_golden.npz")
+    for nm in sorted(k[:-7] for k in g.files if k.endswith("_maps_t")):
+        maps = g[nm + "_maps_t"]
+        G = graph_search.create_graph_structure((maps.shape[1], maps.shape[2], 1))
+        pred, err, pm = graph_search.segment_maps(maps, None, G)
+        assert pred.dtype == np.uint16 and np.array_equal(pred, g[nm + "_pred"]), nm
+        assert pm.dtype == np.float64
+    rng = np.random.default_rng(12)
+    for shape in ((3, 37, 29), (2, 64, 48), (1, 8, 1), (1, 1, 5)):
+        maps = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        maps[rng.random(shape) < 0.3] = 255        # many exact ties
+        got = graph_search.segment_maps(maps, None, None, n_threads=2)[0]
+        assert np.array_equal(got, min_path.segment_maps(maps)), shape
