@@ -84,6 +84,13 @@ int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, 
                             int32_t w, float *probs, uint8_t *labels);
 int32_t octseg_predict_device(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
                               int32_t w, float *probs, uint8_t *labels, void *stream);
+/* predict + argmax + boundary probability maps on the device: replaces
+ * perform_argmax(bin=True) + convert_predictions_to_maps_semantic (reference common/utils.py:80-168),
+ * which depend on the label map only.  maps: uint8 [n, K-1, h, w], or [n, K-1, w, h] when
+ * `transposed` (the layout graph_search.segment_maps wants); labels may be NULL. */
+int32_t octseg_predict_maps_host(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
+                                 int32_t w, int32_t bg_ilm, int32_t bg_csi, int32_t transposed, uint8_t *labels,
+                                 uint8_t *maps);
 /* wait for all work queued on the handle's stream */
 int32_t octseg_synchronize(octseg_net *net);
 

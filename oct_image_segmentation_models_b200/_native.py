@@ -45,6 +45,8 @@ _PROTOS = {
                                         C.c_void_p, C.c_void_p]),
     "octseg_predict_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+    "octseg_predict_maps_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "octseg_synchronize": (C.c_int32, [C.c_void_p]),
     "octseg_train_begin": (C.c_int32, [C.c_void_p, C.POINTER(OctsegTrainConfig), C.c_void_p]),
     "octseg_comm_unique_id": (C.c_int32, [C.c_void_p]),

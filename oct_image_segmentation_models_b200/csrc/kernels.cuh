@@ -40,6 +40,10 @@ template <typename T>
 int launch_head(View<const T> in, const float *wgt /*[cin][K]*/, const float *bias, int cin, int K,
                 float *probs, uint8_t *labels, cudaStream_t st);
 
+// u8 labels [n,h,w] -> u8 boundary maps [n,K-1,h,w] (or [n,K-1,w,h] when transposed), reference semantics
+int launch_boundary_maps(const uint8_t *labels, int n, int h, int w, int K, int bg_ilm, int bg_csi, int transposed,
+                         uint8_t *maps, cudaStream_t st);
+
 // BN folding for inference: scale = gamma*rsqrt(var+eps), shift = (bias-mean)*scale+beta
 int launch_bn_fold(const float *bias, const float *gamma, const float *beta, const float *mean,
                    const float *var, float eps, int c, float *scale, float *shift, cudaStream_t st);

@@ -417,6 +417,60 @@ int launch_head(View<const T> in, const float *wgt, const float *bias, int cin, 
 }
 
 // ---------------------------------------------------------------------------------
+// labels -> boundary probability maps.  Integer restatement of
+// perform_argmax(bin=True) + convert_predictions_to_maps_semantic (reference common/utils.py:73-168):
+// with c = one-hot plane (region above for the ILM/CSI flags, else region k), along rows:
+//   g = +-np.gradient(c)  -> clamp<0 -> *2      == s[i] in {0,1,2}: interior max(+-(c[i+1]-c[i-1]),0),
+//                                                  edges 2*max(+-(one-sided diff),0)
+//   g -= np.roll(g,-1) (wraps) -> clamp<0 -> *255 -> uint8   == (max(s[i]-s[(i+1)%H],0)*255) & 0xFF
+// (510 wraps to 254 exactly as the float->uint8 cast does in the reference.)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ int bm_s(const uint8_t *col, int stride, int i, int H, int cls, int sign) {
+  // c[j] = (label[j] == cls)
+  auto c = [&](int j) { return (int)(col[(long long)j * stride] == cls); };
+  int d;
+  if (H == 1) return 0;
+  if (i == 0) d = 2 * (c(1) - c(0));
+  else if (i == H - 1) d = 2 * (c(H - 1) - c(H - 2));
+  else d = c(i + 1) - c(i - 1);
+  d *= sign;
+  return d > 0 ? d : 0;
+}
+
+__global__ void __launch_bounds__(256) boundary_maps_kernel(const uint8_t *__restrict__ labels, int n, int H, int W,
+                                                            int K, int bg_ilm, int bg_csi, int transposed,
+                                                            uint8_t *__restrict__ maps) {
+  const long long total = (long long)n * (K - 1) * H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    // idx enumerates OUTPUT elements so that stores are coalesced
+    int i, x;
+    long long t = idx;
+    if (transposed) { i = (int)(t % H); t /= H; x = (int)(t % W); t /= W; }
+    else { x = (int)(t % W); t /= W; i = (int)(t % H); t /= H; }
+    const int m = (int)(t % (K - 1)) + 1;
+    const int b = (int)(t / (K - 1));
+    const bool above = (m == 1 && bg_ilm) || (m == K - 1 && bg_csi);
+    const int cls = above ? m - 1 : m, sign = above ? -1 : 1;
+    const uint8_t *col = labels + (long long)b * H * W + x;
+    const int s0 = bm_s(col, W, i, H, cls, sign);
+    const int s1 = bm_s(col, W, (i + 1) % H, H, cls, sign);
+    const int v = s0 - s1;
+    maps[idx] = (uint8_t)(((v > 0 ? v : 0) * 255) & 0xFF);
+  }
+}
+
+int launch_boundary_maps(const uint8_t *labels, int n, int h, int w, int K, int bg_ilm, int bg_csi, int transposed,
+                         uint8_t *maps, cudaStream_t st) {
+  const long long total = (long long)n * (K - 1) * h * w;
+  if (total <= 0) return 0;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  boundary_maps_kernel<<<grid, 256, 0, st>>>(labels, n, h, w, K, bg_ilm, bg_csi, transposed, maps);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
 __global__ void bn_fold_kernel(const float *bias, const float *gamma, const float *beta,
                                const float *mean, const float *var, float eps, int c, float *scale,
                                float *shift) {

@@ -454,7 +454,7 @@ int32_t octseg_destroy(octseg_net *net) {
   if (net->copy_out) cudaStreamDestroy(net->copy_out);
   for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); }
   cudaFree(net->d_params); cudaFree(net->ws); cudaFree(net->d_img); cudaFree(net->d_probs);
-  cudaFree(net->d_labels); cudaFree(net->d_status);
+  cudaFree(net->d_labels); cudaFree(net->d_maps); cudaFree(net->d_status);
   if (net->h_status) cudaFreeHost(net->h_status);
   if (net->stream) cudaStreamDestroy(net->stream);
   delete net;
@@ -561,6 +561,26 @@ int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, 
   }
   OCTSEG_CUDA(cudaEventRecord(net->pipe_events[2], net->copy_out));
   OCTSEG_CUDA(cudaStreamWaitEvent(net->stream, net->pipe_events[2], 0));
+  return check_status(net);
+}
+
+int32_t octseg_predict_maps_host(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
+                                 int32_t w, int32_t bg_ilm, int32_t bg_csi, int32_t transposed, uint8_t *labels,
+                                 uint8_t *maps) {
+  if (!net || !images || !maps) { set_error("null argument"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  const int K = net->cfg.num_classes;
+  const size_t img_bytes = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)n * h * w * net->cfg.input_channels;
+  const size_t lb_bytes = (size_t)n * h * w, mp_bytes = lb_bytes * (K - 1);
+  if (grow(&net->d_img, &net->d_img_bytes, img_bytes)) return 1;
+  if (grow(reinterpret_cast<void **>(&net->d_labels), &net->d_labels_bytes, lb_bytes)) return 1;
+  if (grow(reinterpret_cast<void **>(&net->d_maps), &net->d_maps_bytes, mp_bytes)) return 1;
+  OCTSEG_CUDA(cudaMemcpyAsync(net->d_img, images, img_bytes, cudaMemcpyHostToDevice, net->stream));
+  if (octseg_predict_device(net, net->d_img, dtype, n, h, w, nullptr, net->d_labels, net->stream)) return 1;
+  if (launch_boundary_maps(net->d_labels, n, h, w, K, bg_ilm, bg_csi, transposed, net->d_maps, net->stream)) return 1;
+  ++net->launches;
+  if (labels) OCTSEG_CUDA(cudaMemcpyAsync(labels, net->d_labels, lb_bytes, cudaMemcpyDeviceToHost, net->stream));
+  OCTSEG_CUDA(cudaMemcpyAsync(maps, net->d_maps, mp_bytes, cudaMemcpyDeviceToHost, net->stream));
   return check_status(net);
 }
 

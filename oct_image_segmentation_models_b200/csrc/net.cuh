@@ -79,6 +79,7 @@ struct octseg_net {
   void *d_img = nullptr; size_t d_img_bytes = 0;
   float *d_probs = nullptr; size_t d_probs_bytes = 0;
   uint8_t *d_labels = nullptr; size_t d_labels_bytes = 0;
+  uint8_t *d_maps = nullptr; size_t d_maps_bytes = 0;
   int *d_status = nullptr;
   int *h_status = nullptr;            // pinned
   int64_t launches = 0;

@@ -182,3 +182,24 @@ def test_wide_net_parity_bf16():
     eng.close()
     assert rel_err(p, ref).max() <= BF16_REL
     assert (l == ref.argmax(-1)).mean() >= 0.999
+
+
+def test_device_boundary_maps_match_reference_semantics(engines):
+    """f-3: argmax + boundary maps on the GPU == the reference's numpy chain on the same labels
+    (incl. the edge quirks: rows 0/1, the 254 wrap row), and min-path on both gives equal boundaries."""
+    from oct_image_segmentation_models_b200.min_path_processing import graph_search
+    _, e32, _ = engines
+    imgs, _ = synthetic_batch(50, 3, 64, 48)
+    labels, maps = e32.predict_maps(imgs)
+    labels_t, maps_t = e32.predict_maps(imgs, transposed=True)
+    probs, lab2 = e32.predict(imgs, want_labels=True)
+    assert np.array_equal(labels, lab2) and np.array_equal(labels_t, lab2)
+    _, cat = postproc.perform_argmax(probs)
+    ref = postproc.convert_predictions_to_maps_semantic(cat, bg_ilm=True, bg_csi=False)
+    assert np.array_equal(maps, ref)
+    assert np.array_equal(maps_t, np.transpose(ref, (0, 1, 3, 2)))
+    _, maps_csi = e32.predict_maps(imgs, bg_ilm=False, bg_csi=True)
+    assert np.array_equal(maps_csi, postproc.convert_predictions_to_maps_semantic(cat, bg_ilm=False, bg_csi=True))
+    seg = graph_search.segment_maps(maps_t.reshape(-1, 48, 64), None, None)[0].reshape(3, 3, 48)
+    for i in range(3):
+        assert np.array_equal(seg[i], postproc.boundaries_from_probs(probs[i:i + 1]))
