@@ -33,10 +33,8 @@ def load_model_and_config(model_path: Union[Path, PurePosixPath], **kwargs) -> T
         exit(1)
     with open(Path(model_path).parent / Path("model_config.json"), "r") as config_file:
         model_config = json.load(config_file)
-    with np.load(Path(model_path)) as z:
-        name = bytes(z["__model_name__"]).decode() if "__model_name__" in z.files else "unet"
-        n = len([k for k in z.files if k.startswith("w")])
-        weights = [z[f"w{i:03d}"] for i in range(n)]
+    from ..models.keras_like import read_weight_file
+    name, weights = read_weight_file(Path(model_path))
     model_class = get_model_class(name)
     loaded_model = model_class(**model_config).build_model(precision=kwargs.pop("precision", None),
                                                            device=kwargs.pop("device", 0))

@@ -36,6 +36,9 @@ class B200Model:
         # Keras initialises a freshly built model: glorot_uniform kernels, zero biases,
         # BatchNormalization (gamma, beta, moving_mean, moving_variance) = (1, 0, 0, 1)
         from ..common.synthetic import synthetic_weights
+        import os as _os
+        if init_seed is None and _os.environ.get("OCTSEG_INIT_SEED"):
+            init_seed = int(_os.environ["OCTSEG_INIT_SEED"])
         seed = int(np.random.SeedSequence().entropy % (2 ** 31)) if init_seed is None else init_seed
         self.engine.set_weights(synthetic_weights(seed=seed, random_bn_stats=False, **spec_kwargs))
 
@@ -72,20 +75,63 @@ class B200Model:
         print_fn(f"Total params: {self.count_params():,}")
 
     # ---- persistence ---------------------------------------------------------------
+    def _layer_weights(self):
+        """[(layer_name, [(weight_name, array)])] in Keras model.layers order (weighted layers only)."""
+        out, cur = [], None
+        for (name, _), w in zip(self.engine.param_specs, self.get_weights()):
+            layer, wname = name.split("/", 1)
+            if cur is None or cur[0] != layer:
+                cur = (layer, [])
+                out.append(cur)
+            cur[1].append((wname, w))
+        return out
+
     def save(self, path, **_):
-        """Weights container next to `model_config.json`.  (.npz payload; a Keras-compatible
-        HDF5 writer is the f-1 'next' row of SURVEY section 8.)"""
+        """`.hdf5` / `.h5`: Keras-2.x weight layout (root attrs + model_weights/<layer>/<layer>/<w>:0,
+        layer_names / weight_names attributes) written by the built-in minimal HDF5 writer, which is what
+        ModelCheckpoint produces in the reference (training/training.py:319-326).  Other suffixes: .npz."""
         path = Path(path)
+        if path.suffix.lower() in (".hdf5", ".h5"):
+            from ..common import hdf5_min
+            cfg = json.dumps({"class_name": "Functional", "config": {"name": self.name},
+                              "octseg_b200": {k: (list(v) if isinstance(v, tuple) else v)
+                                              for k, v in self.spec_kwargs.items()}})
+            hdf5_min.save_keras_weights(path, self._layer_weights(), model_config=cfg)
+            return
         arrays = {f"w{i:03d}": w for i, w in enumerate(self.get_weights())}
-        names = json.dumps([n for n, _ in self.engine.param_specs])
         with open(path, "wb") as f:
-            np.savez(f, __names__=np.frombuffer(names.encode(), dtype=np.uint8),
-                     __model_name__=np.frombuffer(self.name.encode(), dtype=np.uint8), **arrays)
+            np.savez(f, __model_name__=np.frombuffer(self.name.encode(), dtype=np.uint8), **arrays)
 
     def load_weights(self, path):
-        with np.load(Path(path)) as z:
-            n = len([k for k in z.files if k.startswith("w")])
-            self.set_weights([z[f"w{i:03d}"] for i in range(n)])
+        self.set_weights(read_weight_file(path)[1])
 
     def close(self):
         self.engine.close()
+
+
+def read_weight_file(path):
+    """(model_name, [weights in Keras get_weights() order]) from a Keras-style HDF5 or an .npz container.
+    HDF5 layers are mapped by ORDER and TYPE, never by exact name (Keras auto-names depend on a
+    process-global counter)."""
+    path = Path(path)
+    with open(path, "rb") as fh:
+        magic = fh.read(8)
+    if magic.startswith(b"\x89HDF"):
+        from ..common import hdf5_min
+        layers, cfg = hdf5_min.load_keras_weights(path)
+        name = "unet"
+        if cfg:
+            try:
+                name = json.loads(cfg)["config"]["name"]
+            except (ValueError, KeyError, TypeError):
+                pass
+        order = {"kernel": 0, "bias": 1, "gamma": 0, "beta": 1, "moving_mean": 2, "moving_variance": 3}
+        weights = []
+        for _, ws in layers:
+            ws = sorted(ws, key=lambda kv: order.get(kv[0].split("/")[-1].split(":")[0], 99))
+            weights += [np.asarray(a, np.float32) for _, a in ws]
+        return name, weights
+    with np.load(path) as z:
+        name = bytes(z["__model_name__"]).decode() if "__model_name__" in z.files else "unet"
+        n = len([k for k in z.files if k.startswith("w")])
+        return name, [z[f"w{i:03d}"] for i in range(n)]

@@ -21,10 +21,13 @@ from .training_parameters import TrainingParams
 
 
 def _load_dataset(path: Path):
-    """train_images / train_labels / val_images / val_labels, the reference's HDF5 dataset keys
-    (common/dataset_loader.py:9-22), stored as .npz (no h5py offline)."""
-    with np.load(path) as z:
-        return z["train_images"], z["train_labels"], z["val_images"], z["val_labels"]
+    """train_images / train_labels / val_images / val_labels: the reference's HDF5 dataset keys
+    (common/dataset_loader.py:9-22), read with the built-in minimal HDF5 reader (or from an .npz)."""
+    from ..common import dataset_loader as dl
+    ds = dl.open_dataset(path)
+    tr_i, tr_l = dl.load_training_data(ds)
+    va_i, va_l = dl.load_validation_data(ds)
+    return tr_i, tr_l, va_i, va_l
 
 
 def _class_weights(training_params: TrainingParams, train_labels, num_classes):
