@@ -43,7 +43,9 @@ typedef struct octseg_config {
   int32_t dec_kh, dec_kw;  /* default 2,2 */
 } octseg_config;
 
-enum { OCTSEG_FP32 = 0, OCTSEG_BF16 = 1 };          /* precision modes            */
+/* precision modes: fp32 (CUDA cores, 1e-4 gate), bf16 (tcgen05, train + predict), fp16 (tcgen05, predict
+ * only: same speed as bf16, 8x finer mantissa -> argmax / boundary fidelity on confident trained nets) */
+enum { OCTSEG_FP32 = 0, OCTSEG_BF16 = 1, OCTSEG_FP16 = 2 };
 /* image dtypes: raw uint8, raw float32 (0..255, x/255 applied on the device), or float32 that the
  * caller already preprocessed with the reference's x/255.0 (models/unet.py:87-91) */
 enum { OCTSEG_U8 = 0, OCTSEG_F32 = 1, OCTSEG_F32_PRE = 2 };

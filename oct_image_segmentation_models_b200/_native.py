@@ -26,7 +26,7 @@ class OctsegTrainConfig(C.Structure):
                 ("global_batch", C.c_int32)]
 
 
-FP32, BF16 = 0, 1
+FP32, BF16, FP16 = 0, 1, 2
 U8, F32, F32_PRE = 0, 1, 2
 
 # name -> (restype, argtypes); mirrors include/octseg.h one to one

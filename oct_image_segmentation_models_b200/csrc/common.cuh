@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string>
 
@@ -50,6 +51,24 @@ __device__ __forceinline__ Vec8f load8(const __nv_bfloat16 *p) {
     r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y;
   }
   return r;
+}
+__device__ __forceinline__ Vec8f load8(const __half *p) {
+  Vec8f r;
+  uint4 u = *reinterpret_cast<const uint4 *>(p);
+  const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void store8(__half *p, const Vec8f &r) {
+  uint4 u;
+  __half2 *h = reinterpret_cast<__half2 *>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(r.v[2 * i], r.v[2 * i + 1]);
+  *reinterpret_cast<uint4 *>(p) = u;
 }
 __device__ __forceinline__ void store8(float *p, const Vec8f &r) {
   *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);

@@ -32,6 +32,8 @@
 #include <cmath>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 namespace octseg {
 
 // ----------------------------------------------------------------------------------
@@ -129,6 +131,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 16-bit storage helpers (bf16 or fp16 selected per launch; warp-uniform branch)
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
+  if (fp16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t *>(&h); }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int fp16) {
+  if (fp16) { __half2 r = __hmax2(*reinterpret_cast<__half2 *>(&a), *reinterpret_cast<__half2 *>(&b)); return *reinterpret_cast<uint32_t *>(&r); }
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162 *>(&a), *reinterpret_cast<__nv_bfloat162 *>(&b));
+  return *reinterpret_cast<uint32_t *>(&r);
+}
 
 // K-major, no-swizzle shared-memory matrix descriptor (sm_100 "version 1").
 //   core matrix = 8 rows x 16 B, rows 16 B apart; SBO = bytes between 8-row groups,
@@ -270,8 +284,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // the tensor pipe accepts one M128xN16xK16 MMA per ~39 clk, so the M-tiles of a super-tile
       // are dealt round-robin to kTcIssuers threads, each with its own commits.
       const int issuer = warp - 1;
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_cols >> 3) << 17) |
-                             ((128u >> 4) << 24);
+      // instruction descriptor: D = f32, A/B = bf16 (format 1) or fp16 (format 0), K-major, N, M = 128
+      const uint32_t ab_fmt = p.fp16 ? 0u : ((1u << 7) | (1u << 10));
+      const uint32_t idesc = (1u << 4) | ab_fmt | ((uint32_t)(p.n_cols >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t pitch = (uint32_t)p.box_w * 16u;
       const uint32_t lbo_b = (uint32_t)p.n_cols * 16u;
       const uint32_t kstep_b = 32u * (uint32_t)p.n_cols;
@@ -436,9 +451,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             } else {
               uint4 pk;
-              __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&pk);
+              uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+              for (int k = 0; k < 4; ++k) h2[k] = pack2(o[2 * k], o[2 * k + 1], p.fp16);
               if (inside)
                 *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)(col_base >> 3) * plane_elems +
                                            ((long long)y * p.out_w + x) * 8) = pk;
@@ -446,12 +461,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   uint32_t w0 = reinterpret_cast<uint32_t *>(&pk)[k];
-                  uint32_t w1 = __shfl_xor_sync(0xffffffffu, w0, 1);
-                  __nv_bfloat162 a = __hmax2(*reinterpret_cast<__nv_bfloat162 *>(&w0), *reinterpret_cast<__nv_bfloat162 *>(&w1));
-                  w0 = *reinterpret_cast<uint32_t *>(&a);
-                  w1 = __shfl_xor_sync(0xffffffffu, w0, 8);
-                  a = __hmax2(a, *reinterpret_cast<__nv_bfloat162 *>(&w1));
-                  h2[k] = a;
+                  w0 = max2(w0, __shfl_xor_sync(0xffffffffu, w0, 1), p.fp16);
+                  w0 = max2(w0, __shfl_xor_sync(0xffffffffu, w0, 8), p.fp16);
+                  h2[k] = w0;
                 }
                 if (inside && !(px & 1) && !(r & 1))
                   *reinterpret_cast<uint4 *>(p.pool_out + (long long)img * p.pool_img_stride +
@@ -543,11 +555,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               uint4 pk[2];
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
-                __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&pk[u]);
+                uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk[u]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  h2[k] = __floats2bfloat162_rn(fmaxf(fmaf(__uint_as_float(v[u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
-                                                fmaxf(fmaf(__uint_as_float(v[u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor));
+                  h2[k] = pack2(fmaxf(fmaf(__uint_as_float(v[u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
+                                fmaxf(fmaf(__uint_as_float(v[u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor), p.fp16);
               }
               if (inside) {
                 __nv_bfloat16 *dst = p.out + (long long)img * p.out_img_stride + (long long)c8 * plane_elems +
@@ -582,11 +594,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
               const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
               uint4 pk;
-              __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&pk);
+              uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                h2[k] = __floats2bfloat162_rn(fmaxf(fmaf(__uint_as_float(v[u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
-                                              fmaxf(fmaf(__uint_as_float(v[u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor));
+                h2[k] = pack2(fmaxf(fmaf(__uint_as_float(v[u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
+                              fmaxf(fmaf(__uint_as_float(v[u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor), p.fp16);
               if (inside)
                 *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)(co0 >> 3) * plane_elems + off) = pk;
               if (p.pool_out) {
@@ -595,12 +607,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   uint32_t w0 = reinterpret_cast<uint32_t *>(&pk)[k];
-                  uint32_t w1 = __shfl_xor_sync(0xffffffffu, w0, 1);
-                  __nv_bfloat162 a = __hmax2(*reinterpret_cast<__nv_bfloat162 *>(&w0), *reinterpret_cast<__nv_bfloat162 *>(&w1));
-                  w0 = *reinterpret_cast<uint32_t *>(&a);
-                  w1 = __shfl_xor_sync(0xffffffffu, w0, 8);
-                  a = __hmax2(a, *reinterpret_cast<__nv_bfloat162 *>(&w1));
-                  h2[k] = a;
+                  w0 = max2(w0, __shfl_xor_sync(0xffffffffu, w0, 1), p.fp16);
+                  w0 = max2(w0, __shfl_xor_sync(0xffffffffu, w0, 8), p.fp16);
+                  h2[k] = w0;
                 }
                 if (inside && !(px & 1) && !(r & 1))
                   *reinterpret_cast<uint4 *>(p.pool_out + (long long)img * p.pool_img_stride +
@@ -716,6 +725,10 @@ int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, 
   return 0;
 }
 
+static inline uint16_t f2h(float f) {
+  const __half_raw r = static_cast<__half_raw>(__float2half_rn(f));   // host-callable, round to nearest even
+  return r.x;
+}
 static inline uint16_t f2bf(float f) {
   uint32_t u;
   std::memcpy(&u, &f, 4);
@@ -724,7 +737,7 @@ static inline uint16_t f2bf(float f) {
   return (uint16_t)(u >> 16);
 }
 
-void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> *out) {
+void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> *out, int fp16) {
   const int pt = g.pt, pl = g.pl;
   const size_t per_step = (size_t)2 * g.n_cols * 8;
   out->assign((size_t)g.n_tiles_n * g.cin_chunks * g.ksteps * per_step, 0);
@@ -752,7 +765,7 @@ void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> 
                       val += w[(((size_t)a * g.kw + b) * g.cin + ci) * g.cout + co];
               }
               (*out)[(((size_t)(nt * g.cin_chunks + ch) * g.ksteps + s) * 2 + hf) * g.n_cols * 8 +
-                     (size_t)n * 8 + kk] = f2bf(val);
+                     (size_t)n * 8 + kk] = fp16 ? f2h(val) : f2bf(val);
             }
           }
         }
@@ -969,6 +982,7 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
   TcConvParams &p = plan->p;
   if (tc_fill_params(g, n, h, w, &p, &plan->smem_bytes)) return 1;
   p.relu = epi.relu;
+  p.fp16 = epi.fp16;
   p.scale = epi.scale; p.shift = epi.shift;
   p.out = epi.out.ptr; p.out_img_stride = epi.out.img_stride; p.out_h = epi.out.h; p.out_w = epi.out.w;
   p.pool_out = epi.pool_out; p.pool_img_stride = epi.pool_img_stride;

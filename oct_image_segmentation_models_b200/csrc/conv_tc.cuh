@@ -36,6 +36,7 @@ struct TcConvParams {
                                // 2: fused 1x1-conv + softmax head (activation never stored)
   int cout;                    // channels per parity (mode 1) or total (mode 0)
   int relu;
+  int fp16;                    // 16-bit storage type of activations / packed weights: 0 = bf16, 1 = fp16
   const float *scale, *shift;  // [cout]
   __nv_bfloat16 *out;          // plane 0 of image 0 of the destination view
   long long out_img_stride;    // elements
@@ -76,7 +77,7 @@ bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w);
 // pad_top/pad_left < 0: Keras "same" padding ((k-1)/2 before); otherwise explicit (data-gradient convs)
 int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, int pad_top = -1, int pad_left = -1);
 // packs fp32 HWIO weights into the bf16 smem image the kernel streams (host memory)
-void tc_pack_weights(const TcGeometry &g, const float *w_hwio, std::vector<uint16_t> *out);
+void tc_pack_weights(const TcGeometry &g, const float *w_hwio, std::vector<uint16_t> *out, int fp16 = 0);
 // same packing on the device, from fp32 weights in device memory (training)
 int tc_pack_weights_device(const TcGeometry &g, const float *w_dev, int transposed, __nv_bfloat16 *out,
                            cudaStream_t st);
@@ -92,6 +93,7 @@ int tc_pack_all_device(const TcPackJob *jobs_dev, int n_jobs, cudaStream_t st);
 int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *p, size_t *smem_bytes);
 struct TcEpilogue {
   int relu = 1;
+  int fp16 = 0;
   const float *scale = nullptr, *shift = nullptr;
   View<__nv_bfloat16> out{};                 // unused when the head is fused
   __nv_bfloat16 *pool_out = nullptr;         // fused 2x2 max-pool (encoder-final blocks)

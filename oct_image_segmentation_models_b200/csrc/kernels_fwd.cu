@@ -503,5 +503,6 @@ int launch_bn_fold(const float *bias, const float *gamma, const float *beta, con
                               uint8_t *, cudaStream_t);
 INST(float)
 INST(__nv_bfloat16)
+INST(__half)
 
 }  // namespace octseg

@@ -96,7 +96,7 @@ int build_graph(const octseg_config &c, std::vector<BlockSpec> *blocks, std::vec
   return 0;
 }
 
-static size_t elem_size(const octseg_net *net) { return net->precision == OCTSEG_BF16 ? 2 : 4; }
+static size_t elem_size(const octseg_net *net) { return net->precision == OCTSEG_FP32 ? 4 : 2; }
 
 static int check_supported(const octseg_net *net) {
   for (auto &b : net->blocks) {
@@ -131,9 +131,10 @@ int prepare_derived(octseg_net *net) {
                        P + net->params[b.p_var].offset, kBnEps, b.cout, st.scale, st.shift, net->stream))
       return 1;
     ++net->launches;
-    if (net->precision == OCTSEG_BF16 && st.geo_ok) {
+    if (net->precision != OCTSEG_FP32 && st.geo_ok) {
       std::vector<uint16_t> packed;
-      tc_pack_weights(st.geo, net->h_params.data() + net->params[b.p_kernel].offset, &packed);
+      tc_pack_weights(st.geo, net->h_params.data() + net->params[b.p_kernel].offset, &packed,
+                      net->precision == OCTSEG_FP16);
       if (packed.size() != st.wpack_elems) { set_error("internal: wpack size"); return 1; }
       OCTSEG_CUDA(cudaMemcpyAsync(st.wpack, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice,
                                   net->stream));
@@ -224,9 +225,10 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
     else { prev = io.out; prev_planes = f / 8; prev_h = lh; prev_w = lw; }
     // ---- tensor-core plan
     io.use_tc = false;
-    if (net->precision == OCTSEG_BF16 && !net->disable_tc && b.index > 0 && b.role != 4 &&
+    if (net->precision != OCTSEG_FP32 && !net->disable_tc && b.index > 0 && b.role != 4 &&
         net->bstate[b.index].geo_ok && tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, io.in_h, io.in_w)) {
       TcEpilogue epi;
+      epi.fp16 = net->precision == OCTSEG_FP16;
       epi.scale = net->bstate[b.index].scale; epi.shift = net->bstate[b.index].shift;
       epi.out = make_view(reinterpret_cast<__nv_bfloat16 *>(io.out), n, io.out_planes_total, io.out_plane0,
                           io.out_planes, io.out_h, io.out_w);
@@ -318,6 +320,8 @@ int forward(octseg_net *net, const void *d_img, int dtype, int n, int h, int w, 
   if (ensure_workspace(net, n, h, w)) return 1;
   if (net->precision == OCTSEG_BF16)
     return forward_t<__nv_bfloat16>(net, d_img, dtype, n, h, w, d_probs, d_labels, st);
+  if (net->precision == OCTSEG_FP16)
+    return forward_t<__half>(net, d_img, dtype, n, h, w, d_probs, d_labels, st);
   return forward_t<float>(net, d_img, dtype, n, h, w, d_probs, d_labels, st);
 }
 
@@ -347,7 +351,7 @@ static int pick_microbatch(const octseg_net *net, int n, int h, int w) {
   const int P = net->cfg.pool_layers, s = net->cfg.start_neurons;
   double per_img = 0;
   for (int l = 0; l <= P; ++l) per_img += 7.0 * (s << l) * (double)(h >> l) * (w >> l);
-  per_img *= (net->precision == OCTSEG_BF16 ? 2 : 4);
+  per_img *= (net->precision == OCTSEG_FP32 ? 4 : 2);
   int mb = (int)std::max(1.0, std::min((double)n, 32e9 / per_img));
   return mb;
 }
@@ -396,7 +400,7 @@ int32_t octseg_param_info(const octseg_config *cfg, int32_t index, char *name, i
 
 int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precision, octseg_net **out) {
   if (!cfg || !out) { set_error("null argument"); return 1; }
-  if (precision != OCTSEG_FP32 && precision != OCTSEG_BF16) { set_error("bad precision"); return 1; }
+  if (precision != OCTSEG_FP32 && precision != OCTSEG_BF16 && precision != OCTSEG_FP16) { set_error("bad precision"); return 1; }
   int ndev = octseg_device_count();
   if (ndev <= 0) { set_error("no CUDA device: liboctseg has no CPU fallback"); return 1; }
   if (device < 0 || device >= ndev) { set_error("device index out of range"); return 1; }
@@ -431,7 +435,7 @@ int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precisio
       OCTSEG_CUDA(cudaMalloc(&st.scale, b.cout * sizeof(float)));
       OCTSEG_CUDA(cudaMalloc(&st.shift, b.cout * sizeof(float)));
     }
-    if (precision == OCTSEG_BF16 && b.index > 0 && b.role != 4 && b.cin % 8 == 0 &&
+    if (precision != OCTSEG_FP32 && b.index > 0 && b.role != 4 && b.cin % 8 == 0 &&
         tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, kTcTileH, kTcTileW) &&
         tc_make_geometry(b.kh, b.kw, b.cin, b.cout, b.ups ? 1 : 0, &st.geo) == 0) {
       st.geo_ok = true;
@@ -619,7 +623,7 @@ int32_t octseg_get_block_times(octseg_net *net, float *ms, int32_t cap, int32_t 
 int32_t octseg_layer_uses_tensor_core(octseg_net *net, int32_t conv_index, int32_t h, int32_t w) {
   if (!net || conv_index < 0 || conv_index >= (int)net->blocks.size()) return 0;
   const BlockSpec &b = net->blocks[conv_index];
-  if (net->precision != OCTSEG_BF16 || net->disable_tc || b.index == 0 || b.role == 4) return 0;
+  if (net->precision == OCTSEG_FP32 || net->disable_tc || b.index == 0 || b.role == 4) return 0;
   if (!net->bstate[b.index].geo_ok) return 0;
   int lh = h >> b.level, lw = w >> b.level;
   if (b.ups) { lh >>= 1; lw >>= 1; }
@@ -651,11 +655,11 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
   OCTSEG_CUDA(cudaMalloc(&d_out, out_elems * es));
   OCTSEG_CUDA(cudaMemset(d_out, 0xFF, out_elems * es));   // poison: unwritten outputs show up as NaN
   std::vector<uint16_t> h16;
-  if (net->precision == OCTSEG_BF16) {
+  if (net->precision != OCTSEG_FP32) {
     h16.resize(in_elems);
     for (size_t i = 0; i < in_elems; ++i) {
-      __nv_bfloat16 v = __float2bfloat16(blk[i]);
-      std::memcpy(&h16[i], &v, 2);
+      if (net->precision == OCTSEG_BF16) { __nv_bfloat16 v = __float2bfloat16(blk[i]); std::memcpy(&h16[i], &v, 2); }
+      else { __half v = __float2half(blk[i]); std::memcpy(&h16[i], &v, 2); }
     }
     OCTSEG_CUDA(cudaMemcpy(d_in, h16.data(), in_elems * 2, cudaMemcpyHostToDevice));
   } else {
@@ -670,11 +674,12 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
   const int reps = ms_out ? 5 : 1;
   TcPlan plan;
   if (path == 1) {
-    if (net->precision != OCTSEG_BF16 || !bs.geo_ok || !tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, h, w)) {
+    if (net->precision == OCTSEG_FP32 || !bs.geo_ok || !tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, h, w)) {
       set_error("tensor-core path not available for this block/shape");
       rc = 1;
     } else {
       TcEpilogue epi;
+      epi.fp16 = net->precision == OCTSEG_FP16;
       epi.scale = bs.scale; epi.shift = bs.shift;
       epi.out = make_view(reinterpret_cast<__nv_bfloat16 *>(d_out), n, b.cout / 8, 0, b.cout / 8, oh, ow);
       rc = tc_make_plan(bs.geo, reinterpret_cast<const __nv_bfloat16 *>(d_in), n, h, w, bs.wpack, epi,
@@ -695,6 +700,11 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
     if (rep == reps - 1) cudaEventRecord(e0, net->stream);
     if (path == 1) {
       rc = tc_launch(plan, net->stream);
+    } else if (net->precision == OCTSEG_FP16) {
+      View<const __half> iv = make_view(reinterpret_cast<const __half *>(d_in), n, b.cin / 8, 0, b.cin / 8, h, w);
+      View<__half> ov = make_view(reinterpret_cast<__half *>(d_out), n, b.cout / 8, 0, b.cout / 8, oh, ow);
+      rc = launch_conv_direct<__half>(iv, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout,
+                                      b.ups ? 1 : 0, bs.scale, bs.shift, 1, ov, net->stream);
     } else if (net->precision == OCTSEG_BF16) {
       View<const __nv_bfloat16> iv = make_view(reinterpret_cast<const __nv_bfloat16 *>(d_in), n, b.cin / 8, 0, b.cin / 8, h, w);
       View<__nv_bfloat16> ov = make_view(reinterpret_cast<__nv_bfloat16 *>(d_out), n, b.cout / 8, 0, b.cout / 8, oh, ow);
@@ -722,12 +732,12 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
   cudaEventDestroy(e1);
   if (rc == 0) {
     std::vector<float> ob(out_elems);
-    if (net->precision == OCTSEG_BF16) {
+    if (net->precision != OCTSEG_FP32) {
       std::vector<uint16_t> o16(out_elems);
       cudaMemcpy(o16.data(), d_out, out_elems * 2, cudaMemcpyDeviceToHost);
       for (size_t i = 0; i < out_elems; ++i) {
-        uint32_t u = (uint32_t)o16[i] << 16;
-        std::memcpy(&ob[i], &u, 4);
+        if (net->precision == OCTSEG_BF16) { uint32_t u = (uint32_t)o16[i] << 16; std::memcpy(&ob[i], &u, 4); }
+        else { __half hv; std::memcpy(&hv, &o16[i], 2); ob[i] = __half2float(hv); }
       }
     } else {
       cudaMemcpy(ob.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost);

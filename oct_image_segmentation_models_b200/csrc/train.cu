@@ -564,6 +564,7 @@ int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc, const
   if (!net || !tc || !class_weights) { set_error("null argument"); return 1; }
   if (tc->global_batch <= 0) { set_error("global_batch must be positive"); return 1; }
   if (tc->dropout_rate < 0.f || tc->dropout_rate >= 1.f) { set_error("dropout_rate must be in [0,1)"); return 1; }
+  if (net->precision == OCTSEG_FP16) { set_error("training runs in fp32 or bf16 mode (fp16 storage is inference-only)"); return 1; }
   OCTSEG_CUDA(cudaSetDevice(net->device));
   TrainState *S = ts(net);
   if (!S) {

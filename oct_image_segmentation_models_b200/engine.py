@@ -19,8 +19,8 @@ class UNetEngine:
     def __init__(self, *, input_channels: int, num_classes: int, start_neurons: int = 8,
                  pool_layers: int = 4, conv_layers: int = 2, enc_kernel=(3, 3), dec_kernel=(2, 2),
                  precision: str = "bf16", device: int = 0):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ("fp32", "bf16", "fp16"):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
         self.spec_kwargs = dict(input_channels=input_channels, num_classes=num_classes,
                                 start_neurons=start_neurons, pool_layers=pool_layers,
                                 conv_layers=conv_layers, enc_kernel=tuple(enc_kernel),
@@ -34,7 +34,7 @@ class UNetEngine:
         self.param_specs = unet_param_specs(**self.spec_kwargs)
         self._h = C.c_void_p()
         nat.check(self._lib.octseg_create(C.byref(self._cfg), device,
-                                          nat.BF16 if precision == "bf16" else nat.FP32,
+                                          {"fp32": nat.FP32, "bf16": nat.BF16, "fp16": nat.FP16}[precision],
                                           C.byref(self._h)))
 
     # ---- lifetime ----------------------------------------------------------------

@@ -59,9 +59,9 @@ def main():
     # ---- evaluate
     imgs, labs = synthetic_batch(0, args.n, H, W)
     res = {}
-    for prec in ("bf16", "fp32"):
-        e = eng if prec == "bf16" else UNetEngine(precision="fp32", **cfg)
-        if prec == "fp32":
+    for prec in ("bf16", "fp16", "fp32"):
+        e = eng if prec == "bf16" else UNetEngine(precision=prec, **cfg)
+        if prec != "bf16":
             e.set_weights(weights)
         t1 = time.time()
         labels = np.empty((args.n, H, W), np.uint8)
@@ -81,12 +81,14 @@ def main():
                          acc=float((labels == labs[..., 0]).mean()))
         print(f"{prec}: predict {args.n / t_pred:.0f} B-scans/s (labels + boundary maps, host API), native min-path "
               f"{args.n / t_path:.0f} B-scans/s on {os.cpu_count()} cores, pixel acc vs truth {res[prec]['acc']:.4f}", flush=True)
-        if prec == "fp32":
+        if prec != "bf16":
             e.close()
-    d = np.abs(res["bf16"]["segs"].astype(np.int32) - res["fp32"]["segs"].astype(np.int32))
-    agree_lab = float((res["bf16"]["labels"] == res["fp32"]["labels"]).mean())
-    print(f"bf16 vs fp32: argmax agreement {agree_lab:.5f}, boundary positions identical {float((d == 0).mean()):.5f}, "
-          f"max |delta| {int(d.max())} rows")
+    for lo in ("bf16", "fp16"):
+        d = np.abs(res[lo]["segs"].astype(np.int32) - res["fp32"]["segs"].astype(np.int32))
+        agree_lab = float((res[lo]["labels"] == res["fp32"]["labels"]).mean())
+        print(f"{lo} vs fp32 over all {args.n}: argmax agreement {agree_lab:.5f}, boundary positions identical "
+              f"{float((d == 0).mean()):.5f}, max |delta| {int(d.max())} rows, B-scans with every boundary identical "
+              f"{int((d.reshape(args.n, -1).max(1) == 0).sum())}")
     # ---- CPU oracle on a subset
     from oracle import postproc
     from oracle.unet_oracle import OracleUNet
@@ -98,7 +100,7 @@ def main():
     ref_lab = probs.argmax(-1).astype(np.uint8)
     ref_segs = np.stack([postproc.boundaries_from_probs(probs[i:i + 1]) for i in range(m)])
     out = {"n": args.n, "oracle_subset": m, "cpu_oracle_bscans_per_s": m / t_cpu}
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "fp16", "bf16"):
         dd = np.abs(res[prec]["segs"][:m].astype(np.int32) - ref_segs.astype(np.int32))
         out[prec] = {"argmax_agreement_vs_oracle": float((res[prec]["labels"][:m] == ref_lab).mean()),
                      "boundaries_identical_frac": float((dd == 0).mean()), "max_row_delta": int(dd.max()),
