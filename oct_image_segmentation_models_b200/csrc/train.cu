@@ -99,6 +99,15 @@ struct TrainState {
   std::vector<TrainBlock> tb;
   std::vector<void *> dcat;         // gradient wrt each level's concat buffer [n][2f/8][h][w][8]
   std::vector<void *> gA, gB;       // ping-pong gradient buffers per level (f channels... sized 2f)
+  StepState *d_state = nullptr;     // step counter + bias-corrected learning rate, advanced on the device
+  // CUDA graph of the whole step (captured after one eager step with the same arguments)
+  cudaGraphExec_t graph_exec = nullptr;
+  const void *g_img = nullptr, *g_lab = nullptr, *g_mask = nullptr;
+  float *g_loss = nullptr;
+  int g_n = 0, g_h = 0, g_w = 0, g_dtype = -1;
+  cudaStream_t g_stream = nullptr;
+  bool warm = false;
+  long long launches_per_step = 0;
   TcPackJob *d_pack_jobs = nullptr; // all tensor-core weight images of the net, packed in one launch per step
   int n_pack_jobs = 0;
   void *img_blocked = nullptr;      // stem input as a 1-plane blocked tensor
@@ -311,14 +320,28 @@ static View<const T> block_input(octseg_net *net, const BlockSpec &b, int n) {
   return make_view((const T *)pt.a, n, pt.a_planes_total, pt.a_plane0, pb.cout / 8, pt.h, pt.w);
 }
 
+// gradient all-reduce (sum over ranks; the loss is already scaled by the GLOBAL batch) + Keras-Adam
+static int train_tail(octseg_net *net, cudaStream_t st) {
+  TrainState *S = ts(net);
+  if (S->comm && S->world > 1)
+    OCTSEG_NCCL(g_nccl.AllReduce(S->d_grads, S->d_grads, (size_t)net->total_floats, /*ncclFloat*/ 7, /*ncclSum*/ 0,
+                                 S->comm, st));
+  if (launch_adam(net->d_params, S->d_grads, S->d_m, S->d_v, net->total_floats, S->d_state, S->tc.beta_1,
+                  S->tc.beta_2, S->tc.epsilon, st))
+    return 1;
+  ++net->launches;
+  return 0;
+}
+
 template <typename T>
 static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uint8_t *d_labels, int n, int h,
-                        int w, const uint8_t *d_mask_in, cudaStream_t st) {
+                        int w, const uint8_t *d_mask_in, cudaStream_t st, bool with_tail) {
   TrainState *S = ts(net);
   const float *P = net->d_params;
   float *G = S->d_grads;
   const int nblk = (int)net->blocks.size();
   const BlockSpec &head = net->blocks.back();
+  if (launch_step_advance(S->d_state, S->tc.learning_rate, S->tc.beta_1, S->tc.beta_2, st)) return 1;
   PhaseProf prof;
   prof.on = std::getenv("OCTSEG_TRAIN_PROFILE") != nullptr;
   prof.detail = prof.on && std::getenv("OCTSEG_TRAIN_PROFILE")[0] == '2';
@@ -339,7 +362,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   const bool use_dropout = mid_last && (d_mask_in || S->tc.dropout_rate > 0.f);
   if (use_dropout) {
     const TrainBlock &t = S->tb[mid_last->index];
-    if (launch_dropout_mask<T>(d_mask_in, S->tc.dropout_seed + (unsigned long long)S->step * 0x51ED27ULL,
+    if (launch_dropout_mask<T>(d_mask_in, S->tc.dropout_seed, S->d_state,
                                S->tc.dropout_rate > 0.f ? S->tc.dropout_rate : 0.5f, n, mid_last->cout, t.h, t.w,
                                (T *)S->mask, st))
       return 1;
@@ -520,17 +543,10 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     OCTSEG_CUDA(cudaEventRecord(S->ev_wg_done, wst));
     OCTSEG_CUDA(cudaStreamWaitEvent(st, S->ev_wg_done, 0));
   }
-  prof.begin(PH_AR);
-  if (S->comm && S->world > 1)
-    OCTSEG_NCCL(g_nccl.AllReduce(G, G, (size_t)net->total_floats, /*ncclFloat*/ 7, /*ncclSum*/ 0, S->comm, st));
-  prof.begin(PH_ADAM);
-  ++S->step;
-  const double b1 = S->tc.beta_1, b2 = S->tc.beta_2;
-  const float lr_t = (float)(S->tc.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)S->step)) /
-                             (1.0 - std::pow(b1, (double)S->step)));
-  if (launch_adam(net->d_params, G, S->d_m, S->d_v, net->total_floats, lr_t, S->tc.beta_1, S->tc.beta_2, S->tc.epsilon, st))
-    return 1;
-  ++net->launches;
+  if (with_tail) {
+    prof.begin(PH_AR);
+    if (train_tail(net, st)) return 1;
+  }
   prof.report();
   net->host_stale = true;
   net->derived_dirty = true;
@@ -554,7 +570,8 @@ void octseg_train_free(octseg_net *net) {
   for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); cudaFree(t.wpack_dgrad); }
   cudaFree(S->d_class_w); cudaFree(S->d_grads); cudaFree(S->d_m); cudaFree(S->d_v); cudaFree(S->d_ones); cudaFree(S->d_zeros);
   cudaFree(S->d_sums); cudaFree(S->d_loss); cudaFree(S->d_stem_tmp); cudaFree(S->ws); cudaFree(S->d_img);
-  cudaFree(S->d_labels); cudaFree(S->d_mask_in); cudaFree(S->d_pack_jobs);
+  cudaFree(S->d_labels); cudaFree(S->d_mask_in); cudaFree(S->d_pack_jobs); cudaFree(S->d_state);
+  if (S->graph_exec) cudaGraphExecDestroy(S->graph_exec);
   if (S->h_loss) cudaFreeHost(S->h_loss);
   delete S;
   net->train = nullptr;
@@ -585,6 +602,7 @@ int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc, const
     OCTSEG_CUDA(cudaMemset(S->d_zeros, 0, maxc * sizeof(float)));
     OCTSEG_CUDA(cudaMalloc(&S->d_sums, net->blocks.size() * 2 * 2 * maxc * sizeof(double)));
     OCTSEG_CUDA(cudaMalloc(&S->d_loss, sizeof(double)));
+    OCTSEG_CUDA(cudaMalloc(&S->d_state, sizeof(StepState)));
     OCTSEG_CUDA(cudaMallocHost(&S->h_loss, sizeof(double)));
     const BlockSpec &b0 = net->blocks[0];
     OCTSEG_CUDA(cudaMalloc(&S->d_stem_tmp, (size_t)b0.kh * b0.kw * 8 * b0.cout * sizeof(float)));
@@ -615,6 +633,9 @@ int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc, const
   }
   S->tc = *tc;
   S->step = 0;
+  OCTSEG_CUDA(cudaMemset(S->d_state, 0, sizeof(StepState)));
+  if (S->graph_exec) { cudaGraphExecDestroy(S->graph_exec); S->graph_exec = nullptr; }
+  S->warm = false;
   OCTSEG_CUDA(cudaMemset(S->d_m, 0, net->total_floats * sizeof(float)));
   OCTSEG_CUDA(cudaMemset(S->d_v, 0, net->total_floats * sizeof(float)));
   OCTSEG_CUDA(cudaMemset(S->d_grads, 0, net->total_floats * sizeof(float)));
@@ -638,6 +659,8 @@ int32_t octseg_comm_init(octseg_net *net, const uint8_t *unique_id, int32_t rank
   if (world < 1 || rank < 0 || rank >= world) { set_error("bad rank/world"); return 1; }
   OCTSEG_CUDA(cudaSetDevice(net->device));
   S->rank = rank; S->world = world;
+  if (S->graph_exec) { cudaGraphExecDestroy(S->graph_exec); S->graph_exec = nullptr; }   // captured without the all-reduce
+  S->warm = false;
   if (world == 1) return 0;
   if (load_nccl()) return 1;
   ncclUniqueId id;
@@ -656,17 +679,64 @@ int32_t octseg_train_step_device(octseg_net *net, const void *images, int32_t dt
   OCTSEG_CUDA(cudaSetDevice(net->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : net->stream;
   if (ensure_train_workspace(net, n, h, w)) return 1;
-  int rc = net->precision == OCTSEG_BF16
-               ? train_step_t<__nv_bfloat16>(net, images, dtype, labels, n, h, w, dropout_mask, st)
-               : train_step_t<float>(net, images, dtype, labels, n, h, w, dropout_mask, st);
-  if (rc) return 1;
-  // loss is accumulated in double on the device; pinned host copy for the host API,
-  // float copy into the caller's device word for the device API
-  OCTSEG_CUDA(cudaMemcpyAsync(S->h_loss, S->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (loss_out_device) {
-    store_loss_kernel<<<1, 1, 0, st>>>(S->d_loss, loss_out_device);
-    OCTSEG_CUDA(cudaGetLastError());
+  auto run_eager = [&](bool with_tail) -> int {
+    int rc = net->precision == OCTSEG_BF16
+                 ? train_step_t<__nv_bfloat16>(net, images, dtype, labels, n, h, w, dropout_mask, st, with_tail)
+                 : train_step_t<float>(net, images, dtype, labels, n, h, w, dropout_mask, st, with_tail);
+    if (rc) return 1;
+    // loss is accumulated in double on the device; pinned host copy for the host API,
+    // float copy into the caller's device word for the device API
+    OCTSEG_CUDA(cudaMemcpyAsync(S->h_loss, S->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (loss_out_device) {
+      store_loss_kernel<<<1, 1, 0, st>>>(S->d_loss, loss_out_device);
+      OCTSEG_CUDA(cudaGetLastError());
+    }
+    return 0;
+  };
+  // The whole step is stream-ordered and every per-step scalar lives on the device, so after one eager
+  // step with the same arguments the step is captured into a CUDA graph and replayed (the default net is
+  // ~230 launches of a few microseconds each at a per-GPU batch of 32).  With more than one rank the
+  // NCCL all-reduce and the Adam launch behind it stay outside the graph and are issued eagerly.
+  const char *genv = std::getenv("OCTSEG_TRAIN_GRAPH");
+  const bool graphs_on = !(genv && genv[0] == '0');
+  const bool same = S->warm && S->g_img == images && S->g_lab == labels && S->g_mask == dropout_mask && S->g_n == n &&
+                    S->g_h == h && S->g_w == w && S->g_dtype == dtype && S->g_stream == st && S->g_loss == loss_out_device;
+  const bool profiling = std::getenv("OCTSEG_TRAIN_PROFILE") != nullptr;
+  const bool tail_in_graph = !(S->comm && S->world > 1);
+  if (graphs_on && !profiling && same) {
+    if (!S->graph_exec) {
+      cudaGraph_t graph = nullptr;
+      const long long l0 = net->launches;
+      OCTSEG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      const int rc = run_eager(tail_in_graph);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc) return 1;
+        set_error(std::string("train-step graph capture failed: ") + cudaGetErrorString(ce));
+        return 1;
+      }
+      S->launches_per_step = net->launches - l0;
+      net->launches = l0;
+      ce = cudaGraphInstantiate(&S->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { S->graph_exec = nullptr; set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); return 1; }
+    }
+    OCTSEG_CUDA(cudaGraphLaunch(S->graph_exec, st));
+    net->launches += S->launches_per_step;
+    if (!tail_in_graph && train_tail(net, st)) return 1;
+    ++S->step;
+    net->host_stale = true;
+    net->derived_dirty = true;
+    return 0;
   }
+  if (!same && S->graph_exec) { cudaGraphExecDestroy(S->graph_exec); S->graph_exec = nullptr; }
+  if (run_eager(true)) return 1;
+  ++S->step;
+  S->warm = true;
+  S->g_img = images; S->g_lab = labels; S->g_mask = dropout_mask; S->g_n = n; S->g_h = h; S->g_w = w; S->g_dtype = dtype;
+  S->g_stream = st; S->g_loss = loss_out_device;
   return 0;
 }
 

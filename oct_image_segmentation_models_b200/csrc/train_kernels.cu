@@ -154,9 +154,11 @@ __device__ __forceinline__ uint32_t hash_u64(unsigned long long x) {
 }
 
 template <typename T>
-__global__ void dropout_mask_kernel(const uint8_t *__restrict__ mask_nhwc, unsigned long long seed, float rate,
+__global__ void dropout_mask_kernel(const uint8_t *__restrict__ mask_nhwc, unsigned long long seed,
+                                    const StepState *__restrict__ state, float rate,
                                     int n, int c, int h, int w, T *__restrict__ out) {
   const long long total = (long long)n * c * h * w;
+  if (state) seed += state->step * 0x51ED27ULL;     // per-step stream, read on the device (graph-replay safe)
   const float keep_scale = 1.f / (1.f - rate);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -176,11 +178,11 @@ __global__ void dropout_mask_kernel(const uint8_t *__restrict__ mask_nhwc, unsig
 }
 
 template <typename T>
-int launch_dropout_mask(const uint8_t *mask_nhwc, unsigned long long seed, float rate, int n, int c,
-                        int h, int w, T *out, cudaStream_t st) {
+int launch_dropout_mask(const uint8_t *mask_nhwc, unsigned long long seed, const StepState *state, float rate,
+                        int n, int c, int h, int w, T *out, cudaStream_t st) {
   const long long total = (long long)n * c * h * w;
   unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
-  dropout_mask_kernel<T><<<grid, 256, 0, st>>>(mask_nhwc, seed, rate, n, c, h, w, out);
+  dropout_mask_kernel<T><<<grid, 256, 0, st>>>(mask_nhwc, seed, state, rate, n, c, h, w, out);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -715,9 +717,21 @@ int launch_stem_wgrad_extract(const float *tmp, int taps, int cin, int cout, flo
 }
 
 // ---------------------------------------------------------------------------------
+__global__ void step_advance_kernel(StepState *s, float lr, float b1, float b2) {
+  s->step += 1;
+  const double t = (double)s->step;
+  s->lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));   // Keras optimizer_v2
+}
+int launch_step_advance(StepState *s, float lr, float b1, float b2, cudaStream_t st) {
+  step_advance_kernel<<<1, 1, 0, st>>>(s, lr, b1, b2);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float4 *__restrict__ p, const float4 *__restrict__ g,
                                                    float4 *__restrict__ m, float4 *__restrict__ v, long long n4,
-                                                   float lr_t, float b1, float b2, float eps) {
+                                                   const StepState *__restrict__ state, float b1, float b2, float eps) {
+  const float lr_t = state->lr_t;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
@@ -730,11 +744,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float4 *__restrict__ p, const
     p[i] = pp; m[i] = mm; v[i] = vv;
   }
 }
-int launch_adam(float *p, const float *g, float *m, float *v, long long n, float lr_t, float b1, float b2,
+int launch_adam(float *p, const float *g, float *m, float *v, long long n, const StepState *state, float b1, float b2,
                 float eps, cudaStream_t st) {
   const long long n4 = n / 4;   // flat buffers are padded to 16 floats per tensor
   unsigned grid = (unsigned)std::min<long long>((n4 + 255) / 256, 148 * 8);
-  adam_kernel<<<grid, 256, 0, st>>>((float4 *)p, (const float4 *)g, (float4 *)m, (float4 *)v, n4, lr_t, b1, b2, eps);
+  adam_kernel<<<grid, 256, 0, st>>>((float4 *)p, (const float4 *)g, (float4 *)m, (float4 *)v, n4, state, b1, b2, eps);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -743,8 +757,8 @@ int launch_adam(float *p, const float *g, float *m, float *v, long long n, float
   template int launch_bn_stats<T>(View<const T>, double *, cudaStream_t);                                   \
   template int launch_bn_apply_relu<T>(View<const T>, const float *, const float *, const T *, View<T>,     \
                                        cudaStream_t);                                                       \
-  template int launch_dropout_mask<T>(const uint8_t *, unsigned long long, float, int, int, int, int, T *,  \
-                                      cudaStream_t);                                                        \
+  template int launch_dropout_mask<T>(const uint8_t *, unsigned long long, const StepState *, float, int, int, \
+                                      int, int, T *, cudaStream_t);                                         \
   template int launch_head_loss<T>(View<const T>, const float *, const float *, int, int, const uint8_t *,  \
                                    const float *, float, View<T>, float *, float *, double *, cudaStream_t); \
   template int launch_bn_bwd_reduce<T>(View<const T>, View<const T>, const float *, const float *,          \

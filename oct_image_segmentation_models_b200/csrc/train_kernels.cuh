@@ -4,6 +4,14 @@
 
 namespace octseg {
 
+// per-step scalars that live on the device so that a captured CUDA graph of the train step replays correctly
+struct StepState {
+  unsigned long long step;
+  float lr_t;
+  float pad;
+};
+int launch_step_advance(StepState *s, float lr, float b1, float b2, cudaStream_t st);
+
 // per-channel sum / sum of squares of z over all N*H*W pixels (double accumulators, [2*C])
 template <typename T>
 int launch_bn_stats(View<const T> z, double *sums, cudaStream_t st);
@@ -22,8 +30,8 @@ int launch_bn_apply_relu(View<const T> z, const float *scale, const float *shift
 // dropout multiplier tensor (0 or 1/(1-rate)) in blocked layout, from an injected NHWC uint8
 // mask or from a counter-based hash RNG
 template <typename T>
-int launch_dropout_mask(const uint8_t *mask_nhwc, unsigned long long seed, float rate, int n, int c,
-                        int h, int w, T *out, cudaStream_t st);
+int launch_dropout_mask(const uint8_t *mask_nhwc, unsigned long long seed, const StepState *state, float rate,
+                        int n, int c, int h, int w, T *out, cudaStream_t st);
 
 // fused head: 1x1 conv + softmax + weighted CE + dlogits + d(head weights) + d(input)
 template <typename T>
@@ -78,7 +86,7 @@ int launch_upconv_dgrad_weights(const float *w, int kh, int kw, int cin, int cou
 int launch_stem_wgrad_extract(const float *tmp, int taps, int cin, int cout, float *dW, cudaStream_t st);
 
 // Keras optimizer_v2 Adam over the flat parameter buffer
-int launch_adam(float *p, const float *g, float *m, float *v, long long n, float lr_t, float b1, float b2,
-                float eps, cudaStream_t st);
+int launch_adam(float *p, const float *g, float *m, float *v, long long n, const StepState *state, float b1,
+                float b2, float eps, cudaStream_t st);
 
 }  // namespace octseg

@@ -130,3 +130,33 @@ def test_loss_decreases_and_tracks_oracle_curve():
     p_ora = ora.predict(imgs[:2])
     assert np.abs(p_eng - p_ora).max() <= 5e-3
     eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graph_replay_equals_eager_steps(precision, monkeypatch):
+    """From the second step with identical arguments the train step is replayed from a captured CUDA
+    graph (step counter, Adam lr_t and the dropout stream live on the device); it must walk the same
+    trajectory as launching every kernel eagerly, including the library-generated dropout masks."""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    cfg = dict(input_channels=1, num_classes=4, start_neurons=8, pool_layers=2, conv_layers=2)
+    weights = synthetic_weights(seed=11, random_bn_stats=False, **cfg)
+    imgs, labs = synthetic_batch(77, 8, 64, 64)
+    runs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("OCTSEG_TRAIN_GRAPH", mode)
+        eng = UNetEngine(precision=precision, **cfg)
+        eng.set_weights(weights)
+        eng.train_begin(CW, learning_rate=1e-3, dropout_rate=0.5, dropout_seed=123, global_batch=8)
+        losses = [eng.train_step(imgs, labs) for _ in range(3)]   # longer runs diverge chaotically even eager-vs-eager
+        runs[mode] = (losses, eng.get_weights())
+        eng.close()
+    tol = 1e-5 if precision == "fp32" else 5e-3
+    np.testing.assert_allclose(runs["1"][0], runs["0"][0], rtol=tol)
+    assert len(set(np.round(runs["1"][0], 6))) == 3           # a fresh dropout mask and a new lr_t every step
+    names = [nm for nm, _ in unet_param_specs(**cfg)]
+    wtol = 1e-3 if precision == "fp32" else 5e-2
+    for nm, a, b in zip(names, runs["1"][1], runs["0"][1]):
+        if nm.endswith("bias:0") and nm != names[-1]:
+            continue      # pre-BN bias: its gradient is rounding noise and Adam turns noise into +-lr steps
+        err = np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-12)
+        assert err <= wtol, (nm, err)

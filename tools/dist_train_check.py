@@ -63,8 +63,22 @@ def main():
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     worst_t = torch.tensor([worst], device="cuda")
     dist.all_reduce(worst_t, op=dist.ReduceOp.MAX)
+    # four more steps: from the second identical call the step (NCCL all-reduce included) is replayed from a
+    # captured CUDA graph; ranks must stay bit-identical and the summed loss must fall
+    losses = []
+    for _ in range(4):
+        t = torch.tensor([eng.train_step(imgs[s:e], labs[s:e])], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        losses.append(t.item())
+    flat = torch.from_numpy(np.concatenate([w.ravel() for w, nm in zip(eng.get_weights(), names) if "moving" not in nm])).cuda()
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    g_same = torch.tensor([1.0 if torch.equal(flat, ref) else 0.0], device="cuda")
+    dist.all_reduce(g_same, op=dist.ReduceOp.MIN)
+    graph_ok = g_same.item() == 1.0 and losses[-1] < lt.item()
     if rank == 0:
-        ok = flags[0].item() == 1.0 and worst_t.item() < 1e-2 and abs(lt.item() - loss_ref) < 1e-4 * max(1, abs(loss_ref))
+        print(f"graph-replayed steps: losses {[round(x, 5) for x in losses]} ranks identical {g_same.item() == 1.0}")
+        ok = graph_ok and flags[0].item() == 1.0 and worst_t.item() < 1e-2 and abs(lt.item() - loss_ref) < 1e-4 * max(1, abs(loss_ref))
         print(f"world {world}: worst rel grad err {worst_t.item():.2e}, loss sum {lt.item():.6f} vs oracle {loss_ref:.6f}, "
               f"weights identical across ranks {flags[0].item() == 1.0} -> {'PASS' if ok else 'FAIL'}")
     eng.close()
