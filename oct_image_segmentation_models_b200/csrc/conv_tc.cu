@@ -375,9 +375,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     bool ok = true;
     long long w_epi = 0;
     const long long t_start = clock64();
+    int wgr = wg;                           // warpgroup -> M-tile assignment, rotated every super-tile
     for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
       int n_tile, tx, ty, img;
       decode_tile(p, tile, n_tile, tx, ty, img);
+      // the M-tile count of a super-tile is a power of two and there are 3 warpgroups: rotating the
+      // assignment spreads the odd tile over the warpgroups across consecutive super-tiles (the two
+      // accumulator stages absorb the skew) instead of always loading warpgroup 0
+      const int wg_cur = wgr;
+      if (++wgr == kTcEpiWarps / 4) wgr = 0;
       ok = mbar_wait(smem_u32(&bars->acc_full[acc]), accph, p.status, 6, &w_epi);
       if (!ok) break;
       tc_fence_after();
@@ -394,7 +400,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const float4 ha = *reinterpret_cast<const float4 *>(s_shift + col_base), hb = *reinterpret_cast<const float4 *>(s_shift + col_base + 4);
         const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
         const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-        for (int t0 = wg; t0 < mt; t0 += kEpiBatch * kWG) {
+        for (int t0 = wg_cur; t0 < mt; t0 += kEpiBatch * kWG) {
           uint32_t v[kEpiBatch][8];
 #pragma unroll
           for (int bb = 0; bb < kEpiBatch; ++bb) {
@@ -474,7 +480,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       } else
-      for (int t = wg; t < mt; t += kTcEpiWarps / 4) {
+      for (int t = wg_cur; t < mt; t += kTcEpiWarps / 4) {
         const int iy = t >> p.mt_x_log2, ix = t & (p.mt_x - 1);
         const int y = (ty * p.mt_y + iy) * kTcTileH + r, x = (tx * p.mt_x + ix) * kTcTileW + px;
         const bool inside = (y < p.h) && (x < p.w);
@@ -568,6 +574,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 *reinterpret_cast<uint4 *>(dst + 8) = pk[1];
               }
             }
+          }
+        } else if (p.mode == 3) {
+          // ---- stem groups: a GEMM row is 8 adjacent pixels of one image row and the 64 columns of a
+          //      plane are the 64 contiguous elements [pixel][channel] of the blocked layout, i.e. every
+          //      thread owns one whole 128-byte line.  Storing straight from registers would touch 32
+          //      lines per instruction, so the warp transposes through its own 4 KB of shared memory
+          //      (16-byte slots XOR-swizzled by row: conflict-free both ways) and writes 512 contiguous
+          //      bytes per instruction.
+          uint8_t *stg = reinterpret_cast<uint8_t *>(s_scale) + p.stage_off + (size_t)(warp - 4) * 4096;
+          const uint32_t stg_u32 = smem_u32(stg);
+          for (int j0 = 0; j0 < my_nch; j0 += 8) {
+            // software-pipelined TMEM reads: the loads of chunk pair k+1 are in flight while pair k is
+            // scaled, packed and staged
+            uint32_t v[2][2][8];
+            tmem_ld8(t_base + (uint32_t)(j0 * 8), v[0][0]);
+            tmem_ld8(t_base + (uint32_t)(j0 * 8 + 8), v[0][1]);
+#pragma unroll
+            for (int jj = 0; jj < 8; jj += 2) {
+              const int cur = (jj >> 1) & 1;
+              tmem_ld_wait();
+              if (jj + 2 < 8) {
+                tmem_ld8(t_base + (uint32_t)((j0 + jj + 2) * 8), v[cur ^ 1][0]);
+                tmem_ld8(t_base + (uint32_t)((j0 + jj + 2) * 8 + 8), v[cur ^ 1][1]);
+              }
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int col = col_base + (j0 + jj + u) * 8;
+                const float4 sa = *reinterpret_cast<const float4 *>(s_scale + col), sb = *reinterpret_cast<const float4 *>(s_scale + col + 4);
+                const float4 ha = *reinterpret_cast<const float4 *>(s_shift + col), hb = *reinterpret_cast<const float4 *>(s_shift + col + 4);
+                const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                uint32_t h2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  h2[k] = pack2(fmaxf(fmaf(__uint_as_float(v[cur][u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
+                                fmaxf(fmaf(__uint_as_float(v[cur][u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor), p.fp16);
+                const uint32_t slot = (uint32_t)((jj + u) ^ (lane & 7));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_u32 + (uint32_t)lane * 128u + slot * 16u),
+                             "r"(h2[0]), "r"(h2[1]), "r"(h2[2]), "r"(h2[3]) : "memory");
+              }
+            }
+            __syncwarp();
+            const long long plane_off = (long long)((col_base >> 6) + (j0 >> 3)) * (plane_elems << 3);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + (lane >> 3), c = lane & 7;          // staged row, 16-byte slot
+              uint32_t a, b, cc, d;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(cc), "=r"(d)
+                           : "r"(stg_u32 + (uint32_t)rr * 128u + (uint32_t)((c ^ (rr & 7)) * 16)) : "memory");
+              const int y2 = (ty * p.mt_y + iy) * kTcTileH + q * 4 + (rr >> 3);
+              const int x2 = (tx * p.mt_x + ix) * kTcTileW + (rr & 7);
+              if (y2 < p.h && x2 < p.w)
+                *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + plane_off +
+                                           (((long long)y2 * p.out_w + x2) << 6) + c * 8) = make_uint4(a, b, cc, d);
+            }
+            __syncwarp();
           }
         } else {
           // ---- plain store (+ optional fused 2x2 max-pool); generic pixel shuffle falls back here
@@ -908,7 +970,12 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
     b_bytes_total = (size_t)p.b_stages * ((p.b_stage_bytes + 127u) & ~127u);
   }
   // ---- super-tile: mt_x x mt_y M-tiles of 8 px x 16 rows share one TMA halo box
-  const size_t epi_bytes = ((size_t)g.cout * (2 + kTcMaxClasses) + kTcMaxClasses) * sizeof(float);
+  size_t epi_bytes = ((size_t)g.cout * (2 + kTcMaxClasses) + kTcMaxClasses) * sizeof(float);
+  if (g.stem_groups) {     // + per-epilogue-warp store staging (32 rows x 128 B)
+    epi_bytes = (epi_bytes + 127) & ~(size_t)127;
+    p.stage_off = (uint32_t)epi_bytes;
+    epi_bytes += (size_t)kTcEpiWarps * 4096;
+  }
   const size_t budget = 208 * 1024 - b_bytes_total - sizeof(TcBarriers) - epi_bytes - 1024;
   const int max_mt = std::max(1, 256 / g.n_cols);          // 2 accumulator stages in 512 TMEM columns
   static const int cand[][2] = {{8, 2}, {4, 2}, {8, 1}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
@@ -992,6 +1059,10 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
     p.head_w = epi.head_w; p.head_b = epi.head_b; p.head_k = epi.head_k;
     p.probs = epi.probs; p.labels = epi.labels;
     p.out_h = h; p.out_w = w;
+  }
+  if (g.stem_groups) {
+    if (g.ups || epi.head_w || epi.pool_out || g.n_cols % 64 || g.cols_valid % 64) { set_error("tc plan: stem-group epilogue not applicable"); return 1; }
+    p.mode = 3;
   }
   if (epi.pool_out && (g.ups || (h & 1) || (w & 1))) { set_error("tc plan: pool fusion not applicable"); return 1; }
   p.wpack = wpack_dev;

@@ -48,6 +48,7 @@ struct TcConvParams {
   float *probs;                // mode 2 outputs (NHWC fp32 / u8), either may be NULL
   uint8_t *labels;
   const __nv_bfloat16 *wpack;  // packed weights [n_tile][chunk][kstep][2][n_cols][8]
+  uint32_t stage_off;          // mode 3: byte offset (from the epilogue tables) of the per-warp store staging
   int *status;                 // device word: non-zero = pipeline timeout code
   long long *dbg;              // optional [8] cycle counters of block 0 (NULL = off)
 };
@@ -69,6 +70,7 @@ struct TcGeometry {
   int dy_min, dy_max, dx_min, dx_max;  // low-res tap range
   int planes_per_chunk, cin_chunks, ksteps, n_cols, n_tiles_n, cols_valid, bgroup;
   int box_w, box_h;                    // halo px / rows added around a super-tile
+  int stem_groups;                     // set by the caller: GEMM row = 8 adjacent pixels, columns = [plane][pixel][8 ch]
   // per k-step, per half: tap (dy,dx relative to dy_min/dx_min) and plane within chunk; tap -1 = zero
   int half_ty[kTcMaxKSteps][2], half_tx[kTcMaxKSteps][2], half_pl[kTcMaxKSteps][2];
 };

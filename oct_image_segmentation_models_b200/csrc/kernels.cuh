@@ -31,6 +31,11 @@ int launch_conv_direct_ex(View<const T> in, const float *wgt, int kh, int kw, in
                           const float *shift, int relu, View<T> out, cudaStream_t st);
 
 // 2x2/stride-2 max pool (reference models/unet.py:37)
+// TC stem helpers: widen a uint8 image to the activation type; replicate folded BN per GEMM column
+template <typename T>
+int launch_u8_to_act(const uint8_t *img, long long count, T *out, cudaStream_t st);
+int launch_stem_rep(const float *scale, const float *shift, int cout, float *rep_scale, float *rep_shift, cudaStream_t st);
+
 template <typename T>
 int launch_maxpool2(View<const T> in, View<T> out, cudaStream_t st);
 

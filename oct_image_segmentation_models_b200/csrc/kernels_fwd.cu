@@ -158,6 +158,117 @@ __global__ void __launch_bounds__(256) conv_stem3x3_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Tiled 3x3 / 1-channel stem (the default path): block = 128 x 16 output pixels.  The raw
+// halo tile is fetched and preprocessed ONCE per pixel into shared memory; every warp then
+// owns two rows and every lane the pixels lane, lane+32, lane+64, lane+96 of a row, so each
+// 16-byte (bf16) / 32-byte (fp32) store instruction of a warp covers one contiguous run and
+// every shared-memory read is conflict-free.  The 72 weights of an output plane sit in
+// registers as float2 pairs and the MACs are packed FFMA2 (sm_100 f32x2 pipe).
+// ---------------------------------------------------------------------------------
+constexpr int kStemTW = 128, kStemTH = 16, kStemPitch = kStemTW + 8, kStemX = 4;   // body starts at column 4 (16 B aligned)
+
+template <typename IMG>
+__device__ __forceinline__ float stem_preprocess(IMG raw, int pre) {
+  if constexpr (sizeof(IMG) == 1) return __fdiv_rn((float)raw, 255.0f);   // == float32(float64(u) / 255)
+  else return pre ? (float)raw : (float)((double)raw / 255.0);
+}
+
+template <typename T, typename IMG>
+__global__ void __launch_bounds__(256, 2) conv_stem3x3_tile_kernel(
+    const IMG *__restrict__ img, int h, int w, const float *__restrict__ wgt, int cout,
+    const float *__restrict__ scale, const float *__restrict__ shift, int relu, View<T> out, int pre) {
+  __shared__ __align__(16) float tile[kStemTH + 2][kStemPitch];
+  __shared__ float2 ss[2][64];                 // scale / shift pairs, cout <= 128
+  for (int i = threadIdx.x; i < cout / 2; i += 256) {
+    ss[0][i] = *reinterpret_cast<const float2 *>(scale + 2 * i);
+    ss[1][i] = *reinterpret_cast<const float2 *>(shift + 2 * i);
+  }
+  const int x0 = blockIdx.x * kStemTW, y0 = blockIdx.y * kStemTH, b = blockIdx.z;
+  const IMG *src = img + (long long)b * h * w;
+  // halo tile: 16-byte vector loads, all issued before the first use (one exposed latency per block);
+  // launcher guarantees w % 16 == 0 and a 16-byte aligned image, so a vector is inside the row or outside it
+  constexpr int kPerVec = 16 / (int)sizeof(IMG);                 // pixels per 16-byte load
+  constexpr int kVecPerRow = kStemTW / kPerVec;
+  constexpr int kVecs = (kStemTH + 2) * kVecPerRow;
+  constexpr int kIter = (kVecs + 255) / 256;
+  uint4 raw[kIter];
+#pragma unroll
+  for (int it = 0; it < kIter; ++it) {
+    const int i = threadIdx.x + it * 256;
+    const int r = i / kVecPerRow, v = i - r * kVecPerRow;
+    const int gy = y0 - 1 + r, gx = x0 + v * kPerVec;
+    raw[it] = make_uint4(0, 0, 0, 0);
+    if (i < kVecs && gy >= 0 && gy < h && gx < w) raw[it] = *reinterpret_cast<const uint4 *>(src + (long long)gy * w + gx);
+  }
+  if (threadIdx.x < 2 * (kStemTH + 2)) {        // left / right halo columns
+    const int r = threadIdx.x >> 1, side = threadIdx.x & 1;
+    const int gy = y0 - 1 + r, gx = side ? x0 + kStemTW : x0 - 1;
+    float v = 0.f;
+    if (gy >= 0 && gy < h && gx >= 0 && gx < w) v = stem_preprocess<IMG>(src[(long long)gy * w + gx], pre);
+    tile[r][side ? kStemX + kStemTW : kStemX - 1] = v;
+  }
+#pragma unroll
+  for (int it = 0; it < kIter; ++it) {
+    const int i = threadIdx.x + it * 256;
+    const int r = i / kVecPerRow, v = i - r * kVecPerRow;
+    if (i < kVecs) {
+      float *dst = &tile[r][kStemX + v * kPerVec];
+      if constexpr (sizeof(IMG) == 1) {
+        const uint32_t wds[4] = {raw[it].x, raw[it].y, raw[it].z, raw[it].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4 *>(dst + 4 * q) =
+              make_float4(stem_preprocess<uint8_t>(wds[q] & 0xFF, 0), stem_preprocess<uint8_t>((wds[q] >> 8) & 0xFF, 0),
+                          stem_preprocess<uint8_t>((wds[q] >> 16) & 0xFF, 0), stem_preprocess<uint8_t>(wds[q] >> 24, 0));
+      } else {
+        *reinterpret_cast<float4 *>(dst) =
+            make_float4(stem_preprocess<float>(__uint_as_float(raw[it].x), pre), stem_preprocess<float>(__uint_as_float(raw[it].y), pre),
+                        stem_preprocess<float>(__uint_as_float(raw[it].z), pre), stem_preprocess<float>(__uint_as_float(raw[it].w), pre));
+      }
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  for (int cog = 0; cog < cout / 8; ++cog) {
+    float2 wr[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wr[t][k] = *reinterpret_cast<const float2 *>(wgt + t * cout + cog * 8 + 2 * k);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r = wy * 2 + j, y = y0 + r;
+      if (y >= h) break;
+      T *row = out.ptr + b * out.img_stride + ((long long)cog * h + y) * w * 8;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int xl = lane + 32 * p, x = x0 + xl;
+        float2 acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float v = tile[r + dy][xl + dx + kStemX - 1];
+            const float2 vv = make_float2(v, v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(vv, wr[dy * 3 + dx][k], acc[k]);
+          }
+        Vec8f o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 y2 = __ffma2_rn(acc[k], ss[0][cog * 4 + k], ss[1][cog * 4 + k]);
+          o.v[2 * k] = relu ? fmaxf(y2.x, 0.f) : y2.x;
+          o.v[2 * k + 1] = relu ? fmaxf(y2.y, 0.f) : y2.y;
+        }
+        if (x < w) store8(row + (long long)x * 8, o);
+      }
+    }
+  }
+}
+
 template <typename T>
 int launch_conv_first(const void *img, int img_dtype, int n, int h, int w, int cin_img,
                       const float *wgt, int kh, int kw, int cout, const float *scale,
@@ -167,6 +278,18 @@ int launch_conv_first(const void *img, int img_dtype, int n, int h, int w, int c
   const long long total = (long long)n * h * w;
   unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
   size_t smem = ((size_t)kh * kw * cin_img * cout + 2 * cout) * sizeof(float);
+  if (kh == 3 && kw == 3 && cin_img == 1 && n <= 65535 && (cout % 8) == 0 && cout <= 128 && (w % 16) == 0 &&
+      ((uintptr_t)img % 16) == 0) {
+    dim3 gt((w + kStemTW - 1) / kStemTW, (h + kStemTH - 1) / kStemTH, n);
+    if (img_dtype == 0)
+      conv_stem3x3_tile_kernel<T, uint8_t><<<gt, 256, 0, st>>>((const uint8_t *)img, h, w, wgt, cout, scale, shift,
+                                                               relu, out, 0);
+    else
+      conv_stem3x3_tile_kernel<T, float><<<gt, 256, 0, st>>>((const float *)img, h, w, wgt, cout, scale, shift, relu,
+                                                             out, pre);
+    OCTSEG_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (kh == 3 && kw == 3 && cin_img == 1 && (w % 4) == 0 && ((uintptr_t)img % 16) == 0) {
     const long long quads = total / 4;
     unsigned g4 = (unsigned)std::min<long long>((quads + 255) / 256, 148 * 16);
@@ -196,6 +319,53 @@ int launch_conv_first(const void *img, int img_dtype, int n, int h, int w, int c
       conv_first_kernel<T, float, 0, 0, 0><<<grid, 256, smem, st>>>((const float *)img, n, h, w, cin_img, wgt,
                                                                     kh, kw, cout, scale, shift, relu, out, pre);
   }
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// TC stem helpers.  The tensor-core stem (net.cu) treats 8 adjacent pixels of a row as the 8 input
+// channels of one GEMM row, so its A operand is just the image widened to 16 bits: integers 0..255
+// are exact in bf16 and fp16, and the 1/255 of the reference's preprocessing is folded into the
+// per-column scale.
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) u8_to_act_kernel(const uint8_t *__restrict__ img, long long n16, T *__restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 raw = *reinterpret_cast<const uint4 *>(img + i * 16);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      Vec8f v;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v.v[k] = (float)((w[hh * 2 + (k >> 2)] >> ((k & 3) * 8)) & 0xFFu);
+      store8(out + i * 16 + hh * 8, v);
+    }
+  }
+}
+template <typename T>
+int launch_u8_to_act(const uint8_t *img, long long count, T *out, cudaStream_t st) {
+  if (count % 16 || ((uintptr_t)img % 16)) { set_error("u8_to_act: count and pointer must be 16-aligned"); return 1; }
+  const long long n16 = count / 16;
+  unsigned grid = (unsigned)std::min<long long>((n16 + 255) / 256, 148 * 16);
+  u8_to_act_kernel<T><<<grid, 256, 0, st>>>(img, n16, out);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+template int launch_u8_to_act<__nv_bfloat16>(const uint8_t *, long long, __nv_bfloat16 *, cudaStream_t);
+template int launch_u8_to_act<__half>(const uint8_t *, long long, __half *, cudaStream_t);
+template int launch_u8_to_act<float>(const uint8_t *, long long, float *, cudaStream_t);
+
+__global__ void stem_rep_kernel(const float *__restrict__ scale, const float *__restrict__ shift, int cout,
+                                float *__restrict__ rep_scale, float *__restrict__ rep_shift) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;       // col = plane*64 + pixel*8 + c8
+  if (col >= cout * 8) return;
+  const int c = (col >> 6) * 8 + (col & 7);
+  rep_scale[col] = scale[c] / 255.0f;
+  rep_shift[col] = shift[c];
+}
+int launch_stem_rep(const float *scale, const float *shift, int cout, float *rep_scale, float *rep_shift, cudaStream_t st) {
+  stem_rep_kernel<<<(cout * 8 + 127) / 128, 128, 0, st>>>(scale, shift, cout, rep_scale, rep_shift);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }

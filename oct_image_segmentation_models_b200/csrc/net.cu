@@ -119,6 +119,24 @@ int sync_host_mirror(octseg_net *net) {
   return 0;
 }
 
+// Banded weights of the tensor-core stem.  GEMM row (y, g) holds pixels 8g..8g+7 of image row y as its
+// 8 input channels; GEMM column plane*64 + jo*8 + c8 is output pixel 8g+jo, channel plane*8+c8.  Tap
+// (dy, dgx) of the 3x3 conv over the GROUP grid connects input pixel 8(g+dgx-1)+ji to output pixel 8g+jo
+// with the original filter tap dx = 8(dgx-1) + ji - jo + 1 when that lies in 0..2, else zero.
+static void stem_group_weights(const float *w, int cout, std::vector<float> *out) {
+  const int cols = 8 * cout;
+  out->assign((size_t)9 * 8 * cols, 0.f);
+  for (int dy = 0; dy < 3; ++dy)
+    for (int dgx = 0; dgx < 3; ++dgx)
+      for (int ji = 0; ji < 8; ++ji)
+        for (int col = 0; col < cols; ++col) {
+          const int jo = (col >> 3) & 7, c = (col >> 6) * 8 + (col & 7);
+          const int dx = 8 * (dgx - 1) + ji - jo + 1;
+          if (dx < 0 || dx > 2) continue;
+          (*out)[(((size_t)dy * 3 + dgx) * 8 + ji) * cols + col] = w[((size_t)dy * 3 + dx) * cout + c];
+        }
+}
+
 int prepare_derived(octseg_net *net) {
   if (!net->derived_dirty) return 0;
   if (sync_host_mirror(net)) return 1;
@@ -133,7 +151,15 @@ int prepare_derived(octseg_net *net) {
     ++net->launches;
     if (net->precision != OCTSEG_FP32 && st.geo_ok) {
       std::vector<uint16_t> packed;
-      tc_pack_weights(st.geo, net->h_params.data() + net->params[b.p_kernel].offset, &packed,
+      const float *wk = net->h_params.data() + net->params[b.p_kernel].offset;
+      std::vector<float> grouped;
+      if (b.index == 0) {
+        stem_group_weights(wk, b.cout, &grouped);
+        wk = grouped.data();
+        if (launch_stem_rep(st.scale, st.shift, b.cout, st.rep_scale, st.rep_shift, net->stream)) return 1;
+        ++net->launches;
+      }
+      tc_pack_weights(st.geo, wk, &packed,
                       net->precision == OCTSEG_FP16);
       if (packed.size() != st.wpack_elems) { set_error("internal: wpack size"); return 1; }
       OCTSEG_CUDA(cudaMemcpyAsync(st.wpack, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice,
@@ -175,6 +201,9 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
   }
   const int fm = s << P;
   size_t midT0 = bump.take(bytes(fm, P)), midT1 = bump.take(bytes(fm, P));
+  const bool stem_tc = net->precision != OCTSEG_FP32 && !net->disable_tc && net->bstate[0].geo_ok && (w % 8) == 0 &&
+                       tc_supported(3, 3, 8, 8 * s, 0, h, w / 8);
+  size_t stem_in = stem_tc ? bump.take((size_t)n * h * w * es) : 0;
   if (bump.off > net->ws_bytes) {
     if (net->ws) OCTSEG_CUDA(cudaFree(net->ws));
     net->ws = nullptr;
@@ -225,6 +254,19 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
     else { prev = io.out; prev_planes = f / 8; prev_h = lh; prev_w = lw; }
     // ---- tensor-core plan
     io.use_tc = false;
+    if (b.index == 0 && stem_tc) {
+      TcEpilogue epi;
+      epi.fp16 = net->precision == OCTSEG_FP16;
+      epi.scale = net->bstate[0].rep_scale; epi.shift = net->bstate[0].rep_shift;
+      epi.out = make_view(reinterpret_cast<__nv_bfloat16 *>(io.out), n, io.out_planes_total, io.out_plane0,
+                          io.out_planes, io.out_h, io.out_w);
+      epi.out.w = w / 8;                      // the epilogue indexes GEMM rows = pixel groups
+      io.stem_in = base + stem_in;
+      if (tc_make_plan(net->bstate[0].geo, reinterpret_cast<const __nv_bfloat16 *>(io.stem_in), n, h, w / 8,
+                       net->bstate[0].wpack, epi, net->d_status, &io.plan))
+        return 1;
+      io.use_tc = true;
+    }
     if (net->precision != OCTSEG_FP32 && !net->disable_tc && b.index > 0 && b.role != 4 &&
         net->bstate[b.index].geo_ok && tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, io.in_h, io.in_w)) {
       TcEpilogue epi;
@@ -284,7 +326,14 @@ static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h
     }
     View<T> out = make_view(reinterpret_cast<T *>(io.out), n, io.out_planes_total, io.out_plane0,
                             io.out_planes, io.out_h, io.out_w);
-    if (b.index == 0) {
+    if (b.index == 0 && io.use_tc && dtype == OCTSEG_U8 && ((uintptr_t)d_img % 16) == 0) {
+      // tensor-core stem: widen the image to 16 bits (exact), then one conv_tc launch over pixel groups
+      if (launch_u8_to_act<T>(reinterpret_cast<const uint8_t *>(d_img), (long long)n * h * w,
+                              reinterpret_cast<T *>(io.stem_in), st))
+        return 1;
+      ++net->launches;
+      if (tc_launch(io.plan, st)) return 1;
+    } else if (b.index == 0) {
       if (launch_conv_first<T>(d_img, dtype, n, h, w, b.cin, P + net->params[b.p_kernel].offset, b.kh, b.kw,
                                b.cout, bs.scale, bs.shift, 1, out, st))
         return 1;
@@ -442,6 +491,17 @@ int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precisio
       st.wpack_elems = (size_t)st.geo.n_tiles_n * st.geo.cin_chunks * st.geo.ksteps * 2 * st.geo.n_cols * 8;
       OCTSEG_CUDA(cudaMalloc(&st.wpack, st.wpack_elems * 2));
     }
+    // tensor-core stem: 3x3, one input channel; GEMM row = 8 adjacent pixels (K = 8 per tap),
+    // GEMM columns = 8 pixels x cout channels (a banded weight matrix, see stem_group_weights)
+    if (precision != OCTSEG_FP32 && !net->disable_tc && b.index == 0 && b.kh == 3 && b.kw == 3 && b.cin == 1 &&
+        b.cout <= 32 && tc_make_geometry(3, 3, 8, 8 * b.cout, 0, &st.geo) == 0) {
+      st.geo_ok = true;
+      st.geo.stem_groups = 1;
+      st.wpack_elems = (size_t)st.geo.n_tiles_n * st.geo.cin_chunks * st.geo.ksteps * 2 * st.geo.n_cols * 8;
+      OCTSEG_CUDA(cudaMalloc(&st.wpack, st.wpack_elems * 2));
+      OCTSEG_CUDA(cudaMalloc(&st.rep_scale, 8 * b.cout * sizeof(float)));
+      OCTSEG_CUDA(cudaMalloc(&st.rep_shift, 8 * b.cout * sizeof(float)));
+    }
   }
   *out = net;
   return 0;
@@ -456,7 +516,7 @@ int32_t octseg_destroy(octseg_net *net) {
   for (auto &e : net->pipe_events) cudaEventDestroy(e);
   if (net->copy_in) cudaStreamDestroy(net->copy_in);
   if (net->copy_out) cudaStreamDestroy(net->copy_out);
-  for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); }
+  for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); cudaFree(st.rep_scale); cudaFree(st.rep_shift); }
   cudaFree(net->d_params); cudaFree(net->ws); cudaFree(net->d_img); cudaFree(net->d_probs);
   cudaFree(net->d_labels); cudaFree(net->d_maps); cudaFree(net->d_status);
   if (net->h_status) cudaFreeHost(net->h_status);
@@ -511,20 +571,22 @@ int32_t octseg_predict_device(octseg_net *net, const void *images, int32_t dtype
   return 0;
 }
 
-int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
-                            int32_t w, float *probs, uint8_t *labels) {
-  if (!net || !images) { set_error("null argument"); return 1; }
+// Chunked three-stage pipeline shared by the host-buffer entry points: H2D of chunk i+1, forward (+ boundary
+// maps) of chunk i and D2H of chunk i-1 overlap on three streams (PCIe is full duplex).  Any of
+// probs / labels / maps may be null; maps need labels on the device but not necessarily on the host.
+static int predict_pipeline(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h, int32_t w,
+                            float *probs, uint8_t *labels, uint8_t *maps, int bg_ilm, int bg_csi, int transposed) {
   if (n <= 0 || h <= 0 || w <= 0) { set_error("bad image batch shape"); return 1; }
   if (dtype != OCTSEG_U8 && dtype != OCTSEG_F32 && dtype != OCTSEG_F32_PRE) { set_error("bad image dtype"); return 1; }
   OCTSEG_CUDA(cudaSetDevice(net->device));
-  const size_t img_bytes = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)n * h * w * net->cfg.input_channels;
-  const size_t pr_bytes = (size_t)n * h * w * net->cfg.num_classes * sizeof(float);
-  const size_t lb_bytes = (size_t)n * h * w;
-  if (grow(&net->d_img, &net->d_img_bytes, img_bytes)) return 1;
-  if (probs && grow(reinterpret_cast<void **>(&net->d_probs), &net->d_probs_bytes, pr_bytes)) return 1;
-  if (labels && grow(reinterpret_cast<void **>(&net->d_labels), &net->d_labels_bytes, lb_bytes)) return 1;
-  // Chunked three-stage pipeline: H2D of chunk i+1, forward of chunk i and D2H of chunk i-1 overlap
-  // on three streams (PCIe is full duplex; the fp32 probabilities going back dominate the bytes).
+  const int K = net->cfg.num_classes;
+  const size_t img_per = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)h * w * net->cfg.input_channels;
+  const size_t pr_per = (size_t)h * w * K * sizeof(float), lb_per = (size_t)h * w, mp_per = lb_per * (K - 1);
+  const bool need_labels = labels || maps;
+  if (grow(&net->d_img, &net->d_img_bytes, img_per * n)) return 1;
+  if (probs && grow(reinterpret_cast<void **>(&net->d_probs), &net->d_probs_bytes, pr_per * n)) return 1;
+  if (need_labels && grow(reinterpret_cast<void **>(&net->d_labels), &net->d_labels_bytes, lb_per * n)) return 1;
+  if (maps && grow(reinterpret_cast<void **>(&net->d_maps), &net->d_maps_bytes, mp_per * n)) return 1;
   const int chunk = std::max(1, std::min(n, (net->microbatch > 0 ? net->microbatch : 16)));
   if (!net->copy_in) {
     OCTSEG_CUDA(cudaStreamCreateWithFlags(&net->copy_in, cudaStreamNonBlocking));
@@ -537,8 +599,6 @@ int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, 
     for (size_t i = old; i < net->pipe_events.size(); ++i)
       OCTSEG_CUDA(cudaEventCreateWithFlags(&net->pipe_events[i], cudaEventDisableTiming));
   }
-  const size_t img_per = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)h * w * net->cfg.input_channels;
-  const size_t pr_per = (size_t)h * w * net->cfg.num_classes * sizeof(float), lb_per = (size_t)h * w;
   // the pipeline streams must not start before earlier work on the handle's stream is done
   OCTSEG_CUDA(cudaEventRecord(net->pipe_events[0], net->stream));
   OCTSEG_CUDA(cudaStreamWaitEvent(net->copy_in, net->pipe_events[0], 0));
@@ -551,16 +611,24 @@ int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, 
                                 (size_t)cur * img_per, cudaMemcpyHostToDevice, net->copy_in));
     OCTSEG_CUDA(cudaEventRecord(ev_in, net->copy_in));
     OCTSEG_CUDA(cudaStreamWaitEvent(net->stream, ev_in, 0));
-    float *dpr = probs ? net->d_probs + (size_t)i0 * h * w * net->cfg.num_classes : nullptr;
-    uint8_t *dlb = labels ? net->d_labels + (size_t)i0 * lb_per : nullptr;
+    float *dpr = probs ? net->d_probs + (size_t)i0 * h * w * K : nullptr;
+    uint8_t *dlb = need_labels ? net->d_labels + (size_t)i0 * lb_per : nullptr;
+    uint8_t *dmp = maps ? net->d_maps + (size_t)i0 * mp_per : nullptr;
     if (forward(net, dimg, dtype, cur, h, w, dpr, dlb, net->stream)) return 1;
+    if (maps) {
+      if (launch_boundary_maps(dlb, cur, h, w, K, bg_ilm, bg_csi, transposed, dmp, net->stream)) return 1;
+      ++net->launches;
+    }
     OCTSEG_CUDA(cudaEventRecord(ev_fw, net->stream));
     OCTSEG_CUDA(cudaStreamWaitEvent(net->copy_out, ev_fw, 0));
     if (probs)
-      OCTSEG_CUDA(cudaMemcpyAsync(probs + (size_t)i0 * h * w * net->cfg.num_classes, dpr, (size_t)cur * pr_per,
-                                  cudaMemcpyDeviceToHost, net->copy_out));
+      OCTSEG_CUDA(cudaMemcpyAsync(probs + (size_t)i0 * h * w * K, dpr, (size_t)cur * pr_per, cudaMemcpyDeviceToHost,
+                                  net->copy_out));
     if (labels)
       OCTSEG_CUDA(cudaMemcpyAsync(labels + (size_t)i0 * lb_per, dlb, (size_t)cur * lb_per, cudaMemcpyDeviceToHost,
+                                  net->copy_out));
+    if (maps)
+      OCTSEG_CUDA(cudaMemcpyAsync(maps + (size_t)i0 * mp_per, dmp, (size_t)cur * mp_per, cudaMemcpyDeviceToHost,
                                   net->copy_out));
   }
   OCTSEG_CUDA(cudaEventRecord(net->pipe_events[2], net->copy_out));
@@ -568,24 +636,17 @@ int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, 
   return check_status(net);
 }
 
+int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
+                            int32_t w, float *probs, uint8_t *labels) {
+  if (!net || !images) { set_error("null argument"); return 1; }
+  return predict_pipeline(net, images, dtype, n, h, w, probs, labels, nullptr, 0, 0, 0);
+}
+
 int32_t octseg_predict_maps_host(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
                                  int32_t w, int32_t bg_ilm, int32_t bg_csi, int32_t transposed, uint8_t *labels,
                                  uint8_t *maps) {
   if (!net || !images || !maps) { set_error("null argument"); return 1; }
-  OCTSEG_CUDA(cudaSetDevice(net->device));
-  const int K = net->cfg.num_classes;
-  const size_t img_bytes = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)n * h * w * net->cfg.input_channels;
-  const size_t lb_bytes = (size_t)n * h * w, mp_bytes = lb_bytes * (K - 1);
-  if (grow(&net->d_img, &net->d_img_bytes, img_bytes)) return 1;
-  if (grow(reinterpret_cast<void **>(&net->d_labels), &net->d_labels_bytes, lb_bytes)) return 1;
-  if (grow(reinterpret_cast<void **>(&net->d_maps), &net->d_maps_bytes, mp_bytes)) return 1;
-  OCTSEG_CUDA(cudaMemcpyAsync(net->d_img, images, img_bytes, cudaMemcpyHostToDevice, net->stream));
-  if (octseg_predict_device(net, net->d_img, dtype, n, h, w, nullptr, net->d_labels, net->stream)) return 1;
-  if (launch_boundary_maps(net->d_labels, n, h, w, K, bg_ilm, bg_csi, transposed, net->d_maps, net->stream)) return 1;
-  ++net->launches;
-  if (labels) OCTSEG_CUDA(cudaMemcpyAsync(labels, net->d_labels, lb_bytes, cudaMemcpyDeviceToHost, net->stream));
-  OCTSEG_CUDA(cudaMemcpyAsync(maps, net->d_maps, mp_bytes, cudaMemcpyDeviceToHost, net->stream));
-  return check_status(net);
+  return predict_pipeline(net, images, dtype, n, h, w, nullptr, labels, maps, bg_ilm, bg_csi, transposed);
 }
 
 int32_t octseg_synchronize(octseg_net *net) {
@@ -623,8 +684,10 @@ int32_t octseg_get_block_times(octseg_net *net, float *ms, int32_t cap, int32_t 
 int32_t octseg_layer_uses_tensor_core(octseg_net *net, int32_t conv_index, int32_t h, int32_t w) {
   if (!net || conv_index < 0 || conv_index >= (int)net->blocks.size()) return 0;
   const BlockSpec &b = net->blocks[conv_index];
-  if (net->precision == OCTSEG_FP32 || net->disable_tc || b.index == 0 || b.role == 4) return 0;
+  if (net->precision == OCTSEG_FP32 || net->disable_tc || b.role == 4) return 0;
   if (!net->bstate[b.index].geo_ok) return 0;
+  if (b.index == 0)      // tensor-core stem over pixel groups (uint8 input only)
+    return ((w % 8) == 0 && tc_supported(3, 3, 8, 8 * b.cout, 0, h, w / 8)) ? 1 : 0;
   int lh = h >> b.level, lw = w >> b.level;
   if (b.ups) { lh >>= 1; lw >>= 1; }
   return tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, lh, lw) ? 1 : 0;

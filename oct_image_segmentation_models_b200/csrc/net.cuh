@@ -42,6 +42,7 @@ struct BlockState {
   TcGeometry geo{};
   __nv_bfloat16 *wpack = nullptr;
   size_t wpack_elems = 0;
+  float *rep_scale = nullptr, *rep_shift = nullptr;   // TC stem only: per-GEMM-column scale/255 and shift
 };
 
 // Workspace views for one (n,h,w)
@@ -52,6 +53,7 @@ struct BlockIO {
   bool use_tc = false;
   bool pool_fused = false;   // 2x2 max-pool written by the conv epilogue
   bool head_fused = false;   // 1x1 conv + softmax computed in this block's epilogue
+  void *stem_in = nullptr;   // TC stem: the uint8 image widened to the activation type ([N][H][W/8][8])
   TcPlan plan;
 };
 

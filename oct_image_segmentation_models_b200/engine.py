@@ -89,7 +89,8 @@ class UNetEngine:
         nat.check(self._lib.octseg_predict_host(self._h, _ptr(images), dt, n, h, w, _ptr(probs), _ptr(labels)))
         return probs, labels
 
-    def predict_maps(self, images: np.ndarray, bg_ilm: bool = True, bg_csi: bool = False, transposed: bool = False):
+    def predict_maps(self, images: np.ndarray, bg_ilm: bool = True, bg_csi: bool = False, transposed: bool = False,
+                     labels_out: Optional[np.ndarray] = None, maps_out: Optional[np.ndarray] = None):
         """uint8/float images -> (labels uint8 [N,H,W], boundary maps uint8 [N,K-1,H,W] or [N,K-1,W,H]);
         argmax and the reference's map construction run on the GPU, only 1 + (K-1) bytes per pixel
         come back instead of 4*K."""
@@ -100,9 +101,12 @@ class UNetEngine:
             dt = nat.F32
         images = np.ascontiguousarray(images)
         n, h, w, _ = images.shape
-        labels = np.empty((n, h, w), np.uint8)
         shape = (n, self.num_classes - 1, w, h) if transposed else (n, self.num_classes - 1, h, w)
-        maps = np.empty(shape, np.uint8)
+        labels = labels_out if labels_out is not None else np.empty((n, h, w), np.uint8)
+        maps = maps_out if maps_out is not None else np.empty(shape, np.uint8)
+        if labels.shape != (n, h, w) or maps.shape != shape or labels.dtype != np.uint8 or maps.dtype != np.uint8 \
+                or not labels.flags.c_contiguous or not maps.flags.c_contiguous:
+            raise ValueError("labels_out / maps_out must be C-contiguous uint8 of shape (n,h,w) / " + str(shape))
         nat.check(self._lib.octseg_predict_maps_host(self._h, _ptr(images), dt, n, h, w, int(bg_ilm), int(bg_csi),
                                                      int(transposed), _ptr(labels), _ptr(maps)))
         return labels, maps

@@ -79,7 +79,7 @@ def test_default_net_uses_tensor_cores(engines):
     _, e32, e16 = engines
     blocks = unet_blocks(**CFG)
     tc = [i for i in range(len(blocks)) if e16.layer_uses_tensor_core(i, 512, 512)]
-    assert tc == list(range(1, 22)), tc            # every conv block except the Cin=1 stem and the head
+    assert tc == list(range(0, 22)), tc            # every conv block (the stem as a pixel-group GEMM); not the 1x1 head
     assert not any(e32.layer_uses_tensor_core(i, 512, 512) for i in range(len(blocks)))
 
 
@@ -97,6 +97,26 @@ def test_predict_parity_fp32_and_bf16(engines, n, h, w):
     assert np.array_equal(l16, p16.argmax(-1))
     if n * h * w >= 16384:
         assert (l16 == ref.argmax(-1)).mean() >= 0.999
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 24, 136), (1, 16, 64), (3, 40, 392)])
+def test_tensor_core_stem_matches_cuda_core_stem(n, h, w):
+    """uint8 images take the tcgen05 stem (8 adjacent pixels = one GEMM row, banded weights); float32 images
+    take the CUDA-core stem.  Same network otherwise, so the outputs must agree to bf16 noise, including
+    ragged group counts (w/8 not a multiple of the 16-wide tile) and the oracle."""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    cfg = dict(input_channels=1, num_classes=4, start_neurons=8, pool_layers=2, conv_layers=2)
+    weights = synthetic_weights(seed=21, **cfg)
+    imgs, _ = synthetic_batch(31, n, h, w)
+    eng = UNetEngine(precision="bf16", **cfg)
+    eng.set_weights(weights)
+    assert eng.layer_uses_tensor_core(0, h, w)
+    p_tc, _ = eng.predict(imgs)
+    p_cc, _ = eng.predict(imgs.astype(np.float32))
+    ref = OracleUNet(weights, **cfg).predict(imgs)
+    assert np.abs(p_tc - p_cc).max() <= 2e-2
+    assert rel_err(p_tc, ref).max() <= BF16_REL
+    eng.close()
 
 
 def test_predict_float_input_equals_uint8_input(engines):

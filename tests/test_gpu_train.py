@@ -150,13 +150,19 @@ def test_graph_replay_equals_eager_steps(precision, monkeypatch):
         losses = [eng.train_step(imgs, labs) for _ in range(3)]   # longer runs diverge chaotically even eager-vs-eager
         runs[mode] = (losses, eng.get_weights())
         eng.close()
-    tol = 1e-5 if precision == "fp32" else 5e-3
+    # bf16: split-K wgrad atomics reorder fp32 sums, bf16 rounding and Adam's sign-like first steps amplify
+    # that even between two eager runs (small beta tensors differ by ~1e-1), so the bf16 check is global
+    tol = 1e-5 if precision == "fp32" else 2e-3
     np.testing.assert_allclose(runs["1"][0], runs["0"][0], rtol=tol)
     assert len(set(np.round(runs["1"][0], 6))) == 3           # a fresh dropout mask and a new lr_t every step
     names = [nm for nm, _ in unet_param_specs(**cfg)]
-    wtol = 1e-3 if precision == "fp32" else 5e-2
-    for nm, a, b in zip(names, runs["1"][1], runs["0"][1]):
-        if nm.endswith("bias:0") and nm != names[-1]:
-            continue      # pre-BN bias: its gradient is rounding noise and Adam turns noise into +-lr steps
-        err = np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-12)
-        assert err <= wtol, (nm, err)
+    keep = [i for i, nm in enumerate(names) if not (nm.endswith("bias:0") and nm != names[-1])]
+    if precision == "fp32":
+        for i in keep:     # pre-BN biases skipped: their gradient is rounding noise and Adam turns noise into +-lr steps
+            a, b = runs["1"][1][i], runs["0"][1][i]
+            err = np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-12)
+            assert err <= 1e-3, (names[i], err)
+    else:
+        a = np.concatenate([runs["1"][1][i].ravel() for i in keep])
+        b = np.concatenate([runs["0"][1][i].ravel() for i in keep])
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) <= 1e-2
