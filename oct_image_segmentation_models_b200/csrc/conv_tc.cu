@@ -30,6 +30,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_fp16.h>
@@ -192,13 +193,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   float *s_scale = reinterpret_cast<float *>(bars + 1);     // [cout] folded BN scale
   float *s_shift = s_scale + p.cout;                        // [cout] folded BN shift
   float *s_head = s_shift + p.cout;                         // [cout][HK] + [HK] fused-head weights
-  for (int i = threadIdx.x; i < p.cout; i += blockDim.x) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
-  if constexpr (HK > 0) {
-    for (int i = threadIdx.x; i < p.cout * HK; i += blockDim.x) s_head[i] = p.head_w[i];
-    for (int i = threadIdx.x; i < HK; i += blockDim.x) s_head[p.cout * HK + i] = p.head_b[i];
-  } else {
-    (void)s_head;
-  }
+  // Programmatic dependent launch: let the next kernel of the stream be scheduled as SMs drain; its
+  // barrier init / TMEM allocation below then overlap this grid's tail.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int mt = p.mt_x * p.mt_y;                 // M-tiles (128 rows each) per super-tile
   const uint32_t acc_cols = (uint32_t)(mt * p.n_cols);
 
@@ -217,6 +214,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (p.b_resident && p.static_weights && lane == 0) {
+      // inference: the packed weights do not depend on the preceding kernels, so the resident weight
+      // image is fetched before the dependency wait (lane 0 initialised the barrier above)
+      const uint32_t wfull = smem_u32(&bars->w_full);
+      mbar_expect_tx(wfull, p.b_stage_bytes);
+      uint32_t done = 0;
+      while (done < p.b_stage_bytes) {
+        const uint32_t part = min(p.b_stage_bytes - done, 32768u);
+        bulk_load(smem_u32(b_smem) + done, reinterpret_cast<const uint8_t *>(p.wpack) + done, part, wfull);
+        done += part;
+      }
+    }
+  }
+  // Everything above touches no global memory.  From here on the kernel reads what earlier kernels of
+  // the stream wrote (activations, and in training the BN tables and repacked weights): wait for them.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (int i = threadIdx.x; i < p.cout; i += blockDim.x) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+  if constexpr (HK > 0) {
+    for (int i = threadIdx.x; i < p.cout * HK; i += blockDim.x) s_head[i] = p.head_w[i];
+    for (int i = threadIdx.x; i < HK; i += blockDim.x) s_head[p.cout * HK + i] = p.head_b[i];
+  } else {
+    (void)s_head;
   }
   tc_fence_before();
   __syncthreads();
@@ -228,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // ===================== TMA producer (warp-uniform; elected lane issues) =====================
       const bool leader = elect_one_sync() != 0;
       if (leader) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-      if (p.b_resident && leader) {
+      if (p.b_resident && !p.static_weights && leader) {
         // whole packed weight image of the layer stays in smem for the kernel's lifetime
         const uint32_t wfull = smem_u32(&bars->w_full);
         mbar_expect_tx(wfull, p.b_stage_bytes);
@@ -1050,6 +1069,7 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
   if (tc_fill_params(g, n, h, w, &p, &plan->smem_bytes)) return 1;
   p.relu = epi.relu;
   p.fp16 = epi.fp16;
+  p.static_weights = epi.static_weights;
   p.scale = epi.scale; p.shift = epi.shift;
   p.out = epi.out.ptr; p.out_img_stride = epi.out.img_stride; p.out_h = epi.out.h; p.out_w = epi.out.w;
   p.pool_out = epi.pool_out; p.pool_img_stride = epi.pool_img_stride;
@@ -1095,8 +1115,15 @@ static int tc_launch_k(const TcPlan &plan, cudaStream_t st) {
     OCTSEG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<HK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<HK><<<plan.grid, kTcThreads, plan.smem_bytes, st>>>(plan.tmap, plan.p);
-  OCTSEG_CUDA(cudaGetLastError());
+  static const bool pdl = []() { const char *e = std::getenv("OCTSEG_NO_PDL"); return !(e && e[0] == '1'); }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = plan.smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  OCTSEG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<HK>, plan.tmap, plan.p));
   return 0;
 }
 

@@ -48,6 +48,7 @@ struct TcConvParams {
   float *probs;                // mode 2 outputs (NHWC fp32 / u8), either may be NULL
   uint8_t *labels;
   const __nv_bfloat16 *wpack;  // packed weights [n_tile][chunk][kstep][2][n_cols][8]
+  int static_weights;          // packed weights are not written by earlier kernels of the stream (inference)
   uint32_t stage_off;          // mode 3: byte offset (from the epilogue tables) of the per-warp store staging
   int *status;                 // device word: non-zero = pipeline timeout code
   long long *dbg;              // optional [8] cycle counters of block 0 (NULL = off)
@@ -102,6 +103,7 @@ struct TcEpilogue {
   long long pool_img_stride = 0;
   const float *head_w = nullptr, *head_b = nullptr;   // fused 1x1 conv + softmax head
   int head_k = 0;
+  int static_weights = 0;                    // weights final before the stream's preceding kernels ran (inference)
   float *probs = nullptr;
   uint8_t *labels = nullptr;
 };

@@ -630,10 +630,54 @@ __global__ void __launch_bounds__(256) boundary_maps_kernel(const uint8_t *__res
   }
 }
 
+// Row-major maps, 4 pixels per thread: the four label rows a pixel quad needs (i-1 .. i+2, with the
+// reference's one-sided differences at the first/last row and its wrap-around of the last row) are
+// fetched once as 32-bit words and reused for all K-1 maps; one 32-bit store per map.
+__global__ void __launch_bounds__(256) boundary_maps_quad_kernel(const uint8_t *__restrict__ labels, int H, int W, int K,
+                                                                 int bg_ilm, int bg_csi, uint8_t *__restrict__ maps) {
+  const int xq = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int i = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int b = blockIdx.z;
+  if (xq * 4 >= W || i >= H) return;
+  const uint8_t *img = labels + (long long)b * H * W + xq * 4;
+  auto row = [&](int j) { return *reinterpret_cast<const uint32_t *>(img + (long long)j * W); };
+  // s(i) = relu(sign * mult * (c(ja) - c(jb)))
+  auto pick = [&](int r, int &ja, int &jb, int &mult) {
+    if (r == 0) { ja = 1; jb = 0; mult = 2; }
+    else if (r == H - 1) { ja = H - 1; jb = H - 2; mult = 2; }
+    else { ja = r + 1; jb = r - 1; mult = 1; }
+  };
+  int a0, b0, m0, a1, b1, m1;
+  pick(i, a0, b0, m0);
+  pick((i + 1) % H, a1, b1, m1);
+  const uint32_t wa0 = row(a0), wb0 = row(b0), wa1 = row(a1), wb1 = row(b1);
+  for (int m = 1; m < K; ++m) {
+    const bool above = (m == 1 && bg_ilm) || (m == K - 1 && bg_csi);
+    const uint32_t cls = above ? m - 1 : m;
+    const int sign = above ? -1 : 1;
+    uint32_t outw = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      auto c = [&](uint32_t wv) { return (int)(((wv >> (8 * k)) & 0xFFu) == cls); };
+      int s0 = sign * m0 * (c(wa0) - c(wb0)), s1 = sign * m1 * (c(wa1) - c(wb1));
+      s0 = s0 > 0 ? s0 : 0; s1 = s1 > 0 ? s1 : 0;
+      const int v = s0 - s1;
+      outw |= (uint32_t)(((v > 0 ? v : 0) * 255) & 0xFF) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t *>(maps + (((long long)b * (K - 1) + (m - 1)) * H + i) * W + xq * 4) = outw;
+  }
+}
+
 int launch_boundary_maps(const uint8_t *labels, int n, int h, int w, int K, int bg_ilm, int bg_csi, int transposed,
                          uint8_t *maps, cudaStream_t st) {
   const long long total = (long long)n * (K - 1) * h * w;
   if (total <= 0) return 0;
+  if (!transposed && h >= 2 && (w % 4) == 0 && n <= 65535 && ((uintptr_t)labels % 4) == 0 && ((uintptr_t)maps % 4) == 0) {
+    dim3 grid((w / 4 + 63) / 64, (h + 3) / 4, n);
+    boundary_maps_quad_kernel<<<grid, 256, 0, st>>>(labels, h, w, K, bg_ilm, bg_csi, maps);
+    OCTSEG_CUDA(cudaGetLastError());
+    return 0;
+  }
   unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
   boundary_maps_kernel<<<grid, 256, 0, st>>>(labels, n, h, w, K, bg_ilm, bg_csi, transposed, maps);
   OCTSEG_CUDA(cudaGetLastError());

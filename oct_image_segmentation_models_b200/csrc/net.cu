@@ -257,6 +257,7 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
     if (b.index == 0 && stem_tc) {
       TcEpilogue epi;
       epi.fp16 = net->precision == OCTSEG_FP16;
+      epi.static_weights = 1;
       epi.scale = net->bstate[0].rep_scale; epi.shift = net->bstate[0].rep_shift;
       epi.out = make_view(reinterpret_cast<__nv_bfloat16 *>(io.out), n, io.out_planes_total, io.out_plane0,
                           io.out_planes, io.out_h, io.out_w);
@@ -271,6 +272,7 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
         net->bstate[b.index].geo_ok && tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, io.in_h, io.in_w)) {
       TcEpilogue epi;
       epi.fp16 = net->precision == OCTSEG_FP16;
+      epi.static_weights = 1;
       epi.scale = net->bstate[b.index].scale; epi.shift = net->bstate[b.index].shift;
       epi.out = make_view(reinterpret_cast<__nv_bfloat16 *>(io.out), n, io.out_planes_total, io.out_plane0,
                           io.out_planes, io.out_h, io.out_w);
@@ -587,7 +589,16 @@ static int predict_pipeline(octseg_net *net, const void *images, int32_t dtype, 
   if (probs && grow(reinterpret_cast<void **>(&net->d_probs), &net->d_probs_bytes, pr_per * n)) return 1;
   if (need_labels && grow(reinterpret_cast<void **>(&net->d_labels), &net->d_labels_bytes, lb_per * n)) return 1;
   if (maps && grow(reinterpret_cast<void **>(&net->d_maps), &net->d_maps_bytes, mp_per * n)) return 1;
-  const int chunk = std::max(1, std::min(n, (net->microbatch > 0 ? net->microbatch : 16)));
+  // Chunk size: total ~ H2D(chunk) + sum of forwards + D2H(last chunk), and a forward costs a fixed ~0.2 ms
+  // (22 launches) plus ~0.022 ms per 512x512 B-scan.  With fp32 probabilities going back (4*K bytes per
+  // pixel) the call is D2H-bound and small chunks start the return traffic early; with only label / boundary
+  // maps (1 + K-1 bytes per pixel) the forwards dominate and fewer, larger chunks win (measured on B200).
+  int chunk;
+  if (net->microbatch > 0) chunk = std::min(n, net->microbatch);
+  else if (probs) chunk = std::min(n, 8);
+  else if (n < 16) chunk = n;
+  else { const int nc = std::max(2, (n + 31) / 32); chunk = (n + nc - 1) / nc; }
+  chunk = std::max(1, std::min(chunk, pick_microbatch(net, n, h, w)));   // workspace memory bound
   if (!net->copy_in) {
     OCTSEG_CUDA(cudaStreamCreateWithFlags(&net->copy_in, cudaStreamNonBlocking));
     OCTSEG_CUDA(cudaStreamCreateWithFlags(&net->copy_out, cudaStreamNonBlocking));
@@ -743,6 +754,7 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
     } else {
       TcEpilogue epi;
       epi.fp16 = net->precision == OCTSEG_FP16;
+      epi.static_weights = 1;
       epi.scale = bs.scale; epi.shift = bs.shift;
       epi.out = make_view(reinterpret_cast<__nv_bfloat16 *>(d_out), n, b.cout / 8, 0, b.cout / 8, oh, ow);
       rc = tc_make_plan(bs.geo, reinterpret_cast<const __nv_bfloat16 *>(d_in), n, h, w, bs.wpack, epi,

@@ -225,6 +225,21 @@ def test_device_boundary_maps_match_reference_semantics(engines):
         assert np.array_equal(seg[i], postproc.boundaries_from_probs(probs[i:i + 1]))
 
 
+def test_predict_maps_chunked_pipeline_equals_single_chunk(engines, monkeypatch):
+    """predict_maps_host runs H2D / forward+maps / D2H as a chunked 3-stream pipeline; ragged chunking
+    (5 B-scans in chunks of 2) must give the bytes of the one-chunk call."""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    weights, e32, _ = engines
+    imgs, _ = synthetic_batch(51, 5, 32, 64)
+    lab_ref, maps_ref = e32.predict_maps(imgs)
+    monkeypatch.setenv("OCTSEG_MICROBATCH", "2")
+    eng = UNetEngine(precision="fp32", **CFG)
+    eng.set_weights(weights)
+    lab, maps = eng.predict_maps(imgs)
+    assert np.array_equal(lab, lab_ref) and np.array_equal(maps, maps_ref)
+    eng.close()
+
+
 def test_fp16_storage_mode_parity():
     """fp16 storage (tensor-core path, same kernels as bf16): 8x finer mantissa -- tighter probability
     parity on random weights and >= 99.9 % argmax agreement + boundaries within one row on the trained net."""
