@@ -179,7 +179,11 @@ constexpr int kTcEpiWarps = 12;   // epilogue warps 4..15 (three warpgroups)
 constexpr int kTcThreads = (4 + kTcEpiWarps) * 32;
 
 // HK: compile-time class count of the fused 1x1-conv + softmax head (0 = no head fusion)
-template <int HK>
+// EPI: epilogue specialisation chosen on the host (tc_epi_kind) so that every layer type gets its own
+// register allocation: 0 = generic chunk loop (wide layers, unpaired pixel shuffle, wide fused head),
+// 1 = 8-column layers (batched TMEM loads; plain / pool / fused head), 2 = 16-column plain / pool layers,
+// 3 = stem pixel groups, 4 = paired pixel-shuffle up-conv.  Dead paths are dropped at compile time.
+template <int HK, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ TcConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -193,9 +197,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   float *s_scale = reinterpret_cast<float *>(bars + 1);     // [cout] folded BN scale
   float *s_shift = s_scale + p.cout;                        // [cout] folded BN shift
   float *s_head = s_shift + p.cout;                         // [cout][HK] + [HK] fused-head weights
-  // Programmatic dependent launch: let the next kernel of the stream be scheduled as SMs drain; its
-  // barrier init / TMEM allocation below then overlap this grid's tail.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (!p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int mt = p.mt_x * p.mt_y;                 // M-tiles (128 rows each) per super-tile
   const uint32_t acc_cols = (uint32_t)(mt * p.n_cols);
 
@@ -294,6 +296,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
+      // Programmatic dependent launch: this CTA has requested its last tile, so the next kernel of the
+      // stream may be scheduled; its barrier init / TMEM allocation / weight fetch then overlap the MMA
+      // and epilogue tail of this grid.  (Signalling at kernel entry instead lets the dependent CTAs
+      // co-reside for the whole kernel -- two ~113 KB CTAs fit one SM -- and slows this grid down.)
+      if (p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
       if (p.dbg && blockIdx.x == 0 && leader) { p.dbg[0] = w_prod; p.dbg[1] = clock64() - t_start; }
     }
   } else if (warp <= kTcIssuers) {
@@ -408,7 +415,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const int col_base = n_tile * p.n_cols;
       const int my_nch = min(nch, (p.cols_valid - col_base) >> 3);
-      if (my_nch == 1 && p.mode != 1) {
+      if (EPI == 1) {
         // ---- 8-channel layers (the full-resolution layers that carry most of the bytes): one
         //      chunk per M-tile, so batch the TMEM loads of up to kEpiBatch M-tiles behind ONE
         //      tcgen05.wait::ld and process them back to back (hides the TMEM/LDS/shuffle latency
@@ -498,6 +505,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         }
+      } else if (EPI == 2 && HK == 0) {
+        // ---- 16-channel layers: same idea, two chunks (planes) per M-tile and two M-tiles per wait
+        constexpr int kB2 = 2;
+        constexpr int kWG = kTcEpiWarps / 4;
+        for (int t0 = wg_cur; t0 < mt; t0 += kB2 * kWG) {
+          uint32_t v[kB2][2][8];
+#pragma unroll
+          for (int bb = 0; bb < kB2; ++bb) {
+            const int t = t0 + bb * kWG;
+            if (t < mt) {
+              const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * p.n_cols);
+              tmem_ld8(ta, v[bb][0]);
+              tmem_ld8(ta + 8u, v[bb][1]);
+            }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int bb = 0; bb < kB2; ++bb) {
+            const int t = t0 + bb * kWG;
+            if (t >= mt) break;
+            const int iy = t >> p.mt_x_log2, ix = t & (p.mt_x - 1);
+            const int y = (ty * p.mt_y + iy) * kTcTileH + r, x = (tx * p.mt_x + ix) * kTcTileW + px;
+            const bool inside = (y < p.h) && (x < p.w);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int co0 = col_base + u * 8;
+              const float4 sa = *reinterpret_cast<const float4 *>(s_scale + co0), sb = *reinterpret_cast<const float4 *>(s_scale + co0 + 4);
+              const float4 ha = *reinterpret_cast<const float4 *>(s_shift + co0), hb = *reinterpret_cast<const float4 *>(s_shift + co0 + 4);
+              const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+              const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+              uint4 pk;
+              uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                h2[k] = pack2(fmaxf(fmaf(__uint_as_float(v[bb][u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
+                              fmaxf(fmaf(__uint_as_float(v[bb][u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor), p.fp16);
+              if (inside)
+                *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)(co0 >> 3) * plane_elems +
+                                           ((long long)y * p.out_w + x) * 8) = pk;
+              if (p.pool_out) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  uint32_t w0 = h2[k];
+                  w0 = max2(w0, __shfl_xor_sync(0xffffffffu, w0, 1), p.fp16);
+                  w0 = max2(w0, __shfl_xor_sync(0xffffffffu, w0, 8), p.fp16);
+                  h2[k] = w0;
+                }
+                if (inside && !(px & 1) && !(r & 1))
+                  *reinterpret_cast<uint4 *>(p.pool_out + (long long)img * p.pool_img_stride +
+                                             (long long)(co0 >> 3) * (plane_elems >> 2) +
+                                             ((long long)(y >> 1) * (p.out_w >> 1) + (x >> 1)) * 8) = pk;
+              }
+            }
+          }
+        }
       } else
       for (int t = wg_cur; t < mt; t += kTcEpiWarps / 4) {
         const int iy = t >> p.mt_x_log2, ix = t & (p.mt_x - 1);
@@ -559,7 +621,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             if (p.labels) p.labels[pix] = (uint8_t)pa;
           }
-        } else if (p.mode == 1 && p.shuffle_pairs) {
+        } else if (EPI == 4) {
           // ---- up-conv pixel shuffle: the two x-parities of one (y-parity, plane) are loaded
           //      together so each thread stores 32 contiguous bytes (2 output pixels)
           const int planes_per_par = p.cout >> 3;
@@ -594,7 +656,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             }
           }
-        } else if (p.mode == 3) {
+        } else if (EPI == 3) {
           // ---- stem groups: a GEMM row is 8 adjacent pixels of one image row and the 64 columns of a
           //      plane are the 64 contiguous elements [pixel][channel] of the blocked layout, i.e. every
           //      thread owns one whole 128-byte line.  Storing straight from registers would touch 32
@@ -1104,15 +1166,26 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   plan->grid = std::min(p.num_tiles, sms);
+  {
+    // Programmatic dependent launch works best (measured, B200, default net: 1.53 -> 1.47 ms per 64 B-scans)
+    // when dependents are signalled after this CTA's last tile request and when two CTAs can never share an
+    // SM: the dynamic smem request is padded to 116 KB so a dependent CTA only starts on an SM whose CTA
+    // of the previous kernel has exited.  OCTSEG_PDL_LATE=0 / OCTSEG_TC_MIN_SMEM_KB=n override (experiments).
+    const char *e = std::getenv("OCTSEG_PDL_LATE");
+    p.pdl_late = (e && e[0] == '0') ? 0 : 1;
+    const char *m = std::getenv("OCTSEG_TC_MIN_SMEM_KB");
+    plan->smem_bytes = std::max(plan->smem_bytes, (size_t)(m ? std::atoi(m) : 116) * 1024);
+    plan->smem_bytes = std::min(plan->smem_bytes, (size_t)227 * 1024);
+  }
   plan->valid = true;
   return 0;
 }
 
-template <int HK>
+template <int HK, int EPI>
 static int tc_launch_k(const TcPlan &plan, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    OCTSEG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<HK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OCTSEG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<HK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   static const bool pdl = []() { const char *e = std::getenv("OCTSEG_NO_PDL"); return !(e && e[0] == '1'); }();
@@ -1123,22 +1196,45 @@ static int tc_launch_k(const TcPlan &plan, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  OCTSEG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<HK>, plan.tmap, plan.p));
+  OCTSEG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<HK, EPI>, plan.tmap, plan.p));
   return 0;
 }
 
 bool tc_head_fusable(int num_classes) { return num_classes >= 2 && num_classes <= 8; }
 
+// epilogue specialisation of a plan (see conv_tc_kernel)
+static int tc_epi_kind(const TcConvParams &p) {
+  const bool one_ntile = p.n_tiles_n == 1;
+  if (p.mode == 3) return 3;
+  if (p.mode == 1) return p.shuffle_pairs ? 4 : 0;
+  if (one_ntile && p.cols_valid == 8) return 1;                     // mode 0 or 2 (fused head)
+  if (one_ntile && p.cols_valid == 16 && p.mode == 0) return 2;
+  return 0;
+}
+
+template <int HK>
+static int tc_launch_head(const TcPlan &plan, cudaStream_t st) {
+  return tc_epi_kind(plan.p) == 1 ? tc_launch_k<HK, 1>(plan, st) : tc_launch_k<HK, 0>(plan, st);
+}
+
 int tc_launch(const TcPlan &plan, cudaStream_t st) {
-  if (plan.p.mode != 2) return tc_launch_k<0>(plan, st);
+  if (plan.p.mode != 2) {
+    switch (tc_epi_kind(plan.p)) {
+      case 1: return tc_launch_k<0, 1>(plan, st);
+      case 2: return tc_launch_k<0, 2>(plan, st);
+      case 3: return tc_launch_k<0, 3>(plan, st);
+      case 4: return tc_launch_k<0, 4>(plan, st);
+    }
+    return tc_launch_k<0, 0>(plan, st);
+  }
   switch (plan.p.head_k) {
-    case 2: return tc_launch_k<2>(plan, st);
-    case 3: return tc_launch_k<3>(plan, st);
-    case 4: return tc_launch_k<4>(plan, st);
-    case 5: return tc_launch_k<5>(plan, st);
-    case 6: return tc_launch_k<6>(plan, st);
-    case 7: return tc_launch_k<7>(plan, st);
-    case 8: return tc_launch_k<8>(plan, st);
+    case 2: return tc_launch_head<2>(plan, st);
+    case 3: return tc_launch_head<3>(plan, st);
+    case 4: return tc_launch_head<4>(plan, st);
+    case 5: return tc_launch_head<5>(plan, st);
+    case 6: return tc_launch_head<6>(plan, st);
+    case 7: return tc_launch_head<7>(plan, st);
+    case 8: return tc_launch_head<8>(plan, st);
   }
   set_error("tc launch: fused head supports 2..8 classes");
   return 1;

@@ -48,6 +48,7 @@ struct TcConvParams {
   float *probs;                // mode 2 outputs (NHWC fp32 / u8), either may be NULL
   uint8_t *labels;
   const __nv_bfloat16 *wpack;  // packed weights [n_tile][chunk][kstep][2][n_cols][8]
+  int pdl_late;                // signal dependent launch after the last tile request (else at entry)
   int static_weights;          // packed weights are not written by earlier kernels of the stream (inference)
   uint32_t stage_off;          // mode 3: byte offset (from the epilogue tables) of the per-warp store staging
   int *status;                 // device word: non-zero = pipeline timeout code

@@ -11,7 +11,6 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from ..engine import UNetEngine
 from .. import _native as nat
 
 
@@ -29,6 +28,7 @@ class B200Model:
         self.name = name
         self.spec_kwargs = dict(spec_kwargs)
         self.precision = precision or os.environ.get("OCTSEG_PRECISION", "bf16")
+        from ..engine import UNetEngine   # late import: engine imports models.unet_spec
         self.engine = UNetEngine(precision=self.precision, device=device, **spec_kwargs)
         self.output = _Output(spec_kwargs["num_classes"])
         self.input_channels = spec_kwargs["input_channels"]
