@@ -232,9 +232,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // Everything above touches no global memory.  From here on the kernel reads what earlier kernels of
   // the stream wrote (activations, and in training the BN tables and repacked weights): wait for them.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  for (int i = threadIdx.x; i < p.cout; i += blockDim.x) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+  for (int i = threadIdx.x; i < p.cout; i += blockDim.x) {
+    const int c = i % p.scale_mod;           // row-pair mode: columns [parity][channel] share the channel tables
+    s_scale[i] = p.scale[c]; s_shift[i] = p.shift[c];
+  }
   if constexpr (HK > 0) {
-    for (int i = threadIdx.x; i < p.cout * HK; i += blockDim.x) s_head[i] = p.head_w[i];
+    for (int i = threadIdx.x; i < p.cout * HK; i += blockDim.x) s_head[i] = p.head_w[((i / HK) % p.scale_mod) * HK + (i % HK)];
     for (int i = threadIdx.x; i < HK; i += blockDim.x) s_head[p.cout * HK + i] = p.head_b[i];
   } else {
     (void)s_head;
@@ -278,7 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_expect_tx(afull, p.a_stage_bytes);
             // tensor map is declared in 8-byte elements: x coordinate = px * 2
             tma_load_4d(smem_u32(a_smem + (size_t)as * a_stride), &tmap_a, afull,
-                        (tx * p.mt_x * kTcTileW - p.pad_x) * 2, ty * p.mt_y * kTcTileH - p.pad_y,
+                        (tx * p.mt_x * kTcTileW - p.pad_x) * 2, ty * p.mt_y * kTcTileH * p.row_mul - p.pad_y,
                         ch * p.planes_per_chunk, img);
           }
           if (++as == p.a_stages) { as = 0; aph ^= 1u; }
@@ -326,7 +329,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         t_desc[j] = 0; t_col[j] = 0;
         if (t < mt) {
           const int iy = t / p.mt_x, ix = t - iy * p.mt_x;
-          t_desc[j] = ((uint32_t)iy * kTcTileH * pitch + (uint32_t)ix * 128u) >> 4;
+          t_desc[j] = ((uint32_t)iy * kTcTileH * (uint32_t)p.row_mul * pitch + (uint32_t)ix * 128u) >> 4;
           t_col[j] = (uint32_t)(t * p.n_cols);
           n_mine = j + 1;
         }
@@ -364,7 +367,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const int ks = g + s;
               const uint64_t db = make_desc(b_base + (uint32_t)s * kstep_b, lbo_b, 128u);
               // descriptors of the M-tiles differ only in the 14-bit start-address field
-              const uint64_t da0 = make_desc(a_base + p.a_off[ks], p.a_lbo[ks], pitch);
+              const uint64_t da0 = make_desc(a_base + p.a_off[ks], p.a_lbo[ks], pitch * (uint32_t)p.row_mul);
               const uint32_t accum = (ch | ks) != 0 ? 1u : 0u;
 #pragma unroll
               for (int j = 0; j < kMaxMine; ++j)
@@ -501,6 +504,112 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   *reinterpret_cast<uint4 *>(p.pool_out + (long long)img * p.pool_img_stride +
                                              (long long)(col_base >> 3) * (plane_elems >> 2) +
                                              ((long long)(y >> 1) * (p.out_w >> 1) + (x >> 1)) * 8) = pk;
+              }
+            }
+          }
+        }
+      } else if (EPI == 5 || EPI == 6) {
+        // ---- row pairs: this thread's GEMM row is pixel (2r, x); columns [parity][channel] are the
+        //      outputs (2r + parity, x).  EPI 5: 8 channels (2 chunks, two M-tiles per TMEM wait; plain /
+        //      pool / fused head), EPI 6: 16 channels (4 chunks, one M-tile per wait; plain / pool).
+        constexpr int PL = (EPI == 5) ? 1 : 2;         // output planes
+        constexpr int kB = (EPI == 5) ? 2 : 1;
+        constexpr int kWG = kTcEpiWarps / 4;
+        for (int t0 = wg_cur; t0 < mt; t0 += kB * kWG) {
+          uint32_t v[kB][2 * PL][8];
+#pragma unroll
+          for (int bb = 0; bb < kB; ++bb) {
+            const int t = t0 + bb * kWG;
+            if (t < mt) {
+              const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * p.n_cols);
+#pragma unroll
+              for (int c = 0; c < 2 * PL; ++c) tmem_ld8(ta + (uint32_t)(c * 8), v[bb][c]);
+            }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int bb = 0; bb < kB; ++bb) {
+            const int t = t0 + bb * kWG;
+            if (t >= mt) break;
+            const int iy = t >> p.mt_x_log2, ix = t & (p.mt_x - 1);
+            const int yb = ((ty * p.mt_y + iy) * kTcTileH + r) * 2, x = (tx * p.mt_x + ix) * kTcTileW + px;
+            uint4 pk[2][PL];
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+              const int y = yb + par;
+              const bool inside = (y < p.h) && (x < p.w);
+#pragma unroll
+              for (int c8 = 0; c8 < PL; ++c8) {
+                const int co0 = c8 * 8;
+                const float4 sa = *reinterpret_cast<const float4 *>(s_scale + co0), sb = *reinterpret_cast<const float4 *>(s_scale + co0 + 4);
+                const float4 ha = *reinterpret_cast<const float4 *>(s_shift + co0), hb = *reinterpret_cast<const float4 *>(s_shift + co0 + 4);
+                const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = fmaxf(fmaf(__uint_as_float(v[bb][par * PL + c8][k]), sc[k], sh[k]), relu_floor);
+                if constexpr (HK > 0) {
+                  float z[HK];
+#pragma unroll
+                  for (int k = 0; k < HK; ++k) z[k] = s_head[p.cout * HK + k];
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const float *wr = s_head + (co0 + c) * HK;
+#pragma unroll
+                    for (int k = 0; k < HK; ++k) z[k] = fmaf(o[c], wr[k], z[k]);
+                  }
+                  if (inside) {
+                    float mx = z[0];
+#pragma unroll
+                    for (int k = 1; k < HK; ++k) mx = fmaxf(mx, z[k]);
+                    float ssum = 0.f;
+#pragma unroll
+                    for (int k = 0; k < HK; ++k) { z[k] = __expf(z[k] - mx); ssum += z[k]; }
+                    const float inv = __frcp_rn(ssum);
+                    const long long pix = ((long long)img * p.h + y) * p.w + x;
+                    float pm = -1.f;
+                    int pa = 0;
+#pragma unroll
+                    for (int k = 0; k < HK; ++k) {
+                      z[k] *= inv;
+                      if (z[k] > pm) { pm = z[k]; pa = k; }
+                    }
+                    if (p.probs) {
+                      float *dst = p.probs + pix * HK;
+                      if constexpr (HK == 4) *reinterpret_cast<float4 *>(dst) = make_float4(z[0], z[1], z[2], z[3]);
+                      else {
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) dst[k] = z[k];
+                      }
+                    }
+                    if (p.labels) p.labels[pix] = (uint8_t)pa;
+                  }
+                } else {
+                  uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk[par][c8]);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) h2[k] = pack2(o[2 * k], o[2 * k + 1], p.fp16);
+                  if (inside)
+                    *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)c8 * plane_elems +
+                                               ((long long)y * p.out_w + x) * 8) = pk[par][c8];
+                }
+              }
+            }
+            if constexpr (HK == 0) {
+              if (p.pool_out) {
+                // 2x2 max: the vertical partner is the other parity of this thread, the horizontal one is lane ^ 1
+#pragma unroll
+                for (int c8 = 0; c8 < PL; ++c8) {
+                  uint4 pm;
+                  uint32_t *m2 = reinterpret_cast<uint32_t *>(&pm);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    uint32_t w0 = max2(reinterpret_cast<uint32_t *>(&pk[0][c8])[k], reinterpret_cast<uint32_t *>(&pk[1][c8])[k], p.fp16);
+                    m2[k] = max2(w0, __shfl_xor_sync(0xffffffffu, w0, 1), p.fp16);
+                  }
+                  if (yb + 1 < p.h && x < p.w && !(px & 1))
+                    *reinterpret_cast<uint4 *>(p.pool_out + (long long)img * p.pool_img_stride + (long long)c8 * (plane_elems >> 2) +
+                                               ((long long)(yb >> 1) * (p.out_w >> 1) + (x >> 1)) * 8) = pm;
+                }
               }
             }
           }
@@ -880,6 +989,20 @@ static inline uint16_t f2bf(float f) {
   return (uint16_t)(u >> 16);
 }
 
+void tc_rowpair_weights(const float *w, int cin, int cout, std::vector<float> *out) {
+  const int cols = 2 * cout;
+  out->assign((size_t)4 * 3 * cin * cols, 0.f);
+  for (int a = 0; a < 4; ++a)
+    for (int par = 0; par < 2; ++par) {
+      const int dy = a - par;
+      if (dy < 0 || dy > 2) continue;
+      for (int b = 0; b < 3; ++b)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int co = 0; co < cout; ++co)
+            (*out)[(((size_t)a * 3 + b) * cin + ci) * cols + par * cout + co] = w[(((size_t)dy * 3 + b) * cin + ci) * cout + co];
+    }
+}
+
 void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> *out, int fp16) {
   const int pt = g.pt, pl = g.pl;
   const size_t per_step = (size_t)2 * g.n_cols * 8;
@@ -1059,16 +1182,20 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
   }
   const size_t budget = 208 * 1024 - b_bytes_total - sizeof(TcBarriers) - epi_bytes - 1024;
   const int max_mt = std::max(1, 256 / g.n_cols);          // 2 accumulator stages in 512 TMEM columns
+  const int tile_h = kTcTileH * (g.rows2 ? 2 : 1);          // image rows covered by one M-tile
+  p.row_mul = g.rows2 ? 2 : 1;
+  p.scale_mod = g.rows2 ? g.cout / 2 : g.cout;
   static const int cand[][2] = {{8, 2}, {4, 2}, {8, 1}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
   int best_x = 1, best_y = 1;
   for (auto &c : cand) {
     const int mx = c[0], my = c[1];
     if (mx * my > max_mt) continue;
-    if (mx * kTcTileW > std::max(w, kTcTileW) || my * kTcTileH > std::max(h, kTcTileH)) continue;
-    const size_t stage = (size_t)g.planes_per_chunk * (mx * kTcTileW + g.box_w) * (my * kTcTileH + g.box_h) * 16;
-    if (stage > 48 * 1024 || 3 * stage > budget) continue;
+    if (mx * kTcTileW > std::max(w, kTcTileW) || my * tile_h > std::max(h, tile_h)) continue;
+    const size_t stage = (size_t)g.planes_per_chunk * (mx * kTcTileW + g.box_w) * (my * tile_h + g.box_h) * 16;
+    // three stages of <= 48 KB, or (row-pair tiles are twice as tall) two stages of <= 80 KB
+    if (!((stage <= 48 * 1024 && 3 * stage <= budget) || (g.rows2 && stage <= 80 * 1024 && 2 * stage <= budget))) continue;
     const long long tiles = (long long)n * ((w + mx * kTcTileW - 1) / (mx * kTcTileW)) *
-                            ((h + my * kTcTileH - 1) / (my * kTcTileH)) * g.n_tiles_n;
+                            ((h + my * tile_h - 1) / (my * tile_h)) * g.n_tiles_n;
     if (tiles < 2 * 148 && mx * my > 1) continue;            // keep every SM busy
     best_x = mx; best_y = my;
     break;
@@ -1077,9 +1204,9 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
   p.mt_x_log2 = best_x == 8 ? 3 : best_x == 4 ? 2 : best_x == 2 ? 1 : 0;
   p.shuffle_pairs = (g.ups && (g.n_cols % (2 * g.cout)) == 0 && (g.cols_valid % (2 * g.cout)) == 0) ? 1 : 0;
   p.box_w = best_x * kTcTileW + g.box_w;
-  p.box_h = best_y * kTcTileH + g.box_h;
+  p.box_h = best_y * tile_h + g.box_h;
   p.tiles_x = (w + best_x * kTcTileW - 1) / (best_x * kTcTileW);
-  p.tiles_y = (h + best_y * kTcTileH - 1) / (best_y * kTcTileH);
+  p.tiles_y = (h + best_y * tile_h - 1) / (best_y * tile_h);
   p.num_tiles = n * p.tiles_x * p.tiles_y * p.n_tiles_n;
   const uint32_t pitch = (uint32_t)p.box_w * 16u;
   const uint32_t plane = pitch * (uint32_t)p.box_h;
@@ -1141,6 +1268,10 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
     p.head_w = epi.head_w; p.head_b = epi.head_b; p.head_k = epi.head_k;
     p.probs = epi.probs; p.labels = epi.labels;
     p.out_h = h; p.out_w = w;
+  }
+  if (g.rows2) {
+    const int cr = g.cout / 2;
+    if (g.ups || g.n_tiles_n != 1 || (cr != 8 && cr != 16) || (epi.head_w && cr != 8)) { set_error("tc plan: row-pair mode not applicable"); return 1; }
   }
   if (g.stem_groups) {
     if (g.ups || epi.head_w || epi.pool_out || g.n_cols % 64 || g.cols_valid % 64) { set_error("tc plan: stem-group epilogue not applicable"); return 1; }
@@ -1205,6 +1336,7 @@ bool tc_head_fusable(int num_classes) { return num_classes >= 2 && num_classes <
 // epilogue specialisation of a plan (see conv_tc_kernel)
 static int tc_epi_kind(const TcConvParams &p) {
   const bool one_ntile = p.n_tiles_n == 1;
+  if (p.row_mul == 2) return p.scale_mod == 8 ? 5 : 6;
   if (p.mode == 3) return 3;
   if (p.mode == 1) return p.shuffle_pairs ? 4 : 0;
   if (one_ntile && p.cols_valid == 8) return 1;                     // mode 0 or 2 (fused head)
@@ -1214,7 +1346,9 @@ static int tc_epi_kind(const TcConvParams &p) {
 
 template <int HK>
 static int tc_launch_head(const TcPlan &plan, cudaStream_t st) {
-  return tc_epi_kind(plan.p) == 1 ? tc_launch_k<HK, 1>(plan, st) : tc_launch_k<HK, 0>(plan, st);
+  const int kind = tc_epi_kind(plan.p);
+  if (kind == 5) return tc_launch_k<HK, 5>(plan, st);
+  return kind == 1 ? tc_launch_k<HK, 1>(plan, st) : tc_launch_k<HK, 0>(plan, st);
 }
 
 int tc_launch(const TcPlan &plan, cudaStream_t st) {
@@ -1224,6 +1358,8 @@ int tc_launch(const TcPlan &plan, cudaStream_t st) {
       case 2: return tc_launch_k<0, 2>(plan, st);
       case 3: return tc_launch_k<0, 3>(plan, st);
       case 4: return tc_launch_k<0, 4>(plan, st);
+      case 5: return tc_launch_k<0, 5>(plan, st);
+      case 6: return tc_launch_k<0, 6>(plan, st);
     }
     return tc_launch_k<0, 0>(plan, st);
   }

@@ -48,6 +48,8 @@ struct TcConvParams {
   float *probs;                // mode 2 outputs (NHWC fp32 / u8), either may be NULL
   uint8_t *labels;
   const __nv_bfloat16 *wpack;  // packed weights [n_tile][chunk][kstep][2][n_cols][8]
+  int row_mul;                 // image rows per GEMM row (2 in row-pair mode, else 1)
+  int scale_mod;               // entries of scale / shift / head tables (real cout); table index = column % scale_mod
   int pdl_late;                // signal dependent launch after the last tile request (else at entry)
   int static_weights;          // packed weights are not written by earlier kernels of the stream (inference)
   uint32_t stage_off;          // mode 3: byte offset (from the epilogue tables) of the per-warp store staging
@@ -72,6 +74,8 @@ struct TcGeometry {
   int dy_min, dy_max, dx_min, dx_max;  // low-res tap range
   int planes_per_chunk, cin_chunks, ksteps, n_cols, n_tiles_n, cols_valid, bgroup;
   int box_w, box_h;                    // halo px / rows added around a super-tile
+  int rows2;                           // set by the caller: every GEMM row yields TWO vertically adjacent output pixels
+                                       // (geometry built for the 4x3 banded filter of tc_rowpair_weights)
   int stem_groups;                     // set by the caller: GEMM row = 8 adjacent pixels, columns = [plane][pixel][8 ch]
   // per k-step, per half: tap (dy,dx relative to dy_min/dx_min) and plane within chunk; tap -1 = zero
   int half_ty[kTcMaxKSteps][2], half_tx[kTcMaxKSteps][2], half_pl[kTcMaxKSteps][2];
@@ -80,6 +84,12 @@ struct TcGeometry {
 bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w);
 // pad_top/pad_left < 0: Keras "same" padding ((k-1)/2 before); otherwise explicit (data-gradient convs)
 int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, int pad_top = -1, int pad_left = -1);
+// Row-pair filter: GEMM row = pixel (2r, x) computes outputs (2r, x) and (2r+1, x) from the 4x3 input window
+// rows 2r-1 .. 2r+2; column par*cout + co holds output row 2r+par.  Weff[a][b][ci][par*cout+co] = w[a-par][b][ci][co]
+// for 0 <= a-par <= 2, else 0 (fp32 HWIO in, [4][3][cin][2*cout] out).  Geometry: tc_make_geometry(4, 3, cin,
+// 2*cout, 0, &g, 1, 1) and g.rows2 = 1.  Nine taps per pixel become six: the A operand (the smem-bandwidth-bound
+// side of narrow layers, 4 KB per K=16 step) is read 12 times per TWO output rows instead of 9 times per row.
+void tc_rowpair_weights(const float *w_hwio, int cin, int cout, std::vector<float> *out);
 // packs fp32 HWIO weights into the bf16 smem image the kernel streams (host memory)
 void tc_pack_weights(const TcGeometry &g, const float *w_hwio, std::vector<uint16_t> *out, int fp16 = 0);
 // same packing on the device, from fp32 weights in device memory (training)

@@ -165,6 +165,14 @@ int prepare_derived(octseg_net *net) {
       OCTSEG_CUDA(cudaMemcpyAsync(st.wpack, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice,
                                   net->stream));
       OCTSEG_CUDA(cudaStreamSynchronize(net->stream));   // `packed` is a stack-lifetime buffer
+      if (st.geo2_ok) {
+        std::vector<float> pair_w;
+        tc_rowpair_weights(net->h_params.data() + net->params[b.p_kernel].offset, b.cin, b.cout, &pair_w);
+        tc_pack_weights(st.geo2, pair_w.data(), &packed, net->precision == OCTSEG_FP16);
+        if (packed.size() != st.wpack2_elems) { set_error("internal: wpack2 size"); return 1; }
+        OCTSEG_CUDA(cudaMemcpyAsync(st.wpack2, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, net->stream));
+        OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+      }
     }
   }
   net->derived_dirty = false;
@@ -289,8 +297,10 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
         epi.head_k = last.cout;
         io.head_fused = true;
       }
-      if (tc_make_plan(net->bstate[b.index].geo, reinterpret_cast<const __nv_bfloat16 *>(io.in), n, io.in_h,
-                       io.in_w, net->bstate[b.index].wpack, epi, net->d_status, &io.plan))
+      const BlockState &bst = net->bstate[b.index];
+      const bool pair = bst.geo2_ok && (io.in_h % 2) == 0 && io.in_h >= 2 * kTcTileH && !epi.head_w;   // the fused head is epilogue-bound: fewer MMAs do not help it
+      if (tc_make_plan(pair ? bst.geo2 : bst.geo, reinterpret_cast<const __nv_bfloat16 *>(io.in), n, io.in_h,
+                       io.in_w, pair ? bst.wpack2 : bst.wpack, epi, net->d_status, &io.plan))
         return 1;
       io.use_tc = true;
     }
@@ -467,6 +477,7 @@ int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precisio
   }
   const char *e = std::getenv("OCTSEG_DISABLE_TC");
   net->disable_tc = e && e[0] == '1';
+  { const char *rp = std::getenv("OCTSEG_DISABLE_ROWPAIR"); net->disable_rowpair = rp && rp[0] == '1'; }
   e = std::getenv("OCTSEG_DISABLE_FUSION");
   net->disable_fusion = e && e[0] == '1';
   e = std::getenv("OCTSEG_MICROBATCH");
@@ -493,6 +504,15 @@ int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precisio
       st.wpack_elems = (size_t)st.geo.n_tiles_n * st.geo.cin_chunks * st.geo.ksteps * 2 * st.geo.n_cols * 8;
       OCTSEG_CUDA(cudaMalloc(&st.wpack, st.wpack_elems * 2));
     }
+    // row-pair variant (inference): 3x3 layers with 8 or 16 output channels are bound by the smem reads of
+    // the A operand; computing two output rows per GEMM row cuts those by a third
+    if (st.geo_ok && !net->disable_rowpair && !b.ups && b.kh == 3 && b.kw == 3 && (b.cout == 8 || b.cout == 16) &&
+        tc_make_geometry(4, 3, b.cin, 2 * b.cout, 0, &st.geo2, 1, 1) == 0 && st.geo2.n_tiles_n == 1) {
+      st.geo2_ok = true;
+      st.geo2.rows2 = 1;
+      st.wpack2_elems = (size_t)st.geo2.n_tiles_n * st.geo2.cin_chunks * st.geo2.ksteps * 2 * st.geo2.n_cols * 8;
+      OCTSEG_CUDA(cudaMalloc(&st.wpack2, st.wpack2_elems * 2));
+    }
     // tensor-core stem: 3x3, one input channel; GEMM row = 8 adjacent pixels (K = 8 per tap),
     // GEMM columns = 8 pixels x cout channels (a banded weight matrix, see stem_group_weights)
     if (precision != OCTSEG_FP32 && !net->disable_tc && b.index == 0 && b.kh == 3 && b.kw == 3 && b.cin == 1 &&
@@ -518,7 +538,7 @@ int32_t octseg_destroy(octseg_net *net) {
   for (auto &e : net->pipe_events) cudaEventDestroy(e);
   if (net->copy_in) cudaStreamDestroy(net->copy_in);
   if (net->copy_out) cudaStreamDestroy(net->copy_out);
-  for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); cudaFree(st.rep_scale); cudaFree(st.rep_shift); }
+  for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); cudaFree(st.rep_scale); cudaFree(st.rep_shift); cudaFree(st.wpack2); }
   cudaFree(net->d_params); cudaFree(net->ws); cudaFree(net->d_img); cudaFree(net->d_probs);
   cudaFree(net->d_labels); cudaFree(net->d_maps); cudaFree(net->d_status);
   if (net->h_status) cudaFreeHost(net->h_status);

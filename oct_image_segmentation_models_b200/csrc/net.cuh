@@ -42,6 +42,11 @@ struct BlockState {
   TcGeometry geo{};
   __nv_bfloat16 *wpack = nullptr;
   size_t wpack_elems = 0;
+  // inference-only row-pair variant of narrow 3x3 layers (cout 8 / 16): see tc_rowpair_weights
+  bool geo2_ok = false;
+  TcGeometry geo2{};
+  __nv_bfloat16 *wpack2 = nullptr;
+  size_t wpack2_elems = 0;
   float *rep_scale = nullptr, *rep_shift = nullptr;   // TC stem only: per-GEMM-column scale/255 and shift
 };
 
@@ -69,6 +74,7 @@ struct octseg_net {
   int64_t total_floats = 0;
   float *d_params = nullptr;          // flat fp32 master weights (Keras order)
   std::vector<float> h_params;        // host mirror
+  bool disable_rowpair = false;       // env OCTSEG_DISABLE_ROWPAIR=1 (experiments / tests)
   bool host_stale = false;            // device params changed (training) since last mirror
   bool derived_dirty = true;          // folded BN / packed weights need a rebuild
   std::vector<octseg::BlockState> bstate;
