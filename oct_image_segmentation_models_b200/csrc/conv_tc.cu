@@ -1192,8 +1192,8 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
     if (mx * my > max_mt) continue;
     if (mx * kTcTileW > std::max(w, kTcTileW) || my * tile_h > std::max(h, tile_h)) continue;
     const size_t stage = (size_t)g.planes_per_chunk * (mx * kTcTileW + g.box_w) * (my * tile_h + g.box_h) * 16;
-    // three stages of <= 48 KB, or (row-pair tiles are twice as tall) two stages of <= 80 KB
-    if (!((stage <= 48 * 1024 && 3 * stage <= budget) || (g.rows2 && stage <= 80 * 1024 && 2 * stage <= budget))) continue;
+    // three stages of <= 48 KB, or two stages of <= 80 KB (tall row-pair tiles, 8-plane chunks)
+    if (!((stage <= 48 * 1024 && 3 * stage <= budget) || (stage <= 80 * 1024 && 2 * stage <= budget))) continue;
     const long long tiles = (long long)n * ((w + mx * kTcTileW - 1) / (mx * kTcTileW)) *
                             ((h + my * tile_h - 1) / (my * tile_h)) * g.n_tiles_n;
     if (tiles < 2 * 148 && mx * my > 1) continue;            // keep every SM busy
