@@ -129,6 +129,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  "=r"(r[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -164,15 +174,30 @@ struct __align__(8) TcBarriers {
   uint32_t pad;
 };
 
-__device__ __forceinline__ void decode_tile(const TcConvParams &p, int tile, int &n_tile, int &tx,
-                                            int &ty, int &img) {
-  n_tile = tile % p.n_tiles_n;
-  int t = tile / p.n_tiles_n;
-  tx = t % p.tiles_x;
-  t /= p.tiles_x;
-  ty = t % p.tiles_y;
-  img = t / p.tiles_y;
-}
+// Tile coordinates of a persistent CTA, advanced by gridDim.x tiles per step with carries instead of
+// the four integer divisions per tile (measured: ~10 % of all instructions of the narrow layers).
+struct TileIter {
+  int n_tile, tx, ty, img;
+  int dn, dx, dy, dimg;
+  __device__ __forceinline__ void init(const TcConvParams &p, int tile, int step) {
+    n_tile = tile % p.n_tiles_n; int t = tile / p.n_tiles_n;
+    tx = t % p.tiles_x; t /= p.tiles_x;
+    ty = t % p.tiles_y; img = t / p.tiles_y;
+    dn = step % p.n_tiles_n; t = step / p.n_tiles_n;
+    dx = t % p.tiles_x; t /= p.tiles_x;
+    dy = t % p.tiles_y; dimg = t / p.tiles_y;
+  }
+  __device__ __forceinline__ void advance(const TcConvParams &p) {
+    n_tile += dn;
+    int c = 0;
+    if (n_tile >= p.n_tiles_n) { n_tile -= p.n_tiles_n; c = 1; }
+    tx += dx + c; c = 0;
+    if (tx >= p.tiles_x) { tx -= p.tiles_x; c = 1; }
+    ty += dy + c; c = 0;
+    if (ty >= p.tiles_y) { ty -= p.tiles_y; c = 1; }
+    img += dimg + c;
+  }
+};
 
 constexpr int kTcIssuers = 3;    // MMA-issuing threads (warps 1..3)
 constexpr int kTcEpiWarps = 12;   // epilogue warps 4..15 (three warpgroups)
@@ -268,9 +293,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       bool ok = true;
       long long w_prod = 0;
       const long long t_start = clock64();
-      for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
-        int n_tile, tx, ty, img;
-        decode_tile(p, tile, n_tile, tx, ty, img);
+      TileIter ti;
+      ti.init(p, blockIdx.x, gridDim.x);
+      for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x, ti.advance(p)) {
+        const int n_tile = ti.n_tile, tx = ti.tx, ty = ti.ty, img = ti.img;
         const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.wpack) +
                               (size_t)n_tile * p.cin_chunks * p.ksteps * 32u * p.n_cols;
         for (int ch = 0; ok && ch < p.cin_chunks; ++ch) {
@@ -405,9 +431,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     long long w_epi = 0;
     const long long t_start = clock64();
     int wgr = wg;                           // warpgroup -> M-tile assignment, rotated every super-tile
-    for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
-      int n_tile, tx, ty, img;
-      decode_tile(p, tile, n_tile, tx, ty, img);
+    TileIter ti;
+    ti.init(p, blockIdx.x, gridDim.x);
+    for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x, ti.advance(p)) {
+      const int n_tile = ti.n_tile, tx = ti.tx, ty = ti.ty, img = ti.img;
       // the M-tile count of a super-tile is a power of two and there are 3 warpgroups: rotating the
       // assignment spreads the odd tile over the warpgroups across consecutive super-tiles (the two
       // accumulator stages absorb the skew) instead of always loading warpgroup 0
@@ -462,10 +489,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 float mx = z[0];
 #pragma unroll
                 for (int k = 1; k < HK; ++k) mx = fmaxf(mx, z[k]);
+                mx *= 1.4426950408889634f;          // softmax in base 2: exp(z - max) = 2^((z - max) * log2 e)
                 float ssum = 0.f;
 #pragma unroll
-                for (int k = 0; k < HK; ++k) { z[k] = __expf(z[k] - mx); ssum += z[k]; }
-                const float inv = __frcp_rn(ssum);
+                for (int k = 0; k < HK; ++k) { z[k] = fast_exp2(fmaf(z[k], 1.4426950408889634f, -mx)); ssum += z[k]; }
+                const float inv = fast_rcp(ssum);
                 const long long pix = ((long long)img * p.h + y) * p.w + x;
                 float pm = -1.f;
                 int pa = 0;
@@ -562,10 +590,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     float mx = z[0];
 #pragma unroll
                     for (int k = 1; k < HK; ++k) mx = fmaxf(mx, z[k]);
+                    mx *= 1.4426950408889634f;
                     float ssum = 0.f;
 #pragma unroll
-                    for (int k = 0; k < HK; ++k) { z[k] = __expf(z[k] - mx); ssum += z[k]; }
-                    const float inv = __frcp_rn(ssum);
+                    for (int k = 0; k < HK; ++k) { z[k] = fast_exp2(fmaf(z[k], 1.4426950408889634f, -mx)); ssum += z[k]; }
+                    const float inv = fast_rcp(ssum);
                     const long long pix = ((long long)img * p.h + y) * p.w + x;
                     float pm = -1.f;
                     int pa = 0;
