@@ -477,13 +477,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int k = 0; k < 8; ++k) o[k] = fmaxf(fmaf(__uint_as_float(v[bb][k]), sc[k], sh[k]), relu_floor);
             if constexpr (HK > 0) {
               float z[HK];
+              if constexpr ((HK & 1) == 0) {
+                // even class count: the 1x1 conv runs on the packed f32x2 pipe (class pairs)
+                float2 z2[HK / 2];
 #pragma unroll
-              for (int k = 0; k < HK; ++k) z[k] = s_head[p.cout * HK + k];
+                for (int k = 0; k < HK / 2; ++k) z2[k] = *reinterpret_cast<const float2 *>(s_head + p.cout * HK + 2 * k);
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float *wr = s_head + (col_base + c) * HK;
+                for (int c = 0; c < 8; ++c) {
+                  const float2 *wr = reinterpret_cast<const float2 *>(s_head + (col_base + c) * HK);
+                  const float2 oo = make_float2(o[c], o[c]);
 #pragma unroll
-                for (int k = 0; k < HK; ++k) z[k] = fmaf(o[c], wr[k], z[k]);
+                  for (int k = 0; k < HK / 2; ++k) z2[k] = __ffma2_rn(oo, wr[k], z2[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < HK / 2; ++k) { z[2 * k] = z2[k].x; z[2 * k + 1] = z2[k].y; }
+              } else {
+#pragma unroll
+                for (int k = 0; k < HK; ++k) z[k] = s_head[p.cout * HK + k];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float *wr = s_head + (col_base + c) * HK;
+#pragma unroll
+                  for (int k = 0; k < HK; ++k) z[k] = fmaf(o[c], wr[k], z[k]);
+                }
               }
               if (inside) {
                 float mx = z[0];

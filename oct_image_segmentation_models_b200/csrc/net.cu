@@ -612,12 +612,12 @@ static int predict_pipeline(octseg_net *net, const void *images, int32_t dtype, 
   // Chunk size: total ~ H2D(chunk) + sum of forwards + D2H(last chunk), and a forward costs a fixed ~0.2 ms
   // (22 launches) plus ~0.022 ms per 512x512 B-scan.  With fp32 probabilities going back (4*K bytes per
   // pixel) the call is D2H-bound and small chunks start the return traffic early; with only label / boundary
-  // maps (1 + K-1 bytes per pixel) the forwards dominate and fewer, larger chunks win (measured on B200).
+  // maps (1 + K-1 bytes per pixel) the forwards dominate and fewer, larger chunks (~22 B-scans) win (measured on B200).
   int chunk;
   if (net->microbatch > 0) chunk = std::min(n, net->microbatch);
   else if (probs) chunk = std::min(n, 8);
   else if (n < 16) chunk = n;
-  else { const int nc = std::max(2, (n + 31) / 32); chunk = (n + nc - 1) / nc; }
+  else { const int nc = std::max(2, (n + 21) / 22); chunk = (n + nc - 1) / nc; }
   chunk = std::max(1, std::min(chunk, pick_microbatch(net, n, h, w)));   // workspace memory bound
   if (!net->copy_in) {
     OCTSEG_CUDA(cudaStreamCreateWithFlags(&net->copy_in, cudaStreamNonBlocking));
