@@ -1102,7 +1102,15 @@ __global__ void tc_pack_kernel(TcGeometry g, const float *__restrict__ w, int tr
     if (g.half_ty[s][hf] >= 0 && col < g.cols_valid) {
       const int dy = g.half_ty[s][hf] + g.dy_min, dx = g.half_tx[s][hf] + g.dx_min;
       const int ci = (ch * g.planes_per_chunk + g.half_pl[s][hf]) * 8 + kk;
-      if (!g.ups) {
+      if (g.rows2) {
+        // banded 4x3 row-pair filter built on the fly from the 3x3 kernel (tc_rowpair_weights)
+        const int cr = g.cout >> 1, par = col / cr, co = col - par * cr;
+        const int a = dy + pt - par, b = dx + pl;
+        if (a >= 0 && a <= 2) {
+          if (!transposed) val = w[(((long long)a * 3 + b) * g.cin + ci) * cr + co];
+          else val = w[(((long long)(2 - a) * 3 + (2 - b)) * cr + co) * g.cin + ci];
+        }
+      } else if (!g.ups) {
         const int a = dy + pt, b = dx + pl;
         if (!transposed) val = w[(((long long)a * g.kw + b) * g.cin + ci) * g.cout + col];
         else val = w[(((long long)(g.kh - 1 - a) * g.kw + (g.kw - 1 - b)) * g.cout + col) * g.cin + ci];
@@ -1140,7 +1148,14 @@ __global__ void tc_pack_all_kernel(const TcPackJob *__restrict__ jobs) {
     if (g.half_ty[s][hf] >= 0 && col < g.cols_valid) {
       const int dy = g.half_ty[s][hf] + g.dy_min, dx = g.half_tx[s][hf] + g.dx_min;
       const int ci = (ch * g.planes_per_chunk + g.half_pl[s][hf]) * 8 + kk;
-      if (!g.ups) {
+      if (g.rows2) {
+        const int cr = g.cout >> 1, par = col / cr, co = col - par * cr;
+        const int a = dy + pt - par, b = dx + pl;
+        if (a >= 0 && a <= 2) {
+          if (!j.transposed) val = j.w[(((long long)a * 3 + b) * g.cin + ci) * cr + co];
+          else val = j.w[(((long long)(2 - a) * 3 + (2 - b)) * cr + co) * g.cin + ci];
+        }
+      } else if (!g.ups) {
         const int a = dy + pt, b = dx + pl;
         if (!j.transposed) val = j.w[(((long long)a * g.kw + b) * g.cin + ci) * g.cout + col];
         else val = j.w[(((long long)(g.kh - 1 - a) * g.kw + (g.kw - 1 - b)) * g.cout + col) * g.cin + ci];

@@ -77,6 +77,10 @@ struct TrainBlock {
   TcGeometry geo_dgrad{};
   bool geo_dgrad_ok = false;
   __nv_bfloat16 *wpack_dgrad = nullptr;
+  // row-pair variants (conv_tc.cuh: tc_rowpair_weights) for narrow 3x3 layers
+  TcGeometry geo_dgrad2{};
+  bool geo_dgrad2_ok = false, fwd_pair = false, dgrad_pair = false;
+  __nv_bfloat16 *wpack_dgrad2 = nullptr;
   TcPlan plan_fwd, plan_dgrad;
 };
 
@@ -269,12 +273,16 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
       epi.scale = S->d_ones;
       epi.shift = net->d_params + net->params[b.p_bias].offset;
       epi.out = make_view((__nv_bfloat16 *)t.z, n, b.cout / 8, 0, b.cout / 8, t.h, t.w);
-      if (tc_make_plan(bs.geo, in_ptr, n, in_h, in_w, bs.wpack, epi, net->d_status, &t.plan_fwd)) return 1;
+      t.fwd_pair = bs.geo2_ok && (in_h % 2) == 0 && in_h >= 2 * kTcTileH;
+      if (tc_make_plan(t.fwd_pair ? bs.geo2 : bs.geo, in_ptr, n, in_h, in_w, t.fwd_pair ? bs.wpack2 : bs.wpack, epi,
+                       net->d_status, &t.plan_fwd))
+        return 1;
       t.tc_fwd = true;
     }
     if (t.geo_dgrad_ok && tc_supported(b.kh, b.kw, b.cout, b.cin, 0, t.h, t.w)) {
       // destination of the data gradient: fixed per block (see the buffer walk in train_step_t)
       t.tc_dgrad = true;
+      t.dgrad_pair = t.geo_dgrad2_ok && !b.ups && (t.h % 2) == 0 && t.h >= 2 * kTcTileH;
     }
   }
   for (auto &b : net->blocks) S->tb[b.index].plan_dgrad.valid = false;
@@ -284,14 +292,17 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
     TrainBlock &t = S->tb[b.index];
     if (t.tc_fwd) {
       TcPackJob j;
-      j.g = net->bstate[b.index].geo; j.w = net->d_params + net->params[b.p_kernel].offset;
-      j.out = net->bstate[b.index].wpack; j.total = (long long)net->bstate[b.index].wpack_elems; j.transposed = 0;
+      const BlockState &bs = net->bstate[b.index];
+      j.g = t.fwd_pair ? bs.geo2 : bs.geo; j.w = net->d_params + net->params[b.p_kernel].offset;
+      j.out = t.fwd_pair ? bs.wpack2 : bs.wpack; j.total = (long long)(t.fwd_pair ? bs.wpack2_elems : bs.wpack_elems);
+      j.transposed = 0;
       jobs.push_back(j);
     }
     if (t.tc_dgrad) {
       TcPackJob j;
-      j.g = t.geo_dgrad; j.w = net->d_params + net->params[b.p_kernel].offset; j.out = t.wpack_dgrad;
-      j.total = (long long)t.geo_dgrad.n_tiles_n * t.geo_dgrad.cin_chunks * t.geo_dgrad.ksteps * 2 * t.geo_dgrad.n_cols * 8;
+      const TcGeometry &gd = t.dgrad_pair ? t.geo_dgrad2 : t.geo_dgrad;
+      j.g = gd; j.w = net->d_params + net->params[b.p_kernel].offset; j.out = t.dgrad_pair ? t.wpack_dgrad2 : t.wpack_dgrad;
+      j.total = (long long)gd.n_tiles_n * gd.cin_chunks * gd.ksteps * 2 * gd.n_cols * 8;
       j.transposed = 1;
       jobs.push_back(j);
     }
@@ -498,8 +509,8 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
         epi.out = make_view((__nv_bfloat16 *)dst, n, dst_total, 0, b.cin / 8, t.h, t.w);
         // the destination buffer of a block never changes between steps: build the plan once
         if (!t.plan_dgrad.valid || t.plan_dgrad.p.out != epi.out.ptr) {
-          if (tc_make_plan(t.geo_dgrad, (const __nv_bfloat16 *)t.dz, n, t.h, t.w, t.wpack_dgrad, epi, net->d_status,
-                           &t.plan_dgrad))
+          if (tc_make_plan(t.dgrad_pair ? t.geo_dgrad2 : t.geo_dgrad, (const __nv_bfloat16 *)t.dz, n, t.h, t.w,
+                           t.dgrad_pair ? t.wpack_dgrad2 : t.wpack_dgrad, epi, net->d_status, &t.plan_dgrad))
             return 1;
         }
         if (tc_launch(t.plan_dgrad, st)) return 1;
@@ -567,7 +578,7 @@ void octseg_train_free(octseg_net *net) {
   if (S->ev_wg_done) cudaEventDestroy(S->ev_wg_done);
   if (S->ev_step_start) cudaEventDestroy(S->ev_step_start);
   if (S->wg_stream) cudaStreamDestroy(S->wg_stream);
-  for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); cudaFree(t.wpack_dgrad); }
+  for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); cudaFree(t.wpack_dgrad); cudaFree(t.wpack_dgrad2); }
   cudaFree(S->d_class_w); cudaFree(S->d_grads); cudaFree(S->d_m); cudaFree(S->d_v); cudaFree(S->d_ones); cudaFree(S->d_zeros);
   cudaFree(S->d_sums); cudaFree(S->d_loss); cudaFree(S->d_stem_tmp); cudaFree(S->ws); cudaFree(S->d_img);
   cudaFree(S->d_labels); cudaFree(S->d_mask_in); cudaFree(S->d_pack_jobs); cudaFree(S->d_state);
@@ -628,6 +639,15 @@ int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc, const
         const size_t elems = (size_t)t.geo_dgrad.n_tiles_n * t.geo_dgrad.cin_chunks * t.geo_dgrad.ksteps * 2 *
                              t.geo_dgrad.n_cols * 8;
         OCTSEG_CUDA(cudaMalloc(&t.wpack_dgrad, elems * 2));
+        // data gradient of a 3x3 layer whose INPUT has 8 / 16 channels: row-pair variant
+        if (!net->disable_rowpair && !b.ups && b.kh == 3 && b.kw == 3 && (b.cin == 8 || b.cin == 16) &&
+            tc_make_geometry(4, 3, b.cout, 2 * b.cin, 0, &t.geo_dgrad2, 1, 1) == 0 && t.geo_dgrad2.n_tiles_n == 1) {
+          t.geo_dgrad2_ok = true;
+          t.geo_dgrad2.rows2 = 1;
+          const size_t e2 = (size_t)t.geo_dgrad2.n_tiles_n * t.geo_dgrad2.cin_chunks * t.geo_dgrad2.ksteps * 2 *
+                            t.geo_dgrad2.n_cols * 8;
+          OCTSEG_CUDA(cudaMalloc(&t.wpack_dgrad2, e2 * 2));
+        }
       }
     }
   }
