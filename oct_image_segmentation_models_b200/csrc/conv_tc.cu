@@ -1017,7 +1017,7 @@ int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, 
   }
   if (ks > kTcMaxKSteps) return 1;
   g->ksteps = ks;
-  g->bgroup = (ks * 32 * nc <= 32768) ? ks : g->planes_per_chunk / 2;
+  g->bgroup = (ks * 32 * nc <= 32768) ? ks : std::max(1, g->planes_per_chunk / 2);   // (>= 1: one-plane chunks pair taps)
   if (ks % g->bgroup) return 1;
   return 0;
 }

@@ -267,3 +267,40 @@ def test_fp16_storage_mode_parity():
     segs = np.stack([postproc.boundaries_from_probs(probs[i:i + 1]) for i in range(len(g["images"]))])
     d = np.abs(segs.astype(np.int32) - g["segs"].astype(np.int32))
     assert d.max() <= 1 and (d == 0).mean() >= 0.998
+
+
+SWEEP = [
+    # (config, n, h, w): ragged tiles, shapes on both sides of the row-pair / tensor-core-stem thresholds,
+    # class counts with and without the packed-pair head, nets whose narrow layers are 16 / 32 wide
+    (dict(input_channels=1, num_classes=2, start_neurons=8, pool_layers=2, conv_layers=1), 3, 40, 72),
+    (dict(input_channels=1, num_classes=3, start_neurons=8, pool_layers=3, conv_layers=2), 2, 96, 136),
+    (dict(input_channels=1, num_classes=5, start_neurons=16, pool_layers=2, conv_layers=2), 2, 64, 128),
+    (dict(input_channels=1, num_classes=9, start_neurons=8, pool_layers=2, conv_layers=3), 1, 32, 64),
+    (dict(input_channels=1, num_classes=4, start_neurons=16, pool_layers=3, conv_layers=2), 1, 136, 72),
+    (dict(input_channels=1, num_classes=7, start_neurons=32, pool_layers=1, conv_layers=2), 2, 34, 66),
+    (dict(input_channels=3, num_classes=4, start_neurons=8, pool_layers=2, conv_layers=2), 2, 48, 64),
+    (dict(input_channels=1, num_classes=4, start_neurons=32, pool_layers=2, conv_layers=2), 1, 64, 128),   # 256-column TC stem
+    (dict(input_channels=1, num_classes=6, start_neurons=16, pool_layers=4, conv_layers=2), 1, 32, 96),
+]
+
+
+@pytest.mark.parametrize("cfg,n,h,w", SWEEP)
+def test_config_sweep_all_precisions_vs_oracle(cfg, n, h, w):
+    """Other members of the reference's U-Net family (unet.py:106-153 is parameterised by start_neurons,
+    pool_layers, conv_layers, num_classes, input_channels) through every kernel specialisation."""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    weights = synthetic_weights(seed=77, **cfg)
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(0, 256, size=(n, h, w, cfg["input_channels"]), dtype=np.uint8)
+    ref = OracleUNet(weights, **cfg).predict(imgs)
+    for precision, tol in (("fp32", FP32_REL), ("bf16", BF16_REL), ("fp16", BF16_REL)):
+        eng = UNetEngine(precision=precision, **cfg)
+        eng.set_weights(weights)
+        p, lab = eng.predict(imgs, want_labels=True)
+        assert rel_err(p, ref).max() <= tol, (precision, float(rel_err(p, ref).max()))
+        assert np.array_equal(lab, p.argmax(-1))
+        lab2, maps = eng.predict_maps(imgs)
+        assert np.array_equal(lab2, lab)
+        _, cat = postproc.perform_argmax(p)
+        assert np.array_equal(maps, postproc.convert_predictions_to_maps_semantic(cat, bg_ilm=True, bg_csi=False))
+        eng.close()
