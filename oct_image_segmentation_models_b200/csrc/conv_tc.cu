@@ -254,19 +254,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   }
-  // Everything above touches no global memory.  From here on the kernel reads what earlier kernels of
-  // the stream wrote (activations, and in training the BN tables and repacked weights): wait for them.
+  // Everything above touches no global memory written by earlier kernels.  From here on the kernel reads
+  // what earlier kernels of the stream wrote (activations, and in training the BN tables and repacked
+  // weights): wait for them.  In inference the epilogue tables are static too and are fetched first.
+  auto load_tables = [&]() {
+    for (int i = threadIdx.x; i < p.cout; i += blockDim.x) {
+      const int c = i % p.scale_mod;           // row-pair mode: columns [parity][channel] share the channel tables
+      s_scale[i] = p.scale[c]; s_shift[i] = p.shift[c];
+    }
+    if constexpr (HK > 0) {
+      for (int i = threadIdx.x; i < p.cout * HK; i += blockDim.x) s_head[i] = p.head_w[((i / HK) % p.scale_mod) * HK + (i % HK)];
+      for (int i = threadIdx.x; i < HK; i += blockDim.x) s_head[p.cout * HK + i] = p.head_b[i];
+    } else {
+      (void)s_head;
+    }
+  };
+  if (p.static_weights) load_tables();
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  for (int i = threadIdx.x; i < p.cout; i += blockDim.x) {
-    const int c = i % p.scale_mod;           // row-pair mode: columns [parity][channel] share the channel tables
-    s_scale[i] = p.scale[c]; s_shift[i] = p.shift[c];
-  }
-  if constexpr (HK > 0) {
-    for (int i = threadIdx.x; i < p.cout * HK; i += blockDim.x) s_head[i] = p.head_w[((i / HK) % p.scale_mod) * HK + (i % HK)];
-    for (int i = threadIdx.x; i < HK; i += blockDim.x) s_head[p.cout * HK + i] = p.head_b[i];
-  } else {
-    (void)s_head;
-  }
+  if (!p.static_weights) load_tables();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
