@@ -350,6 +350,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t pitch = (uint32_t)p.box_w * 16u;
       const uint32_t lbo_b = (uint32_t)p.n_cols * 16u;
       const uint32_t kstep_b = 32u * (uint32_t)p.n_cols;
+      const uint32_t a_hi = ((pitch * (uint32_t)p.row_mul) >> 4) | (1u << 14);   // SBO | descriptor version bit 46
+      const uint32_t b_hi = (128u >> 4) | (1u << 14);
       // this issuer's M-tiles: descriptor start-address deltas (16 B units) and TMEM column offsets
       constexpr int kMaxMine = (16 + kTcIssuers - 1) / kTcIssuers;
       uint32_t t_desc[kMaxMine], t_col[kMaxMine];
@@ -394,15 +396,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tc_fence_after();
               b_base = smem_u32(b_smem + (size_t)bs * b_stride);
             }
+            // Descriptors are assembled from precomputed 32-bit halves: the low word is a table entry
+            // plus the stage base (all operands are 16-byte aligned and below 256 KB, so the 14-bit
+            // address field cannot carry into the stride field), the high word is constant.  A single
+            // issuing thread is latency-bound on this loop, so it is kept to a handful of instructions.
+            uint32_t b_lo = ((b_base >> 4) & 0x3FFFu) | ((lbo_b >> 4) << 16);
+            const uint32_t a_base16 = (a_base >> 4) & 0x3FFFu;
+#pragma unroll 2
             for (int s = 0; s < p.bgroup; ++s) {
               const int ks = g + s;
-              const uint64_t db = make_desc(b_base + (uint32_t)s * kstep_b, lbo_b, 128u);
-              // descriptors of the M-tiles differ only in the 14-bit start-address field
-              const uint64_t da0 = make_desc(a_base + p.a_off[ks], p.a_lbo[ks], pitch * (uint32_t)p.row_mul);
+              const uint32_t a_lo = p.a_desc_lo[ks] + a_base16;
+              const uint64_t db = ((uint64_t)b_hi << 32) | b_lo;
               const uint32_t accum = (ch | ks) != 0 ? 1u : 0u;
 #pragma unroll
               for (int j = 0; j < kMaxMine; ++j)
-                if (j < n_mine) umma_bf16(d_tmem + t_col[j], da0 + t_desc[j], db, idesc, accum);
+                if (j < n_mine) umma_bf16(d_tmem + t_col[j], ((uint64_t)a_hi << 32) | (a_lo + t_desc[j]), db, idesc, accum);
+              b_lo += kstep_b >> 4;
             }
             if (!p.b_resident) {
               umma_commit(smem_u32(&bars->b_empty[bs]));
@@ -1261,7 +1270,9 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
     if (!((stage <= 48 * 1024 && 3 * stage <= budget) || (stage <= 80 * 1024 && 2 * stage <= budget))) continue;
     const long long tiles = (long long)n * ((w + mx * kTcTileW - 1) / (mx * kTcTileW)) *
                             ((h + my * tile_h - 1) / (my * tile_h)) * g.n_tiles_n;
-    if (tiles < 2 * 148 && mx * my > 1) continue;            // keep every SM busy
+    // keep every SM busy, but prefer >= 2 M-tiles per super-tile while one full round remains: a lone
+    // M-tile is issued by a single thread (~2x slower than the tensor pipe, see the issuer comment)
+    if (tiles < 148 && mx * my > 1) continue;
     best_x = mx; best_y = my;
     break;
   }
@@ -1286,6 +1297,7 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
     if (off[1] <= off[0]) { set_error("tc plan: non-positive LBO"); return 1; }
     p.a_off[s] = off[0];
     p.a_lbo[s] = off[1] - off[0];
+    p.a_desc_lo[s] = (off[0] >> 4) | (((off[1] - off[0]) >> 4) << 16);
     if (p.a_lbo[s] >= (1u << 18) || pitch >= (1u << 18)) { set_error("tc plan: descriptor stride overflow"); return 1; }
   }
   const uint32_t a_stride = (p.a_stage_bytes + 127u) & ~127u;

@@ -31,6 +31,7 @@ struct TcConvParams {
   uint32_t a_stage_bytes, b_stage_bytes;
   uint32_t a_off[kTcMaxKSteps];   // byte offset of the k-step's first 8-channel half
   uint32_t a_lbo[kTcMaxKSteps];   // byte distance to its second half
+  uint32_t a_desc_lo[kTcMaxKSteps];   // (a_off >> 4) | ((a_lbo >> 4) << 16): low descriptor word minus the stage base
   // epilogue
   int mode;                    // 0: plain blocked store, 1: 2x2 pixel-shuffle store (up-conv),
                                // 2: fused 1x1-conv + softmax head (activation never stored)
