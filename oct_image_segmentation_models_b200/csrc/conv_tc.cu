@@ -155,6 +155,15 @@ __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int fp16) {
   return *reinterpret_cast<uint32_t *>(&r);
 }
 
+// Folded BN + ReLU + 16-bit pack of two accumulator values: one packed f32x2 FMA, one convert, one packed
+// 16-bit max against `floor2` (0 | 0 with ReLU, the most negative finite pair without).  ReLU after the
+// rounding equals ReLU before it (rounding is monotonic and keeps 0).
+__device__ __forceinline__ uint32_t bn_relu_pack2(uint32_t v0, uint32_t v1, float s0, float s1, float h0, float h1,
+                                                 uint32_t floor2, int fp16) {
+  const float2 y = __ffma2_rn(make_float2(__uint_as_float(v0), __uint_as_float(v1)), make_float2(s0, s1), make_float2(h0, h1));
+  return max2(pack2(y.x, y.y, fp16), floor2, fp16);
+}
+
 // K-major, no-swizzle shared-memory matrix descriptor (sm_100 "version 1").
 //   core matrix = 8 rows x 16 B, rows 16 B apart; SBO = bytes between 8-row groups,
 //   LBO = bytes between the two 8-element K halves of one K=16 step.
@@ -437,6 +446,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int m = q * 32 + lane;            // GEMM row == TMEM lane
     const int r = m >> 3, px = m & 7;       // row / px inside the 8x16 M-tile
     const float relu_floor = p.relu ? 0.f : -3.0e38f;
+    const uint32_t floor2 = p.relu ? 0u : (p.fp16 ? 0xFBFFFBFFu : 0xFF7FFF7Fu);   // packed 16-bit ReLU floor
     const int nch = (min(p.cols_valid, p.n_cols)) >> 3;      // chunks per n-tile holding valid columns
     const long long plane_elems = (long long)p.out_h * p.out_w * 8;
     int acc = 0;
@@ -546,7 +556,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               uint4 pk;
               uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) h2[k] = pack2(o[2 * k], o[2 * k + 1], p.fp16);
+              for (int k = 0; k < 4; ++k)
+                h2[k] = bn_relu_pack2(v[bb][2 * k], v[bb][2 * k + 1], sc[2 * k], sc[2 * k + 1], sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
               if (inside)
                 *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)(col_base >> 3) * plane_elems +
                                            ((long long)y * p.out_w + x) * 8) = pk;
@@ -646,7 +657,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 } else {
                   uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk[par][c8]);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) h2[k] = pack2(o[2 * k], o[2 * k + 1], p.fp16);
+                  for (int k = 0; k < 4; ++k)
+                    h2[k] = bn_relu_pack2(v[bb][par * PL + c8][2 * k], v[bb][par * PL + c8][2 * k + 1], sc[2 * k], sc[2 * k + 1],
+                                          sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
                   if (inside)
                     *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)c8 * plane_elems +
                                                ((long long)y * p.out_w + x) * 8) = pk[par][c8];
@@ -707,8 +720,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                h2[k] = pack2(fmaxf(fmaf(__uint_as_float(v[bb][u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
-                              fmaxf(fmaf(__uint_as_float(v[bb][u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor), p.fp16);
+                h2[k] = bn_relu_pack2(v[bb][u][2 * k], v[bb][u][2 * k + 1], sc[2 * k], sc[2 * k + 1], sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
               if (inside)
                 *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)(co0 >> 3) * plane_elems +
                                            ((long long)y * p.out_w + x) * 8) = pk;
@@ -813,8 +825,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk[u]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  h2[k] = pack2(fmaxf(fmaf(__uint_as_float(v[u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
-                                fmaxf(fmaf(__uint_as_float(v[u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor), p.fp16);
+                  h2[k] = bn_relu_pack2(v[u][2 * k], v[u][2 * k + 1], sc[2 * k], sc[2 * k + 1], sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
               }
               if (inside) {
                 __nv_bfloat16 *dst = p.out + (long long)img * p.out_img_stride + (long long)c8 * plane_elems +
@@ -857,8 +868,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 uint32_t h2[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  h2[k] = pack2(fmaxf(fmaf(__uint_as_float(v[cur][u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
-                                fmaxf(fmaf(__uint_as_float(v[cur][u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor), p.fp16);
+                  h2[k] = bn_relu_pack2(v[cur][u][2 * k], v[cur][u][2 * k + 1], sc[2 * k], sc[2 * k + 1], sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
                 const uint32_t slot = (uint32_t)((jj + u) ^ (lane & 7));
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_u32 + (uint32_t)lane * 128u + slot * 16u),
                              "r"(h2[0]), "r"(h2[1]), "r"(h2[2]), "r"(h2[3]) : "memory");
@@ -908,8 +918,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                h2[k] = pack2(fmaxf(fmaf(__uint_as_float(v[u][2 * k]), sc[2 * k], sh[2 * k]), relu_floor),
-                              fmaxf(fmaf(__uint_as_float(v[u][2 * k + 1]), sc[2 * k + 1], sh[2 * k + 1]), relu_floor), p.fp16);
+                h2[k] = bn_relu_pack2(v[u][2 * k], v[u][2 * k + 1], sc[2 * k], sc[2 * k + 1], sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
               if (inside)
                 *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)(co0 >> 3) * plane_elems + off) = pk;
               if (p.pool_out) {
