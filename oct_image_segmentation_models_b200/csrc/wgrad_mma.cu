@@ -197,6 +197,9 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgParams p) {
 // TMA-pipelined variant (non-upsampled inputs): warp 0 streams (input halo tile, dz tile)
 // pairs through an mbarrier ring, warps 1..8 run the MMAs; no staging instructions at all.
 // ----------------------------------------------------------------------------------
+constexpr int kWmCW = 16;                          // compute warps of the TMA kernel: 8 tile rows x 2 halves of the m16 tiles
+constexpr int kWmLocalMT = (kWmMaxMT + 1) / 2;     // m16 tiles per compute warp (accumulators: 7 x NB x 4 registers)
+constexpr int kWmTmaThreads = 32 * (1 + kWmCW);
 constexpr int kWmMaxStages = 8;   // ring depth is chosen per launch: small tiles need many loads in flight
 
 __device__ __forceinline__ uint32_t wm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -212,7 +215,7 @@ __device__ __forceinline__ bool wm_wait(uint32_t bar, uint32_t parity) {
 }
 
 template <int NB>
-__global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(kWmTmaThreads) wgrad_mma_tma_kernel(const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_d,
                                                             const WgParams p, int th, int n_stages, int *status) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
   if (threadIdx.x == 0) {
     for (int i = 0; i < n_stages; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[i])), "r"(1) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[n_stages + i])), "r"(8) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[n_stages + i])), "r"(kWmCW) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -277,16 +280,24 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
       if (++st == n_stages) { st = 0; ph ^= 1u; }
     }
   } else {
-    // ---------------- consumers: warp w-1 owns rows (w-1), (w-1)+8, ... of every tile ----------------
-    const int cw = warp - 1;
-    uint32_t a_off[kWmMaxMT];
+    // ---------------- consumers: 16 warps = 8 tile rows x 2 halves of the m16 tiles ----------------
+    // Warp (row cw, half) owns rows cw, cw+8, ... of every tile and the m16 tiles [mt_base, mt_base+n_loc):
+    // splitting M instead of pixels halves the accumulator registers per thread, so twice as many warps
+    // fit and hide the ldmatrix -> mma latency (the 8-warp version kept the tensor pipe 22-28 % busy).
+    const int cwi = warp - 1;
+    const int cw = cwi & 7, half = cwi >> 3;
+    const int split = (n_mt + 1) / 2;
+    const int mt_base = half ? split : 0;
+    const int n_loc = half ? (n_mt - split) : split;
+    uint32_t a_off[kWmLocalMT];
     {
       const int i = lane >> 3, r = lane & 7;
 #pragma unroll
-      for (int mt = 0; mt < kWmMaxMT; ++mt) {
+      for (int j = 0; j < kWmLocalMT; ++j) {
+        const int mt = mt_base + j;
         int g = 2 * mt + (i & 1);
         uint32_t off = 0;
-        if (mt < n_mt) {
+        if (j < n_loc) {
           if (g >= ng_all) g = 0;
           if (g == ones_group) off = 0x80000000u | (uint32_t)(r * 16);
           else {
@@ -296,13 +307,13 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
             off = (uint32_t)((((cgl * ah + dy) * aw + dx) + r + 8 * (i >> 1)) * 16);
           }
         }
-        a_off[mt] = off;
+        a_off[j] = off;
       }
     }
     const uint32_t so_base = wm_smem_u32(s_ones);
-    float acc[kWmMaxMT][NB][4];
+    float acc[kWmLocalMT][NB][4];
 #pragma unroll
-    for (int mt = 0; mt < kWmMaxMT; ++mt)
+    for (int mt = 0; mt < kWmLocalMT; ++mt)
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
@@ -328,8 +339,8 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
           }
           const uint32_t row_off = (uint32_t)((y * aw + ks * 16) * 16);
 #pragma unroll
-          for (int mt = 0; mt < kWmMaxMT; ++mt) {
-            if (mt < n_mt) {
+          for (int mt = 0; mt < kWmLocalMT; ++mt) {
+            if (mt < n_loc) {
               uint32_t afrag[4];
               const uint32_t o = a_off[mt];
               const uint32_t addr = (o & 0x80000000u) ? so_base + (o & 0x7FFFFFFFu) : sa_base + o + row_off;
@@ -345,15 +356,16 @@ __global__ void __launch_bounds__(288) wgrad_mma_tma_kernel(const __grid_constan
       if (++st == n_stages) { st = 0; ph ^= 1u; }
     }
 #pragma unroll
-    for (int mt = 0; mt < kWmMaxMT; ++mt) {
-      if (mt < n_mt) {
+    for (int mt = 0; mt < kWmLocalMT; ++mt) {
+      if (mt < n_loc) {
+        const int gm = mt_base + mt;            // global m16 tile
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
           const int ci = lane >> 2, co = nb * 8 + (lane & 3) * 2;
-          atomicAdd(&s_acc[((2 * mt) * 8 + ci) * (NB * 8) + co], acc[mt][nb][0]);
-          atomicAdd(&s_acc[((2 * mt) * 8 + ci) * (NB * 8) + co + 1], acc[mt][nb][1]);
-          atomicAdd(&s_acc[((2 * mt + 1) * 8 + ci) * (NB * 8) + co], acc[mt][nb][2]);
-          atomicAdd(&s_acc[((2 * mt + 1) * 8 + ci) * (NB * 8) + co + 1], acc[mt][nb][3]);
+          atomicAdd(&s_acc[((2 * gm) * 8 + ci) * (NB * 8) + co], acc[mt][nb][0]);
+          atomicAdd(&s_acc[((2 * gm) * 8 + ci) * (NB * 8) + co + 1], acc[mt][nb][1]);
+          atomicAdd(&s_acc[((2 * gm + 1) * 8 + ci) * (NB * 8) + co], acc[mt][nb][2]);
+          atomicAdd(&s_acc[((2 * gm + 1) * 8 + ci) * (NB * 8) + co + 1], acc[mt][nb][3]);
         }
       }
     }
@@ -418,8 +430,8 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
       const int blocks_y2 = p.n_pchunks * p.n_gblocks * p.n_nchunks;
       int gx2 = std::max(1, std::min(p.num_tiles, (148 + blocks_y2 - 1) / blocks_y2));
       dim3 grid2(gx2, blocks_y2);
-      if (p.d_planes == 1) wgrad_mma_tma_kernel<1><<<grid2, 288, smem2, st>>>(map_a, map_d, p, th, n_stages, status);
-      else wgrad_mma_tma_kernel<2><<<grid2, 288, smem2, st>>>(map_a, map_d, p, th, n_stages, status);
+      if (p.d_planes == 1) wgrad_mma_tma_kernel<1><<<grid2, kWmTmaThreads, smem2, st>>>(map_a, map_d, p, th, n_stages, status);
+      else wgrad_mma_tma_kernel<2><<<grid2, kWmTmaThreads, smem2, st>>>(map_a, map_d, p, th, n_stages, status);
       OCTSEG_CUDA(cudaGetLastError());
       return 0;
     }
