@@ -197,8 +197,9 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgParams p) {
 // TMA-pipelined variant (non-upsampled inputs): warp 0 streams (input halo tile, dz tile)
 // pairs through an mbarrier ring, warps 1..8 run the MMAs; no staging instructions at all.
 // ----------------------------------------------------------------------------------
-constexpr int kWmCW = 16;                          // compute warps of the TMA kernel: 8 tile rows x 2 halves of the m16 tiles
-constexpr int kWmLocalMT = (kWmMaxMT + 1) / 2;     // m16 tiles per compute warp (accumulators: 7 x NB x 4 registers)
+constexpr int kWmSplit = 3;                        // warp groups sharing the m16 tiles of a CTA
+constexpr int kWmCW = 8 * kWmSplit;                // compute warps of the TMA kernel: 8 tile rows x kWmSplit parts of the m16 tiles
+constexpr int kWmLocalMT = (kWmMaxMT + kWmSplit - 1) / kWmSplit;   // m16 tiles per compute warp
 constexpr int kWmTmaThreads = 32 * (1 + kWmCW);
 constexpr int kWmMaxStages = 8;   // ring depth is chosen per launch: small tiles need many loads in flight
 
@@ -285,10 +286,10 @@ __global__ void __launch_bounds__(kWmTmaThreads) wgrad_mma_tma_kernel(const __gr
     // splitting M instead of pixels halves the accumulator registers per thread, so twice as many warps
     // fit and hide the ldmatrix -> mma latency (the 8-warp version kept the tensor pipe 22-28 % busy).
     const int cwi = warp - 1;
-    const int cw = cwi & 7, half = cwi >> 3;
-    const int split = (n_mt + 1) / 2;
-    const int mt_base = half ? split : 0;
-    const int n_loc = half ? (n_mt - split) : split;
+    const int cw = cwi & 7, part = cwi >> 3;
+    const int per = (n_mt + kWmSplit - 1) / kWmSplit;
+    const int mt_base = part * per;
+    const int n_loc = max(0, min(per, n_mt - mt_base));
     uint32_t a_off[kWmLocalMT];
     {
       const int i = lane >> 3, r = lane & 7;
