@@ -44,16 +44,30 @@ def predict(predict_params: PredictionParams, batch_size: int = 64) -> List[Pred
     for i0 in range(0, len(images), batch_size):
         chunk = np.asarray(images[i0:i0 + batch_size])
         t0 = time.time()
-        if chunk.dtype == np.uint8:
+        engine = getattr(model, "engine", None)
+        dev_labels = dev_maps = probs = None
+        if chunk.dtype == np.uint8 and engine is not None:
+            # What the reference keeps of a forward pass is the argmax and the boundary maps built from it
+            # (reference prediction.py:97-104); both are produced on the GPU and 1 + (K-1) bytes per pixel come
+            # back instead of 4*K bytes of probabilities (bit-identical to the numpy chain on the same labels:
+            # tests/test_gpu_parity.py::test_device_boundary_maps_match_reference_semantics).
+            dev_labels, dev_maps = engine.predict_maps(np.ascontiguousarray(chunk), bg_ilm=True, bg_csi=False)
+        elif chunk.dtype == np.uint8:
             probs = model.predict(chunk)                       # fused on-device x/255
         else:
             probs = model.predict(preprocess(chunk), verbose=2, batch_size=1)
         predict_time = (time.time() - t0) / len(chunk)
         for k in range(len(chunk)):
             i = i0 + k
-            predicted_labels, categorical_pred = utils.perform_argmax(probs[k:k + 1], bin=True)
-            boundary_maps = utils.convert_predictions_to_maps_semantic(np.array(categorical_pred),
-                                                                       bg_ilm=True, bg_csi=False)
+            if dev_labels is not None:
+                num_maps = predict_params.num_classes
+                predicted_labels = dev_labels[k:k + 1].astype(np.int64)          # np.argmax's dtype
+                categorical_pred = np.transpose(utils.to_categorical(predicted_labels, num_maps), axes=(0, 3, 1, 2))
+                boundary_maps = dev_maps[k:k + 1]
+            else:
+                predicted_labels, categorical_pred = utils.perform_argmax(probs[k:k + 1], bin=True)
+                boundary_maps = utils.convert_predictions_to_maps_semantic(np.array(categorical_pred),
+                                                                           bg_ilm=True, bg_csi=False)
             predicted_labels = np.squeeze(predicted_labels)
             categorical_pred = np.squeeze(categorical_pred)
             boundary_maps = np.squeeze(boundary_maps)
