@@ -58,3 +58,46 @@ def gather_in_order(local: Optional[np.ndarray], dist=None) -> Optional[List[np.
     dist.all_gather_object(out, local)
     parts = [p for p in out if p is not None]
     return np.concatenate(parts, axis=0) if parts else None
+
+
+def allreduce_sum_scalar(value: float, dist=None) -> float:
+    """Sum of a host scalar over the ranks (loss / metric logging; the reference reduces its logged values
+    across replicas the same way).  Backend-agnostic (object gather), not on the data path."""
+    if dist is None:
+        import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, float(value))
+    return float(sum(out))
+
+
+def mean_over_ranks(arrays: List[np.ndarray], dist=None) -> List[np.ndarray]:
+    """Element-wise mean over the ranks of a list of small host arrays (every rank gets the result)."""
+    if dist is None:
+        import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [np.asarray(a) for a in arrays]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, [np.asarray(a, dtype=np.float64) for a in arrays])
+    world = len(out)
+    return [(sum(o[i] for o in out) / world).astype(np.asarray(arrays[i]).dtype) for i in range(len(arrays))]
+
+
+def sync_bn_moving_stats(model, names: List[str], dist=None) -> None:
+    """Per-replica BatchNorm moving statistics (every replica normalises with the statistics of its own
+    shard, as under tf.distribute.MirroredStrategy) are averaged over the replicas before validation and
+    checkpointing, so that every rank evaluates and saves the same model.  `model` needs get_weights() /
+    set_weights() in Keras order; `names` are the Keras weight names in the same order."""
+    if dist is None:
+        import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    weights = model.get_weights()
+    idx = [i for i, nm in enumerate(names) if "moving_mean" in nm or "moving_variance" in nm]
+    if not idx:
+        return
+    merged = mean_over_ranks([weights[i] for i in idx], dist)
+    for i, m in zip(idx, merged):
+        weights[i] = m
+    model.set_weights(weights)

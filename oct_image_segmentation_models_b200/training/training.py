@@ -82,10 +82,14 @@ def train_model(training_params: TrainingParams, mlflow_params=None, rank: int =
             a, b = parallel.shard_range(training_params.batch_size, rank, world)
             idx = np.sort(order[g0 + a:g0 + b])
             losses.append(model.engine.train_step(train_images[idx], train_labels[idx]))
+        if world > 1:      # replicas: mean of the per-replica BN moving statistics, one loss for everybody
+            import torch.distributed as dist
+            parallel.sync_bn_moving_stats(model, [nm for nm, _ in model.engine.param_specs], dist)
         probs = model.predict(val_images)
         lab = val_labels.reshape(val_labels.shape[:3]).astype(np.int64)
         pt = np.clip(np.take_along_axis(probs, lab[..., None], -1)[..., 0], 1e-7, 1 - 1e-7)
-        logs = {"loss": float(np.sum(losses) / max(1, len(losses)) * (world if world > 1 else 1)),
+        local_loss = float(np.sum(losses) / max(1, len(losses)))      # already scaled by the GLOBAL batch
+        logs = {"loss": parallel.allreduce_sum_scalar(local_loss) if world > 1 else local_loss,
                 "val_loss": float(np.mean(-cw[lab] * np.log(pt))),
                 "val_acc": float((probs.argmax(-1) == lab).mean()), "epoch_time": time.time() - t0}
         history.append(logs)

@@ -88,3 +88,43 @@ def test_gloo_world2_sharded_predict_and_gradient_sum(tmp_path):
         loss += l
     np.testing.assert_allclose(got["flat"], total.numpy(), rtol=1e-5, atol=1e-8)
     assert abs(float(got["loss"][0]) - loss) < 1e-6
+
+
+class _FakeModel:
+    def __init__(self, weights):
+        self.w = [np.array(x) for x in weights]
+
+    def get_weights(self):
+        return [x.copy() for x in self.w]
+
+    def set_weights(self, ws):
+        self.w = [np.array(x) for x in ws]
+
+
+def _worker_state(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    names = ["conv2d/kernel:0", "batch_normalization/gamma:0", "batch_normalization/moving_mean:0",
+             "batch_normalization/moving_variance:0"]
+    model = _FakeModel([np.full((2, 2), 5.0, np.float32), np.full(3, 1.0 + rank, np.float32),
+                        np.arange(3, dtype=np.float32) + 10 * rank, np.full(3, 2.0 * (rank + 1), np.float32)])
+    parallel.sync_bn_moving_stats(model, names, dist)
+    total = parallel.allreduce_sum_scalar(0.25 * (rank + 1), dist)
+    np.savez(os.path.join(out_dir, f"s{rank}.npz"), *model.get_weights(), total=total)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_replica_state_helpers(tmp_path):
+    """BN moving statistics are averaged over replicas, everything else is left alone (the gradient all-reduce
+    already keeps trainable weights identical); logged scalars are summed; every rank sees the same result."""
+    world = 2
+    mp.spawn(_worker_state, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / f"s{k}.npz") for k in range(world)]
+    for k in range(world):
+        assert np.array_equal(r[k]["arr_0"], np.full((2, 2), 5.0, np.float32))
+        assert np.array_equal(r[k]["arr_1"], np.full(3, 1.0 + k, np.float32))          # per-rank value untouched
+        assert np.allclose(r[k]["arr_2"], np.arange(3) + 5.0)                          # mean of +0 and +10
+        assert np.allclose(r[k]["arr_3"], 3.0)                                         # mean of 2 and 4
+        assert abs(float(r[k]["total"]) - 0.75) < 1e-12
+    # single process: both helpers are no-ops
+    assert parallel.allreduce_sum_scalar(1.5) == 1.5
