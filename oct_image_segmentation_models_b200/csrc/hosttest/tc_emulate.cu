@@ -15,8 +15,14 @@ namespace octseg { void set_error(const std::string &m) { fprintf(stderr, "error
 static float bf2f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
 static uint16_t f2bf(float f) { uint32_t u; memcpy(&u, &f, 4); u += 0x7fffu + ((u >> 16) & 1u); return (uint16_t)(u >> 16); }
 
-static int run(int kh, int kw, int cin, int cout, int ups, int n, int h, int w) {
+// rowpair: the inference / training row-pair variant of a 3x3 layer (two output rows per GEMM row, banded 4x3
+// filter from tc_rowpair_weights, descriptor SBO = 2 x row pitch)
+static int run(int kh, int kw, int cin, int cout, int ups, int n, int h, int w, int rowpair = 0) {
   TcGeometry g;
+  if (rowpair) {
+    if (tc_make_geometry(4, 3, cin, 2 * cout, 0, &g, 1, 1)) { printf("geometry failed\n"); return 1; }
+    g.rows2 = 1;
+  } else
   if (tc_make_geometry(kh, kw, cin, cout, ups, &g)) { printf("geometry failed\n"); return 1; }
   TcConvParams p; size_t smem;
   if (tc_fill_params(g, n, h, w, &p, &smem)) return 1;
@@ -27,7 +33,13 @@ static int run(int kh, int kw, int cin, int cout, int ups, int n, int h, int w) 
   std::vector<uint16_t> x((size_t)n * cin * h * w);   // blocked [n][cg][h][w][8]
   for (auto &v : x) v = f2bf(U(rng));
   std::vector<uint16_t> wp;
+  if (rowpair) {
+    std::vector<float> banded;
+    tc_rowpair_weights(wt.data(), cin, cout, &banded);
+    tc_pack_weights(g, banded.data(), &wp);
+  } else
   tc_pack_weights(g, wt.data(), &wp);
+  const int RM = p.row_mul;
   const int oh = ups ? 2 * h : h, ow = ups ? 2 * w : w, cg = cin / 8;
   std::vector<double> out((size_t)n * oh * ow * cout, 1e30), ref((size_t)n * oh * ow * cout, 0);
   // reference (double, bf16 inputs, fp32 weights)
@@ -56,7 +68,7 @@ static int run(int kh, int kw, int cin, int cout, int ups, int n, int h, int w) 
       // TMA box: dims (W*8, H, CG, N), start ((tx*8-pad_x)*8, ty*16-pad_y, ch*CGC, img)
       uint16_t *s16 = reinterpret_cast<uint16_t *>(stage.data());
       for (int pc = 0; pc < p.planes_per_chunk; ++pc) for (int r = 0; r < p.box_h; ++r) for (int e = 0; e < p.box_w * 8; ++e) {
-        int gx = (tx * p.mt_x * kTcTileW - p.pad_x) * 8 + e, gy = ty * p.mt_y * kTcTileH - p.pad_y + r, gp = ch * p.planes_per_chunk + pc;
+        int gx = (tx * p.mt_x * kTcTileW - p.pad_x) * 8 + e, gy = ty * p.mt_y * kTcTileH * RM - p.pad_y + r, gp = ch * p.planes_per_chunk + pc;
         uint16_t v = 0;
         if (gx >= 0 && gx < w * 8 && gy >= 0 && gy < h) v = x[(((size_t)img * cg + gp) * h + gy) * w * 8 + gx];
         s16[((size_t)pc * p.box_h + r) * p.box_w * 8 + e] = v;
@@ -65,8 +77,9 @@ static int run(int kh, int kw, int cin, int cout, int ups, int n, int h, int w) 
         const uint16_t *bbase = wp.data() + ((size_t)(n_tile * p.cin_chunks + ch) * p.ksteps + ks) * 2 * p.n_cols * 8;
         for (int t = 0; t < MT; ++t) for (int m = 0; m < 128; ++m) for (int k = 0; k < 16; ++k) {
           const int iy = t / p.mt_x, ix = t % p.mt_x;
-          size_t aoff = p.a_off[ks] + (size_t)iy * kTcTileH * p.box_w * 16 + (size_t)ix * 128 +
-                        (size_t)(k / 8) * p.a_lbo[ks] + (size_t)(m / 8) * p.box_w * 16 + (m % 8) * 16 + (k % 8) * 2;
+          size_t aoff = p.a_off[ks] + (size_t)iy * kTcTileH * RM * p.box_w * 16 + (size_t)ix * 128 +
+                        (size_t)(k / 8) * p.a_lbo[ks] + (size_t)(m / 8) * RM * p.box_w * 16 + (m % 8) * 16 + (k % 8) * 2;
+          if (p.a_desc_lo[ks] != ((p.a_off[ks] >> 4) | ((p.a_lbo[ks] >> 4) << 16))) { printf("a_desc_lo mismatch\n"); return 1; }
           if (aoff + 2 > p.a_stage_bytes) { printf("A read out of stage: ks %d m %d k %d off %zu\n", ks, m, k, aoff); return 1; }
           float av = bf2f(*reinterpret_cast<uint16_t *>(stage.data() + aoff));
           for (int nn = 0; nn < p.n_cols; ++nn) {
@@ -79,12 +92,13 @@ static int run(int kh, int kw, int cin, int cout, int ups, int n, int h, int w) 
     for (int t = 0; t < MT; ++t) for (int m = 0; m < 128; ++m) {
       const int iy = t / p.mt_x, ix = t % p.mt_x;
       int r = m >> 3, px = m & 7, y = (ty * p.mt_y + iy) * kTcTileH + r, xx = (tx * p.mt_x + ix) * kTcTileW + px;
-      if (y >= h || xx >= w) continue;
+      if (y * RM >= h || xx >= w) continue;
       for (int j = 0; j < p.n_cols; ++j) {
         int col = n_tile * p.n_cols + j;
         if (col >= p.cols_valid) break;
         int co, oy, ox;
-        if (p.mode == 0) { co = col; oy = y; ox = xx; }
+        if (RM == 2) { int par = col / p.scale_mod; co = col - par * p.scale_mod; oy = 2 * y + par; ox = xx; if (oy >= h) continue; }
+        else if (p.mode == 0) { co = col; oy = y; ox = xx; }
         else { int par = col / p.cout; co = col - par * p.cout; oy = 2 * y + (par >> 1); ox = 2 * xx + (par & 1); }
         out[(((size_t)img * oh + oy) * ow + ox) * cout + co] = D[((size_t)t * 128 + m) * p.n_cols + j];
       }
@@ -115,6 +129,12 @@ int main() {
   bad += run(3, 3, 64, 64, 0, 40, 32, 32);
   bad += run(3, 3, 512, 512, 0, 1, 16, 8); // wide net: n-tiles + chunks
   bad += run(2, 2, 256, 128, 1, 1, 16, 8); // wide up-conv: 512 columns
+  // row pairs (inference + training plans of the 8 / 16-channel 3x3 layers)
+  bad += run(3, 3, 8, 8, 0, 2, 32, 24, 1);
+  bad += run(3, 3, 16, 8, 0, 1, 64, 40, 1);
+  bad += run(3, 3, 32, 16, 0, 1, 34, 16, 1);   // ragged: 34 rows in 32-row tiles
+  bad += run(3, 3, 16, 16, 0, 40, 64, 64, 1);  // super-tiles
+  bad += run(3, 3, 8, 16, 0, 3, 96, 72, 1);
   printf(bad ? "FAILED %d\n" : "ALL OK\n", bad);
   return bad;
 }
