@@ -117,6 +117,14 @@ class ClockSampler:
                 "samples": len(sm), "in_timed_region": bool(inside)}
 
 
+def host_threads():
+    """Host cores this process may use (affinity mask, not the machine total: containers are often pinned)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def cpu_reference_throughput(n_images, per_call, threads):
     """The reference's CPU path restated (oracle port, torch-CPU/oneDNN), timed on host cores."""
     import torch
@@ -139,7 +147,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import torch
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     per_call = 4                                 # BASELINE configs[0] batches 4
     per_step = 8                                 # bounded sample of the 64-image batch per step
     for _ in range(max(args.warmup, 1)):
@@ -438,7 +446,7 @@ def main():
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         v, secs, done = cpu_reference_throughput(480, 4, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{done} synthetic 512x512 B-scans in batches of 4 ({secs:.1f} s), torch-CPU restatement "
