@@ -284,7 +284,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
@@ -369,7 +369,7 @@ def main():
         per_block = bt if per_block is None else per_block + bt
     eng.set_profiling(False)
     per_block /= prof_steps
-    elem = 2 if args.precision == "bf16" else 4
+    elem = 4 if args.precision == "fp32" else 2
     lb = np.asarray(layer_bytes(H, W, elem), dtype=np.float64) * n
     tc_idx = [i for i in range(len(lb)) if eng.layer_uses_tensor_core(i, H, W)]
     dom_idx = tc_idx if tc_idx else list(range(1, len(lb) - 1))
