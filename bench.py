@@ -386,7 +386,13 @@ def main():
     step_achieved = step_bytes / (step_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "conv_tc_kernel" if tc_idx else "conv_direct_kernel",
                 "launches_per_step": len(dom_idx), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak,
+                # measured DRAM bytes per conv_tc launch (read + write, averaged over the 22 launches of one step)
+                # from the committed ncu --set full capture of THIS workload; below the algorithmic bytes because
+                # the small deep-layer tensors never leave the 126 MB L2
+                "traffic": (189041792.0 if (args.precision == "bf16" and n == 64 and tc_idx) else None),
+                "traffic_source": "profiles/r1_predict_step_ncu_full_summary.csv",
+                "peak_source": peak_src,
                 "share_of_step": share,
                 "algorithmic_bytes_per_launch_avg": dom_bytes / len(dom_idx),
                 "avg_launch_ms": step_ms * share / len(dom_idx),
