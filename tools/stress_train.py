@@ -1,0 +1,51 @@
+"""Randomised config / shape stress of the bf16 training step: tensor-core path (tcgen05 forward and data
+gradient incl. row pairs, mma.sync weight gradient) against the CUDA-core kernels (OCTSEG_DISABLE_TC=1) on the
+same bf16 storage: loss, head gradients and the decoder-end kernel gradients must agree closely; every tensor
+must be finite and no tensor may be grossly off (a mis-wired tap shows up as an O(1) error).
+usage: python tools/stress_train.py [draws=30] [seed=0]"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from oct_image_segmentation_models_b200.common.synthetic import synthetic_batch, synthetic_weights  # noqa: E402
+from oct_image_segmentation_models_b200.engine import UNetEngine  # noqa: E402
+from oct_image_segmentation_models_b200.models.unet_spec import unet_param_specs  # noqa: E402
+
+draws = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+for d in range(draws):
+    P = int(rng.integers(1, 4))
+    K = int(rng.integers(2, 6))
+    cfg = dict(input_channels=1, num_classes=K, start_neurons=int(rng.choice([8, 16])), pool_layers=P,
+               conv_layers=int(rng.integers(1, 3)))
+    q = 1 << P
+    h = int(rng.integers(2, 1 + 128 // q)) * q
+    w = int(rng.integers(2, 1 + 160 // q)) * q
+    n = int(rng.integers(2, 7))
+    weights = synthetic_weights(seed=int(rng.integers(1 << 30)), random_bn_stats=True, **cfg)
+    imgs, labs = synthetic_batch(int(rng.integers(1000)), n, h, w, K)
+    cw = list(rng.uniform(0.5, 2.0, K))
+    names = [nm for nm, _ in unet_param_specs(**cfg)]
+    res = {}
+    for mode in ("1", "0"):
+        os.environ["OCTSEG_DISABLE_TC"] = mode
+        e = UNetEngine(precision="bf16", **cfg); e.set_weights(weights)
+        e.train_begin(cw, dropout_rate=0.0, global_batch=n)
+        res[mode] = (e.train_step(imgs, labs), e.get_grads())
+        e.close()
+    (l_cc, g_cc), (l_tc, g_tc) = res["1"], res["0"]
+    errs = []
+    for nm, a, b in zip(names, g_tc, g_cc):
+        if a is None or b is None or "moving" in nm or (nm.endswith("bias:0") and nm != names[-1]):
+            continue
+        assert np.isfinite(a).all(), nm
+        errs.append((float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-12)), nm))
+    tail = max(e for e, _ in errs[-3:])
+    ok = abs(l_tc - l_cc) <= 5e-3 * max(1.0, abs(l_cc)) and tail <= 0.12 and max(errs)[0] <= 0.8
+    print(f"draw {d:3d} {cfg} {(n, h, w)} loss {l_tc:.5f}/{l_cc:.5f} tail {tail:.1e} worst {max(errs)[0]:.2f} {'ok' if ok else 'FAIL'}", flush=True)
+    if not ok:
+        print(sorted(errs, reverse=True)[:6]); sys.exit(1)
+print("ALL OK")
