@@ -10,6 +10,9 @@
 // reduction + one global atomic per element per CTA at the end.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include <cuda.h>
 
 #include "conv_tc.cuh"
@@ -387,6 +390,199 @@ __global__ void __launch_bounds__(kWmTmaThreads) wgrad_mma_tma_kernel(const __gr
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Deep layers (Cin >= 32: few pixels, many channels).  The kernel above replicates every activation tile
+// over (group block, Cout chunk) CTAs -- 24 CTAs fetch the same tile for a 128->128 layer -- and each CTA
+// does little math per fetched tile, so those layers were L2->smem and latency bound (0.14 ms for 9.7 GFLOP).
+// Here one CTA owns ALL (tap, plane) groups of an 8-plane input chunk and up to 64 output channels: the 24
+// compute warps tile the output block as MP x NP (3 m16 tiles x NBW n8 tiles per warp, accumulators in
+// registers), every warp walks all rows of the pixel tile, and each A fragment feeds NBW MMAs.  No smem
+// reduction: a warp owns its accumulators exclusively and adds them to dW with 8-byte vector atomics.
+// The bias gradient (the ones-row of the kernel above) is a separate tiny reduction (bias_grad_kernel).
+// ---------------------------------------------------------------------------------
+constexpr int kWdLocalMT = 3;
+constexpr int kWdCW = 24;
+constexpr int kWdThreads = 32 * (1 + kWdCW);
+
+template <int NBW>
+__global__ void __launch_bounds__(kWdThreads) wgrad_deep_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_d,
+                                                                const WgParams p, int th, int n_stages, int MP, int NP,
+                                                                int *status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int aw = kWmTW + p.kw - 1, ah = th + p.kh - 1;
+  const int nchunk = blockIdx.y % p.n_nchunks;
+  const int pchunk = blockIdx.y / p.n_nchunks;
+  const int plane0 = pchunk * p.pc;
+  const int pc_cur = min(p.pc, p.cin_planes - plane0);
+  const int g_total = p.kh * p.kw * pc_cur;
+  const int n_mt = (g_total + 1) / 2;
+  const int nb0 = nchunk * NP * NBW;                       // first output plane (n8 tile) of this CTA
+  const int nb_cur = min(NP * NBW, p.cout_planes - nb0);
+
+  const uint32_t a_bytes = (uint32_t)p.pc * ah * aw * 16, d_bytes = (uint32_t)p.d_planes * th * kWmTW * 16;
+  const uint32_t stage_bytes = ((a_bytes + 127u) & ~127u) + ((d_bytes + 127u) & ~127u);
+  uint8_t *s_stage = smem_raw;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes);   // full[S], empty[S]
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[i])), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[n_stages + i])), "r"(kWdCW) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    // ---------------- producer ----------------
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xFFFFFFFFu));
+    int st = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int txi = tile % p.tiles_x;
+      const int tyi = (tile / p.tiles_x) % p.tiles_y;
+      const int img = tile / (p.tiles_x * p.tiles_y);
+      if (!wm_wait(wm_smem_u32(&bars[n_stages + st]), ph ^ 1u)) { if (pred) atomicCAS(status, 0, 23); break; }
+      if (pred) {
+        const uint32_t full = wm_smem_u32(&bars[st]);
+        const uint32_t dst_a = wm_smem_u32(s_stage + (size_t)st * stage_bytes);
+        const uint32_t dst_d = dst_a + ((a_bytes + 127u) & ~127u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(a_bytes + d_bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(dst_a), "l"(&map_a), "r"(full), "r"((txi * kWmTW - p.pl) * 2), "r"(tyi * th - p.pt), "r"(plane0), "r"(img) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(dst_d), "l"(&map_d), "r"(full), "r"(txi * kWmTW * 2), "r"(tyi * th), "r"(nb0), "r"(img) : "memory");
+      }
+      if (++st == n_stages) { st = 0; ph ^= 1u; }
+    }
+  } else {
+    // ---------------- consumers: warp (mpart, npart) owns 3 m16 tiles x NBW n8 tiles of the CTA's block ----------------
+    const int cwi = warp - 1;
+    const bool active = cwi < MP * NP;
+    const int mpart = cwi / NP, npart = cwi - mpart * NP;
+    const int mt_base = mpart * kWdLocalMT;
+    const int n_loc = active ? max(0, min(kWdLocalMT, n_mt - mt_base)) : 0;
+    const int nbw0 = npart * NBW;                           // first n8 tile of this warp inside the CTA's dz box
+    const int nbw_cur = active ? max(0, min(NBW, nb_cur - nbw0)) : 0;
+    uint32_t a_off[kWdLocalMT];
+    {
+      const int i = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int j = 0; j < kWdLocalMT; ++j) {
+        int g = 2 * (mt_base + j) + (i & 1);
+        uint32_t off = 0;
+        if (j < n_loc) {
+          if (g >= g_total) g = 0;                          // odd group count: the unused half reads valid memory, result dropped
+          const int t = g / pc_cur, cgl = g - t * pc_cur;
+          const int dy = t / p.kw, dx = t - dy * p.kw;
+          off = (uint32_t)((((cgl * ah + dy) * aw + dx) + r + 8 * (i >> 1)) * 16);
+        }
+        a_off[j] = off;
+      }
+    }
+    float acc[kWdLocalMT][NBW][4];
+#pragma unroll
+    for (int j = 0; j < kWdLocalMT; ++j)
+#pragma unroll
+      for (int nb = 0; nb < NBW; ++nb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[j][nb][k] = 0.f;
+    int st = 0;
+    uint32_t ph = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
+      ok = wm_wait(wm_smem_u32(&bars[st]), ph);
+      if (!ok) { if (lane == 0) atomicCAS(status, 0, 24); break; }
+      const uint32_t sa_base = wm_smem_u32(s_stage + (size_t)st * stage_bytes);
+      const uint32_t sd_base = sa_base + ((a_bytes + 127u) & ~127u);
+      if (n_loc > 0 && nbw_cur > 0) {
+        for (int y = 0; y < th; ++y) {
+#pragma unroll
+          for (int ks = 0; ks < kWmTW / 16; ++ks) {
+            uint32_t bfrag[NBW][2];
+#pragma unroll
+            for (int nb = 0; nb < NBW; ++nb) {
+              if (nb < nbw_cur) {
+                const int i = (lane >> 3) & 1, r = lane & 7;
+                ldmatrix_x2_trans(sd_base + (uint32_t)(((((nbw0 + nb) * th + y) * kWmTW) + ks * 16 + i * 8 + r) * 16), bfrag[nb]);
+              } else { bfrag[nb][0] = 0u; bfrag[nb][1] = 0u; }
+            }
+            const uint32_t row_off = (uint32_t)((y * aw + ks * 16) * 16);
+#pragma unroll
+            for (int j = 0; j < kWdLocalMT; ++j) {
+              if (j < n_loc) {
+                uint32_t afrag[4];
+                ldmatrix_x4_trans(sa_base + a_off[j] + row_off, afrag);
+#pragma unroll
+                for (int nb = 0; nb < NBW; ++nb) mma_bf16_16816(acc[j][nb], afrag, bfrag[nb]);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wm_smem_u32(&bars[n_stages + st])) : "memory");
+      if (++st == n_stages) { st = 0; ph ^= 1u; }
+    }
+    // ---- this warp's block goes straight to global memory: 8-byte vector atomics (two adjacent output channels)
+#pragma unroll
+    for (int j = 0; j < kWdLocalMT; ++j) {
+      if (j < n_loc) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int g = 2 * (mt_base + j) + hf;
+          if (g < g_total) {
+            const int t = g / pc_cur, cgl = g - t * pc_cur;
+            const int ci = (plane0 + cgl) * 8 + (lane >> 2);
+#pragma unroll
+            for (int nb = 0; nb < NBW; ++nb) {
+              if (nb < nbw_cur) {
+                const int co = (nb0 + nbw0 + nb) * 8 + (lane & 3) * 2;
+                float2 *dst = reinterpret_cast<float2 *>(&p.dW[((long long)t * p.cin + ci) * p.cout + co]);
+                atomicAdd(dst, make_float2(acc[j][nb][2 * hf], acc[j][nb][2 * hf + 1]));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// bias gradient of the deep layers: db[co] += sum over pixels of dz[.., co]  (dz is dense [n][planes][h][w][8])
+__global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16 *__restrict__ dz, long long img_stride, int hw,
+                                                        float *__restrict__ db) {
+  const int pl = blockIdx.y, img = blockIdx.z;
+  const __nv_bfloat16 *base = dz + (long long)img * img_stride + (long long)pl * hw * 8;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < hw; v += gridDim.x * blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4 *>(base + (long long)v * 8);
+    const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+  }
+  __shared__ float red[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = 0.f;
+    for (int wv = 0; wv < 8; ++wv) v += red[wv][threadIdx.x];
+    atomicAdd(&db[pl * 8 + threadIdx.x], v);
+  }
+}
+
 int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> dz, int kh, int kw, int pad_top,
                      int pad_left, int ups, int cin, int cout, float *dW, float *db, int *status,
                      cudaStream_t st) {
@@ -406,6 +602,58 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
   p.dW = dW; p.db = db;
   const bool dense = a_in.img_stride == (long long)a_in.planes * a_in.h * a_in.w * 8 &&
                      dz.img_stride == (long long)dz.planes * dz.h * dz.w * 8 && a_in.planes == p.cin_planes;
+  static const bool no_deep = []() { const char *e = std::getenv("OCTSEG_NO_DEEP_WGRAD"); return e && e[0] == '1'; }();
+  if (!ups && dense && status && !no_deep && p.cin_planes >= 4) {
+    // ---- deep-layer kernel: pick the warp tiling MP x NP (3 m16 tiles x NBW n8 tiles per warp)
+    const int g_total = kh * kw * p.pc, n_mt = (g_total + 1) / 2;
+    const int MP = (n_mt + kWdLocalMT - 1) / kWdLocalMT;
+    int NBW = 0, NP = 0;
+    for (int cand : {4, 2, 1}) {
+      const int np = std::min(kWdCW / std::max(1, MP), (p.cout_planes + cand - 1) / cand);
+      if (MP <= kWdCW && np >= 1 && MP * np >= 16) { NBW = cand; NP = np; break; }
+    }
+    if (NBW) {
+      const int th = 8;
+      p.tiles_y = (dz.h + th - 1) / th;
+      p.num_tiles = dz.n * p.tiles_x * p.tiles_y;
+      p.d_planes = std::min(NP * NBW, p.cout_planes);
+      p.n_nchunks = (p.cout_planes + NP * NBW - 1) / (NP * NBW);
+      const int aw2 = kWmTW + kw - 1, ah2 = th + kh - 1;
+      CUtensorMap map_a, map_d;
+      if (tc_encode_map_4d(a_in.ptr, a_in.w, a_in.h, p.cin_planes, a_in.n, aw2, ah2, p.pc, &map_a)) return 1;
+      if (tc_encode_map_4d(dz.ptr, dz.w, dz.h, p.cout_planes, dz.n, kWmTW, th, p.d_planes, &map_d)) return 1;
+      const size_t a_bytes = (size_t)p.pc * ah2 * aw2 * 16, d_bytes = (size_t)p.d_planes * th * kWmTW * 16;
+      const size_t stage = ((a_bytes + 127) & ~(size_t)127) + ((d_bytes + 127) & ~(size_t)127);
+      const size_t fixed = 2 * kWmMaxStages * 8 + 1024;
+      int n_stages = (int)std::min<size_t>(kWmMaxStages, (200 * 1024 - fixed) / stage);
+      if (n_stages >= 2) {
+        const size_t smem3 = n_stages * stage + fixed;
+        static bool attr3 = false;
+        if (!attr3) {
+          OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_deep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+          OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_deep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+          OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_deep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+          attr3 = true;
+        }
+        const int blocks_y3 = p.n_pchunks * p.n_nchunks;
+        const int gx3 = std::max(1, std::min(p.num_tiles, (148 + blocks_y3 - 1) / blocks_y3));
+        dim3 grid3(gx3, blocks_y3);
+        if (NBW == 4) wgrad_deep_kernel<4><<<grid3, kWdThreads, smem3, st>>>(map_a, map_d, p, th, n_stages, MP, NP, status);
+        else if (NBW == 2) wgrad_deep_kernel<2><<<grid3, kWdThreads, smem3, st>>>(map_a, map_d, p, th, n_stages, MP, NP, status);
+        else wgrad_deep_kernel<1><<<grid3, kWdThreads, smem3, st>>>(map_a, map_d, p, th, n_stages, MP, NP, status);
+        OCTSEG_CUDA(cudaGetLastError());
+        if (db) {
+          const int hw = dz.h * dz.w;
+          dim3 gb(std::max(1, std::min((hw + 2047) / 2048, 32)), p.cout_planes, dz.n);
+          bias_grad_kernel<<<gb, 256, 0, st>>>(dz.ptr, dz.img_stride, hw, db);
+          OCTSEG_CUDA(cudaGetLastError());
+        }
+        return 0;
+      }
+      // fall through to the generic kernels with the original decomposition
+      p.n_nchunks = (p.cout_planes + kWmNB - 1) / kWmNB;
+    }
+  }
   if (!ups && dense && status) {
     const int th = p.pc == 1 ? 32 : (p.pc == 2 ? 16 : 8);
     p.tiles_y = (dz.h + th - 1) / th;
