@@ -610,7 +610,7 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
     int NBW = 0, NP = 0;
     for (int cand : {4, 2, 1}) {
       const int np = std::min(kWdCW / std::max(1, MP), (p.cout_planes + cand - 1) / cand);
-      if (MP <= kWdCW && np >= 1 && MP * np >= 16) { NBW = cand; NP = np; break; }
+      if (MP <= kWdCW && np >= 1 && MP * np >= 12) { NBW = cand; NP = np; break; }
     }
     if (NBW) {
       const int th = 8;
