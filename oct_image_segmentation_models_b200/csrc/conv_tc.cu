@@ -1057,6 +1057,24 @@ static inline uint16_t f2bf(float f) {
   return (uint16_t)(u >> 16);
 }
 
+// Banded weights of the tensor-core stem.  GEMM row (y, g) holds pixels 8g..8g+7 of image row y as its
+// 8 input channels; GEMM column plane*64 + jo*8 + c8 is output pixel 8g+jo, channel plane*8+c8.  Tap
+// (dy, dgx) of the 3x3 conv over the GROUP grid connects input pixel 8(g+dgx-1)+ji to output pixel 8g+jo
+// with the original filter tap dx = 8(dgx-1) + ji - jo + 1 when that lies in 0..2, else zero.
+void tc_stem_group_weights(const float *w, int cout, std::vector<float> *out) {
+  const int cols = 8 * cout;
+  out->assign((size_t)9 * 8 * cols, 0.f);
+  for (int dy = 0; dy < 3; ++dy)
+    for (int dgx = 0; dgx < 3; ++dgx)
+      for (int ji = 0; ji < 8; ++ji)
+        for (int col = 0; col < cols; ++col) {
+          const int jo = (col >> 3) & 7, c = (col >> 6) * 8 + (col & 7);
+          const int dx = 8 * (dgx - 1) + ji - jo + 1;
+          if (dx < 0 || dx > 2) continue;
+          (*out)[(((size_t)dy * 3 + dgx) * 8 + ji) * cols + col] = w[((size_t)dy * 3 + dx) * cout + c];
+        }
+}
+
 void tc_rowpair_weights(const float *w, int cin, int cout, std::vector<float> *out) {
   const int cols = 2 * cout;
   out->assign((size_t)4 * 3 * cin * cols, 0.f);

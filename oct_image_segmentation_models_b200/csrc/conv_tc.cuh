@@ -91,6 +91,9 @@ int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, 
 // 2*cout, 0, &g, 1, 1) and g.rows2 = 1.  Nine taps per pixel become six: the A operand (the smem-bandwidth-bound
 // side of narrow layers, 4 KB per K=16 step) is read 12 times per TWO output rows instead of 9 times per row.
 void tc_rowpair_weights(const float *w_hwio, int cin, int cout, std::vector<float> *out);
+// Banded 3x3 filter over pixel GROUPS for the tensor-core stem (see the definition): [3][3][1][cout] in,
+// [3][3][8][8*cout] out; geometry tc_make_geometry(3, 3, 8, 8*cout, 0, &g) with g.stem_groups = 1.
+void tc_stem_group_weights(const float *w, int cout, std::vector<float> *out);
 // packs fp32 HWIO weights into the bf16 smem image the kernel streams (host memory)
 void tc_pack_weights(const TcGeometry &g, const float *w_hwio, std::vector<uint16_t> *out, int fp16 = 0);
 // same packing on the device, from fp32 weights in device memory (training)

@@ -112,8 +112,88 @@ static int run(int kh, int kw, int cin, int cout, int ups, int n, int h, int w, 
   return maxerr < 0.02 * maxref ? 0 : 1;
 }
 
+// Tensor-core stem: the uint8 image widened to bf16 is read as [n][1][h][w/8][8] (8 adjacent pixels = the 8 input
+// channels of a GEMM row), banded weights from tc_stem_group_weights, output columns [plane][pixel][8 channels]
+// = the blocked activation layout.  Checked against a direct 3x3 / 1-channel convolution.
+static int run_stem(int cout, int n, int h, int w) {
+  TcGeometry g;
+  if (tc_make_geometry(3, 3, 8, 8 * cout, 0, &g)) { printf("geometry failed\n"); return 1; }
+  g.stem_groups = 1;
+  const int wg = w / 8;
+  TcConvParams p; size_t smem;
+  if (tc_fill_params(g, n, h, wg, &p, &smem)) return 1;
+  std::mt19937 rng(7);
+  std::uniform_real_distribution<float> U(-1, 1);
+  std::vector<float> wt((size_t)9 * cout);
+  for (auto &v : wt) v = U(rng);
+  std::vector<uint16_t> x((size_t)n * h * w);            // pixel values 0..255, exact in bf16
+  for (auto &v : x) v = f2bf((float)(rng() % 256));
+  std::vector<float> banded;
+  tc_stem_group_weights(wt.data(), cout, &banded);
+  std::vector<uint16_t> wp;
+  tc_pack_weights(g, banded.data(), &wp);
+  std::vector<double> out((size_t)n * h * w * cout, 1e30), ref((size_t)n * h * w * cout, 0);
+  for (int b = 0; b < n; ++b) for (int y = 0; y < h; ++y) for (int xx = 0; xx < w; ++xx) for (int co = 0; co < cout; ++co) {
+    double acc = 0;
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) {
+      const int iy = y + a - 1, ix = xx + c - 1;
+      if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
+      acc += (double)bf2f(x[((size_t)b * h + iy) * w + ix]) * bf2f(f2bf(wt[(a * 3 + c) * cout + co]));
+    }
+    ref[(((size_t)b * h + y) * w + xx) * cout + co] = acc;
+  }
+  std::vector<uint8_t> stage(p.a_stage_bytes + 4096, 0xFF);
+  for (int tile = 0; tile < p.num_tiles; ++tile) {
+    int n_tile = tile % p.n_tiles_n, t = tile / p.n_tiles_n;
+    int tx = t % p.tiles_x; t /= p.tiles_x; int ty = t % p.tiles_y; int img = t / p.tiles_y;
+    const int MT = p.mt_x * p.mt_y;
+    std::vector<double> D((size_t)MT * 128 * p.n_cols, 0.0);
+    uint16_t *s16 = reinterpret_cast<uint16_t *>(stage.data());
+    for (int r = 0; r < p.box_h; ++r) for (int e = 0; e < p.box_w * 8; ++e) {
+      const int gx = (tx * p.mt_x * kTcTileW - p.pad_x) * 8 + e, gy = ty * p.mt_y * kTcTileH - p.pad_y + r;
+      uint16_t v = 0;
+      if (gx >= 0 && gx < wg * 8 && gy >= 0 && gy < h) v = x[((size_t)img * h + gy) * w + gx];
+      s16[(size_t)r * p.box_w * 8 + e] = v;
+    }
+    for (int ks = 0; ks < p.ksteps; ++ks) {
+      const uint16_t *bbase = wp.data() + ((size_t)n_tile * p.ksteps + ks) * 2 * p.n_cols * 8;
+      for (int tt = 0; tt < MT; ++tt) for (int m = 0; m < 128; ++m) for (int k = 0; k < 16; ++k) {
+        const int iy = tt / p.mt_x, ix = tt % p.mt_x;
+        size_t aoff = p.a_off[ks] + (size_t)iy * kTcTileH * p.box_w * 16 + (size_t)ix * 128 + (size_t)(k / 8) * p.a_lbo[ks] +
+                      (size_t)(m / 8) * p.box_w * 16 + (m % 8) * 16 + (k % 8) * 2;
+        if (aoff + 2 > p.a_stage_bytes) { printf("stem A read out of stage\n"); return 1; }
+        const float av = bf2f(*reinterpret_cast<uint16_t *>(stage.data() + aoff));
+        for (int nn = 0; nn < p.n_cols; ++nn) {
+          size_t boff = (size_t)(k / 8) * p.n_cols * 16 + (size_t)(nn / 8) * 128 + (nn % 8) * 16 + (k % 8) * 2;
+          D[((size_t)tt * 128 + m) * p.n_cols + nn] += (double)av * bf2f(bbase[boff / 2]);
+        }
+      }
+    }
+    for (int tt = 0; tt < MT; ++tt) for (int m = 0; m < 128; ++m) {
+      const int iy = tt / p.mt_x, ix = tt % p.mt_x;
+      const int r = m >> 3, px = m & 7, y = (ty * p.mt_y + iy) * kTcTileH + r, gx = (tx * p.mt_x + ix) * kTcTileW + px;
+      if (y >= h || gx >= wg) continue;
+      for (int j = 0; j < p.n_cols; ++j) {
+        const int col = n_tile * p.n_cols + j;
+        if (col >= p.cols_valid) break;
+        const int plane = col >> 6, pix = (col >> 3) & 7, c8 = col & 7;      // epilogue mode 3 mapping
+        out[(((size_t)img * h + y) * w + gx * 8 + pix) * cout + plane * 8 + c8] = D[((size_t)tt * 128 + m) * p.n_cols + j];
+      }
+    }
+  }
+  double maxerr = 0, maxref = 0;
+  for (size_t i = 0; i < ref.size(); ++i) { maxerr = std::max(maxerr, std::fabs(out[i] - ref[i])); maxref = std::max(maxref, std::fabs(ref[i])); }
+  printf("stem groups cout %d %dx%dx%d: mt %dx%d ksteps %d n_cols %d n_tiles %d smem %zu | max err %.4g (ref max %.3g) %s\n", cout, n, h, w,
+         p.mt_x, p.mt_y, p.ksteps, p.n_cols, p.n_tiles_n, smem, maxerr, maxref, maxerr < 1e-6 * maxref + 1e-9 ? "OK" : "MISMATCH");
+  return maxerr < 1e-6 * maxref + 1e-9 ? 0 : 1;
+}
+
 int main() {
   int bad = 0;
+  bad += run_stem(8, 2, 32, 128);
+  bad += run_stem(8, 1, 40, 136);     // ragged group count
+  bad += run_stem(16, 1, 16, 64);
+  bad += run_stem(32, 1, 16, 128);    // 256 columns
   bad += run(3, 3, 8, 8, 0, 2, 32, 24);
   bad += run(3, 3, 8, 16, 0, 1, 16, 16);
   bad += run(3, 3, 16, 16, 0, 1, 32, 16);

@@ -119,24 +119,6 @@ int sync_host_mirror(octseg_net *net) {
   return 0;
 }
 
-// Banded weights of the tensor-core stem.  GEMM row (y, g) holds pixels 8g..8g+7 of image row y as its
-// 8 input channels; GEMM column plane*64 + jo*8 + c8 is output pixel 8g+jo, channel plane*8+c8.  Tap
-// (dy, dgx) of the 3x3 conv over the GROUP grid connects input pixel 8(g+dgx-1)+ji to output pixel 8g+jo
-// with the original filter tap dx = 8(dgx-1) + ji - jo + 1 when that lies in 0..2, else zero.
-static void stem_group_weights(const float *w, int cout, std::vector<float> *out) {
-  const int cols = 8 * cout;
-  out->assign((size_t)9 * 8 * cols, 0.f);
-  for (int dy = 0; dy < 3; ++dy)
-    for (int dgx = 0; dgx < 3; ++dgx)
-      for (int ji = 0; ji < 8; ++ji)
-        for (int col = 0; col < cols; ++col) {
-          const int jo = (col >> 3) & 7, c = (col >> 6) * 8 + (col & 7);
-          const int dx = 8 * (dgx - 1) + ji - jo + 1;
-          if (dx < 0 || dx > 2) continue;
-          (*out)[(((size_t)dy * 3 + dgx) * 8 + ji) * cols + col] = w[((size_t)dy * 3 + dx) * cout + c];
-        }
-}
-
 int prepare_derived(octseg_net *net) {
   if (!net->derived_dirty) return 0;
   if (sync_host_mirror(net)) return 1;
@@ -154,7 +136,7 @@ int prepare_derived(octseg_net *net) {
       const float *wk = net->h_params.data() + net->params[b.p_kernel].offset;
       std::vector<float> grouped;
       if (b.index == 0) {
-        stem_group_weights(wk, b.cout, &grouped);
+        tc_stem_group_weights(wk, b.cout, &grouped);
         wk = grouped.data();
         if (launch_stem_rep(st.scale, st.shift, b.cout, st.rep_scale, st.rep_shift, net->stream)) return 1;
         ++net->launches;
