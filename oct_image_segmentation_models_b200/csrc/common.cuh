@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 
 namespace octseg {
@@ -81,12 +82,50 @@ __device__ __forceinline__ void store8(__nv_bfloat16 *p, const Vec8f &r) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
   *reinterpret_cast<uint4 *>(p) = u;
 }
+// Storage tag of the fp32-accurate tensor-core mode: every logical 8-channel plane is a PAIR of fp16 planes,
+// hi = rn(a) and lo' = rn((a - hi) * 2^11), so a == hi + lo' * 2^-11 to 2^-22 relative (|a| <= 65504).
+struct SplitHalf { uint16_t bits; };
+template <typename T> struct PlaneMul { static constexpr int v = 1; };
+template <> struct PlaneMul<SplitHalf> { static constexpr int v = 2; };
+
+// store the 8 channels of one pixel of a LOGICAL plane; p = that pixel in the plane's first physical plane
+template <typename T>
+__device__ __forceinline__ void store_plane8(T *p, long long plane_elems, const Vec8f &r) { (void)plane_elems; store8(p, r); }
+template <>
+__device__ __forceinline__ void store_plane8<SplitHalf>(SplitHalf *p, long long plane_elems, const Vec8f &r) {
+  uint4 hi, lo;
+  uint32_t *h = reinterpret_cast<uint32_t *>(&hi), *l = reinterpret_cast<uint32_t *>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h2 = __floats2half2_rn(r.v[2 * i], r.v[2 * i + 1]);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn((r.v[2 * i] - hf.x) * 2048.f, (r.v[2 * i + 1] - hf.y) * 2048.f);
+    h[i] = *reinterpret_cast<const uint32_t *>(&h2);
+    l[i] = *reinterpret_cast<const uint32_t *>(&l2);
+  }
+  *reinterpret_cast<uint4 *>(p) = hi;
+  *reinterpret_cast<uint4 *>(p + plane_elems) = lo;
+}
+
 __device__ __forceinline__ Vec8f zero8() {
   Vec8f r;
 #pragma unroll
   for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
   return r;
 }
+
+// One-time per-DEVICE initialisation (e.g. cudaFuncSetAttribute, which is a per-device setting): a process may
+// drive several GPUs with one host thread each, so a plain `static bool` is both wrong and a data race.
+struct PerDeviceOnce {
+  std::atomic<bool> done[64];
+  // returns the current device index when its initialisation has not run yet, else -1
+  int pending() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    return done[dev].load(std::memory_order_acquire) ? -1 : dev;
+  }
+  void mark(int dev) { done[dev].store(true, std::memory_order_release); }
+};
 
 // error plumbing -------------------------------------------------------------------
 void set_error(const std::string &msg);

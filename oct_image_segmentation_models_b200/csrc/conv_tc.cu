@@ -129,6 +129,25 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  "=r"(r[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+// fp32 -> error-compensated fp16 pair: hi = rn(o), lo' = rn((o - hi) * 2^11); o == hi + lo' * 2^-11 to 2^-22 relative
+// (o - hi is exact in fp32, so is the power-of-two scaling)
+__device__ __forceinline__ void split_pack8(const float (&o)[8], uint4 &hi, uint4 &lo) {
+  uint32_t *h = reinterpret_cast<uint32_t *>(&hi), *l = reinterpret_cast<uint32_t *>(&lo);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __half2 h2 = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn((o[2 * k] - hf.x) * 2048.f, (o[2 * k + 1] - hf.y) * 2048.f);
+    h[k] = *reinterpret_cast<const uint32_t *>(&h2);
+    l[k] = *reinterpret_cast<const uint32_t *>(&l2);
+  }
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -269,7 +288,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto load_tables = [&]() {
     for (int i = threadIdx.x; i < p.cout; i += blockDim.x) {
       const int c = i % p.scale_mod;           // row-pair mode: columns [parity][channel] share the channel tables
-      s_scale[i] = p.scale[c]; s_shift[i] = p.shift[c];
+      s_scale[i] = EPI == 7 ? p.scale[c] * p.scale_mul : p.scale[c];   // split mode: undo the weight pre-scale (a power of two)
+      s_shift[i] = p.shift[c];
     }
     if constexpr (HK > 0) {
       for (int i = threadIdx.x; i < p.cout * HK; i += blockDim.x) s_head[i] = p.head_w[((i / HK) % p.scale_mod) * HK + (i % HK)];
@@ -686,6 +706,117 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         }
+      } else if (EPI == 7) {
+        // ---- fp32-accurate split mode: every logical 8-channel output plane is the 16 accumulator columns
+        //      [main 8 | corr 8] (main = hi x W_hi, corr = hi x W_lo' + lo' x W_hi, both scaled by the weight
+        //      pre-scale): value = main + corr * 2^-11.  BN + ReLU in fp32, then either the fused fp32 head or
+        //      the (hi, lo') fp16 plane pair (+ pooled pair) of the next layer.
+        const int groups = min(p.n_cols, p.cols_valid - col_base) >> 4;
+        constexpr int kWG = kTcEpiWarps / 4;
+        for (int t = wg_cur; t < mt; t += kWG) {
+          const int iy = t >> p.mt_x_log2, ix = t & (p.mt_x - 1);
+          const int y = (ty * p.mt_y + iy) * kTcTileH + r, x = (tx * p.mt_x + ix) * kTcTileW + px;
+          const bool inside = (y < p.h) && (x < p.w);
+          const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * p.n_cols);
+          float z[HK > 0 ? HK : 1];
+          if constexpr (HK > 0) {
+#pragma unroll
+            for (int k = 0; k < HK; ++k) z[k] = s_head[p.cout * HK + k];
+          }
+          float amax = 0.f;
+          for (int j = 0; j < groups; j += 2) {
+            uint32_t v[2][16];
+            const bool two = (j + 1 < groups);
+            tmem_ld16(t_base + (uint32_t)(j * 16), v[0]);
+            if (two) tmem_ld16(t_base + (uint32_t)(j * 16 + 16), v[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (u == 1 && !two) break;
+              const int colp = col_base + (j + u) * 16;          // physical column of the group
+              int co0 = (colp >> 4) << 3;                        // logical channel of its first column
+              long long off = ((long long)y * p.out_w + x) * 8;
+              if (p.mode == 1) {
+                const int par = colp / p.cout;                   // p.cout = physical columns per parity
+                co0 = ((colp - par * p.cout) >> 4) << 3;
+                off = ((long long)(2 * y + (par >> 1)) * p.out_w + 2 * x + (par & 1)) * 8;
+              }
+              const float4 sa = *reinterpret_cast<const float4 *>(s_scale + co0), sb = *reinterpret_cast<const float4 *>(s_scale + co0 + 4);
+              const float4 ha = *reinterpret_cast<const float4 *>(s_shift + co0), hb = *reinterpret_cast<const float4 *>(s_shift + co0 + 4);
+              const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+              const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+              float o[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float val = fmaf(__uint_as_float(v[u][8 + k]), 4.8828125e-4f, __uint_as_float(v[u][k]));
+                o[k] = fmaxf(fmaf(val, sc[k], sh[k]), relu_floor);
+              }
+              if constexpr (HK > 0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float *wr = s_head + (co0 + c) * HK;
+#pragma unroll
+                  for (int k = 0; k < HK; ++k) z[k] = fmaf(o[c], wr[k], z[k]);
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(o[k]));
+                uint4 hi, lo;
+                split_pack8(o, hi, lo);
+                __nv_bfloat16 *dst = p.out + (long long)img * p.out_img_stride + (long long)(co0 >> 2) * plane_elems + off;
+                if (inside) {
+                  *reinterpret_cast<uint4 *>(dst) = hi;
+                  *reinterpret_cast<uint4 *>(dst + plane_elems) = lo;
+                }
+                if (p.pool_out) {
+                  // 2x2 max on the fp32 values (partners: lanes ^1 in x, ^8 in y), then split again
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    o[k] = fmaxf(o[k], __shfl_xor_sync(0xffffffffu, o[k], 1));
+                    o[k] = fmaxf(o[k], __shfl_xor_sync(0xffffffffu, o[k], 8));
+                  }
+                  split_pack8(o, hi, lo);
+                  if (inside && !(px & 1) && !(r & 1)) {
+                    __nv_bfloat16 *pd = p.pool_out + (long long)img * p.pool_img_stride + (long long)(co0 >> 2) * (plane_elems >> 2) +
+                                        ((long long)(y >> 1) * (p.out_w >> 1) + (x >> 1)) * 8;
+                    *reinterpret_cast<uint4 *>(pd) = hi;
+                    *reinterpret_cast<uint4 *>(pd + (plane_elems >> 2)) = lo;
+                  }
+                }
+              }
+            }
+          }
+          if constexpr (HK > 0) {
+            if (inside) {
+              float mx = z[0];
+#pragma unroll
+              for (int k = 1; k < HK; ++k) mx = fmaxf(mx, z[k]);
+              float ssum = 0.f;
+#pragma unroll
+              for (int k = 0; k < HK; ++k) { z[k] = expf(z[k] - mx); ssum += z[k]; }
+              const float inv = 1.f / ssum;
+              const long long pix = ((long long)img * p.h + y) * p.w + x;
+              float pm = -1.f;
+              int pa = 0;
+#pragma unroll
+              for (int k = 0; k < HK; ++k) {
+                z[k] *= inv;
+                if (z[k] > pm) { pm = z[k]; pa = k; }   // first max, computed on the float32 probabilities
+              }
+              if (p.probs) {
+                float *dst = p.probs + pix * HK;
+                if constexpr (HK == 4) *reinterpret_cast<float4 *>(dst) = make_float4(z[0], z[1], z[2], z[3]);
+                else {
+#pragma unroll
+                  for (int k = 0; k < HK; ++k) dst[k] = z[k];
+                }
+              }
+              if (p.labels) p.labels[pix] = (uint8_t)pa;
+            }
+          } else {
+            if (inside && !(amax <= 65000.f) && p.overflow) atomicOr(p.overflow, 1);   // also catches NaN
+          }
+        }
       } else if (EPI == 2 && HK == 0) {
         // ---- 16-channel layers: same idea, two chunks (planes) per M-tile and two M-tiles per wait
         constexpr int kB2 = 2;
@@ -978,6 +1109,7 @@ bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w) {
 int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, int pad_top, int pad_left) {
   std::memset(g, 0, sizeof(*g));
   g->kh = kh; g->kw = kw; g->cin = cin; g->cout = cout; g->ups = ups;
+  g->cin_l = cin; g->cout_l = cout; g->wscale = 1.f;
   const int pt = pad_top >= 0 ? pad_top : (kh - 1) / 2, pl = pad_left >= 0 ? pad_left : (kw - 1) / 2;
   g->pt = pt; g->pl = pl;
   if (!ups) {
@@ -1089,8 +1221,44 @@ void tc_rowpair_weights(const float *w, int cin, int cout, std::vector<float> *o
     }
 }
 
-void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> *out, int fp16) {
+int tc_make_geometry_split(int kh, int kw, int cin, int cout, int ups, TcGeometry *g) {
+  if (tc_make_geometry(kh, kw, 2 * cin, 2 * cout, ups, g)) return 1;
+  g->split = 1; g->cin_l = cin; g->cout_l = cout; g->wscale = 1.f;
+  return 0;
+}
+
+float tc_split_weight_scale(const float *w, size_t count) {
+  float mx = 0.f;
+  for (size_t i = 0; i < count; ++i) mx = std::max(mx, std::fabs(w[i]));
+  if (!(mx > 0.f) || !std::isfinite(mx)) return 1.f;
+  int e;
+  std::frexp(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)
+  return std::ldexp(1.f, 4 - e);            // mx * scale in [2^3, 2^4)
+}
+
+// Value of the (tap-folded) filter for half `hf` of k-step `s`, LOGICAL input channel ci and LOGICAL GEMM column col
+static double tc_folded_weight(const TcGeometry &g, const float *w, int s, int hf, int ci, int col) {
+  const int cin = g.split ? g.cin_l : g.cin, cout = g.split ? g.cout_l : g.cout;
   const int pt = g.pt, pl = g.pl;
+  const int dy = g.half_ty[s][hf] + g.dy_min, dx = g.half_tx[s][hf] + g.dx_min;
+  if (!g.ups) {
+    const int a = dy + pt, b = dx + pl;
+    return w[(((size_t)a * g.kw + b) * cin + ci) * cout + col];
+  }
+  const int par = col / cout, co = col % cout;
+  const int py = par >> 1, px = par & 1;
+  double val = 0.0;
+  float valf = 0.f;     // the 16-bit modes sum in float, as the device-side packer does
+  for (int a = 0; a < g.kh; ++a)
+    for (int b = 0; b < g.kw; ++b)
+      if (floordiv2(py + a - pt) == dy && floordiv2(px + b - pl) == dx) {
+        val += w[(((size_t)a * g.kw + b) * cin + ci) * cout + co];
+        valf += w[(((size_t)a * g.kw + b) * cin + ci) * cout + co];
+      }
+  return g.split ? val : (double)valf;
+}
+
+void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> *out, int fp16) {
   const size_t per_step = (size_t)2 * g.n_cols * 8;
   out->assign((size_t)g.n_tiles_n * g.cin_chunks * g.ksteps * per_step, 0);
   for (int nt = 0; nt < g.n_tiles_n; ++nt)
@@ -1098,26 +1266,26 @@ void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> 
       for (int s = 0; s < g.ksteps; ++s)
         for (int hf = 0; hf < 2; ++hf) {
           if (g.half_ty[s][hf] < 0) continue;   // dummy half: zero weights
-          const int dy = g.half_ty[s][hf] + g.dy_min, dx = g.half_tx[s][hf] + g.dx_min;
+          const int plane = ch * g.planes_per_chunk + g.half_pl[s][hf];
           for (int n = 0; n < g.n_cols; ++n) {
             const int col = nt * g.n_cols + n;
             if (col >= g.cols_valid) continue;
             for (int kk = 0; kk < 8; ++kk) {
-              const int ci = (ch * g.planes_per_chunk + g.half_pl[s][hf]) * 8 + kk;
-              float val = 0.f;
-              if (!g.ups) {
-                const int a = dy + pt, b = dx + pl;
-                val = w[(((size_t)a * g.kw + b) * g.cin + ci) * g.cout + col];
+              uint16_t bits;
+              if (!g.split) {
+                const float val = (float)tc_folded_weight(g, w, s, hf, plane * 8 + kk, col);
+                bits = fp16 ? f2h(val) : f2bf(val);
               } else {
-                const int par = col / g.cout, co = col % g.cout;
-                const int py = par >> 1, px = par & 1;
-                for (int a = 0; a < g.kh; ++a)
-                  for (int b = 0; b < g.kw; ++b)
-                    if (floordiv2(py + a - pt) == dy && floordiv2(px + b - pl) == dx)
-                      val += w[(((size_t)a * g.kw + b) * g.cin + ci) * g.cout + co];
+                // physical plane 2p = hi, 2p+1 = lo' of logical plane p; physical columns 16j.. = [main 8 | corr 8]
+                const int part_k = plane & 1, part_n = (col >> 3) & 1;
+                const float v = (float)(tc_folded_weight(g, w, s, hf, (plane >> 1) * 8 + kk, (col >> 4) * 8 + (col & 7)) * (double)g.wscale);
+                const uint16_t hi = f2h(v);
+                __half_raw hr; hr.x = hi;
+                const float lo = (v - __half2float(__half(hr))) * 2048.f;
+                if (part_k == 0) bits = part_n == 0 ? hi : f2h(lo);          // hi x (W_hi | W_lo')
+                else bits = part_n == 0 ? (uint16_t)0 : hi;                  // lo' x (0 | W_hi)
               }
-              (*out)[(((size_t)(nt * g.cin_chunks + ch) * g.ksteps + s) * 2 + hf) * g.n_cols * 8 +
-                     (size_t)n * 8 + kk] = fp16 ? f2h(val) : f2bf(val);
+              (*out)[(((size_t)(nt * g.cin_chunks + ch) * g.ksteps + s) * 2 + hf) * g.n_cols * 8 + (size_t)n * 8 + kk] = bits;
             }
           }
         }
@@ -1285,7 +1453,10 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
   const int max_mt = std::max(1, 256 / g.n_cols);          // 2 accumulator stages in 512 TMEM columns
   const int tile_h = kTcTileH * (g.rows2 ? 2 : 1);          // image rows covered by one M-tile
   p.row_mul = g.rows2 ? 2 : 1;
-  p.scale_mod = g.rows2 ? g.cout / 2 : g.cout;
+  p.scale_mod = g.split ? g.cout_l : (g.rows2 ? g.cout / 2 : g.cout);
+  p.split = g.split;
+  p.scale_mul = g.split ? 1.f / g.wscale : 1.f;
+  if (g.split && (g.rows2 || g.stem_groups)) { set_error("tc plan: split mode has no row-pair / stem-group variant"); return 1; }
   static const int cand[][2] = {{8, 2}, {4, 2}, {8, 1}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
   int best_x = 1, best_y = 1;
   for (auto &c : cand) {
@@ -1363,6 +1534,8 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
   p.relu = epi.relu;
   p.fp16 = epi.fp16;
   p.static_weights = epi.static_weights;
+  p.overflow = epi.overflow;
+  if (g.split && !epi.fp16) { set_error("tc plan: split mode stores fp16 pairs"); return 1; }
   p.scale = epi.scale; p.shift = epi.shift;
   p.out = epi.out.ptr; p.out_img_stride = epi.out.img_stride; p.out_h = epi.out.h; p.out_w = epi.out.w;
   p.pool_out = epi.pool_out; p.pool_img_stride = epi.pool_img_stride;
@@ -1418,10 +1591,11 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
 
 template <int HK, int EPI>
 static int tc_launch_k(const TcPlan &plan, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the attribute is per device (one process may drive several GPUs, one host thread each)
+  static PerDeviceOnce attr_set;
+  if (const int dev = attr_set.pending(); dev >= 0) {
     OCTSEG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<HK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set.mark(dev);
   }
   static const bool pdl = []() { const char *e = std::getenv("OCTSEG_NO_PDL"); return !(e && e[0] == '1'); }();
   cudaLaunchConfig_t cfg = {};
@@ -1440,6 +1614,7 @@ bool tc_head_fusable(int num_classes) { return num_classes >= 2 && num_classes <
 // epilogue specialisation of a plan (see conv_tc_kernel)
 static int tc_epi_kind(const TcConvParams &p) {
   const bool one_ntile = p.n_tiles_n == 1;
+  if (p.split) return 7;
   if (p.row_mul == 2) return p.scale_mod == 8 ? 5 : 6;
   if (p.mode == 3) return 3;
   if (p.mode == 1) return p.shuffle_pairs ? 4 : 0;
@@ -1451,6 +1626,7 @@ static int tc_epi_kind(const TcConvParams &p) {
 template <int HK>
 static int tc_launch_head(const TcPlan &plan, cudaStream_t st) {
   const int kind = tc_epi_kind(plan.p);
+  if (kind == 7) return tc_launch_k<HK, 7>(plan, st);
   if (kind == 5) return tc_launch_k<HK, 5>(plan, st);
   return kind == 1 ? tc_launch_k<HK, 1>(plan, st) : tc_launch_k<HK, 0>(plan, st);
 }
@@ -1464,6 +1640,7 @@ int tc_launch(const TcPlan &plan, cudaStream_t st) {
       case 4: return tc_launch_k<0, 4>(plan, st);
       case 5: return tc_launch_k<0, 5>(plan, st);
       case 6: return tc_launch_k<0, 6>(plan, st);
+      case 7: return tc_launch_k<0, 7>(plan, st);
     }
     return tc_launch_k<0, 0>(plan, st);
   }

@@ -51,6 +51,9 @@ struct TcConvParams {
   const __nv_bfloat16 *wpack;  // packed weights [n_tile][chunk][kstep][2][n_cols][8]
   int row_mul;                 // image rows per GEMM row (2 in row-pair mode, else 1)
   int scale_mod;               // entries of scale / shift / head tables (real cout); table index = column % scale_mod
+  int split;                   // fp32-accurate mode: fp16 (hi, lo') plane pairs in, [main 8 | corr 8] column groups, (hi, lo') planes out
+  float scale_mul;             // split mode: 1 / (power-of-two weight pre-scale), folded into the epilogue scale table
+  int *overflow;               // split mode: device word set when an activation leaves the fp16 range
   int pdl_late;                // signal dependent launch after the last tile request (else at entry)
   int static_weights;          // packed weights are not written by earlier kernels of the stream (inference)
   uint32_t stage_off;          // mode 3: byte offset (from the epilogue tables) of the per-warp store staging
@@ -78,6 +81,12 @@ struct TcGeometry {
   int rows2;                           // set by the caller: every GEMM row yields TWO vertically adjacent output pixels
                                        // (geometry built for the 4x3 banded filter of tc_rowpair_weights)
   int stem_groups;                     // set by the caller: GEMM row = 8 adjacent pixels, columns = [plane][pixel][8 ch]
+  // fp32-accurate split mode (tc_make_geometry_split): cin / cout above are PHYSICAL (2x logical).  Every logical
+  // 8-channel input plane is a pair of fp16 planes (hi, lo' = (a - hi) * 2^11) and every logical 8-column output
+  // group is the 16 GEMM columns [main 8 | corr 8]; the epilogue computes main + corr * 2^-11.
+  int split;
+  int cin_l, cout_l;                   // logical channel counts == strides of the fp32 weight tensor
+  float wscale;                        // power-of-two pre-scale applied to the weights before the fp16 split
   // per k-step, per half: tap (dy,dx relative to dy_min/dx_min) and plane within chunk; tap -1 = zero
   int half_ty[kTcMaxKSteps][2], half_tx[kTcMaxKSteps][2], half_pl[kTcMaxKSteps][2];
 };
@@ -85,6 +94,10 @@ struct TcGeometry {
 bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w);
 // pad_top/pad_left < 0: Keras "same" padding ((k-1)/2 before); otherwise explicit (data-gradient convs)
 int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, int pad_top = -1, int pad_left = -1);
+// fp32-accurate variant: error-compensated fp16 pairs on both operands (see TcGeometry::split); cin / cout logical
+int tc_make_geometry_split(int kh, int kw, int cin, int cout, int ups, TcGeometry *g);
+// power-of-two scale that brings max |w| of a layer into [2^3, 2^4) (fp16 keeps 11 bits for everything within 2^-17 of it)
+float tc_split_weight_scale(const float *w, size_t count);
 // Row-pair filter: GEMM row = pixel (2r, x) computes outputs (2r, x) and (2r+1, x) from the 4x3 input window
 // rows 2r-1 .. 2r+2; column par*cout + co holds output row 2r+par.  Weff[a][b][ci][par*cout+co] = w[a-par][b][ci][co]
 // for 0 <= a-par <= 2, else 0 (fp32 HWIO in, [4][3][cin][2*cout] out).  Geometry: tc_make_geometry(4, 3, cin,
@@ -119,6 +132,7 @@ struct TcEpilogue {
   const float *head_w = nullptr, *head_b = nullptr;   // fused 1x1 conv + softmax head
   int head_k = 0;
   int static_weights = 0;                    // weights final before the stream's preceding kernels ran (inference)
+  int *overflow = nullptr;                   // split mode: fp16 range overflow flag (device)
   float *probs = nullptr;
   uint8_t *labels = nullptr;
 };

@@ -188,8 +188,117 @@ static int run_stem(int cout, int n, int h, int w) {
   return maxerr < 1e-6 * maxref + 1e-9 ? 0 : 1;
 }
 
+// fp32-accurate split mode: fp32 activations stored as fp16 (hi, lo') plane pairs, split-packed weights, epilogue
+// value = (main + corr * 2^-11) / wscale.  Checked against a double-precision convolution of the fp32 data.
+#include <cuda_fp16.h>
+static float h2f(uint16_t b) { __half_raw r; r.x = b; return __half2float(__half(r)); }
+static uint16_t f2h16(float f) { return static_cast<__half_raw>(__float2half_rn(f)).x; }
+static int run_split(int kh, int kw, int cin, int cout, int ups, int n, int h, int w) {
+  TcGeometry g;
+  if (tc_make_geometry_split(kh, kw, cin, cout, ups, &g)) { printf("split geometry failed\n"); return 1; }
+  TcConvParams p; size_t smem;
+  std::mt19937 rng(3);
+  std::uniform_real_distribution<float> U(-1, 1);
+  std::vector<float> wt((size_t)kh * kw * cin * cout);
+  for (auto &v : wt) v = 0.05f * U(rng);
+  g.wscale = tc_split_weight_scale(wt.data(), wt.size());
+  if (tc_fill_params(g, n, h, w, &p, &smem)) return 1;
+  const int cg = cin / 8, cgp = 2 * cg;
+  std::vector<float> xf((size_t)n * cin * h * w);            // logical blocked [n][cg][h][w][8]
+  for (auto &v : xf) v = std::max(0.f, 3.f * U(rng) + 0.5f);
+  std::vector<uint16_t> x((size_t)n * cgp * h * w * 8);      // physical: plane 2p = hi, 2p+1 = lo'
+  for (int b = 0; b < n; ++b) for (int pl = 0; pl < cg; ++pl) for (size_t i = 0; i < (size_t)h * w * 8; ++i) {
+    const float a = xf[((size_t)b * cg + pl) * h * w * 8 + i];
+    const uint16_t hi = f2h16(a);
+    x[((size_t)b * cgp + 2 * pl) * h * w * 8 + i] = hi;
+    x[((size_t)b * cgp + 2 * pl + 1) * h * w * 8 + i] = f2h16((a - h2f(hi)) * 2048.f);
+  }
+  std::vector<uint16_t> wp;
+  tc_pack_weights(g, wt.data(), &wp, 1);
+  const int oh = ups ? 2 * h : h, ow = ups ? 2 * w : w;
+  std::vector<double> out((size_t)n * oh * ow * cout, 1e30), ref((size_t)n * oh * ow * cout, 0), mag((size_t)n * oh * ow * cout, 0);
+  const int pt = (kh - 1) / 2, pl_ = (kw - 1) / 2;
+  for (int b = 0; b < n; ++b) for (int y = 0; y < oh; ++y) for (int xx = 0; xx < ow; ++xx)
+    for (int co = 0; co < cout; ++co) {
+      double acc = 0, m = 0;
+      for (int a = 0; a < kh; ++a) for (int c = 0; c < kw; ++c) {
+        int iy = y + a - pt, ix = xx + c - pl_;
+        if (iy < 0 || iy >= oh || ix < 0 || ix >= ow) continue;
+        if (ups) { iy >>= 1; ix >>= 1; }
+        for (int ci = 0; ci < cin; ++ci) {
+          const double t = (double)xf[((((size_t)b * cg + ci / 8) * h + iy) * w + ix) * 8 + (ci & 7)] * wt[(((size_t)a * kw + c) * cin + ci) * cout + co];
+          acc += t; m += std::fabs(t);
+        }
+      }
+      ref[(((size_t)b * oh + y) * ow + xx) * cout + co] = acc;
+      mag[(((size_t)b * oh + y) * ow + xx) * cout + co] = m;
+    }
+  std::vector<uint8_t> stage(p.a_stage_bytes + 4096, 0xFF);
+  for (int tile = 0; tile < p.num_tiles; ++tile) {
+    int n_tile = tile % p.n_tiles_n, t = tile / p.n_tiles_n;
+    int tx = t % p.tiles_x; t /= p.tiles_x; int ty = t % p.tiles_y; int img = t / p.tiles_y;
+    const int MT = p.mt_x * p.mt_y;
+    std::vector<double> D((size_t)MT * 128 * p.n_cols, 0.0);
+    for (int ch = 0; ch < p.cin_chunks; ++ch) {
+      uint16_t *s16 = reinterpret_cast<uint16_t *>(stage.data());
+      for (int pc = 0; pc < p.planes_per_chunk; ++pc) for (int r = 0; r < p.box_h; ++r) for (int e = 0; e < p.box_w * 8; ++e) {
+        int gx = (tx * p.mt_x * kTcTileW - p.pad_x) * 8 + e, gy = ty * p.mt_y * kTcTileH - p.pad_y + r, gp = ch * p.planes_per_chunk + pc;
+        uint16_t v = 0;
+        if (gx >= 0 && gx < w * 8 && gy >= 0 && gy < h) v = x[(((size_t)img * cgp + gp) * h + gy) * w * 8 + gx];
+        s16[((size_t)pc * p.box_h + r) * p.box_w * 8 + e] = v;
+      }
+      for (int ks = 0; ks < p.ksteps; ++ks) {
+        const uint16_t *bbase = wp.data() + ((size_t)(n_tile * p.cin_chunks + ch) * p.ksteps + ks) * 2 * p.n_cols * 8;
+        for (int tt = 0; tt < MT; ++tt) for (int m = 0; m < 128; ++m) for (int k = 0; k < 16; ++k) {
+          const int iy = tt / p.mt_x, ix = tt % p.mt_x;
+          size_t aoff = p.a_off[ks] + (size_t)iy * kTcTileH * p.box_w * 16 + (size_t)ix * 128 +
+                        (size_t)(k / 8) * p.a_lbo[ks] + (size_t)(m / 8) * p.box_w * 16 + (m % 8) * 16 + (k % 8) * 2;
+          if (aoff + 2 > p.a_stage_bytes) { printf("split A read out of stage\n"); return 1; }
+          const float av = h2f(*reinterpret_cast<uint16_t *>(stage.data() + aoff));
+          if (av == 0.f) continue;
+          for (int nn = 0; nn < p.n_cols; ++nn) {
+            size_t boff = (size_t)(k / 8) * p.n_cols * 16 + (size_t)(nn / 8) * 128 + (nn % 8) * 16 + (k % 8) * 2;
+            D[((size_t)tt * 128 + m) * p.n_cols + nn] += (double)av * h2f(bbase[boff / 2]);
+          }
+        }
+      }
+    }
+    for (int tt = 0; tt < MT; ++tt) for (int m = 0; m < 128; ++m) {
+      const int iy = tt / p.mt_x, ix = tt % p.mt_x;
+      int r = m >> 3, px = m & 7, y = (ty * p.mt_y + iy) * kTcTileH + r, xx = (tx * p.mt_x + ix) * kTcTileW + px;
+      if (y >= h || xx >= w) continue;
+      const int groups = std::min(p.n_cols, p.cols_valid - n_tile * p.n_cols) >> 4;
+      for (int j = 0; j < groups; ++j) {
+        const int colp = n_tile * p.n_cols + j * 16;       // the kernel's EPI 7 mapping
+        int co0 = (colp >> 4) << 3, oy = y, ox = xx;
+        if (p.mode == 1) { const int par = colp / p.cout; co0 = ((colp - par * p.cout) >> 4) << 3; oy = 2 * y + (par >> 1); ox = 2 * xx + (par & 1); }
+        for (int k = 0; k < 8; ++k) {
+          const float mainv = (float)D[((size_t)tt * 128 + m) * p.n_cols + j * 16 + k], corr = (float)D[((size_t)tt * 128 + m) * p.n_cols + j * 16 + 8 + k];
+          const float val = std::fmaf(corr, 4.8828125e-4f, mainv) * p.scale_mul;
+          out[(((size_t)img * oh + oy) * ow + ox) * cout + co0 + k] = val;
+        }
+      }
+    }
+  }
+  double maxrel = 0;
+  for (size_t i = 0; i < ref.size(); ++i) maxrel = std::max(maxrel, std::fabs(out[i] - ref[i]) / std::max(mag[i], 1e-30));
+  const bool ok = maxrel < 2e-6 && p.scale_mod == cout;
+  printf("split k%dx%d cin %d cout %d ups %d %dx%dx%d: mt %dx%d res %d ksteps %d n_cols %d n_tiles %d chunks %d a_st %d smem %zu wscale %g | max err / sum|terms| %.3g %s\n",
+         kh, kw, cin, cout, ups, n, h, w, p.mt_x, p.mt_y, p.b_resident, p.ksteps, p.n_cols, p.n_tiles_n, p.cin_chunks, p.a_stages, smem,
+         g.wscale, maxrel, ok ? "OK" : "MISMATCH");
+  return ok ? 0 : 1;
+}
+
 int main() {
   int bad = 0;
+  bad += run_split(3, 3, 8, 8, 0, 2, 32, 24);
+  bad += run_split(3, 3, 16, 8, 0, 1, 20, 12);
+  bad += run_split(3, 3, 8, 16, 0, 40, 64, 64);
+  bad += run_split(2, 2, 16, 8, 1, 2, 32, 24);
+  bad += run_split(3, 3, 64, 64, 0, 1, 16, 16);
+  bad += run_split(3, 3, 128, 128, 0, 1, 16, 8);
+  bad += run_split(2, 2, 128, 64, 1, 1, 16, 8);
+  bad += run_split(3, 3, 256, 256, 0, 1, 16, 8);   // physical 512 columns: two n-tiles
   bad += run_stem(8, 2, 32, 128);
   bad += run_stem(8, 1, 40, 136);     // ragged group count
   bad += run_stem(16, 1, 16, 64);

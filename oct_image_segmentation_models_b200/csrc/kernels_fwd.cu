@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(256) conv_first_kernel(
         float v = fmaf(acc.v[co], wsm[taps * cout + cog * 8 + co], wsm[taps * cout + cout + cog * 8 + co]);
         acc.v[co] = relu ? fmaxf(v, 0.f) : v;
       }
-      T *dst = out.ptr + b * out.img_stride + (((long long)cog * h + y) * w + x) * 8;
-      store8(dst, acc);
+      T *dst = out.ptr + b * out.img_stride + (((long long)cog * PlaneMul<T>::v * h + y) * w + x) * 8;
+      store_plane8(dst, (long long)h * w * 8, acc);
     }
   }
 }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) conv_stem3x3_kernel(
             acc[p].v[6] = fmaf(v, wb.z, acc[p].v[6]); acc[p].v[7] = fmaf(v, wb.w, acc[p].v[7]);
           }
         }
-      T *dst = out.ptr + b * out.img_stride + (((long long)cog * h + y) * w + x0) * 8;
+      T *dst = out.ptr + b * out.img_stride + (((long long)cog * PlaneMul<T>::v * h + y) * w + x0) * 8;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
 #pragma unroll
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) conv_stem3x3_kernel(
           float v = fmaf(acc[p].v[co], wsm[9 * cout + cog * 8 + co], wsm[10 * cout + cog * 8 + co]);
           acc[p].v[co] = relu ? fmaxf(v, 0.f) : v;
         }
-        store8(dst + p * 8, acc[p]);
+        store_plane8(dst + p * 8, (long long)h * w * 8, acc[p]);
       }
     }
   }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256, 2) conv_stem3x3_tile_kernel(
     for (int j = 0; j < 2; ++j) {
       const int r = wy * 2 + j, y = y0 + r;
       if (y >= h) break;
-      T *row = out.ptr + b * out.img_stride + ((long long)cog * h + y) * w * 8;
+      T *row = out.ptr + b * out.img_stride + ((long long)cog * PlaneMul<T>::v * h + y) * w * 8;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int xl = lane + 32 * p, x = x0 + xl;
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256, 2) conv_stem3x3_tile_kernel(
           o.v[2 * k] = relu ? fmaxf(y2.x, 0.f) : y2.x;
           o.v[2 * k + 1] = relu ? fmaxf(y2.y, 0.f) : y2.y;
         }
-        if (x < w) store8(row + (long long)x * 8, o);
+        if (x < w) store_plane8(row + (long long)x * 8, (long long)h * w * 8, o);
       }
     }
   }
@@ -718,5 +718,7 @@ int launch_bn_fold(const float *bias, const float *gamma, const float *beta, con
 INST(float)
 INST(__nv_bfloat16)
 INST(__half)
+template int launch_conv_first<SplitHalf>(const void *, int, int, int, int, int, const float *, int, int, int,
+                                          const float *, const float *, int, View<SplitHalf>, cudaStream_t);
 
 }  // namespace octseg

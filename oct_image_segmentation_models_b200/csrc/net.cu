@@ -2,6 +2,7 @@
 #include "net.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 #include <cstdio>
@@ -131,6 +132,18 @@ int prepare_derived(octseg_net *net) {
                        P + net->params[b.p_var].offset, kBnEps, b.cout, st.scale, st.shift, net->stream))
       return 1;
     ++net->launches;
+    if (net->precision == OCTSEG_FP32 && st.geo_s_ok) {
+      // fp32 mode on tensor cores: pre-scale by a power of two, split every (tap-folded) weight into an fp16
+      // pair and lay the pairs out as [hi rows: W_hi | W_lo'] / [lo' rows: 0 | W_hi] (tc_pack_weights)
+      const float *wk = net->h_params.data() + net->params[b.p_kernel].offset;
+      const float ws = tc_split_weight_scale(wk, (size_t)net->params[b.p_kernel].count);
+      if (ws != st.geo_s.wscale) { st.geo_s.wscale = ws; net->ws_n = 0; }   // plans carry 1/wscale: re-plan
+      std::vector<uint16_t> packed;
+      tc_pack_weights(st.geo_s, wk, &packed, 1);
+      if (packed.size() != st.wpack_s_elems) { set_error("internal: wpack_s size"); return 1; }
+      OCTSEG_CUDA(cudaMemcpyAsync(st.wpack_s, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, net->stream));
+      OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+    }
     if (net->precision != OCTSEG_FP32 && st.geo_ok) {
       std::vector<uint16_t> packed;
       const float *wk = net->h_params.data() + net->params[b.p_kernel].offset;
@@ -169,15 +182,35 @@ struct Bump {
   size_t take(size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; }
 };
 
+// fp32 mode: can this shape run on the tensor cores (every conv block after the stem has a split plan, the head fuses)?
+static bool split_applicable(const octseg_net *net, int h, int w) {
+  if (net->precision != OCTSEG_FP32 || net->fp32_path != 0 || net->disable_tc || net->disable_fusion) return false;
+  const BlockSpec &last = net->blocks.back();
+  if (last.role != 4 || !tc_head_fusable(last.cout) || net->blocks.size() < 3) return false;
+  for (auto &b : net->blocks) {
+    if (b.index == 0 || b.role == 4) continue;
+    const BlockState &st = net->bstate[b.index];
+    if (!st.geo_s_ok) return false;
+    int lh = h >> b.level, lw = w >> b.level;
+    if (b.ups) { lh >>= 1; lw >>= 1; }
+    if (!tc_supported(b.kh, b.kw, 2 * b.cin, 2 * b.cout, b.ups, lh, lw)) return false;
+    if (b.index == last.index - 1 && st.geo_s.n_tiles_n != 1) return false;
+  }
+  return true;
+}
+
 int ensure_workspace(octseg_net *net, int n, int h, int w) {
-  if (net->ws && net->ws_n == n && net->ws_h == h && net->ws_w == w) return 0;
+  const bool split = split_applicable(net, h, w);
+  if (net->ws && net->ws_n == n && net->ws_h == h && net->ws_w == w && net->ws_split == split) return 0;
   const int P = net->cfg.pool_layers, L = net->cfg.conv_layers, s = net->cfg.start_neurons;
   if ((h % (1 << P)) || (w % (1 << P))) {
     set_error("image height/width must be multiples of 2^pool_layers");
     return 1;
   }
-  const size_t es = elem_size(net);
-  auto bytes = [&](int ch, int lvl) { return (size_t)n * ch * (h >> lvl) * (w >> lvl) * es; };
+  // split layout: fp16 elements, two physical planes (hi, lo') per logical 8-channel plane
+  const size_t es = split ? 2 : elem_size(net);
+  const int pm = split ? 2 : 1;
+  auto bytes = [&](int ch, int lvl) { return (size_t)n * ch * pm * (h >> lvl) * (w >> lvl) * es; };
   Bump bump;
   std::vector<size_t> cat(P), pooled(P), encT0(P), encT1(P), decT0(P), decT1(P);
   for (int l = 0; l < P; ++l) {
@@ -208,11 +241,12 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
     BlockIO &io = net->io[b.index];
     const int lh = h >> b.level, lw = w >> b.level;
     const int f = b.cout;
+    const int fp = f / 8 * pm;           // physical planes of an f-channel tensor
     // ---- input
     if (b.index == 0) {
       io.in = nullptr; io.in_h = h; io.in_w = w;
     } else if (b.concat_level >= 0) {
-      io.in = base + cat[b.level]; io.in_planes_total = io.in_planes = b.cin / 8; io.in_plane0 = 0;
+      io.in = base + cat[b.level]; io.in_planes_total = io.in_planes = b.cin / 8 * pm; io.in_plane0 = 0;
       io.in_h = lh; io.in_w = lw;
     } else {
       io.in = prev; io.in_planes_total = io.in_planes = prev_planes; io.in_plane0 = 0;
@@ -224,26 +258,53 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
       io.out = nullptr;
     } else if (b.role == 0) {
       if (b.pool_after) {
-        io.out = base + cat[b.level]; io.out_planes_total = 2 * f / 8; io.out_plane0 = f / 8; io.out_planes = f / 8;
+        io.out = base + cat[b.level]; io.out_planes_total = 2 * fp; io.out_plane0 = fp; io.out_planes = fp;
         io.pool = base + pooled[b.level]; io.pool_h = lh / 2; io.pool_w = lw / 2;
       } else {
         io.out = base + ((b.conv_j & 1) ? encT1[b.level] : encT0[b.level]);
-        io.out_planes_total = io.out_planes = f / 8; io.out_plane0 = 0;
+        io.out_planes_total = io.out_planes = fp; io.out_plane0 = 0;
       }
     } else if (b.role == 1) {
       io.out = base + ((b.conv_j & 1) ? midT1 : midT0);
-      io.out_planes_total = io.out_planes = f / 8; io.out_plane0 = 0;
+      io.out_planes_total = io.out_planes = fp; io.out_plane0 = 0;
     } else if (b.role == 2) {
-      io.out = base + cat[b.level]; io.out_planes_total = 2 * f / 8; io.out_plane0 = 0; io.out_planes = f / 8;
+      io.out = base + cat[b.level]; io.out_planes_total = 2 * fp; io.out_plane0 = 0; io.out_planes = fp;
     } else {
       io.out = base + ((b.conv_j & 1) ? decT1[b.level] : decT0[b.level]);
-      io.out_planes_total = io.out_planes = f / 8; io.out_plane0 = 0;
+      io.out_planes_total = io.out_planes = fp; io.out_plane0 = 0;
     }
     // what the next block sees
-    if (io.pool) { prev = io.pool; prev_planes = f / 8; prev_h = io.pool_h; prev_w = io.pool_w; }
-    else { prev = io.out; prev_planes = f / 8; prev_h = lh; prev_w = lw; }
+    if (io.pool) { prev = io.pool; prev_planes = fp; prev_h = io.pool_h; prev_w = io.pool_w; }
+    else { prev = io.out; prev_planes = fp; prev_h = lh; prev_w = lw; }
     // ---- tensor-core plan
     io.use_tc = false;
+    if (split && b.index > 0 && b.role != 4) {
+      const BlockState &bst = net->bstate[b.index];
+      TcEpilogue epi;
+      epi.fp16 = 1;
+      epi.static_weights = 1;
+      epi.overflow = net->d_status + 1;
+      epi.scale = bst.scale; epi.shift = bst.shift;
+      epi.out = make_view(reinterpret_cast<__nv_bfloat16 *>(io.out), n, io.out_planes_total, io.out_plane0,
+                          io.out_planes, io.out_h, io.out_w);
+      if (io.pool) {
+        epi.pool_out = reinterpret_cast<__nv_bfloat16 *>(io.pool);
+        epi.pool_img_stride = (long long)io.out_planes * io.pool_h * io.pool_w * 8;
+        io.pool_fused = true;
+      }
+      const BlockSpec &last = net->blocks.back();
+      if (b.index == last.index - 1) {
+        epi.head_w = net->d_params + net->params[last.p_kernel].offset;
+        epi.head_b = net->d_params + net->params[last.p_bias].offset;
+        epi.head_k = last.cout;
+        io.head_fused = true;
+      }
+      if (tc_make_plan(bst.geo_s, reinterpret_cast<const __nv_bfloat16 *>(io.in), n, io.in_h, io.in_w, bst.wpack_s, epi,
+                       net->d_status, &io.plan))
+        return 1;
+      io.use_tc = true;
+      continue;
+    }
     if (b.index == 0 && stem_tc) {
       TcEpilogue epi;
       epi.fp16 = net->precision == OCTSEG_FP16;
@@ -287,7 +348,7 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
       io.use_tc = true;
     }
   }
-  net->ws_n = n; net->ws_h = h; net->ws_w = w;
+  net->ws_n = n; net->ws_h = h; net->ws_w = w; net->ws_split = split;
   return 0;
 }
 
@@ -297,6 +358,7 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
 template <typename T>
 static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h, int w, float *d_probs,
                      uint8_t *d_labels, cudaStream_t st) {
+  constexpr bool kSplit = std::is_same<T, SplitHalf>::value;   // fp32 mode on tensor cores: every block after the stem has a plan
   const float *P = net->d_params;
   const bool prof = net->profiling && net->prof_events.size() == net->blocks.size() + 1;
   if (prof) cudaEventRecord(net->prof_events[0], st);
@@ -309,22 +371,27 @@ static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h
         if (prof) { cudaEventRecord(net->prof_events[net->blocks.size()], st); net->prof_valid = true; }
         continue;
       }
+      if constexpr (kSplit) { set_error("internal: split plan without a fused head"); return 1; }
+      else {
       View<const T> in = make_view(reinterpret_cast<const T *>(io.in), n, io.in_planes_total, io.in_plane0,
                                    io.in_planes, io.in_h, io.in_w);
       if (launch_head<T>(in, P + net->params[b.p_kernel].offset, P + net->params[b.p_bias].offset, b.cin,
                          b.cout, d_probs, d_labels, st))
         return 1;
+      }
       ++net->launches;
       if (prof) { cudaEventRecord(net->prof_events[net->blocks.size()], st); net->prof_valid = true; }
       continue;
     }
     View<T> out = make_view(reinterpret_cast<T *>(io.out), n, io.out_planes_total, io.out_plane0,
                             io.out_planes, io.out_h, io.out_w);
-    if (b.index == 0 && io.use_tc && dtype == OCTSEG_U8 && ((uintptr_t)d_img % 16) == 0) {
+    if (!kSplit && b.index == 0 && io.use_tc && dtype == OCTSEG_U8 && ((uintptr_t)d_img % 16) == 0) {
       // tensor-core stem: widen the image to 16 bits (exact), then one conv_tc launch over pixel groups
+      if constexpr (!kSplit) {
       if (launch_u8_to_act<T>(reinterpret_cast<const uint8_t *>(d_img), (long long)n * h * w,
                               reinterpret_cast<T *>(io.stem_in), st))
         return 1;
+      }
       ++net->launches;
       if (tc_launch(io.plan, st)) return 1;
     } else if (b.index == 0) {
@@ -337,6 +404,9 @@ static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h
         pl.p.probs = d_probs; pl.p.labels = d_labels;
         if (tc_launch(pl, st)) return 1;
       } else if (tc_launch(io.plan, st)) return 1;
+    } else if constexpr (kSplit) {
+      set_error("internal: split plan without a tensor-core block");
+      return 1;
     } else {
       View<const T> in = make_view(reinterpret_cast<const T *>(io.in), n, io.in_planes_total, io.in_plane0,
                                    io.in_planes, io.in_h, io.in_w);
@@ -345,6 +415,7 @@ static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h
         return 1;
     }
     ++net->launches;
+    if constexpr (!kSplit) {
     if (io.pool && !io.pool_fused) {
       View<const T> pin = make_view(reinterpret_cast<const T *>(io.out), n, io.out_planes_total,
                                     io.out_plane0, io.out_planes, io.out_h, io.out_w);
@@ -352,6 +423,7 @@ static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h
                                io.pool_w);
       if (launch_maxpool2<T>(pin, pout, st)) return 1;
       ++net->launches;
+    }
     }
   }
   return 0;
@@ -365,16 +437,26 @@ int forward(octseg_net *net, const void *d_img, int dtype, int n, int h, int w, 
     return forward_t<__nv_bfloat16>(net, d_img, dtype, n, h, w, d_probs, d_labels, st);
   if (net->precision == OCTSEG_FP16)
     return forward_t<__half>(net, d_img, dtype, n, h, w, d_probs, d_labels, st);
+  if (net->ws_split) return forward_t<SplitHalf>(net, d_img, dtype, n, h, w, d_probs, d_labels, st);
   return forward_t<float>(net, d_img, dtype, n, h, w, d_probs, d_labels, st);
 }
 
+// 0 = ok, 1 = error, 2 = an activation left the fp16-pair range of the fp32 tensor-core path: the results of the
+// work since the last check are invalid and the handle has switched to the CUDA-core fp32 path for good
 int check_status(octseg_net *net) {
-  OCTSEG_CUDA(cudaMemcpyAsync(net->h_status, net->d_status, sizeof(int), cudaMemcpyDeviceToHost, net->stream));
+  OCTSEG_CUDA(cudaMemcpyAsync(net->h_status, net->d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, net->stream));
   OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
-  if (*net->h_status != 0) {
-    set_error("tensor-core conv pipeline timed out (code " + std::to_string(*net->h_status) + ")");
-    OCTSEG_CUDA(cudaMemsetAsync(net->d_status, 0, sizeof(int), net->stream));
+  if (net->h_status[0] != 0) {
+    set_error("tensor-core conv pipeline timed out (code " + std::to_string(net->h_status[0]) + ")");
+    OCTSEG_CUDA(cudaMemsetAsync(net->d_status, 0, 2 * sizeof(int), net->stream));
     return 1;
+  }
+  if (net->h_status[1] != 0) {
+    set_error("fp32 tensor-core path: an activation exceeded the fp16-pair range (|a| > 65000); results of this "
+              "call are invalid, the handle now uses the CUDA-core fp32 path");
+    OCTSEG_CUDA(cudaMemsetAsync(net->d_status, 0, 2 * sizeof(int), net->stream));
+    net->fp32_path = 1;
+    return 2;
   }
   return 0;
 }
@@ -468,9 +550,10 @@ int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precisio
   OCTSEG_CUDA(cudaMalloc(&net->d_params, net->total_floats * sizeof(float)));
   OCTSEG_CUDA(cudaMemset(net->d_params, 0, net->total_floats * sizeof(float)));
   net->h_params.assign(net->total_floats, 0.f);
-  OCTSEG_CUDA(cudaMalloc(&net->d_status, sizeof(int)));
-  OCTSEG_CUDA(cudaMemset(net->d_status, 0, sizeof(int)));
-  OCTSEG_CUDA(cudaMallocHost(&net->h_status, sizeof(int)));
+  OCTSEG_CUDA(cudaMalloc(&net->d_status, 2 * sizeof(int)));
+  OCTSEG_CUDA(cudaMemset(net->d_status, 0, 2 * sizeof(int)));
+  OCTSEG_CUDA(cudaMallocHost(&net->h_status, 2 * sizeof(int)));
+  { const char *fp = std::getenv("OCTSEG_FP32_PATH"); net->fp32_path = (fp && (fp[0] == 'c' || fp[0] == 'C')) ? 1 : 0; }
   if (init_preprocess_lut()) { delete net; return 1; }
   net->bstate.resize(net->blocks.size());
   for (auto &b : net->blocks) {
@@ -485,6 +568,13 @@ int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precisio
       st.geo_ok = true;
       st.wpack_elems = (size_t)st.geo.n_tiles_n * st.geo.cin_chunks * st.geo.ksteps * 2 * st.geo.n_cols * 8;
       OCTSEG_CUDA(cudaMalloc(&st.wpack, st.wpack_elems * 2));
+    }
+    if (precision == OCTSEG_FP32 && b.index > 0 && b.role != 4 && b.cin % 8 == 0 &&
+        tc_supported(b.kh, b.kw, 2 * b.cin, 2 * b.cout, b.ups, kTcTileH, kTcTileW) &&
+        tc_make_geometry_split(b.kh, b.kw, b.cin, b.cout, b.ups ? 1 : 0, &st.geo_s) == 0) {
+      st.geo_s_ok = true;
+      st.wpack_s_elems = (size_t)st.geo_s.n_tiles_n * st.geo_s.cin_chunks * st.geo_s.ksteps * 2 * st.geo_s.n_cols * 8;
+      OCTSEG_CUDA(cudaMalloc(&st.wpack_s, st.wpack_s_elems * 2));
     }
     // row-pair variant (inference): 3x3 layers with 8 or 16 output channels are bound by the smem reads of
     // the A operand; computing two output rows per GEMM row cuts those by a third
@@ -520,7 +610,7 @@ int32_t octseg_destroy(octseg_net *net) {
   for (auto &e : net->pipe_events) cudaEventDestroy(e);
   if (net->copy_in) cudaStreamDestroy(net->copy_in);
   if (net->copy_out) cudaStreamDestroy(net->copy_out);
-  for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); cudaFree(st.rep_scale); cudaFree(st.rep_shift); cudaFree(st.wpack2); }
+  for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); cudaFree(st.rep_scale); cudaFree(st.rep_shift); cudaFree(st.wpack2); cudaFree(st.wpack_s); }
   cudaFree(net->d_params); cudaFree(net->ws); cudaFree(net->d_img); cudaFree(net->d_probs);
   cudaFree(net->d_labels); cudaFree(net->d_maps); cudaFree(net->d_status);
   if (net->h_status) cudaFreeHost(net->h_status);
@@ -646,7 +736,10 @@ static int predict_pipeline(octseg_net *net, const void *images, int32_t dtype, 
   }
   OCTSEG_CUDA(cudaEventRecord(net->pipe_events[2], net->copy_out));
   OCTSEG_CUDA(cudaStreamWaitEvent(net->stream, net->pipe_events[2], 0));
-  return check_status(net);
+  const int rc = check_status(net);
+  if (rc == 2)   // fp16-pair range overflow: the handle has switched to the CUDA-core fp32 path, run the call again
+    return predict_pipeline(net, images, dtype, n, h, w, probs, labels, maps, bg_ilm, bg_csi, transposed);
+  return rc;
 }
 
 int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
@@ -697,7 +790,8 @@ int32_t octseg_get_block_times(octseg_net *net, float *ms, int32_t cap, int32_t 
 int32_t octseg_layer_uses_tensor_core(octseg_net *net, int32_t conv_index, int32_t h, int32_t w) {
   if (!net || conv_index < 0 || conv_index >= (int)net->blocks.size()) return 0;
   const BlockSpec &b = net->blocks[conv_index];
-  if (net->precision == OCTSEG_FP32 || net->disable_tc || b.role == 4) return 0;
+  if (net->disable_tc || b.role == 4) return 0;
+  if (net->precision == OCTSEG_FP32) return (b.index > 0 && split_applicable(net, h, w)) ? 1 : 0;
   if (!net->bstate[b.index].geo_ok) return 0;
   if (b.index == 0)      // tensor-core stem over pixel groups (uint8 input only)
     return ((w % 8) == 0 && tc_supported(3, 3, 8, 8 * b.cout, 0, h, w / 8)) ? 1 : 0;
@@ -716,7 +810,9 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
   OCTSEG_CUDA(cudaSetDevice(net->device));
   if (prepare_derived(net)) return 1;
   const int oh = b.ups ? 2 * h : h, ow = b.ups ? 2 * w : w;
-  const size_t es = elem_size(net);
+  // fp32 mode, path 1: the tensor-core path on error-compensated fp16 pairs (two physical planes per logical plane)
+  const bool split = (path == 1 && net->precision == OCTSEG_FP32);
+  const size_t es = split ? 4 : elem_size(net);       // bytes per LOGICAL element
   const size_t in_elems = (size_t)n * b.cin * h * w, out_elems = (size_t)n * b.cout * oh * ow;
   // host re-layout NHWC -> [N][C/8][H][W][8]
   std::vector<float> blk(in_elems);
@@ -731,7 +827,19 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
   OCTSEG_CUDA(cudaMalloc(&d_out, out_elems * es));
   OCTSEG_CUDA(cudaMemset(d_out, 0xFF, out_elems * es));   // poison: unwritten outputs show up as NaN
   std::vector<uint16_t> h16;
-  if (net->precision != OCTSEG_FP32) {
+  if (split) {
+    h16.resize(2 * in_elems);
+    const size_t pe = (size_t)h * w * 8;
+    for (size_t pl = 0; pl < (size_t)n * (b.cin / 8); ++pl)
+      for (size_t i = 0; i < pe; ++i) {
+        const float a = blk[pl * pe + i];
+        const __half hi = __float2half_rn(a);
+        const __half lo = __float2half_rn((a - __half2float(hi)) * 2048.f);
+        std::memcpy(&h16[(2 * pl) * pe + i], &hi, 2);
+        std::memcpy(&h16[(2 * pl + 1) * pe + i], &lo, 2);
+      }
+    OCTSEG_CUDA(cudaMemcpy(d_in, h16.data(), in_elems * 4, cudaMemcpyHostToDevice));
+  } else if (net->precision != OCTSEG_FP32) {
     h16.resize(in_elems);
     for (size_t i = 0; i < in_elems; ++i) {
       if (net->precision == OCTSEG_BF16) { __nv_bfloat16 v = __float2bfloat16(blk[i]); std::memcpy(&h16[i], &v, 2); }
@@ -749,8 +857,22 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
   int rc = 0;
   const int reps = ms_out ? 5 : 1;
   TcPlan plan;
-  if (path == 1) {
-    if (net->precision == OCTSEG_FP32 || !bs.geo_ok || !tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, h, w)) {
+  if (split) {
+    if (!bs.geo_s_ok || !tc_supported(b.kh, b.kw, 2 * b.cin, 2 * b.cout, b.ups, h, w)) {
+      set_error("tensor-core (split fp32) path not available for this block/shape");
+      rc = 1;
+    } else {
+      TcEpilogue epi;
+      epi.fp16 = 1;
+      epi.static_weights = 1;
+      epi.overflow = net->d_status + 1;
+      epi.scale = bs.scale; epi.shift = bs.shift;
+      epi.out = make_view(reinterpret_cast<__nv_bfloat16 *>(d_out), n, b.cout / 4, 0, b.cout / 4, oh, ow);
+      rc = tc_make_plan(bs.geo_s, reinterpret_cast<const __nv_bfloat16 *>(d_in), n, h, w, bs.wpack_s, epi,
+                        net->d_status, &plan);
+    }
+  } else if (path == 1) {
+    if (!bs.geo_ok || !tc_supported(b.kh, b.kw, b.cin, b.cout, b.ups, h, w)) {
       set_error("tensor-core path not available for this block/shape");
       rc = 1;
     } else {
@@ -809,7 +931,18 @@ int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t pat
   cudaEventDestroy(e1);
   if (rc == 0) {
     std::vector<float> ob(out_elems);
-    if (net->precision != OCTSEG_FP32) {
+    if (split) {
+      std::vector<uint16_t> o16(2 * out_elems);
+      cudaMemcpy(o16.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost);
+      const size_t pe = (size_t)oh * ow * 8;
+      for (size_t pl = 0; pl < (size_t)n * (b.cout / 8); ++pl)
+        for (size_t i = 0; i < pe; ++i) {
+          __half hi, lo;
+          std::memcpy(&hi, &o16[(2 * pl) * pe + i], 2);
+          std::memcpy(&lo, &o16[(2 * pl + 1) * pe + i], 2);
+          ob[pl * pe + i] = __half2float(hi) + __half2float(lo) * 4.8828125e-4f;
+        }
+    } else if (net->precision != OCTSEG_FP32) {
       std::vector<uint16_t> o16(out_elems);
       cudaMemcpy(o16.data(), d_out, out_elems * 2, cudaMemcpyDeviceToHost);
       for (size_t i = 0; i < out_elems; ++i) {

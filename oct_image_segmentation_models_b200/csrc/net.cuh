@@ -48,6 +48,11 @@ struct BlockState {
   __nv_bfloat16 *wpack2 = nullptr;
   size_t wpack2_elems = 0;
   float *rep_scale = nullptr, *rep_shift = nullptr;   // TC stem only: per-GEMM-column scale/255 and shift
+  // fp32 mode on tensor cores: error-compensated fp16 pairs (tc_make_geometry_split)
+  bool geo_s_ok = false;
+  TcGeometry geo_s{};
+  __nv_bfloat16 *wpack_s = nullptr;
+  size_t wpack_s_elems = 0;
 };
 
 // Workspace views for one (n,h,w)
@@ -88,8 +93,12 @@ struct octseg_net {
   float *d_probs = nullptr; size_t d_probs_bytes = 0;
   uint8_t *d_labels = nullptr; size_t d_labels_bytes = 0;
   uint8_t *d_maps = nullptr; size_t d_maps_bytes = 0;
-  int *d_status = nullptr;
-  int *h_status = nullptr;            // pinned
+  int *d_status = nullptr;            // [0] pipeline time-out code, [1] fp16-pair range overflow (split mode)
+  int *h_status = nullptr;            // pinned, 2 ints
+  // fp32 mode: 0 = tensor cores on error-compensated fp16 pairs where the shape allows (default), 1 = CUDA cores
+  // (env OCTSEG_FP32_PATH=cuda, or set for good once an activation left the fp16 range)
+  int fp32_path = 0;
+  bool ws_split = false;              // the planned workspace uses the split layout
   int64_t launches = 0;
   bool disable_tc = false;
   bool disable_fusion = false;

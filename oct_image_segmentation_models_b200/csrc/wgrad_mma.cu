@@ -628,12 +628,12 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
       int n_stages = (int)std::min<size_t>(kWmMaxStages, (200 * 1024 - fixed) / stage);
       if (n_stages >= 2) {
         const size_t smem3 = n_stages * stage + fixed;
-        static bool attr3 = false;
-        if (!attr3) {
+        static PerDeviceOnce attr3;
+        if (const int dev_ = attr3.pending(); dev_ >= 0) {
           OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_deep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
           OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_deep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
           OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_deep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-          attr3 = true;
+          attr3.mark(dev_);
         }
         const int blocks_y3 = p.n_pchunks * p.n_nchunks;
         const int gx3 = std::max(1, std::min(p.num_tiles, (148 + blocks_y3 - 1) / blocks_y3));
@@ -669,11 +669,11 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
     int n_stages = (int)std::min<size_t>(kWmMaxStages, (200 * 1024 - fixed) / stage);
     if (n_stages < 2) n_stages = 2;
     const size_t smem2 = n_stages * stage + fixed;
-    static bool attr2 = false;
-    if (!attr2) {
+    static PerDeviceOnce attr2;
+    if (const int dev_ = attr2.pending(); dev_ >= 0) {
       OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_mma_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_mma_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr2 = true;
+      attr2.mark(dev_);
     }
     if (smem2 <= 220 * 1024) {
       const int blocks_y2 = p.n_pchunks * p.n_gblocks * p.n_nchunks;
@@ -690,10 +690,10 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
   const int aw = kWmTW + kw - 1, ah = kWmTH + kh - 1;
   const size_t smem = ((size_t)p.pc * ah * aw * 8 + (size_t)kWmNB * kWmTH * kWmTW * 8 + 64) * 2 +
                       (size_t)(kWmMaxGroups + 2) * 8 * kWmNB * 8 * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (const int dev_ = attr.pending(); dev_ >= 0) {
     OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr = true;
+    attr.mark(dev_);
   }
   if (smem > 100 * 1024) { set_error("wgrad_mma: smem budget exceeded"); return 1; }
   const int blocks_y = p.n_pchunks * p.n_gblocks * p.n_nchunks;

@@ -67,6 +67,11 @@ def test_conv_block_tcgen05_and_direct_vs_oracle(engines, idx, n, h, w):
     got32 = e32.debug_conv_block(idx, x, path=0)
     scale = np.abs(ref32).max()
     assert np.abs(got32 - ref32).max() <= 2e-6 * max(scale, 1.0)
+    # fp32 mode on the tensor cores: error-compensated fp16 pairs (2^-22 per operand).  The tensor core adds
+    # into its fp32 accumulator with truncation, so the error grows with the K-step count (144 for 128->128:
+    # measured 3.6e-6 of the output scale, 7e-7 for the 8/16-channel layers); 25x inside the 1e-4 contract.
+    got32_tc = e32.debug_conv_block(idx, x, path=1)
+    assert np.abs(got32_tc - ref32).max() <= 5e-6 * max(scale, 1.0), float(np.abs(got32_tc - ref32).max())
     ref16 = oracle_block(b, weights, bf16_round(x))
     for path in (0, 1):
         got = e16.debug_conv_block(idx, x, path=path)
@@ -80,7 +85,31 @@ def test_default_net_uses_tensor_cores(engines):
     blocks = unet_blocks(**CFG)
     tc = [i for i in range(len(blocks)) if e16.layer_uses_tensor_core(i, 512, 512)]
     assert tc == list(range(0, 22)), tc            # every conv block (the stem as a pixel-group GEMM); not the 1x1 head
-    assert not any(e32.layer_uses_tensor_core(i, 512, 512) for i in range(len(blocks)))
+    # fp32 mode: every conv after the stem on tcgen05 (fp16 pairs); the exact FFMA stem feeds it, the head is fused
+    tc32 = [i for i in range(len(blocks)) if e32.layer_uses_tensor_core(i, 512, 512)]
+    assert tc32 == list(range(1, 22)), tc32
+    assert not any(e32.layer_uses_tensor_core(i, 64, 64) for i in range(len(blocks)))   # too small: CUDA-core path
+
+
+def test_fp32_tensor_core_path_equals_cuda_core_path(engines, monkeypatch):
+    """fp32 mode has two implementations: tcgen05 on error-compensated fp16 pairs (default where every level is at
+    least one 8x16 tile) and the FFMA kernels.  Same weights, same B-scans: both within 1e-4 of the oracle, and
+    within 2e-5 of each other; identical argmax except on exact near-ties."""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    weights, e32, _ = engines
+    imgs, _ = synthetic_batch(77, 2, 256, 128)
+    assert e32.layer_uses_tensor_core(5, 256, 128)
+    p_tc, l_tc = e32.predict(imgs, want_labels=True)
+    monkeypatch.setenv("OCTSEG_FP32_PATH", "cuda")
+    ecc = UNetEngine(precision="fp32", **CFG)
+    ecc.set_weights(weights)
+    assert not ecc.layer_uses_tensor_core(5, 256, 128)
+    p_cc, l_cc = ecc.predict(imgs, want_labels=True)
+    ecc.close()
+    ref = OracleUNet(weights, **CFG).predict(imgs)
+    assert rel_err(p_tc, ref).max() <= FP32_REL and rel_err(p_cc, ref).max() <= FP32_REL
+    assert rel_err(p_tc, p_cc).max() <= 2e-5
+    assert (l_tc == l_cc).mean() >= 0.99999
 
 
 @pytest.mark.parametrize("n,h,w", [(4, 256, 256), (2, 64, 64), (3, 32, 48), (1, 16, 16)])
