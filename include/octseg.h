@@ -94,6 +94,14 @@ int32_t octseg_predict_device(octseg_net *net, const void *images, int32_t dtype
 int32_t octseg_predict_maps_host(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
                                  int32_t w, int32_t bg_ilm, int32_t bg_csi, int32_t transposed, uint8_t *labels,
                                  uint8_t *maps);
+/* validation pass on the device: replaces model.predict over the validation Sequence +
+ * the Dice monitor metrics (reference common/custom_metrics.py:19-77) + the validation loss of
+ * weighted_categorical_crossentropy (common/custom_losses.py:27-35).  labels: true class ids u8 [n,h,w].
+ *   counts   : int64 [n][K][3] = per image and class |{y == c and p_c > 0.5}|, |{p_c > 0.5}|, |{y == c}|
+ *   loss_sums: double [n] = per-image sum over pixels of -w_y * log(clip(p_y / sum p, 1e-7, 1 - 1e-7))
+ * class_weights: [K] or NULL (= all ones). */
+int32_t octseg_evaluate_host(octseg_net *net, const void *images, int32_t dtype, const uint8_t *labels, int32_t n,
+                             int32_t h, int32_t w, const float *class_weights, int64_t *counts, double *loss_sums);
 /* wait for all work queued on the handle's stream */
 int32_t octseg_synchronize(octseg_net *net);
 
@@ -130,6 +138,10 @@ int32_t octseg_train_step_host(octseg_net *net, const void *images, int32_t dtyp
 int32_t octseg_train_step_device(octseg_net *net, const void *images, int32_t dtype, const uint8_t *labels,
                                  int32_t n, int32_t h, int32_t w, const uint8_t *dropout_mask,
                                  float *loss_out_device, void *stream);
+/* optimizer state, for checkpoints that resume like the reference's ModelCheckpoint files (training.py:319-326):
+ * which = 0 Adam m, 1 Adam v (parameter order and shapes); set != 0 writes, else reads */
+int32_t octseg_opt_state(octseg_net *net, int32_t set, int32_t which, int32_t index, float *host, int64_t count);
+int32_t octseg_opt_iterations(octseg_net *net, int32_t set, int64_t *iterations);
 /* flat float32 gradient of the last step, Keras trainable-weight order (tests) */
 int32_t octseg_get_grad(octseg_net *net, int32_t index, float *host, int64_t count);
 

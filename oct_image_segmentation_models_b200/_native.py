@@ -47,6 +47,8 @@ _PROTOS = {
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "octseg_predict_maps_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "octseg_evaluate_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "octseg_synchronize": (C.c_int32, [C.c_void_p]),
     "octseg_train_begin": (C.c_int32, [C.c_void_p, C.POINTER(OctsegTrainConfig), C.c_void_p]),
     "octseg_comm_unique_id": (C.c_int32, [C.c_void_p]),
@@ -55,6 +57,8 @@ _PROTOS = {
                                            C.c_int32, C.c_void_p, C.POINTER(C.c_float)]),
     "octseg_train_step_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                              C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "octseg_opt_state": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    "octseg_opt_iterations": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "octseg_get_grad": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
     "octseg_min_path_segment": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "octseg_launch_count": (C.c_int64, [C.c_void_p]),

@@ -586,17 +586,30 @@ class H5File(H5Object):
 # Keras model files
 # =====================================================================================
 def save_keras_weights(path, layer_weights: List[Tuple[str, List[Tuple[str, np.ndarray]]]], model_config: str = "",
-                       keras_version: str = "2.9.0", backend: str = "tensorflow"):
-    """Write a Keras-2.x style `.hdf5`: root attrs (keras_version, backend, model_config) and a
+                       keras_version: str = "2.9.0", backend: str = "tensorflow",
+                       optimizer_weights: Optional[List[Tuple[str, np.ndarray]]] = None, training_config: str = ""):
+    """Write a Keras-2.x style `.hdf5`: root attrs (keras_version, backend, model_config, training_config), a
     `model_weights` group with `layer_names`, per-layer `weight_names` and datasets
-    `<layer>/<layer>/<weight>:0` -- the layout `tf.keras.models.load_model` / `load_weights` read
-    (SURVEY.md App. B).  layer_weights: [(layer_name, [(weight_name, array), ...]), ...] in
-    model.layers order (layers without weights appear with an empty list)."""
+    `<layer>/<layer>/<weight>:0` -- the layout Keras `load_weights` reads -- and, when
+    given, an `optimizer_weights` group (attr `weight_names`, one dataset per optimizer variable) as
+    `model.save()` / ModelCheckpoint add for a compiled model.  layer_weights: [(layer_name, [(weight_name,
+    array), ...]), ...] in model.layers order (layers without weights appear with an empty list).
+    NOTE: `model_config` is whatever string the caller passes; this package passes a stub that names the graph
+    hyper-parameters, not Keras' full Functional layer graph, so `tf.keras.models.load_model` cannot rebuild the
+    model from such a file -- `load_weights` into a model built by the reference's `UNet.build_model()` can."""
     with H5Writer(path) as f:
         f.attrs["keras_version"] = keras_version
         f.attrs["backend"] = backend
         if model_config:
             f.attrs["model_config"] = model_config
+        if training_config:
+            f.attrs["training_config"] = training_config
+        if optimizer_weights:
+            og = f.create_group("optimizer_weights")
+            on = [n.encode("utf8") for n, _ in optimizer_weights]
+            og.attrs["weight_names"] = np.array(on, dtype=f"S{max(len(n) for n in on)}")
+            for n, arr in optimizer_weights:
+                f.create_dataset(f"optimizer_weights/{n}", data=np.asarray(arr))
         g = f.create_group("model_weights")
         g.attrs["keras_version"] = keras_version
         g.attrs["backend"] = backend
@@ -627,3 +640,18 @@ def load_keras_weights(path) -> Tuple[List[Tuple[str, List[Tuple[str, np.ndarray
         out.append((ln, ws))
     cfg = f.attrs.get("model_config")
     return out, (_s(cfg) if cfg is not None else None)
+
+
+def load_keras_optimizer_weights(path) -> Tuple[List[Tuple[str, np.ndarray]], Optional[str]]:
+    """([(variable_name, array), ...] in `weight_names` order -- empty when the file has no optimizer state --,
+    training_config string or None)."""
+    def _s(x):
+        return x.decode("utf8") if isinstance(x, (bytes, np.bytes_)) else str(x)
+
+    f = H5File(path)
+    tc = f.attrs.get("training_config")
+    if "optimizer_weights" not in f:
+        return [], (_s(tc) if tc is not None else None)
+    og = f["optimizer_weights"]
+    out = [(n, og[n].read()) for n in [_s(x) for x in np.atleast_1d(og.attrs["weight_names"])]]
+    return out, (_s(tc) if tc is not None else None)

@@ -49,6 +49,13 @@ int launch_head(View<const T> in, const float *wgt /*[cin][K]*/, const float *bi
 int launch_boundary_maps(const uint8_t *labels, int n, int h, int w, int K, int bg_ilm, int bg_csi, int transposed,
                          uint8_t *maps, cudaStream_t st);
 
+// Validation metrics on the device (reference common/custom_metrics.py:19-77 and
+// common/custom_losses.py:27-35): per image and class, |{y == c and p_c > 0.5}|, |{p_c > 0.5}|, |{y == c}| --
+// the three sums thresholded Dice (micro and macro) is made of -- and the per-image sum of the weighted
+// categorical cross-entropy.  probs NHWC fp32 [n,h,w,K], labels u8 [n,h,w]; counts [n][K][3], loss [n] (zeroed by the caller).
+int launch_eval_counts(const float *probs, const uint8_t *labels, int n, int h, int w, int K, const float *class_w,
+                       unsigned long long *counts, double *loss, cudaStream_t st);
+
 // BN folding for inference: scale = gamma*rsqrt(var+eps), shift = (bias-mean)*scale+beta
 int launch_bn_fold(const float *bias, const float *gamma, const float *beta, const float *mean,
                    const float *var, float eps, int c, float *scale, float *shift, cudaStream_t st);

@@ -685,6 +685,84 @@ int launch_boundary_maps(const uint8_t *labels, int n, int h, int w, int K, int 
 }
 
 // ---------------------------------------------------------------------------------
+// validation counts: grid = (spans, images); per-thread register counters, one block reduction, few atomics
+// ---------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) eval_counts_kernel(const float *__restrict__ probs, const uint8_t *__restrict__ labels,
+                                                          int hw, const float *__restrict__ class_w,
+                                                          unsigned long long *__restrict__ counts, double *__restrict__ loss) {
+  const int b = blockIdx.y;
+  const float *pb = probs + (long long)b * hw * K;
+  const uint8_t *lb = labels + (long long)b * hw;
+  int c_int[K], c_pred[K], c_true[K];
+  float l_sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { c_int[k] = 0; c_pred[k] = 0; c_true[k] = 0; }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    float p[K];
+    if constexpr (K == 4) {
+      const float4 v = *reinterpret_cast<const float4 *>(pb + (long long)i * 4);
+      p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) p[k] = pb[(long long)i * K + k];
+    }
+    const int t = lb[i];
+    float s = 0.f, pt = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int on = p[k] > 0.5f, is = (k == t);
+      c_pred[k] += on; c_true[k] += is; c_int[k] += on & is;
+      s += p[k];
+      if (is) pt = p[k];
+    }
+    // weighted CE exactly as the loss: renormalise, clip to [1e-7, 1 - 1e-7], -w_t log p_t
+    const float q = fminf(fmaxf(pt / s, 1e-7f), 1.f - 1e-7f);
+    l_sum += -(class_w && t < K ? class_w[t] : 1.f) * logf(q);
+  }
+  __shared__ int s_cnt[8][3 * K];
+  __shared__ float s_loss[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int a = c_int[k], c = c_pred[k], d = c_true[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    if (lane == 0) { s_cnt[warp][3 * k] = a; s_cnt[warp][3 * k + 1] = c; s_cnt[warp][3 * k + 2] = d; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l_sum += __shfl_xor_sync(0xffffffffu, l_sum, o);
+  if (lane == 0) s_loss[warp] = l_sum;
+  __syncthreads();
+  if (threadIdx.x < 3 * K) {
+    unsigned long long t = 0;
+    for (int wv = 0; wv < 8; ++wv) t += (unsigned long long)s_cnt[wv][threadIdx.x];
+    if (t) atomicAdd(counts + (long long)b * 3 * K + threadIdx.x, t);
+  }
+  if (threadIdx.x == 32) {
+    double t = 0;
+    for (int wv = 0; wv < 8; ++wv) t += (double)s_loss[wv];
+    atomicAdd(loss + b, t);
+  }
+}
+
+int launch_eval_counts(const float *probs, const uint8_t *labels, int n, int h, int w, int K, const float *class_w,
+                       unsigned long long *counts, double *loss, cudaStream_t st) {
+  const int hw = h * w;
+  dim3 grid(std::max(1, std::min((hw + 4095) / 4096, 64)), n);
+  switch (K) {
+#define EK(k) case k: eval_counts_kernel<k><<<grid, 256, 0, st>>>(probs, labels, hw, class_w, counts, loss); break;
+    EK(2) EK(3) EK(4) EK(5) EK(6) EK(7) EK(8) EK(9) EK(10) EK(11) EK(12) EK(13) EK(14) EK(15) EK(16)
+#undef EK
+    default: set_error("eval counts: num_classes must be 2..16"); return 1;
+  }
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
 __global__ void bn_fold_kernel(const float *bias, const float *gamma, const float *beta,
                                const float *mean, const float *var, float eps, int c, float *scale,
                                float *shift) {

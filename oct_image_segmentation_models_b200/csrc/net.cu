@@ -612,7 +612,7 @@ int32_t octseg_destroy(octseg_net *net) {
   if (net->copy_out) cudaStreamDestroy(net->copy_out);
   for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); cudaFree(st.rep_scale); cudaFree(st.rep_shift); cudaFree(st.wpack2); cudaFree(st.wpack_s); }
   cudaFree(net->d_params); cudaFree(net->ws); cudaFree(net->d_img); cudaFree(net->d_probs);
-  cudaFree(net->d_labels); cudaFree(net->d_maps); cudaFree(net->d_status);
+  cudaFree(net->d_labels); cudaFree(net->d_maps); cudaFree(net->d_eval); cudaFree(net->d_status);
   if (net->h_status) cudaFreeHost(net->h_status);
   if (net->stream) cudaStreamDestroy(net->stream);
   delete net;
@@ -753,6 +753,49 @@ int32_t octseg_predict_maps_host(octseg_net *net, const void *images, int32_t dt
                                  uint8_t *maps) {
   if (!net || !images || !maps) { set_error("null argument"); return 1; }
   return predict_pipeline(net, images, dtype, n, h, w, nullptr, labels, maps, bg_ilm, bg_csi, transposed);
+}
+
+// Validation pass on the device: forward + per-image Dice counts + weighted-CE sums; only 24*K + 8 bytes per image come back.
+int32_t octseg_evaluate_host(octseg_net *net, const void *images, int32_t dtype, const uint8_t *labels, int32_t n,
+                             int32_t h, int32_t w, const float *class_weights, int64_t *counts, double *loss_sums) {
+  if (!net || !images || !labels || !counts || !loss_sums) { set_error("null argument"); return 1; }
+  if (n <= 0 || h <= 0 || w <= 0) { set_error("bad image batch shape"); return 1; }
+  if (dtype != OCTSEG_U8 && dtype != OCTSEG_F32 && dtype != OCTSEG_F32_PRE) { set_error("bad image dtype"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  const int K = net->cfg.num_classes;
+  if (K < 2 || K > 16) { set_error("evaluate: num_classes must be 2..16"); return 1; }
+  const size_t img_per = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)h * w * net->cfg.input_channels;
+  const size_t lb_per = (size_t)h * w;
+  const int chunk = std::max(1, std::min(std::min(n, 32), pick_microbatch(net, n, h, w)));
+  if (grow(&net->d_img, &net->d_img_bytes, img_per * chunk)) return 1;
+  if (grow(reinterpret_cast<void **>(&net->d_probs), &net->d_probs_bytes, lb_per * K * sizeof(float) * chunk)) return 1;
+  const size_t off_cnt = (lb_per * chunk + 255) & ~(size_t)255, off_loss = off_cnt + (size_t)n * 3 * K * 8;
+  const size_t off_cw = off_loss + (size_t)n * 8, total = off_cw + 64 * sizeof(float);
+  if (grow(&net->d_eval, &net->d_eval_bytes, total)) return 1;
+  uint8_t *eb = reinterpret_cast<uint8_t *>(net->d_eval);
+  unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(eb + off_cnt);
+  double *d_loss = reinterpret_cast<double *>(eb + off_loss);
+  float *d_cw = reinterpret_cast<float *>(eb + off_cw);
+  OCTSEG_CUDA(cudaMemsetAsync(eb + off_cnt, 0, off_cw - off_cnt, net->stream));
+  if (class_weights)
+    OCTSEG_CUDA(cudaMemcpyAsync(d_cw, class_weights, K * sizeof(float), cudaMemcpyHostToDevice, net->stream));
+  for (int i0 = 0; i0 < n; i0 += chunk) {
+    const int cur = std::min(chunk, n - i0);
+    OCTSEG_CUDA(cudaMemcpyAsync(net->d_img, reinterpret_cast<const uint8_t *>(images) + (size_t)i0 * img_per, cur * img_per,
+                                cudaMemcpyHostToDevice, net->stream));
+    OCTSEG_CUDA(cudaMemcpyAsync(eb, labels + (size_t)i0 * lb_per, cur * lb_per, cudaMemcpyHostToDevice, net->stream));
+    if (forward(net, net->d_img, dtype, cur, h, w, net->d_probs, nullptr, net->stream)) return 1;
+    if (launch_eval_counts(net->d_probs, eb, cur, h, w, K, class_weights ? d_cw : nullptr, d_cnt + (size_t)i0 * 3 * K,
+                           d_loss + i0, net->stream))
+      return 1;
+    ++net->launches;
+  }
+  static_assert(sizeof(unsigned long long) == sizeof(int64_t), "count width");
+  OCTSEG_CUDA(cudaMemcpyAsync(counts, d_cnt, (size_t)n * 3 * K * 8, cudaMemcpyDeviceToHost, net->stream));
+  OCTSEG_CUDA(cudaMemcpyAsync(loss_sums, d_loss, (size_t)n * 8, cudaMemcpyDeviceToHost, net->stream));
+  const int rc = check_status(net);
+  if (rc == 2) return octseg_evaluate_host(net, images, dtype, labels, n, h, w, class_weights, counts, loss_sums);
+  return rc;
 }
 
 int32_t octseg_synchronize(octseg_net *net) {

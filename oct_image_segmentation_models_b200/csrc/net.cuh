@@ -93,6 +93,7 @@ struct octseg_net {
   float *d_probs = nullptr; size_t d_probs_bytes = 0;
   uint8_t *d_labels = nullptr; size_t d_labels_bytes = 0;
   uint8_t *d_maps = nullptr; size_t d_maps_bytes = 0;
+  void *d_eval = nullptr; size_t d_eval_bytes = 0;      // octseg_evaluate_host: true labels, counts, loss sums, class weights
   int *d_status = nullptr;            // [0] pipeline time-out code, [1] fp16-pair range overflow (split mode)
   int *h_status = nullptr;            // pinned, 2 ints
   // fp32 mode: 0 = tensor cores on error-compensated fp16 pairs where the shape allows (default), 1 = CUDA cores

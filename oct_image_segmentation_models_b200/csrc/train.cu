@@ -794,6 +794,46 @@ int32_t octseg_train_step_host(octseg_net *net, const void *images, int32_t dtyp
   return check_status(net);
 }
 
+// Optimizer state for checkpoints (the reference's ModelCheckpoint saves it with the model, training.py:319-326):
+// which = 0: Adam first moment m, 1: second moment v; Keras weight order, same shapes as the parameters.
+int32_t octseg_opt_state(octseg_net *net, int32_t set, int32_t which, int32_t index, float *host, int64_t count) {
+  if (!net || !host) { set_error("null argument"); return 1; }
+  TrainState *S = ts(net);
+  if (!S) { set_error("call octseg_train_begin first"); return 1; }
+  if (index < 0 || index >= (int)net->params.size()) { set_error("param index out of range"); return 1; }
+  if (which != 0 && which != 1) { set_error("which must be 0 (m) or 1 (v)"); return 1; }
+  const ParamSpec &p = net->params[index];
+  if (count != p.count) { set_error("param " + p.name + ": element count mismatch"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+  if (S->g_stream) OCTSEG_CUDA(cudaStreamSynchronize(S->g_stream));
+  float *dev = (which == 0 ? S->d_m : S->d_v) + p.offset;
+  if (set) OCTSEG_CUDA(cudaMemcpy(dev, host, count * sizeof(float), cudaMemcpyHostToDevice));
+  else OCTSEG_CUDA(cudaMemcpy(host, dev, count * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// optimizer iteration count (Keras `optimizer.iterations`): drives Adam's bias correction
+int32_t octseg_opt_iterations(octseg_net *net, int32_t set, int64_t *iterations) {
+  if (!net || !iterations) { set_error("null argument"); return 1; }
+  TrainState *S = ts(net);
+  if (!S) { set_error("call octseg_train_begin first"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+  if (S->g_stream) OCTSEG_CUDA(cudaStreamSynchronize(S->g_stream));
+  StepState h;
+  OCTSEG_CUDA(cudaMemcpy(&h, S->d_state, sizeof(h), cudaMemcpyDeviceToHost));
+  if (set) {
+    if (*iterations < 0) { set_error("iterations must be >= 0"); return 1; }
+    h.step = (unsigned long long)*iterations;
+    OCTSEG_CUDA(cudaMemcpy(S->d_state, &h, sizeof(h), cudaMemcpyHostToDevice));
+    S->step = *iterations;
+  } else {
+    *iterations = (int64_t)h.step;
+  }
+  return 0;
+}
+
 int32_t octseg_get_grad(octseg_net *net, int32_t index, float *host, int64_t count) {
   if (!net || !host) { set_error("null argument"); return 1; }
   TrainState *S = ts(net);

@@ -130,6 +130,24 @@ class UNetEngine:
                                                   C.c_void_p(labels_ptr) if labels_ptr else None,
                                                   C.c_void_p(stream) if stream else None))
 
+    def evaluate_counts(self, images: np.ndarray, labels: np.ndarray, class_weights=None, preprocessed: bool = False):
+        """Validation pass on the device (f-4): returns (counts int64 [N,K,3] = per image and class
+        (|y==c & p_c>0.5|, |p_c>0.5|, |y==c|), loss_sums float64 [N] of the weighted CE over each image's pixels)."""
+        if images.dtype == np.uint8:
+            dt = nat.U8
+        else:
+            images = np.asarray(images, dtype=np.float32)
+            dt = nat.F32_PRE if preprocessed else nat.F32
+        images = np.ascontiguousarray(images)
+        n, h, w, _ = images.shape
+        lab = np.ascontiguousarray(np.asarray(labels).reshape(n, h, w), dtype=np.uint8)
+        cw = None if class_weights is None else np.ascontiguousarray(class_weights, dtype=np.float32)
+        counts = np.zeros((n, self.num_classes, 3), np.int64)
+        loss = np.zeros((n,), np.float64)
+        nat.check(self._lib.octseg_evaluate_host(self._h, _ptr(images), dt, _ptr(lab), n, h, w, _ptr(cw), _ptr(counts),
+                                                 _ptr(loss)))
+        return counts, loss
+
     def synchronize(self):
         nat.check(self._lib.octseg_synchronize(self._h))
 
@@ -154,12 +172,13 @@ class UNetEngine:
         return bytes(buf)
 
     def train_step(self, images: np.ndarray, labels: np.ndarray,
-                   dropout_mask: Optional[np.ndarray] = None) -> float:
+                   dropout_mask: Optional[np.ndarray] = None, preprocessed: bool = False) -> float:
+        """preprocessed=True: float images already divided by 255 (the batches a reference DataGenerator yields)."""
         if images.dtype == np.uint8:
             dt = nat.U8
         else:
             images = np.asarray(images, dtype=np.float32)
-            dt = nat.F32
+            dt = nat.F32_PRE if preprocessed else nat.F32
         images = np.ascontiguousarray(images)
         n, h, w, _ = images.shape
         lab = np.ascontiguousarray(labels.reshape(n, h, w), dtype=np.uint8)
@@ -177,6 +196,28 @@ class UNetEngine:
             self._h, C.c_void_p(images_ptr), dtype, C.c_void_p(labels_ptr), n, h, w,
             C.c_void_p(mask_ptr) if mask_ptr else None, C.c_void_p(loss_ptr) if loss_ptr else None,
             C.c_void_p(stream) if stream else None))
+
+    def get_optimizer_state(self):
+        """(iterations, [m per parameter], [v per parameter]); entries of non-trainable tensors are zeros."""
+        it = C.c_int64()
+        nat.check(self._lib.octseg_opt_iterations(self._h, 0, C.byref(it)))
+        ms, vs = [], []
+        for which, dst in ((0, ms), (1, vs)):
+            for i, (_, shape) in enumerate(self.param_specs):
+                a = np.empty(shape, dtype=np.float32)
+                nat.check(self._lib.octseg_opt_state(self._h, 0, which, i, _ptr(a), a.size))
+                dst.append(a)
+        return int(it.value), ms, vs
+
+    def set_optimizer_state(self, iterations: int, ms: Sequence[np.ndarray], vs: Sequence[np.ndarray]):
+        it = C.c_int64(int(iterations))
+        nat.check(self._lib.octseg_opt_iterations(self._h, 1, C.byref(it)))
+        for which, src in ((0, ms), (1, vs)):
+            for i, ((name, shape), a) in enumerate(zip(self.param_specs, src)):
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                if tuple(a.shape) != tuple(shape):
+                    raise ValueError(f"optimizer slot of {name}: expected shape {shape}, got {a.shape}")
+                nat.check(self._lib.octseg_opt_state(self._h, 1, which, i, _ptr(a), a.size))
 
     def get_grads(self) -> List[Optional[np.ndarray]]:
         out: List[Optional[np.ndarray]] = []

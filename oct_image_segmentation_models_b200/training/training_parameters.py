@@ -1,7 +1,8 @@
 """`TrainingParams` with the reference's constructor signature
-(training/training_parameters.py:50-135).  `opt_con` is an optimizer *constructor* in the
-reference (e.g. tf.keras.optimizers.Adam); here any callable / class named "Adam" (or the string
-"adam") selects the fused Keras-Adam kernel, and `opt_params` carries its hyper-parameters."""
+(training/training_parameters.py:50-135).  `opt_con` is an optimizer *constructor*, called as
+`opt_con(**opt_params)` exactly as the reference does (training/training.py:190-193): pass
+`oct_image_segmentation_models_b200.training.optimizers.Adam` (or tf.keras.optimizers.Adam where TensorFlow exists --
+anything whose instance has a Keras-Adam `get_config()`); the string "adam" is accepted as a shorthand."""
 import logging as log
 from pathlib import Path
 from typing import Callable, Optional, Union
@@ -66,6 +67,5 @@ class TrainingParams:
             # reference: common/augmentation.py (host-side, out of the hot path -- SURVEY section 2 #13)
             log.error("augmentations are outside the B200 hot path; pass aug_mode='none'")
             exit(1)
-        if loss not in ("weighted_categorical_crossentropy", "categorical_crossentropy"):
-            log.error(f"loss '{loss}' is not on the accelerated path (weighted categorical cross-entropy is)")
-            exit(1)
+        # `loss` is looked up in common.custom_losses.custom_loss_objects by train_model (reference training.py:195-198);
+        # names the reference registers but this package has no kernel for fail there with the reason

@@ -1,0 +1,144 @@
+"""GPU parity at the sizes BASELINE.json quotes: the CUDA path through the C ABI against
+the CPU oracle on the same seeded inputs.  cfg2 = default U-Net predict at 512x512 (fp32 1e-4 / bf16 2e-2),
+cfg4 = wide U-Net predict at 1024x512 (bf16), cfg5 = trained default net -> argmax -> boundary maps -> min-path on
+256 B-scans against the committed oracle golden (tests/golden/make_trained_default_golden.py)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle.unet_oracle import OracleUNet
+from oct_image_segmentation_models_b200.common.synthetic import synthetic_batch, synthetic_weights
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+GOLDEN = Path(__file__).resolve().parent / "golden"
+CFG = dict(input_channels=1, num_classes=4)
+FP32_REL, BF16_REL, REL_FLOOR = 1e-4, 2e-2, 1e-3
+
+
+def rel_err(p, ref):
+    return np.abs(p - ref) / np.maximum(ref, REL_FLOOR)
+
+
+def test_cfg2_shape_fp32_and_bf16_vs_oracle():
+    """BASELINE configs[1] shape (512x512x1; 2 B-scans bound the oracle's CPU time): every layer at its real tile
+    count -- multi-M-tile super-tiles, row-pair plans, the fused head -- in all three precisions."""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    w = synthetic_weights(seed=42, **CFG)
+    imgs, _ = synthetic_batch(200, 2, 512, 512)
+    ref = OracleUNet(w, **CFG).predict(imgs)
+    for prec, tol in (("fp32", FP32_REL), ("bf16", BF16_REL), ("fp16", BF16_REL)):
+        eng = UNetEngine(precision=prec, **CFG)
+        eng.set_weights(w)
+        assert all(eng.layer_uses_tensor_core(i, 512, 512) for i in range(1, 22)), prec
+        p, lab = eng.predict(imgs, want_labels=True)
+        eng.close()
+        assert rel_err(p, ref).max() <= tol, (prec, float(rel_err(p, ref).max()))
+        assert np.array_equal(lab, p.argmax(-1))
+        assert (lab == ref.argmax(-1)).mean() >= 0.999, prec
+
+
+def test_cfg4_wide_shape_bf16_vs_oracle():
+    """BASELINE configs[3]: wide U-Net (64..1024 channels) on ONE 1024x512 B-scan -- input-channel chunking, streamed
+    weights, 256-column N tiles and multi-tile super-tiles at the benchmarked geometry."""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    cfg = dict(input_channels=1, num_classes=4, start_neurons=64)
+    w = synthetic_weights(seed=4, **cfg)
+    imgs, _ = synthetic_batch(7, 1, 1024, 512)
+    ref = OracleUNet(w, **cfg).predict(imgs)
+    eng = UNetEngine(precision="bf16", **cfg)
+    eng.set_weights(w)
+    p, lab = eng.predict(imgs, want_labels=True)
+    eng.close()
+    assert rel_err(p, ref).max() <= BF16_REL, float(rel_err(p, ref).max())
+    assert (lab == ref.argmax(-1)).mean() >= 0.999
+
+
+@pytest.fixture(scope="module")
+def trained_default():
+    w = np.load(GOLDEN / "trained_default_unet_weights.npz")
+    g = np.load(GOLDEN / "trained_default_unet_golden.npz")
+    return [w[f"w{i:03d}"] for i in range(len(w.files))], g
+
+
+def _predict_boundaries(eng, imgs, threads):
+    from oct_image_segmentation_models_b200.min_path_processing import graph_search
+    n, h, w, _ = imgs.shape
+    labels = np.empty((n, h, w), np.uint8)
+    maps_t = np.empty((n, 3, w, h), np.uint8)
+    for i0 in range(0, n, 64):
+        l, m = eng.predict_maps(imgs[i0:i0 + 64], transposed=True)
+        labels[i0:i0 + len(l)] = l
+        maps_t[i0:i0 + len(l)] = m
+    segs = graph_search.segment_maps(maps_t.reshape(-1, w, h), None, None, n_threads=threads)[0].reshape(n, 3, w)
+    return labels, segs
+
+
+@pytest.mark.parametrize("path", ["tcgen05", "cuda"])
+def test_cfg5_trained_default_net_fp32_boundaries_on_256_bscans(trained_default, path, monkeypatch):
+    """north_star gate at full size, default precision of the drop-in model object: 256 synthetic 512x512 B-scans
+    (67 M pixels, 393 216 boundary positions) through predict -> argmax -> boundary maps (GPU) -> min-path (native C++,
+    reference min_path_processing/graph_search.py:519-572 semantics) against the oracle chain.
+
+    Both fp32 implementations (tcgen05 on error-compensated fp16 pairs; FFMA on CUDA cores) agree with the oracle to
+    ~3e-7 on the probabilities, i.e. to summation-order noise -- the oracle (oneDNN) is itself one fp32 ordering.  At
+    that level an exact two-way tie of the top classes can resolve differently in a handful of the 67 M pixels, so the
+    gate is: argmax agreement >= 99.9999 %, at most 4 boundary positions differ, none by more than one row, and at
+    least 254 of the 256 B-scans are bit-identical in every boundary."""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    weights, g = trained_default
+    n = g["labels"].shape[0]
+    imgs, _ = synthetic_batch(0, n, 512, 512)
+    if path == "cuda":
+        monkeypatch.setenv("OCTSEG_FP32_PATH", "cuda")
+    eng = UNetEngine(precision="fp32", **CFG)
+    eng.set_weights(weights)
+    assert eng.layer_uses_tensor_core(1, 512, 512) == (path == "tcgen05")
+    p2, _ = eng.predict(imgs[:2])
+    labels, segs = _predict_boundaries(eng, imgs, os.cpu_count() or 1)
+    eng.close()
+    assert rel_err(p2[0, 192:320], g["probs_band"]).max() <= FP32_REL, float(rel_err(p2[0, 192:320], g["probs_band"]).max())
+    agree = float((labels == g["labels"]).mean())
+    d = np.abs(segs.astype(np.int32) - g["segs"].astype(np.int32))
+    identical = int((d.reshape(n, -1).max(1) == 0).sum())
+    print(f"fp32 {path}: argmax agreement {agree:.8f} ({int((labels != g['labels']).sum())} of {labels.size} pixels differ), "
+          f"{int((d != 0).sum())} of {d.size} boundary positions differ (max {int(d.max())} row), {identical}/{n} B-scans identical")
+    assert agree >= 0.999999, agree
+    assert (d != 0).sum() <= 4 and d.max() <= 1, (int((d != 0).sum()), int(d.max()))
+    assert identical >= n - 2, identical
+
+
+def test_cfg5_trained_default_net_16bit_modes_report(trained_default):
+    """The 16-bit storage modes on the same 64 B-scans: argmax >= 99.9 % (fp16) / >= 99.5 % (bf16), boundaries never
+    off by more than one row.  (They do NOT guarantee identical boundaries; fp32 mode does -- see the test above.)"""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    weights, g = trained_default
+    imgs, _ = synthetic_batch(0, 64, 512, 512)
+    for prec, min_agree, min_same in (("fp16", 0.999, 0.995), ("bf16", 0.995, 0.98)):
+        eng = UNetEngine(precision=prec, **CFG)
+        eng.set_weights(weights)
+        labels, segs = _predict_boundaries(eng, imgs, os.cpu_count() or 1)
+        eng.close()
+        agree = float((labels == g["labels"][:64]).mean())
+        d = np.abs(segs.astype(np.int32) - g["segs"][:64].astype(np.int32))
+        print(f"{prec}: argmax agreement {agree:.5f}, boundary columns identical {float((d == 0).mean()):.5f}, max delta {int(d.max())}")
+        assert agree >= min_agree, (prec, agree)
+        assert d.max() <= 1 and (d == 0).mean() >= min_same, (prec, int(d.max()), float((d == 0).mean()))
+
+
+def test_two_gpu_data_parallel_training_parity():
+    """SURVEY 8(e), training: launched as torchrun would (2 ranks, NCCL): the all-reduced gradient equals the sum of
+    the oracle's per-shard gradients and all ranks hold identical weights after graph-replayed steps.  Skips on a
+    one-GPU box (the driver's default); run with `gpurun --gpus 2`."""
+    from oct_image_segmentation_models_b200 import _native as nat
+    if nat.load().octseg_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", str(ROOT / "tools" / "dist_train_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "PASS" in out.stdout, out.stdout[-2000:]

@@ -204,3 +204,35 @@ def test_bf16_tensor_core_gradients_match_cuda_core_gradients(cfg, n, h, w, monk
     worst = max(e for _, e in errs)
     tail = [e for nm, e in errs[-9:]]
     assert worst <= 0.6 and max(tail) <= 6e-2, errs
+
+
+def test_cfg3_shape_train_step_fp32_and_bf16_vs_oracle():
+    """BASELINE configs[2] shape (512x256x1 B-scans, default net; 4 samples bound the oracle's autograd time): the
+    64 / 128-channel layers (deep weight-gradient kernel, chunked data-gradient convs) at their real tile counts.
+    fp32: loss 1e-4, every gradient tensor within 1e-2 of its scale.  bf16: loss 2e-2, whole-gradient cosine
+    >= 0.97 and a per-tensor bound (bf16 storage of z / a / dz: the noise grows from the head to the stem)."""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    cfg = dict(input_channels=1, num_classes=4)
+    n, h, w = 4, 512, 256
+    weights, imgs, labs, mask = _setup(cfg, n, h, w)
+    names = [nm for nm, _ in unet_param_specs(**cfg)]
+    ora = OracleUNet(weights, **cfg)
+    loss_ref, grads_ref, _, _ = ora.loss_and_grads(imgs, labs, CW, dropout_mask=mask)
+    keep = [i for i, nm in enumerate(names) if grads_ref[i] is not None and not (nm.endswith("bias:0") and nm != names[-1])]
+    b = np.concatenate([grads_ref[i].numpy().ravel() for i in keep])
+    # bf16 per-tensor bound: measured 0.58 on the STEM's BatchNorm gamma at 4 samples (sum of +- terms over 524 k pixels
+    # of bf16-stored dy and z: heavy cancellation), < 0.2 from the second encoder level on; the kernels themselves are
+    # held to fp64 on identical inputs in tests/test_gpu_backward_kernels.py
+    for prec, loss_tol, rel_tol, cos_min in (("fp32", 1e-4, 1e-2, 0.99999), ("bf16", 2e-2, 0.75, 0.97)):
+        eng = UNetEngine(precision=prec, **cfg)
+        eng.set_weights(weights)
+        eng.train_begin(CW, global_batch=n)
+        loss = eng.train_step(imgs, labs, dropout_mask=mask)
+        got = eng.get_grads()
+        eng.close()
+        assert abs(loss - loss_ref) <= loss_tol * max(1.0, abs(loss_ref)), (prec, loss, loss_ref)
+        worst = _grad_check(names, got, grads_ref, rel_tol, prec, bias_noise=1e-4 if prec == "fp32" else 2e-2)
+        a = np.concatenate([got[i].ravel() for i in keep])
+        cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+        print(f"cfg3 {prec}: loss {loss:.6f} vs {loss_ref:.6f}, worst per-tensor rel err {worst:.3e}, cosine {cos:.6f}")
+        assert cos >= cos_min, (prec, cos)
