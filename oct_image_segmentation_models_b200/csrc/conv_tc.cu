@@ -148,6 +148,32 @@ __device__ __forceinline__ void split_pack8(const float (&o)[8], uint4 &hi, uint
     l[k] = *reinterpret_cast<const uint32_t *>(&l2);
   }
 }
+// Sum of 8 per-thread values over the 32 lanes of a warp with 7 shuffles (instead of 40): every step halves the
+// number of values a lane carries.  Returns, in EVERY lane, the warp total of value index
+// ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)   (the four lanes of a quad hold the same sum).
+__device__ __forceinline__ float warp_sum8(const float (&v)[8], int lane) {
+  bool hi = (lane & 16) != 0;
+  float a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  hi = (lane & 8) != 0;
+  float b[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = hi ? a[i] : a[i + 2], keep = hi ? a[i + 2] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  hi = (lane & 4) != 0;
+  const float send = hi ? b[0] : b[1], keep = hi ? b[1] : b[0];
+  float c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;
+}
+__device__ __forceinline__ int warp_sum8_index(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -236,7 +262,8 @@ constexpr int kTcThreads = (4 + kTcEpiWarps) * 32;
 // register allocation: 0 = generic chunk loop (wide layers, unpaired pixel shuffle, wide fused head),
 // 1 = 8-column layers (batched TMEM loads; plain / pool / fused head), 2 = 16-column plain / pool layers,
 // 3 = stem pixel groups, 4 = paired pixel-shuffle up-conv.  Dead paths are dropped at compile time.
-template <int HK, int EPI>
+// ST: 1 = the epilogue also accumulates per-channel sum / sum of squares of its fp32 output (training forward)
+template <int HK, int EPI, int ST = 0>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ TcConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -290,6 +317,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int c = i % p.scale_mod;           // row-pair mode: columns [parity][channel] share the channel tables
       s_scale[i] = EPI == 7 ? p.scale[c] * p.scale_mul : p.scale[c];   // split mode: undo the weight pre-scale (a power of two)
       s_shift[i] = p.shift[c];
+    }
+    if constexpr (EPI == 8 || ST == 1) {
+      for (int i = threadIdx.x; i < 2 * p.scale_mod; i += blockDim.x) s_head[i] = 0.f;   // per-CTA sum / sum of squares
     }
     if constexpr (HK > 0) {
       for (int i = threadIdx.x; i < p.cout * HK; i += blockDim.x) s_head[i] = p.head_w[((i / HK) % p.scale_mod) * HK + (i % HK)];
@@ -475,6 +505,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     long long w_epi = 0;
     const long long t_start = clock64();
     int wgr = wg;                           // warpgroup -> M-tile assignment, rotated every super-tile
+    // EPI 8 (training forward): per-thread partial sums of z and z^2 for up to 16 channels, kept across all tiles
+    float st_s[16], st_q[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x, ti.advance(p)) {
@@ -519,6 +553,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             float o[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] = fmaxf(fmaf(__uint_as_float(v[bb][k]), sc[k], sh[k]), relu_floor);
+            if constexpr (ST == 1) {
+              if (inside) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { st_s[k] += o[k]; st_q[k] = fmaf(o[k], o[k], st_q[k]); }
+              }
+            }
             if constexpr (HK > 0) {
               float z[HK];
               if constexpr ((HK & 1) == 0) {
@@ -637,6 +677,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 float o[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) o[k] = fmaxf(fmaf(__uint_as_float(v[bb][par * PL + c8][k]), sc[k], sh[k]), relu_floor);
+                if constexpr (ST == 1) {
+                  if (inside) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { st_s[c8 * 8 + k] += o[k]; st_q[c8 * 8 + k] = fmaf(o[k], o[k], st_q[c8 * 8 + k]); }
+                  }
+                }
                 if constexpr (HK > 0) {
                   float z[HK];
 #pragma unroll
@@ -817,6 +863,74 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (inside && !(amax <= 65000.f) && p.overflow) atomicOr(p.overflow, 1);   // also catches NaN
           }
         }
+      } else if (EPI == 8) {
+        // ---- training forward: z = acc * scale + shift (scale = 1, shift = conv bias), stored as it is (no ReLU:
+        //      BatchNorm comes first), and the per-channel batch statistics sum(z), sum(z^2) of the fp32 values --
+        //      the separate pass that re-read z (bn_stats_kernel) is gone.  Column -> channel: col % scale_mod
+        //      (row pairs: [row parity][channel]; up-conv: [pixel parity][channel]).  Layers with <= 16 channels keep
+        //      their partial sums in registers for the whole kernel; wider layers reduce every 8-column chunk
+        //      over the warp (7 shuffles) and add it to the CTA's shared-memory accumulators.
+        const int C = p.scale_mod;
+        const bool few = (C <= 16);
+        constexpr int kWG = kTcEpiWarps / 4;
+        for (int t = wg_cur; t < mt; t += kWG) {
+          const int iy = t >> p.mt_x_log2, ix = t & (p.mt_x - 1);
+          const int yb = ((ty * p.mt_y + iy) * kTcTileH + r) * p.row_mul, x = (tx * p.mt_x + ix) * kTcTileW + px;
+          const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * p.n_cols);
+          for (int j = 0; j < my_nch; j += 2) {
+            uint32_t v[2][8];
+            const bool two = (j + 1 < my_nch);
+            tmem_ld8(t_base + (uint32_t)(j * 8), v[0]);
+            if (two) tmem_ld8(t_base + (uint32_t)(j * 8 + 8), v[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (u == 1 && !two) break;
+              const int col = col_base + (j + u) * 8;
+              int co0, y = yb, xo = x;
+              if (p.mode == 1) { const int par = col / p.cout; co0 = col - par * p.cout; y = 2 * yb + (par >> 1); xo = 2 * x + (par & 1); }
+              else if (p.row_mul == 2) { const int par = col / C; co0 = col - par * C; y = yb + par; }
+              else co0 = col;
+              const bool inside = (y < p.out_h) && (xo < p.out_w);
+              const float4 sa = *reinterpret_cast<const float4 *>(s_scale + co0), sb = *reinterpret_cast<const float4 *>(s_scale + co0 + 4);
+              const float4 ha = *reinterpret_cast<const float4 *>(s_shift + co0), hb = *reinterpret_cast<const float4 *>(s_shift + co0 + 4);
+              const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+              const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+              float o[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] = fmaxf(fmaf(__uint_as_float(v[u][k]), sc[k], sh[k]), relu_floor);
+              uint4 pk;
+              uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) h2[k] = pack2(o[2 * k], o[2 * k + 1], p.fp16);
+              if (inside)
+                *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)(co0 >> 3) * plane_elems +
+                                           ((long long)y * p.out_w + xo) * 8) = pk;
+              else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = 0.f;
+              }
+              if (few) {
+                if (co0 == 0) {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) { st_s[k] += o[k]; st_q[k] = fmaf(o[k], o[k], st_q[k]); }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) { st_s[8 + k] += o[k]; st_q[8 + k] = fmaf(o[k], o[k], st_q[8 + k]); }
+                }
+              } else {
+                float o2[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o2[k] = o[k] * o[k];
+                const float ws = warp_sum8(o, lane), wq = warp_sum8(o2, lane);
+                if ((lane & 3) == 0) {
+                  atomicAdd(s_head + co0 + warp_sum8_index(lane), ws);
+                  atomicAdd(s_head + C + co0 + warp_sum8_index(lane), wq);
+                }
+              }
+            }
+          }
+        }
       } else if (EPI == 2 && HK == 0) {
         // ---- 16-channel layers: same idea, two chunks (planes) per M-tile and two M-tiles per wait
         constexpr int kB2 = 2;
@@ -852,6 +966,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 h2[k] = bn_relu_pack2(v[bb][u][2 * k], v[bb][u][2 * k + 1], sc[2 * k], sc[2 * k + 1], sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
+              if constexpr (ST == 1) {
+                if (inside) {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float o = fmaxf(fmaf(__uint_as_float(v[bb][u][k]), sc[k], sh[k]), relu_floor);
+                    st_s[u * 8 + k] += o; st_q[u * 8 + k] = fmaf(o, o, st_q[u * 8 + k]);
+                  }
+                }
+              }
               if (inside)
                 *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)(co0 >> 3) * plane_elems +
                                            ((long long)y * p.out_w + x) * 8) = pk;
@@ -1076,11 +1199,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
       if (++acc == 2) { acc = 0; accph ^= 1u; }
     }
+    if constexpr (EPI == 8 || ST == 1) {
+      if (p.scale_mod <= 16) {
+        const int C = p.scale_mod;
+        float g[8];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half * 8 >= C) break;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) g[k] = st_s[half * 8 + k];
+          const float ws = warp_sum8(g, lane);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) g[k] = st_q[half * 8 + k];
+          const float wq = warp_sum8(g, lane);
+          if ((lane & 3) == 0) {
+            atomicAdd(s_head + half * 8 + warp_sum8_index(lane), ws);
+            atomicAdd(s_head + C + half * 8 + warp_sum8_index(lane), wq);
+          }
+        }
+      }
+    }
     if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) { p.dbg[6] = w_epi; p.dbg[7] = clock64() - t_start; }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (EPI == 8 || ST == 1) {
+    if (p.stats)
+      for (int i = threadIdx.x; i < 2 * p.scale_mod; i += blockDim.x) atomicAdd(p.stats + i, (double)s_head[i]);
+  }
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -1535,6 +1682,8 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
   p.fp16 = epi.fp16;
   p.static_weights = epi.static_weights;
   p.overflow = epi.overflow;
+  p.stats = epi.stats;
+  if (epi.stats && (epi.head_w || epi.pool_out || g.split || g.stem_groups)) { set_error("tc plan: batch statistics belong to the plain training epilogue"); return 1; }
   if (g.split && !epi.fp16) { set_error("tc plan: split mode stores fp16 pairs"); return 1; }
   p.scale = epi.scale; p.shift = epi.shift;
   p.out = epi.out.ptr; p.out_img_stride = epi.out.img_stride; p.out_h = epi.out.h; p.out_w = epi.out.w;
@@ -1589,12 +1738,12 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
   return 0;
 }
 
-template <int HK, int EPI>
+template <int HK, int EPI, int ST = 0>
 static int tc_launch_k(const TcPlan &plan, cudaStream_t st) {
   // the attribute is per device (one process may drive several GPUs, one host thread each)
   static PerDeviceOnce attr_set;
   if (const int dev = attr_set.pending(); dev >= 0) {
-    OCTSEG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<HK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OCTSEG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<HK, EPI, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set.mark(dev);
   }
   static const bool pdl = []() { const char *e = std::getenv("OCTSEG_NO_PDL"); return !(e && e[0] == '1'); }();
@@ -1605,7 +1754,7 @@ static int tc_launch_k(const TcPlan &plan, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  OCTSEG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<HK, EPI>, plan.tmap, plan.p));
+  OCTSEG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<HK, EPI, ST>, plan.tmap, plan.p));
   return 0;
 }
 
@@ -1632,6 +1781,18 @@ static int tc_launch_head(const TcPlan &plan, cudaStream_t st) {
 }
 
 int tc_launch(const TcPlan &plan, cudaStream_t st) {
+  if (plan.p.stats) {
+    // training forward: the narrow-layer epilogues (<= 16 channels: register accumulators) exist with the statistics
+    // compiled in; everything else takes the generic statistics epilogue
+    if (plan.p.mode == 2) { set_error("tc launch: batch statistics with a fused head"); return 1; }
+    switch (tc_epi_kind(plan.p)) {
+      case 1: return tc_launch_k<0, 1, 1>(plan, st);
+      case 2: return tc_launch_k<0, 2, 1>(plan, st);
+      case 5: return tc_launch_k<0, 5, 1>(plan, st);
+      case 6: return tc_launch_k<0, 6, 1>(plan, st);
+    }
+    return tc_launch_k<0, 8>(plan, st);
+  }
   if (plan.p.mode != 2) {
     switch (tc_epi_kind(plan.p)) {
       case 1: return tc_launch_k<0, 1>(plan, st);
@@ -1641,6 +1802,7 @@ int tc_launch(const TcPlan &plan, cudaStream_t st) {
       case 5: return tc_launch_k<0, 5>(plan, st);
       case 6: return tc_launch_k<0, 6>(plan, st);
       case 7: return tc_launch_k<0, 7>(plan, st);
+      case 8: return tc_launch_k<0, 8>(plan, st);
     }
     return tc_launch_k<0, 0>(plan, st);
   }

@@ -54,6 +54,7 @@ struct TcConvParams {
   int split;                   // fp32-accurate mode: fp16 (hi, lo') plane pairs in, [main 8 | corr 8] column groups, (hi, lo') planes out
   float scale_mul;             // split mode: 1 / (power-of-two weight pre-scale), folded into the epilogue scale table
   int *overflow;               // split mode: device word set when an activation leaves the fp16 range
+  double *stats;               // training forward: [2 * scale_mod] per-channel sum(z), sum(z^2) accumulated by the epilogue (NULL = off)
   int pdl_late;                // signal dependent launch after the last tile request (else at entry)
   int static_weights;          // packed weights are not written by earlier kernels of the stream (inference)
   uint32_t stage_off;          // mode 3: byte offset (from the epilogue tables) of the per-warp store staging
@@ -133,6 +134,7 @@ struct TcEpilogue {
   int head_k = 0;
   int static_weights = 0;                    // weights final before the stream's preceding kernels ran (inference)
   int *overflow = nullptr;                   // split mode: fp16 range overflow flag (device)
+  double *stats = nullptr;                   // training forward: per-channel sum / sum of squares of the output (device, zeroed by the caller)
   float *probs = nullptr;
   uint8_t *labels = nullptr;
 };

@@ -74,6 +74,7 @@ struct TrainBlock {
   int h = 0, w = 0;         // output grid
   // tensor-core path (bf16 mode): forward z-conv and data-gradient conv through conv_tc_kernel
   bool tc_fwd = false, tc_dgrad = false;
+  bool stats_fused = false;   // the forward conv's epilogue accumulates the BatchNorm batch statistics
   TcGeometry geo_dgrad{};
   bool geo_dgrad_ok = false;
   __nv_bfloat16 *wpack_dgrad = nullptr;
@@ -125,6 +126,11 @@ struct TrainState {
   cudaStream_t wg_stream = nullptr;
   std::vector<cudaEvent_t> ev_dz;   // per block: dz ready
   cudaEvent_t ev_wg_done = nullptr, ev_step_start = nullptr;
+  // gradient all-reduce in two reverse-order buckets on its own stream: the decoder-side bucket (bottleneck, decoder,
+  // head: the tail of the flat buffer, complete first) is reduced while the encoder's backward pass still runs
+  cudaStream_t comm_stream = nullptr;
+  bool tail_sent = false;           // the decoder-side bucket of the current step has been issued
+  cudaEvent_t ev_tail_main = nullptr, ev_tail_wg = nullptr, ev_head_main = nullptr, ev_comm_done = nullptr;
   // communicator
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -256,6 +262,7 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
     if (b.role == 4) continue;
     TrainBlock &t = S->tb[b.index];
     t.tc_fwd = t.tc_dgrad = false;
+    t.stats_fused = false;
     if (net->precision != OCTSEG_BF16 || net->disable_tc || b.index == 0) continue;
     const BlockState &bs = net->bstate[b.index];
     // input view of this block (same rules as block_input)
@@ -273,6 +280,8 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
       epi.scale = S->d_ones;
       epi.shift = net->d_params + net->params[b.p_bias].offset;
       epi.out = make_view((__nv_bfloat16 *)t.z, n, b.cout / 8, 0, b.cout / 8, t.h, t.w);
+      epi.stats = S->d_sums + ((size_t)b.index * 2 + 0) * 2 * S->max_cout;      // == sums_of(b.index, 0)
+      t.stats_fused = true;
       t.fwd_pair = bs.geo2_ok && (in_h % 2) == 0 && in_h >= 2 * kTcTileH;
       if (tc_make_plan(t.fwd_pair ? bs.geo2 : bs.geo, in_ptr, n, in_h, in_w, t.fwd_pair ? bs.wpack2 : bs.wpack, epi,
                        net->d_status, &t.plan_fwd))
@@ -331,12 +340,44 @@ static View<const T> block_input(octseg_net *net, const BlockSpec &b, int n) {
   return make_view((const T *)pt.a, n, pt.a_planes_total, pt.a_plane0, pb.cout / 8, pt.h, pt.w);
 }
 
-// gradient all-reduce (sum over ranks; the loss is already scaled by the GLOBAL batch) + Keras-Adam
+// Gradient all-reduce (sum over ranks; the loss is already scaled by the GLOBAL batch), bucketed and overlapped:
+// bucket 1 = parameters of the bottleneck, decoder and head blocks (the tail of the flat Keras-order buffer, whose
+// gradients are complete when the backward pass enters the encoder), bucket 0 = the encoder blocks.  Both
+// collectives run on `comm_stream`, forked from / joined to the step's streams with events, so they are part of
+// the captured CUDA graph of the step.
+static int64_t bucket_split(const octseg_net *net) {
+  for (auto &b : net->blocks)
+    if (b.role != 0) return b.index == 0 ? 0 : net->params[b.p_kernel].offset;
+  return 0;
+}
+static int allreduce_tail_bucket(octseg_net *net, cudaStream_t st, cudaStream_t wst) {
+  TrainState *S = ts(net);
+  if (!(S->comm && S->world > 1)) return 0;
+  const int64_t split = bucket_split(net);
+  if (split <= 0 || split >= net->total_floats) return 0;
+  OCTSEG_CUDA(cudaEventRecord(S->ev_tail_main, st));
+  OCTSEG_CUDA(cudaStreamWaitEvent(S->comm_stream, S->ev_tail_main, 0));
+  if (wst != st) {
+    OCTSEG_CUDA(cudaEventRecord(S->ev_tail_wg, wst));
+    OCTSEG_CUDA(cudaStreamWaitEvent(S->comm_stream, S->ev_tail_wg, 0));
+  }
+  OCTSEG_NCCL(g_nccl.AllReduce(S->d_grads + split, S->d_grads + split, (size_t)(net->total_floats - split), /*ncclFloat*/ 7,
+                               /*ncclSum*/ 0, S->comm, S->comm_stream));
+  return 0;
+}
+// `st` has already joined the weight-gradient stream
 static int train_tail(octseg_net *net, cudaStream_t st) {
   TrainState *S = ts(net);
-  if (S->comm && S->world > 1)
-    OCTSEG_NCCL(g_nccl.AllReduce(S->d_grads, S->d_grads, (size_t)net->total_floats, /*ncclFloat*/ 7, /*ncclSum*/ 0,
-                                 S->comm, st));
+  if (S->comm && S->world > 1) {
+    int64_t split = bucket_split(net);
+    if (!S->tail_sent || split <= 0 || split >= net->total_floats) split = net->total_floats;     // single bucket
+    OCTSEG_CUDA(cudaEventRecord(S->ev_head_main, st));
+    OCTSEG_CUDA(cudaStreamWaitEvent(S->comm_stream, S->ev_head_main, 0));
+    OCTSEG_NCCL(g_nccl.AllReduce(S->d_grads, S->d_grads, (size_t)split, /*ncclFloat*/ 7, /*ncclSum*/ 0, S->comm,
+                                 S->comm_stream));
+    OCTSEG_CUDA(cudaEventRecord(S->ev_comm_done, S->comm_stream));
+    OCTSEG_CUDA(cudaStreamWaitEvent(st, S->ev_comm_done, 0));
+  }
   if (launch_adam(net->d_params, S->d_grads, S->d_m, S->d_v, net->total_floats, S->d_state, S->tc.beta_1,
                   S->tc.beta_2, S->tc.epsilon, st))
     return 1;
@@ -400,22 +441,22 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
       return 1;
     View<const T> zc = make_view((const T *)t.z, n, b.cout / 8, 0, b.cout / 8, t.h, t.w);
     prof.begin(PH_BNF);
-    if (launch_bn_stats<T>(zc, sums_of(b.index, 0), st)) return 1;
-    if (launch_bn_finalize(sums_of(b.index, 0), (long long)n * t.h * t.w, b.cout, 1e-3f, 0.99f, P + net->params[b.p_gamma].offset,
-                           P + net->params[b.p_beta].offset, net->d_params + net->params[b.p_mean].offset,
-                           net->d_params + net->params[b.p_var].offset, t.mean, t.invstd, t.scale, t.shift, st))
-      return 1;
-    View<T> a = make_view((T *)t.a, n, t.a_planes_total, t.a_plane0, b.cout / 8, t.h, t.w);
-    const T *mask = (use_dropout && b.dropout_after) ? (const T *)S->mask : nullptr;
-    if (launch_bn_apply_relu<T>(zc, t.scale, t.shift, mask, a, st)) return 1;
-    net->launches += 4;
-    if (b.pool_after) {
-      prof.begin(PH_POOLF);
-      View<const T> ac = make_view((const T *)t.a, n, t.a_planes_total, t.a_plane0, b.cout / 8, t.h, t.w);
-      View<T> po = make_view((T *)t.pooled, n, b.cout / 8, 0, b.cout / 8, t.h / 2, t.w / 2);
-      if (launch_maxpool2<T>(ac, po, st)) return 1;
+    if (!t.stats_fused) {      // the tensor-core conv's epilogue has already accumulated sum(z), sum(z^2)
+      if (launch_bn_stats<T>(zc, sums_of(b.index, 0), st)) return 1;
       ++net->launches;
     }
+    View<T> a = make_view((T *)t.a, n, t.a_planes_total, t.a_plane0, b.cout / 8, t.h, t.w);
+    const T *mask = (use_dropout && b.dropout_after) ? (const T *)S->mask : nullptr;
+    View<T> po{};
+    po.ptr = nullptr;
+    if (b.pool_after) po = make_view((T *)t.pooled, n, b.cout / 8, 0, b.cout / 8, t.h / 2, t.w / 2);
+    // batch mean / variance, a = relu(bn(z)) (* dropout), the pooled copy and the moving-statistics update: one pass
+    if (launch_bn_finalize_apply<T>(zc, sums_of(b.index, 0), (long long)n * t.h * t.w, 1e-3f, 0.99f,
+                                    P + net->params[b.p_gamma].offset, P + net->params[b.p_beta].offset,
+                                    net->d_params + net->params[b.p_mean].offset, net->d_params + net->params[b.p_var].offset,
+                                    t.mean, t.invstd, t.scale, t.shift, mask, a, po, st))
+      return 1;
+    net->launches += 2;
   }
   // ------------------------------- loss + head backward -------------------------------
   const BlockSpec &last = net->blocks[nblk - 2];
@@ -435,10 +476,15 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   // `g` = gradient wrt the output activation of the block being processed
   const void *g_ptr = S->gA[0];
   int g_planes_total = last.cout / 8, g_plane0 = 0;
+  S->tail_sent = false;
   for (int bi = nblk - 2; bi >= 0; --bi) {
     const BlockSpec &b = net->blocks[bi];
     TrainBlock &t = S->tb[bi];
     prof.tag = bi;
+    if (with_tail && !S->tail_sent && b.role == 0 && S->comm && S->world > 1) {     // every bottleneck / decoder / head gradient has been issued
+      if (allreduce_tail_bucket(net, st, wst)) return 1;
+      S->tail_sent = true;
+    }
     const int f8 = b.cout / 8;
     View<const T> zc = make_view((const T *)t.z, n, f8, 0, f8, t.h, t.w);
     View<const T> da = make_view((const T *)g_ptr, n, g_planes_total, g_plane0, f8, t.h, t.w);
@@ -573,11 +619,17 @@ extern "C" {
 void octseg_train_free(octseg_net *net) {
   TrainState *S = ts(net);
   if (!S) return;
+  // the captured step holds NCCL's persistent plans: release the graph before the communicator (ncclCommDestroy
+  // otherwise waits for them forever)
+  if (S->graph_exec) { cudaGraphExecDestroy(S->graph_exec); S->graph_exec = nullptr; }
+  cudaDeviceSynchronize();
   if (S->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S->comm);
   for (auto &e : S->ev_dz) cudaEventDestroy(e);
   if (S->ev_wg_done) cudaEventDestroy(S->ev_wg_done);
   if (S->ev_step_start) cudaEventDestroy(S->ev_step_start);
   if (S->wg_stream) cudaStreamDestroy(S->wg_stream);
+  if (S->comm_stream) cudaStreamDestroy(S->comm_stream);
+  for (cudaEvent_t e : {S->ev_tail_main, S->ev_tail_wg, S->ev_head_main, S->ev_comm_done}) if (e) cudaEventDestroy(e);
   for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); cudaFree(t.wpack_dgrad); cudaFree(t.wpack_dgrad2); }
   cudaFree(S->d_class_w); cudaFree(S->d_grads); cudaFree(S->d_m); cudaFree(S->d_v); cudaFree(S->d_ones); cudaFree(S->d_zeros);
   cudaFree(S->d_sums); cudaFree(S->d_loss); cudaFree(S->d_stem_tmp); cudaFree(S->ws); cudaFree(S->d_img);
@@ -623,6 +675,9 @@ int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc, const
     for (auto &e : S->ev_dz) OCTSEG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     OCTSEG_CUDA(cudaEventCreateWithFlags(&S->ev_wg_done, cudaEventDisableTiming));
     OCTSEG_CUDA(cudaEventCreateWithFlags(&S->ev_step_start, cudaEventDisableTiming));
+    OCTSEG_CUDA(cudaStreamCreateWithFlags(&S->comm_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t *e : {&S->ev_tail_main, &S->ev_tail_wg, &S->ev_head_main, &S->ev_comm_done})
+      OCTSEG_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (auto &b : net->blocks) {
       if (b.role == 4) continue;
       TrainBlock &t = S->tb[b.index];
@@ -714,15 +769,16 @@ int32_t octseg_train_step_device(octseg_net *net, const void *images, int32_t dt
     return 0;
   };
   // The whole step is stream-ordered and every per-step scalar lives on the device, so after one eager
-  // step with the same arguments the step is captured into a CUDA graph and replayed (the default net is
-  // ~230 launches of a few microseconds each at a per-GPU batch of 32).  With more than one rank the
-  // NCCL all-reduce and the Adam launch behind it stay outside the graph and are issued eagerly.
+  // step with the same arguments the step is captured into a CUDA graph and replayed.  The bucketed NCCL
+  // all-reduces (on their own stream) and the Adam launch are captured with it; OCTSEG_TRAIN_GRAPH_NCCL=0
+  // keeps them outside the graph (eager), OCTSEG_TRAIN_GRAPH=0 disables graphs altogether.
   const char *genv = std::getenv("OCTSEG_TRAIN_GRAPH");
   const bool graphs_on = !(genv && genv[0] == '0');
   const bool same = S->warm && S->g_img == images && S->g_lab == labels && S->g_mask == dropout_mask && S->g_n == n &&
                     S->g_h == h && S->g_w == w && S->g_dtype == dtype && S->g_stream == st && S->g_loss == loss_out_device;
   const bool profiling = std::getenv("OCTSEG_TRAIN_PROFILE") != nullptr;
-  const bool tail_in_graph = !(S->comm && S->world > 1);
+  const char *gn = std::getenv("OCTSEG_TRAIN_GRAPH_NCCL");
+  const bool tail_in_graph = !(S->comm && S->world > 1) || !(gn && gn[0] == '0');
   if (graphs_on && !profiling && same) {
     if (!S->graph_exec) {
       cudaGraph_t graph = nullptr;
@@ -745,7 +801,7 @@ int32_t octseg_train_step_device(octseg_net *net, const void *images, int32_t dt
     }
     OCTSEG_CUDA(cudaGraphLaunch(S->graph_exec, st));
     net->launches += S->launches_per_step;
-    if (!tail_in_graph && train_tail(net, st)) return 1;
+    if (!tail_in_graph) { S->tail_sent = false; if (train_tail(net, st)) return 1; }
     ++S->step;
     net->host_stale = true;
     net->derived_dirty = true;

@@ -112,6 +112,109 @@ int launch_bn_finalize(const double *sums, long long count, int c, float eps, fl
 }
 
 // ---------------------------------------------------------------------------------
+// BatchNorm forward, second half, in ONE pass: batch mean / variance from the per-channel sums (accumulated by the
+// convolution's epilogue or by bn_stats_kernel), a = relu(z * scale + shift) [* dropout multiplier], and for the
+// encoder-final blocks the 2x2 max-pooled copy.  Block (0,0,0) also publishes mean / invstd / scale / shift for
+// the backward pass and performs the Keras moving-statistics update (momentum 0.99, Bessel-corrected variance).
+// ---------------------------------------------------------------------------------
+struct BnChan { float mean, inv, scale, shift; };
+__device__ __forceinline__ BnChan bn_channel(const double *sums, int c, int ch, double inv_count, float eps,
+                                             const float *gamma, const float *beta, double *var_out = nullptr) {
+  const double m = sums[ch] * inv_count;
+  double var = sums[c + ch] * inv_count - m * m;
+  if (var < 0) var = 0;
+  if (var_out) *var_out = var;
+  BnChan r;
+  r.mean = (float)m;
+  r.inv = 1.0f / sqrtf((float)var + eps);
+  r.scale = r.inv * gamma[ch];
+  r.shift = beta[ch] - r.mean * r.scale;
+  return r;
+}
+
+template <typename T, int POOL>
+__global__ void __launch_bounds__(256) bn_finalize_apply_kernel(
+    View<const T> z, const double *__restrict__ sums, long long count, float eps, float momentum,
+    const float *__restrict__ gamma, const float *__restrict__ beta, float *moving_mean, float *moving_var,
+    float *mean, float *invstd, float *scale, float *shift, const T *__restrict__ mask, View<T> a, View<T> pooled) {
+  const int c = z.planes * 8;
+  const double inv_count = 1.0 / (double)count;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      double var;
+      const BnChan b = bn_channel(sums, c, i, inv_count, eps, gamma, beta, &var);
+      mean[i] = b.mean; invstd[i] = b.inv; scale[i] = b.scale; shift[i] = b.shift;
+      const float unbiased = (float)(var * ((double)count / (double)(count > 1 ? count - 1 : 1)));
+      moving_mean[i] = moving_mean[i] * momentum + b.mean * (1.f - momentum);
+      moving_var[i] = moving_var[i] * momentum + unbiased * (1.f - momentum);
+    }
+  }
+  const int pl = blockIdx.y, img = blockIdx.z;
+  const int hw = z.h * z.w;
+  const T *zb = z.ptr + (long long)img * z.img_stride + (long long)pl * hw * 8;
+  T *ab = a.ptr + (long long)img * a.img_stride + (long long)pl * hw * 8;
+  const T *mb = mask ? mask + ((long long)img * z.planes + pl) * hw * 8 : nullptr;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const BnChan b = bn_channel(sums, c, pl * 8 + k, inv_count, eps, gamma, beta);
+    sc[k] = b.scale; sh[k] = b.shift;
+  }
+  if constexpr (POOL == 0) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < hw; v += gridDim.x * blockDim.x) {
+      Vec8f x = load8(zb + (long long)v * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x.v[k] = fmaxf(fmaf(x.v[k], sc[k], sh[k]), 0.f);
+      if (mb) {
+        const Vec8f mk = load8(mb + (long long)v * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x.v[k] *= mk.v[k];
+      }
+      store8(ab + (long long)v * 8, x);
+    }
+  } else {
+    // one thread = one 2x2 window: four activations out, their maximum to the pooled tensor
+    const int W = z.w, Wo = W >> 1, Ho = z.h >> 1;
+    T *pb = pooled.ptr + (long long)img * pooled.img_stride + (long long)pl * Ho * Wo * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Ho * Wo; i += gridDim.x * blockDim.x) {
+      const int x = i % Wo, y = i / Wo;
+      const long long o00 = ((long long)(2 * y) * W + 2 * x) * 8, o10 = o00 + (long long)W * 8;
+      Vec8f q[4] = {load8(zb + o00), load8(zb + o00 + 8), load8(zb + o10), load8(zb + o10 + 8)};
+      Vec8f m;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[j].v[k] = fmaxf(fmaf(q[j].v[k], sc[k], sh[k]), 0.f);
+        m.v[k] = fmaxf(fmaxf(q[0].v[k], q[1].v[k]), fmaxf(q[2].v[k], q[3].v[k]));
+      }
+      store8(ab + o00, q[0]); store8(ab + o00 + 8, q[1]); store8(ab + o10, q[2]); store8(ab + o10 + 8, q[3]);
+      // the pooled tensor is the maximum of the STORED (rounded) activations; rounding is monotonic, so max-then-round == round-then-max
+      store8(pb + (long long)i * 8, m);
+    }
+  }
+}
+
+template <typename T>
+int launch_bn_finalize_apply(View<const T> z, const double *sums, long long count, float eps, float momentum,
+                             const float *gamma, const float *beta, float *moving_mean, float *moving_var, float *mean,
+                             float *invstd, float *scale, float *shift, const T *mask, View<T> a, View<T> pooled,
+                             cudaStream_t st) {
+  const int hw = z.h * z.w;
+  if (pooled.ptr) {
+    if (mask || (z.h & 1) || (z.w & 1)) { set_error("bn_finalize_apply: pooled variant needs even dims and no dropout"); return 1; }
+    dim3 grid(std::max(1, std::min((hw / 4 + 255) / 256, 64)), z.planes, z.n);
+    bn_finalize_apply_kernel<T, 1><<<grid, 256, 0, st>>>(z, sums, count, eps, momentum, gamma, beta, moving_mean, moving_var,
+                                                         mean, invstd, scale, shift, mask, a, pooled);
+  } else {
+    dim3 grid(std::max(1, std::min((hw + 1023) / 1024, 64)), z.planes, z.n);
+    bn_finalize_apply_kernel<T, 0><<<grid, 256, 0, st>>>(z, sums, count, eps, momentum, gamma, beta, moving_mean, moving_var,
+                                                         mean, invstd, scale, shift, mask, a, pooled);
+  }
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_relu_kernel(View<const T> z, const float *__restrict__ scale,
                                                             const float *__restrict__ shift,
@@ -755,6 +858,9 @@ int launch_adam(float *p, const float *g, float *m, float *v, long long n, const
 
 #define INST(T)                                                                                             \
   template int launch_bn_stats<T>(View<const T>, double *, cudaStream_t);                                   \
+  template int launch_bn_finalize_apply<T>(View<const T>, const double *, long long, float, float, const float *, \
+                                           const float *, float *, float *, float *, float *, float *, float *, \
+                                           const T *, View<T>, View<T>, cudaStream_t);                      \
   template int launch_bn_apply_relu<T>(View<const T>, const float *, const float *, const T *, View<T>,     \
                                        cudaStream_t);                                                       \
   template int launch_dropout_mask<T>(const uint8_t *, unsigned long long, const StepState *, float, int, int, \

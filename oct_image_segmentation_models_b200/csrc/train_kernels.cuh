@@ -22,6 +22,13 @@ int launch_bn_finalize(const double *sums, long long count, int c, float eps, fl
                        const float *gamma, const float *beta, float *moving_mean, float *moving_var,
                        float *mean, float *invstd, float *scale, float *shift, cudaStream_t st);
 
+// bn_finalize + bn_apply_relu (+ 2x2 max-pool when pooled.ptr != NULL) in one pass over z: see the kernel
+template <typename T>
+int launch_bn_finalize_apply(View<const T> z, const double *sums, long long count, float eps, float momentum,
+                             const float *gamma, const float *beta, float *moving_mean, float *moving_var, float *mean,
+                             float *invstd, float *scale, float *shift, const T *mask, View<T> a, View<T> pooled,
+                             cudaStream_t st);
+
 // a = relu(z*scale + shift) [* mask]   (mask: optional multiplier tensor, same layout as z)
 template <typename T>
 int launch_bn_apply_relu(View<const T> z, const float *scale, const float *shift, const T *mask,
