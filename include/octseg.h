@@ -171,6 +171,14 @@ int32_t octseg_layer_uses_tensor_core(octseg_net *net, int32_t conv_index, int32
 int32_t octseg_debug_conv_block(octseg_net *net, int32_t conv_index, int32_t path, const float *in,
                                 int32_t n, int32_t h, int32_t w, float *out, float *ms_out);
 
+/* run the BACKWARD kernels of one conv block (index 1 .. last conv block) on caller data, for per-layer parity tests
+ * against float64 math (SURVEY section 4 "unit (GPU)"): the weight-gradient kernel and the data-gradient convolution the
+ * train step launches in the handle's precision (bf16: tensor cores; fp32: CUDA cores).  Needs octseg_train_begin.
+ *   a_in: float32 NHWC [n,h,w,cin] input activation;  dz: float32 NHWC [n,h_out,w_out,cout] gradient wrt the conv output
+ *   dW: [kh,kw,cin,cout], db: [cout], d_in: float32 NHWC [n,h,w,cin] */
+int32_t octseg_debug_backward_block(octseg_net *net, int32_t conv_index, const float *a_in, const float *dz, int32_t n,
+                                    int32_t h, int32_t w, float *dW, float *db, float *d_in);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,8 @@ _PROTOS = {
     "octseg_set_profiling": (C.c_int32, [C.c_void_p, C.c_int32]),
     "octseg_get_block_times": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]),
     "octseg_layer_uses_tensor_core": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "octseg_debug_backward_block": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "octseg_debug_conv_block": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                             C.c_int32, C.c_void_p, C.POINTER(C.c_float)]),
 }

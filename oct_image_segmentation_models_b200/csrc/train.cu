@@ -610,6 +610,133 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   return 0;
 }
 
+
+// ---- per-block debug entries (tests): the backward kernels of ONE conv block on caller data -------------------------
+// a_in: NHWC fp32 [n,h,w,cin] (the block's input activation), dz: NHWC fp32 [n,oh,ow,cout] (gradient wrt the conv output;
+// oh = 2h for the up-conv).  Runs exactly the launchers the train step uses in the handle's precision (bf16: tensor-core
+// weight gradient + tcgen05 data gradient; fp32: CUDA cores) and returns dW [kh,kw,cin,cout], db [cout], d_in NHWC [n,h,w,cin].
+template <typename T>
+static int debug_backward_t(octseg_net *net, const BlockSpec &b, const float *a_in, const float *dz, int n, int h, int w,
+                            float *dW_out, float *db_out, float *din_out) {
+  TrainState *S = ts(net);
+  TrainBlock &t = S->tb[b.index];
+  cudaStream_t st = net->stream;
+  const int oh = b.ups ? 2 * h : h, ow = b.ups ? 2 * w : w;
+  const size_t in_elems = (size_t)n * b.cin * h * w, dz_elems = (size_t)n * b.cout * oh * ow;
+  auto to_blocked = [&](const float *src, int c, int hh, int ww, std::vector<T> *dst) {
+    dst->resize((size_t)n * c * hh * ww);
+    for (int i = 0; i < n; ++i)
+      for (int y = 0; y < hh; ++y)
+        for (int x = 0; x < ww; ++x)
+          for (int k = 0; k < c; ++k) {
+            const float v = src[(((size_t)i * hh + y) * ww + x) * c + k];
+            T o;
+            if constexpr (sizeof(T) == 2) o = __float2bfloat16(v); else o = v;
+            (*dst)[((((size_t)i * (c / 8) + k / 8) * hh + y) * ww + x) * 8 + (k & 7)] = o;
+          }
+  };
+  std::vector<T> hin, hdz;
+  to_blocked(a_in, b.cin, h, w, &hin);
+  to_blocked(dz, b.cout, oh, ow, &hdz);
+  T *d_in = nullptr, *d_dz = nullptr, *d_din = nullptr, *d_up = nullptr, *d_dup = nullptr;
+  float *d_dW = nullptr, *d_db = nullptr;
+  const size_t w_count = (size_t)b.kh * b.kw * b.cin * b.cout;
+  OCTSEG_CUDA(cudaMalloc(&d_in, in_elems * sizeof(T)));
+  OCTSEG_CUDA(cudaMalloc(&d_dz, dz_elems * sizeof(T)));
+  OCTSEG_CUDA(cudaMalloc(&d_din, in_elems * sizeof(T)));
+  OCTSEG_CUDA(cudaMalloc(&d_dW, w_count * sizeof(float)));
+  OCTSEG_CUDA(cudaMalloc(&d_db, b.cout * sizeof(float)));
+  OCTSEG_CUDA(cudaMemcpyAsync(d_in, hin.data(), in_elems * sizeof(T), cudaMemcpyHostToDevice, st));
+  OCTSEG_CUDA(cudaMemcpyAsync(d_dz, hdz.data(), dz_elems * sizeof(T), cudaMemcpyHostToDevice, st));
+  OCTSEG_CUDA(cudaMemsetAsync(d_din, 0xFF, in_elems * sizeof(T), st));
+  OCTSEG_CUDA(cudaMemsetAsync(d_dW, 0, w_count * sizeof(float), st));
+  OCTSEG_CUDA(cudaMemsetAsync(d_db, 0, b.cout * sizeof(float), st));
+  View<const T> in = make_view((const T *)d_in, n, b.cin / 8, 0, b.cin / 8, h, w);
+  View<const T> dzc = make_view((const T *)d_dz, n, b.cout / 8, 0, b.cout / 8, oh, ow);
+  const int pt = (b.kh - 1) / 2, pl = (b.kw - 1) / 2;
+  const float *P = net->d_params;
+  int rc = 0;
+  // ---- weight gradient (same dispatch as train_step_t)
+  if (b.ups && sizeof(T) == 2 && !net->disable_tc) {
+    OCTSEG_CUDA(cudaMalloc(&d_up, (size_t)n * b.cin * oh * ow * sizeof(T)));
+    View<T> up = make_view(d_up, n, b.cin / 8, 0, b.cin / 8, oh, ow);
+    rc = launch_upsample2x<T>(in, up, st);
+    View<const T> upc = make_view((const T *)d_up, n, b.cin / 8, 0, b.cin / 8, oh, ow);
+    if (!rc) rc = wgrad_dispatch<T>(net, upc, dzc, b.kh, b.kw, pt, pl, 0, b.cin, b.cout, d_dW, d_db, st);
+  } else {
+    rc = wgrad_dispatch<T>(net, in, dzc, b.kh, b.kw, pt, pl, b.ups ? 1 : 0, b.cin, b.cout, d_dW, d_db, st);
+  }
+  // ---- data gradient
+  const bool tc_dgrad = sizeof(T) == 2 && !net->disable_tc && t.geo_dgrad_ok && tc_supported(b.kh, b.kw, b.cout, b.cin, 0, oh, ow);
+  if (!rc && tc_dgrad) {
+    const bool pair = t.geo_dgrad2_ok && !b.ups && (oh % 2) == 0 && oh >= 2 * kTcTileH;
+    const TcGeometry &gd = pair ? t.geo_dgrad2 : t.geo_dgrad;
+    __nv_bfloat16 *wp = pair ? t.wpack_dgrad2 : t.wpack_dgrad;
+    rc = tc_pack_weights_device(gd, P + net->params[b.p_kernel].offset, 1, wp, st);
+    TcEpilogue epi;
+    epi.relu = 0; epi.scale = S->d_ones; epi.shift = S->d_zeros;
+    TcPlan plan;
+    if (!b.ups) {
+      epi.out = make_view((__nv_bfloat16 *)d_din, n, b.cin / 8, 0, b.cin / 8, h, w);
+      if (!rc) rc = tc_make_plan(gd, (const __nv_bfloat16 *)d_dz, n, oh, ow, wp, epi, net->d_status, &plan);
+      if (!rc) rc = tc_launch(plan, st);
+    } else {
+      OCTSEG_CUDA(cudaMalloc(&d_dup, (size_t)n * b.cin * oh * ow * sizeof(T)));
+      epi.out = make_view((__nv_bfloat16 *)d_dup, n, b.cin / 8, 0, b.cin / 8, oh, ow);
+      if (!rc) rc = tc_make_plan(gd, (const __nv_bfloat16 *)d_dz, n, oh, ow, wp, epi, net->d_status, &plan);
+      if (!rc) rc = tc_launch(plan, st);
+      View<const T> dup = make_view((const T *)d_dup, n, b.cin / 8, 0, b.cin / 8, oh, ow);
+      View<T> din = make_view(d_din, n, b.cin / 8, 0, b.cin / 8, h, w);
+      if (!rc) rc = launch_sumpool2x<T>(dup, din, st);
+    }
+  } else if (!rc) {
+    View<T> din = make_view(d_din, n, b.cin / 8, 0, b.cin / 8, h, w);
+    if (!b.ups) {
+      rc = launch_flip_transpose(P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout, t.w_t, st);
+      if (!rc) rc = launch_conv_direct_ex<T>(dzc, t.w_t, b.kh, b.kw, b.cout, b.cin, 0, 1, b.kh - 1 - pt, b.kw - 1 - pl, S->d_ones,
+                                             S->d_zeros, 0, din, st);
+    } else {
+      rc = launch_upconv_dgrad_weights(P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout, t.w_t, st);
+      if (!rc) rc = launch_conv_direct_ex<T>(dzc, t.w_t, b.kh + 1, b.kw + 1, b.cout, b.cin, 0, 2, b.kh - 1 - pt, b.kw - 1 - pl,
+                                             S->d_ones, S->d_zeros, 0, din, st);
+    }
+  }
+  if (!rc) rc = check_status(net);
+  if (!rc) {
+    std::vector<T> hd(in_elems);
+    cudaMemcpy(hd.data(), d_din, in_elems * sizeof(T), cudaMemcpyDeviceToHost);
+    cudaMemcpy(dW_out, d_dW, w_count * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(db_out, d_db, b.cout * sizeof(float), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n; ++i)
+      for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+          for (int k = 0; k < b.cin; ++k) {
+            const T v = hd[((((size_t)i * (b.cin / 8) + k / 8) * h + y) * w + x) * 8 + (k & 7)];
+            float f;
+            if constexpr (sizeof(T) == 2) f = __bfloat162float(v); else f = v;
+            din_out[(((size_t)i * h + y) * w + x) * b.cin + k] = f;
+          }
+  }
+  cudaFree(d_in); cudaFree(d_dz); cudaFree(d_din); cudaFree(d_dW); cudaFree(d_db); cudaFree(d_up); cudaFree(d_dup);
+  return rc;
+}
+
+}  // namespace octseg
+
+extern "C" int32_t octseg_debug_backward_block(octseg_net *net, int32_t conv_index, const float *a_in, const float *dz, int32_t n,
+                                               int32_t h, int32_t w, float *dW, float *db, float *d_in) {
+  if (!net || !a_in || !dz || !dW || !db || !d_in) { set_error("null argument"); return 1; }
+  TrainState *S = ts(net);
+  if (!S) { set_error("call octseg_train_begin first"); return 1; }
+  if (conv_index <= 0 || conv_index >= (int)net->blocks.size() - 1) { set_error("bad conv index (1 .. last conv block)"); return 1; }
+  if (net->precision == OCTSEG_FP16) { set_error("training kernels run in fp32 or bf16"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  const BlockSpec &b = net->blocks[conv_index];
+  return net->precision == OCTSEG_BF16 ? debug_backward_t<__nv_bfloat16>(net, b, a_in, dz, n, h, w, dW, db, d_in)
+                                       : debug_backward_t<float>(net, b, a_in, dz, n, h, w, dW, db, d_in);
+}
+
+namespace octseg {
 __global__ void store_loss_kernel(const double *src, float *dst) { *dst = (float)*src; }
 
 }  // namespace octseg

@@ -246,6 +246,23 @@ class UNetEngine:
     def layer_uses_tensor_core(self, conv_index: int, h: int, w: int) -> bool:
         return bool(self._lib.octseg_layer_uses_tensor_core(self._h, conv_index, h, w))
 
+    def debug_backward_block(self, conv_index: int, a_in_nhwc: np.ndarray, dz_nhwc: np.ndarray):
+        """Weight gradient, bias gradient and data gradient of ONE conv block through the train step's own kernels
+        (needs train_begin): returns (dW [kh,kw,cin,cout], db [cout], d_in NHWC)."""
+        from .models.unet_spec import unet_blocks
+        b = unet_blocks(**self.spec_kwargs)[conv_index]
+        a = np.ascontiguousarray(a_in_nhwc, dtype=np.float32)
+        dz = np.ascontiguousarray(dz_nhwc, dtype=np.float32)
+        n, h, w, c = a.shape
+        oh, ow = (2 * h, 2 * w) if b.upsample_before else (h, w)
+        assert c == b.cin and dz.shape == (n, oh, ow, b.cout)
+        dW = np.empty((b.kh, b.kw, b.cin, b.cout), np.float32)
+        db = np.empty((b.cout,), np.float32)
+        din = np.empty((n, h, w, b.cin), np.float32)
+        nat.check(self._lib.octseg_debug_backward_block(self._h, conv_index, _ptr(a), _ptr(dz), n, h, w, _ptr(dW), _ptr(db),
+                                                        _ptr(din)))
+        return dW, db, din
+
     def debug_conv_block(self, conv_index: int, x_nhwc: np.ndarray, path: int = 0, timed: bool = False):
         """Run one conv block (conv + folded BN + ReLU; x2 upsample first for 'up' blocks)
         on NHWC float32 input.  path 0 = CUDA-core kernel, 1 = tcgen05 kernel."""
