@@ -94,6 +94,15 @@ int32_t octseg_predict_device(octseg_net *net, const void *images, int32_t dtype
 int32_t octseg_predict_maps_host(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
                                  int32_t w, int32_t bg_ilm, int32_t bg_csi, int32_t transposed, uint8_t *labels,
                                  uint8_t *maps);
+/* asynchronous pair of octseg_predict_maps_host for pipelining consecutive batches (reference loop: one predict per
+ * image, prediction/prediction.py:70-81 -- here whole batches in flight): submit() only enqueues the H2D copies, the
+ * forward passes and the D2H copies and returns a ticket; wait(ticket) completes that call.  Host buffers must be
+ * PINNED (cudaHostAlloc / torch pin_memory) and stay valid until the matching wait.  Up to two calls may be in
+ * flight: submit(i+1) before wait(i) overlaps the H2D of batch i+1 with the forward and the D2H of batch i. */
+int32_t octseg_predict_maps_submit(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h, int32_t w,
+                                   int32_t bg_ilm, int32_t bg_csi, int32_t transposed, uint8_t *labels, uint8_t *maps,
+                                   int32_t *ticket);
+int32_t octseg_predict_wait(octseg_net *net, int32_t ticket);
 /* validation pass on the device: replaces model.predict over the validation Sequence +
  * the Dice monitor metrics (reference common/custom_metrics.py:19-77) + the validation loss of
  * weighted_categorical_crossentropy (common/custom_losses.py:27-35).  labels: true class ids u8 [n,h,w].

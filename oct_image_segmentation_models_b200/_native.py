@@ -47,6 +47,9 @@ _PROTOS = {
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "octseg_predict_maps_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "octseg_predict_maps_submit": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "octseg_predict_wait": (C.c_int32, [C.c_void_p, C.c_int32]),
     "octseg_evaluate_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "octseg_synchronize": (C.c_int32, [C.c_void_p]),

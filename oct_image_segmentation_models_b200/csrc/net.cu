@@ -113,6 +113,8 @@ static int check_supported(const octseg_net *net) {
 // ---------------------------------------------------------------------------------
 int sync_host_mirror(octseg_net *net) {
   if (!net->host_stale) return 0;
+  // training writes the parameters on the caller's stream: finish it before reading them on ours
+  if (net->last_train_stream && net->last_train_stream != net->stream) OCTSEG_CUDA(cudaStreamSynchronize(net->last_train_stream));
   OCTSEG_CUDA(cudaMemcpyAsync(net->h_params.data(), net->d_params, net->total_floats * sizeof(float),
                               cudaMemcpyDeviceToHost, net->stream));
   OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
@@ -431,7 +433,13 @@ static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h
 
 int forward(octseg_net *net, const void *d_img, int dtype, int n, int h, int w, float *d_probs,
             uint8_t *d_labels, cudaStream_t st) {
+  const bool rebuilt = net->derived_dirty;
   if (prepare_derived(net)) return 1;
+  if (rebuilt && st != net->stream) {
+    // folded BN tables / packed weights were (re)built on the handle's stream: a caller stream must wait for them
+    OCTSEG_CUDA(cudaEventRecord(net->ev_derived, net->stream));
+    OCTSEG_CUDA(cudaStreamWaitEvent(st, net->ev_derived, 0));
+  }
   if (ensure_workspace(net, n, h, w)) return 1;
   if (net->precision == OCTSEG_BF16)
     return forward_t<__nv_bfloat16>(net, d_img, dtype, n, h, w, d_probs, d_labels, st);
@@ -523,22 +531,9 @@ int32_t octseg_param_info(const octseg_config *cfg, int32_t index, char *name, i
   return 0;
 }
 
-int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precision, octseg_net **out) {
-  if (!cfg || !out) { set_error("null argument"); return 1; }
-  if (precision != OCTSEG_FP32 && precision != OCTSEG_BF16 && precision != OCTSEG_FP16) { set_error("bad precision"); return 1; }
-  int ndev = octseg_device_count();
-  if (ndev <= 0) { set_error("no CUDA device: liboctseg has no CPU fallback"); return 1; }
-  if (device < 0 || device >= ndev) { set_error("device index out of range"); return 1; }
-  OCTSEG_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  OCTSEG_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) { set_error("liboctseg is built for sm_100a (B200) only"); return 1; }
-  octseg_net *net = new octseg_net();
+static int32_t create_impl(const octseg_config *cfg, int32_t device, int32_t precision, octseg_net *net) {
   net->cfg = *cfg; net->device = device; net->precision = precision;
-  if (build_graph(*cfg, &net->blocks, &net->params, &net->total_floats) || check_supported(net)) {
-    delete net;
-    return 1;
-  }
+  if (build_graph(*cfg, &net->blocks, &net->params, &net->total_floats) || check_supported(net)) return 1;
   const char *e = std::getenv("OCTSEG_DISABLE_TC");
   net->disable_tc = e && e[0] == '1';
   { const char *rp = std::getenv("OCTSEG_DISABLE_ROWPAIR"); net->disable_rowpair = rp && rp[0] == '1'; }
@@ -547,6 +542,7 @@ int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precisio
   e = std::getenv("OCTSEG_MICROBATCH");
   net->microbatch = e ? std::atoi(e) : 0;
   OCTSEG_CUDA(cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking));
+  OCTSEG_CUDA(cudaEventCreateWithFlags(&net->ev_derived, cudaEventDisableTiming));
   OCTSEG_CUDA(cudaMalloc(&net->d_params, net->total_floats * sizeof(float)));
   OCTSEG_CUDA(cudaMemset(net->d_params, 0, net->total_floats * sizeof(float)));
   net->h_params.assign(net->total_floats, 0.f);
@@ -554,7 +550,7 @@ int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precisio
   OCTSEG_CUDA(cudaMemset(net->d_status, 0, 2 * sizeof(int)));
   OCTSEG_CUDA(cudaMallocHost(&net->h_status, 2 * sizeof(int)));
   { const char *fp = std::getenv("OCTSEG_FP32_PATH"); net->fp32_path = (fp && (fp[0] == 'c' || fp[0] == 'C')) ? 1 : 0; }
-  if (init_preprocess_lut()) { delete net; return 1; }
+  if (init_preprocess_lut()) return 1;
   net->bstate.resize(net->blocks.size());
   for (auto &b : net->blocks) {
     BlockState &st = net->bstate[b.index];
@@ -597,6 +593,30 @@ int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precisio
       OCTSEG_CUDA(cudaMalloc(&st.rep_shift, 8 * b.cout * sizeof(float)));
     }
   }
+  return 0;
+}
+
+
+int32_t octseg_destroy(octseg_net *net);
+
+int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precision, octseg_net **out) {
+  if (!cfg || !out) { set_error("null argument"); return 1; }
+  if (precision != OCTSEG_FP32 && precision != OCTSEG_BF16 && precision != OCTSEG_FP16) { set_error("bad precision"); return 1; }
+  int ndev = octseg_device_count();
+  if (ndev <= 0) { set_error("no CUDA device: liboctseg has no CPU fallback"); return 1; }
+  if (device < 0 || device >= ndev) { set_error("device index out of range"); return 1; }
+  OCTSEG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  OCTSEG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) { set_error("liboctseg is built for sm_100a (B200) only"); return 1; }
+  octseg_net *net = new octseg_net();
+  if (create_impl(cfg, device, precision, net)) {
+    // every early return above leaves a partly built handle: release whatever exists (the error string is kept)
+    const std::string err = g_err;
+    octseg_destroy(net);
+    g_err = err;
+    return 1;
+  }
   *out = net;
   return 0;
 }
@@ -607,13 +627,20 @@ int32_t octseg_destroy(octseg_net *net) {
   if (net->stream) cudaStreamSynchronize(net->stream);
   octseg_train_free(net);
   for (auto &e : net->prof_events) cudaEventDestroy(e);
-  for (auto &e : net->pipe_events) cudaEventDestroy(e);
+  for (auto &S : net->slot) {
+    for (auto &e : S.ev) cudaEventDestroy(e);
+    if (S.ev_start) cudaEventDestroy(S.ev_start);
+    if (S.ev_done) cudaEventDestroy(S.ev_done);
+    if (S.ev_status) cudaEventDestroy(S.ev_status);
+    if (S.h_status) cudaFreeHost(S.h_status);
+    cudaFree(S.d_img); cudaFree(S.d_probs); cudaFree(S.d_labels); cudaFree(S.d_maps);
+  }
   if (net->copy_in) cudaStreamDestroy(net->copy_in);
   if (net->copy_out) cudaStreamDestroy(net->copy_out);
   for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); cudaFree(st.rep_scale); cudaFree(st.rep_shift); cudaFree(st.wpack2); cudaFree(st.wpack_s); }
-  cudaFree(net->d_params); cudaFree(net->ws); cudaFree(net->d_img); cudaFree(net->d_probs);
-  cudaFree(net->d_labels); cudaFree(net->d_maps); cudaFree(net->d_eval); cudaFree(net->d_status);
+  cudaFree(net->d_params); cudaFree(net->ws); cudaFree(net->d_eval); cudaFree(net->d_status);
   if (net->h_status) cudaFreeHost(net->h_status);
+  if (net->ev_derived) cudaEventDestroy(net->ev_derived);
   if (net->stream) cudaStreamDestroy(net->stream);
   delete net;
   return 0;
@@ -668,25 +695,39 @@ int32_t octseg_predict_device(octseg_net *net, const void *images, int32_t dtype
 // Chunked three-stage pipeline shared by the host-buffer entry points: H2D of chunk i+1, forward (+ boundary
 // maps) of chunk i and D2H of chunk i-1 overlap on three streams (PCIe is full duplex).  Any of
 // probs / labels / maps may be null; maps need labels on the device but not necessarily on the host.
-static int predict_pipeline(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h, int32_t w,
-                            float *probs, uint8_t *labels, uint8_t *maps, int bg_ilm, int bg_csi, int transposed) {
+// The call uses one of two staging slots and only ENQUEUES work; predict_wait() completes it.  Two calls in flight
+// (submit i+1 before waiting for i) overlap the H2D of batch i+1 with the forward and D2H of batch i.
+static int predict_wait(octseg_net *net, int si);
+__global__ void snapshot_status_kernel(const int *__restrict__ dev, int *host_pinned) {
+  if (threadIdx.x < 2) host_pinned[threadIdx.x] = dev[threadIdx.x];
+  __threadfence_system();
+}
+
+static int predict_enqueue(octseg_net *net, int si, const void *images, int32_t dtype, int32_t n, int32_t h, int32_t w,
+                           float *probs, uint8_t *labels, uint8_t *maps, int bg_ilm, int bg_csi, int transposed,
+                           bool pipelined = false) {
   if (n <= 0 || h <= 0 || w <= 0) { set_error("bad image batch shape"); return 1; }
   if (dtype != OCTSEG_U8 && dtype != OCTSEG_F32 && dtype != OCTSEG_F32_PRE) { set_error("bad image dtype"); return 1; }
   OCTSEG_CUDA(cudaSetDevice(net->device));
+  octseg_net::HostSlot &S = net->slot[si];
+  if (S.busy && predict_wait(net, si)) return 1;          // the slot's previous call must have drained
   const int K = net->cfg.num_classes;
   const size_t img_per = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)h * w * net->cfg.input_channels;
   const size_t pr_per = (size_t)h * w * K * sizeof(float), lb_per = (size_t)h * w, mp_per = lb_per * (K - 1);
   const bool need_labels = labels || maps;
-  if (grow(&net->d_img, &net->d_img_bytes, img_per * n)) return 1;
-  if (probs && grow(reinterpret_cast<void **>(&net->d_probs), &net->d_probs_bytes, pr_per * n)) return 1;
-  if (need_labels && grow(reinterpret_cast<void **>(&net->d_labels), &net->d_labels_bytes, lb_per * n)) return 1;
-  if (maps && grow(reinterpret_cast<void **>(&net->d_maps), &net->d_maps_bytes, mp_per * n)) return 1;
+  if (grow(&S.d_img, &S.d_img_bytes, img_per * n)) return 1;
+  if (probs && grow(reinterpret_cast<void **>(&S.d_probs), &S.d_probs_bytes, pr_per * n)) return 1;
+  if (need_labels && grow(reinterpret_cast<void **>(&S.d_labels), &S.d_labels_bytes, lb_per * n)) return 1;
+  if (maps && grow(reinterpret_cast<void **>(&S.d_maps), &S.d_maps_bytes, mp_per * n)) return 1;
   // Chunk size: total ~ H2D(chunk) + sum of forwards + D2H(last chunk), and a forward costs a fixed ~0.2 ms
   // (22 launches) plus ~0.022 ms per 512x512 B-scan.  With fp32 probabilities going back (4*K bytes per
   // pixel) the call is D2H-bound and small chunks start the return traffic early; with only label / boundary
   // maps (1 + K-1 bytes per pixel) the forwards dominate and fewer, larger chunks (~22 B-scans) win (measured on B200).
+  // A pipelined caller (submit / wait) overlaps whole calls instead, so the batch is forwarded in one piece: a chunked
+  // forward pays the fixed per-launch cost three times (3 x 0.68 ms instead of 1.17 ms per 64 B-scans).
   int chunk;
   if (net->microbatch > 0) chunk = std::min(n, net->microbatch);
+  else if (pipelined) chunk = n;
   else if (probs) chunk = std::min(n, 8);
   else if (n < 16) chunk = n;
   else { const int nc = std::max(2, (n + 21) / 22); chunk = (n + nc - 1) / nc; }
@@ -695,28 +736,31 @@ static int predict_pipeline(octseg_net *net, const void *images, int32_t dtype, 
     OCTSEG_CUDA(cudaStreamCreateWithFlags(&net->copy_in, cudaStreamNonBlocking));
     OCTSEG_CUDA(cudaStreamCreateWithFlags(&net->copy_out, cudaStreamNonBlocking));
   }
-  const int n_chunks = (n + chunk - 1) / chunk;
-  if ((int)net->pipe_events.size() < 3 * n_chunks) {
-    const size_t old = net->pipe_events.size();
-    net->pipe_events.resize(3 * n_chunks);
-    for (size_t i = old; i < net->pipe_events.size(); ++i)
-      OCTSEG_CUDA(cudaEventCreateWithFlags(&net->pipe_events[i], cudaEventDisableTiming));
+  if (!S.ev_start) {
+    OCTSEG_CUDA(cudaEventCreateWithFlags(&S.ev_start, cudaEventDisableTiming));
+    OCTSEG_CUDA(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
+    OCTSEG_CUDA(cudaEventCreateWithFlags(&S.ev_status, cudaEventDisableTiming));
+    OCTSEG_CUDA(cudaMallocHost(&S.h_status, 2 * sizeof(int)));
   }
-  // the pipeline streams must not start before earlier work on the handle's stream is done
-  OCTSEG_CUDA(cudaEventRecord(net->pipe_events[0], net->stream));
-  OCTSEG_CUDA(cudaStreamWaitEvent(net->copy_in, net->pipe_events[0], 0));
-  OCTSEG_CUDA(cudaStreamWaitEvent(net->copy_out, net->pipe_events[0], 0));
+  const int n_chunks = (n + chunk - 1) / chunk;
+  if ((int)S.ev.size() < 2 * n_chunks) {
+    const size_t old = S.ev.size();
+    S.ev.resize(2 * n_chunks);
+    for (size_t i = old; i < S.ev.size(); ++i) OCTSEG_CUDA(cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming));
+  }
+  // The upload does not wait for earlier work on the compute stream (that would serialise H2D(i+1) behind forward(i)):
+  // it touches only this slot's image buffer, and the slot was drained above.
   for (int c = 0; c < n_chunks; ++c) {
     const int i0 = c * chunk, cur = std::min(chunk, n - i0);
-    cudaEvent_t ev_in = net->pipe_events[3 * c], ev_fw = net->pipe_events[3 * c + 1];
-    uint8_t *dimg = reinterpret_cast<uint8_t *>(net->d_img) + (size_t)i0 * img_per;
+    cudaEvent_t ev_in = S.ev[2 * c], ev_fw = S.ev[2 * c + 1];
+    uint8_t *dimg = reinterpret_cast<uint8_t *>(S.d_img) + (size_t)i0 * img_per;
     OCTSEG_CUDA(cudaMemcpyAsync(dimg, reinterpret_cast<const uint8_t *>(images) + (size_t)i0 * img_per,
                                 (size_t)cur * img_per, cudaMemcpyHostToDevice, net->copy_in));
     OCTSEG_CUDA(cudaEventRecord(ev_in, net->copy_in));
     OCTSEG_CUDA(cudaStreamWaitEvent(net->stream, ev_in, 0));
-    float *dpr = probs ? net->d_probs + (size_t)i0 * h * w * K : nullptr;
-    uint8_t *dlb = need_labels ? net->d_labels + (size_t)i0 * lb_per : nullptr;
-    uint8_t *dmp = maps ? net->d_maps + (size_t)i0 * mp_per : nullptr;
+    float *dpr = probs ? S.d_probs + (size_t)i0 * h * w * K : nullptr;
+    uint8_t *dlb = need_labels ? S.d_labels + (size_t)i0 * lb_per : nullptr;
+    uint8_t *dmp = maps ? S.d_maps + (size_t)i0 * mp_per : nullptr;
     if (forward(net, dimg, dtype, cur, h, w, dpr, dlb, net->stream)) return 1;
     if (maps) {
       if (launch_boundary_maps(dlb, cur, h, w, K, bg_ilm, bg_csi, transposed, dmp, net->stream)) return 1;
@@ -734,12 +778,51 @@ static int predict_pipeline(octseg_net *net, const void *images, int32_t dtype, 
       OCTSEG_CUDA(cudaMemcpyAsync(maps + (size_t)i0 * mp_per, dmp, (size_t)cur * mp_per, cudaMemcpyDeviceToHost,
                                   net->copy_out));
   }
-  OCTSEG_CUDA(cudaEventRecord(net->pipe_events[2], net->copy_out));
-  OCTSEG_CUDA(cudaStreamWaitEvent(net->stream, net->pipe_events[2], 0));
-  const int rc = check_status(net);
-  if (rc == 2)   // fp16-pair range overflow: the handle has switched to the CUDA-core fp32 path, run the call again
-    return predict_pipeline(net, images, dtype, n, h, w, probs, labels, maps, bg_ilm, bg_csi, transposed);
-  return rc;
+  // Status words as they stand after THIS call's last forward (later calls queued behind it are not waited for).
+  // Written by a one-thread kernel straight into pinned host memory: a cudaMemcpyAsync here would queue behind the
+  // big D2H copies of the previous call on the copy engine and stall the compute stream with it.
+  snapshot_status_kernel<<<1, 32, 0, net->stream>>>(net->d_status, S.h_status);
+  OCTSEG_CUDA(cudaGetLastError());
+  OCTSEG_CUDA(cudaEventRecord(S.ev_status, net->stream));
+  OCTSEG_CUDA(cudaEventRecord(S.ev_done, net->copy_out));
+  S.busy = true;
+  S.images = images; S.dtype = dtype; S.n = n; S.h = h; S.w = w; S.probs = probs; S.labels = labels; S.maps = maps;
+  S.bg_ilm = bg_ilm; S.bg_csi = bg_csi; S.transposed = transposed; S.pipelined = pipelined;
+  return 0;
+}
+
+static int predict_wait(octseg_net *net, int si) {
+  octseg_net::HostSlot &S = net->slot[si];
+  if (!S.busy) return 0;
+  OCTSEG_CUDA(cudaSetDevice(net->device));
+  OCTSEG_CUDA(cudaEventSynchronize(S.ev_status));
+  OCTSEG_CUDA(cudaEventSynchronize(S.ev_done));
+  S.busy = false;
+  if (S.h_status[0] != 0) {
+    set_error("tensor-core conv pipeline timed out (code " + std::to_string(S.h_status[0]) + ")");
+    OCTSEG_CUDA(cudaMemsetAsync(net->d_status, 0, 2 * sizeof(int), net->stream));
+    return 1;
+  }
+  if (S.h_status[1] != 0) {
+    // fp16-pair range overflow of the fp32 tensor-core path: switch the handle to the CUDA-core fp32 path for good
+    // and run this call again (anything else in flight is re-run by its own wait)
+    OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+    OCTSEG_CUDA(cudaMemsetAsync(net->d_status, 0, 2 * sizeof(int), net->stream));
+    net->fp32_path = 1;
+    if (predict_enqueue(net, si, S.images, S.dtype, S.n, S.h, S.w, S.probs, S.labels, S.maps, S.bg_ilm, S.bg_csi, S.transposed,
+                        S.pipelined))
+      return 1;
+    return predict_wait(net, si);
+  }
+  return 0;
+}
+
+static int predict_pipeline(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h, int32_t w,
+                            float *probs, uint8_t *labels, uint8_t *maps, int bg_ilm, int bg_csi, int transposed) {
+  const int si = net->next_slot;
+  net->next_slot ^= 1;
+  if (predict_enqueue(net, si, images, dtype, n, h, w, probs, labels, maps, bg_ilm, bg_csi, transposed)) return 1;
+  return predict_wait(net, si);
 }
 
 int32_t octseg_predict_host(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h,
@@ -767,8 +850,11 @@ int32_t octseg_evaluate_host(octseg_net *net, const void *images, int32_t dtype,
   const size_t img_per = (dtype == OCTSEG_U8 ? 1 : 4) * (size_t)h * w * net->cfg.input_channels;
   const size_t lb_per = (size_t)h * w;
   const int chunk = std::max(1, std::min(std::min(n, 32), pick_microbatch(net, n, h, w)));
-  if (grow(&net->d_img, &net->d_img_bytes, img_per * chunk)) return 1;
-  if (grow(reinterpret_cast<void **>(&net->d_probs), &net->d_probs_bytes, lb_per * K * sizeof(float) * chunk)) return 1;
+  for (int si = 0; si < 2; ++si)
+    if (predict_wait(net, si)) return 1;
+  octseg_net::HostSlot &S0 = net->slot[0];
+  if (grow(&S0.d_img, &S0.d_img_bytes, img_per * chunk)) return 1;
+  if (grow(reinterpret_cast<void **>(&S0.d_probs), &S0.d_probs_bytes, lb_per * K * sizeof(float) * chunk)) return 1;
   const size_t off_cnt = (lb_per * chunk + 255) & ~(size_t)255, off_loss = off_cnt + (size_t)n * 3 * K * 8;
   const size_t off_cw = off_loss + (size_t)n * 8, total = off_cw + 64 * sizeof(float);
   if (grow(&net->d_eval, &net->d_eval_bytes, total)) return 1;
@@ -781,11 +867,11 @@ int32_t octseg_evaluate_host(octseg_net *net, const void *images, int32_t dtype,
     OCTSEG_CUDA(cudaMemcpyAsync(d_cw, class_weights, K * sizeof(float), cudaMemcpyHostToDevice, net->stream));
   for (int i0 = 0; i0 < n; i0 += chunk) {
     const int cur = std::min(chunk, n - i0);
-    OCTSEG_CUDA(cudaMemcpyAsync(net->d_img, reinterpret_cast<const uint8_t *>(images) + (size_t)i0 * img_per, cur * img_per,
+    OCTSEG_CUDA(cudaMemcpyAsync(S0.d_img, reinterpret_cast<const uint8_t *>(images) + (size_t)i0 * img_per, cur * img_per,
                                 cudaMemcpyHostToDevice, net->stream));
     OCTSEG_CUDA(cudaMemcpyAsync(eb, labels + (size_t)i0 * lb_per, cur * lb_per, cudaMemcpyHostToDevice, net->stream));
-    if (forward(net, net->d_img, dtype, cur, h, w, net->d_probs, nullptr, net->stream)) return 1;
-    if (launch_eval_counts(net->d_probs, eb, cur, h, w, K, class_weights ? d_cw : nullptr, d_cnt + (size_t)i0 * 3 * K,
+    if (forward(net, S0.d_img, dtype, cur, h, w, S0.d_probs, nullptr, net->stream)) return 1;
+    if (launch_eval_counts(S0.d_probs, eb, cur, h, w, K, class_weights ? d_cw : nullptr, d_cnt + (size_t)i0 * 3 * K,
                            d_loss + i0, net->stream))
       return 1;
     ++net->launches;
@@ -798,9 +884,29 @@ int32_t octseg_evaluate_host(octseg_net *net, const void *images, int32_t dtype,
   return rc;
 }
 
+// Asynchronous pair of octseg_predict_maps_host for pipelining consecutive batches: submit() only enqueues (host
+// buffers must be PINNED and stay valid until the matching wait()); at most two calls may be in flight.
+int32_t octseg_predict_maps_submit(octseg_net *net, const void *images, int32_t dtype, int32_t n, int32_t h, int32_t w,
+                                   int32_t bg_ilm, int32_t bg_csi, int32_t transposed, uint8_t *labels, uint8_t *maps,
+                                   int32_t *ticket) {
+  if (!net || !images || !maps || !ticket) { set_error("null argument"); return 1; }
+  const int si = net->next_slot;
+  net->next_slot ^= 1;
+  if (predict_enqueue(net, si, images, dtype, n, h, w, nullptr, labels, maps, bg_ilm, bg_csi, transposed, true)) return 1;
+  *ticket = si;
+  return 0;
+}
+
+int32_t octseg_predict_wait(octseg_net *net, int32_t ticket) {
+  if (!net || ticket < 0 || ticket > 1) { set_error("bad ticket"); return 1; }
+  return predict_wait(net, ticket);
+}
+
 int32_t octseg_synchronize(octseg_net *net) {
   if (!net) { set_error("null argument"); return 1; }
   OCTSEG_CUDA(cudaSetDevice(net->device));
+  for (int si = 0; si < 2; ++si)
+    if (predict_wait(net, si)) return 1;
   return check_status(net);
 }
 

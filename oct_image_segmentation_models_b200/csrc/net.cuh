@@ -88,16 +88,30 @@ struct octseg_net {
   void *ws = nullptr;
   size_t ws_bytes = 0;
   std::vector<octseg::BlockIO> io;
-  // host-call staging
-  void *d_img = nullptr; size_t d_img_bytes = 0;
-  float *d_probs = nullptr; size_t d_probs_bytes = 0;
-  uint8_t *d_labels = nullptr; size_t d_labels_bytes = 0;
-  uint8_t *d_maps = nullptr; size_t d_maps_bytes = 0;
+  // host-call staging: two slots, so that the H2D of one call overlaps the forward / D2H of the previous one
+  // (octseg_predict_maps_submit / octseg_predict_wait); the synchronous entry points use them alternately too
+  struct HostSlot {
+    void *d_img = nullptr; size_t d_img_bytes = 0;
+    float *d_probs = nullptr; size_t d_probs_bytes = 0;
+    uint8_t *d_labels = nullptr; size_t d_labels_bytes = 0;
+    uint8_t *d_maps = nullptr; size_t d_maps_bytes = 0;
+    std::vector<cudaEvent_t> ev;          // per chunk: H2D done, forward done
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_status = nullptr;
+    int *h_status = nullptr;              // pinned snapshot of the status words after this call's last forward
+    bool busy = false;
+    // arguments of the call in flight (re-run on the CUDA-core path if the fp16-pair range overflowed)
+    const void *images = nullptr; int dtype = 0, n = 0, h = 0, w = 0;
+    float *probs = nullptr; uint8_t *labels = nullptr, *maps = nullptr; int bg_ilm = 0, bg_csi = 0, transposed = 0;
+    bool pipelined = false;
+  } slot[2];
+  int next_slot = 0;
   void *d_eval = nullptr; size_t d_eval_bytes = 0;      // octseg_evaluate_host: true labels, counts, loss sums, class weights
   int *d_status = nullptr;            // [0] pipeline time-out code, [1] fp16-pair range overflow (split mode)
   int *h_status = nullptr;            // pinned, 2 ints
   // fp32 mode: 0 = tensor cores on error-compensated fp16 pairs where the shape allows (default), 1 = CUDA cores
   // (env OCTSEG_FP32_PATH=cuda, or set for good once an activation left the fp16 range)
+  cudaStream_t last_train_stream = nullptr;   // caller stream of the last octseg_train_step_device (parameters are written there)
+  cudaEvent_t ev_derived = nullptr;           // folded BN / packed weights ready (recorded on `stream`)
   int fp32_path = 0;
   bool ws_split = false;              // the planned workspace uses the split layout
   int64_t launches = 0;
@@ -105,7 +119,6 @@ struct octseg_net {
   bool disable_fusion = false;
   int microbatch = 0;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host-API pipeline: H2D / D2H beside the compute stream
-  std::vector<cudaEvent_t> pipe_events;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;   // blocks+1 events
   bool prof_valid = false;

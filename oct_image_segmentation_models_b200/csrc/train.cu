@@ -116,6 +116,8 @@ struct TrainState {
   TcPackJob *d_pack_jobs = nullptr; // all tensor-core weight images of the net, packed in one launch per step
   int n_pack_jobs = 0;
   void *img_blocked = nullptr;      // stem input as a 1-plane blocked tensor
+  float *d_wg_scratch = nullptr;    // split-K partial sums of the tcgen05 weight gradient (wgrad_tc.cu)
+  size_t wg_scratch_floats = 0;
   void *up_scratch = nullptr;       // materialised x2-upsampled input of an up-conv (weight-gradient stream)
   void *dup_scratch = nullptr;      // gradient wrt the upsampled tensor (main stream), then 2x2 sum-pooled
   void *mask = nullptr;             // dropout multiplier tensor at the bottleneck
@@ -191,7 +193,18 @@ template <typename T>
 static int wgrad_dispatch(octseg_net *net, View<const T> a_in, View<const T> dz, int kh, int kw, int pt, int pl, int ups,
                           int cin, int cout, float *dW, float *db, cudaStream_t st) {
   if constexpr (sizeof(T) == 2) {
-    if (!net->disable_tc) return launch_wgrad_mma(a_in, dz, kh, kw, pt, pl, ups, cin, cout, dW, db, net->d_status, st);
+    if (!net->disable_tc) {
+      TrainState *S = reinterpret_cast<TrainState *>(net->train);
+      // >= 64 input channels, dense tensors: tcgen05 with MN-major operands and a deterministic split-K reduction
+      static const bool tc_off = []() { const char *e = std::getenv("OCTSEG_WGRAD_TC"); return e && e[0] == '0'; }();
+      if (!tc_off && S && S->d_wg_scratch && wgrad_tc_applicable(kh, kw, cin, cout, ups, dz.h, dz.w) &&
+          a_in.h == dz.h && a_in.w == dz.w && a_in.img_stride == (long long)a_in.planes * a_in.h * a_in.w * 8 &&
+          dz.img_stride == (long long)dz.planes * dz.h * dz.w * 8 &&
+          (size_t)wgrad_tc_scratch_floats(kh, kw, cin, cout, dz.n, dz.h, dz.w) <= S->wg_scratch_floats)
+        return launch_wgrad_tc(a_in, dz, kh, kw, pt, pl, cin, cout, dW, db, S->d_wg_scratch, S->wg_scratch_floats,
+                               net->d_status, st);
+      return launch_wgrad_mma(a_in, dz, kh, kw, pt, pl, ups, cin, cout, dW, db, net->d_status, st);
+    }
   }
   return launch_wgrad<T>(a_in, dz, kh, kw, pt, pl, ups, cin, cout, dW, db, st);
 }
@@ -257,6 +270,20 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
   S->dup_scratch = base + o_dup;
   S->mask = base + o_mask;
   S->n = n; S->h = h; S->w = w;
+  if (net->precision == OCTSEG_BF16 && !net->disable_tc) {
+    size_t need = 0;
+    for (auto &b : net->blocks) {
+      if (b.role == 4 || b.index == 0) continue;
+      // the up-conv's weight gradient runs on the materialised x2 tensor, i.e. on this block's OUTPUT grid
+      need = std::max(need, wgrad_tc_scratch_floats(b.kh, b.kw, b.cin, b.cout, n, h >> b.level, w >> b.level));
+    }
+    if (need > S->wg_scratch_floats) {
+      if (S->d_wg_scratch) OCTSEG_CUDA(cudaFree(S->d_wg_scratch));
+      S->d_wg_scratch = nullptr;
+      OCTSEG_CUDA(cudaMalloc(&S->d_wg_scratch, need * sizeof(float)));
+      S->wg_scratch_floats = need;
+    }
+  }
   // ---- tensor-core plans (bf16): z = conv(in)+bias and d(in) = conv(dz, W^T flipped)
   for (auto &b : net->blocks) {
     if (b.role == 4) continue;
@@ -656,6 +683,16 @@ static int debug_backward_t(octseg_net *net, const BlockSpec &b, const float *a_
   const int pt = (b.kh - 1) / 2, pl = (b.kw - 1) / 2;
   const float *P = net->d_params;
   int rc = 0;
+  if (sizeof(T) == 2 && !net->disable_tc) {     // scratch of the tcgen05 weight gradient for THIS shape
+    const size_t need = wgrad_tc_scratch_floats(b.kh, b.kw, b.cin, b.cout, n, oh, ow);
+    if (need > S->wg_scratch_floats) {
+      OCTSEG_CUDA(cudaStreamSynchronize(st));
+      if (S->d_wg_scratch) OCTSEG_CUDA(cudaFree(S->d_wg_scratch));
+      S->d_wg_scratch = nullptr;
+      OCTSEG_CUDA(cudaMalloc(&S->d_wg_scratch, need * sizeof(float)));
+      S->wg_scratch_floats = need;
+    }
+  }
   // ---- weight gradient (same dispatch as train_step_t)
   if (b.ups && sizeof(T) == 2 && !net->disable_tc) {
     OCTSEG_CUDA(cudaMalloc(&d_up, (size_t)n * b.cin * oh * ow * sizeof(T)));
@@ -760,7 +797,7 @@ void octseg_train_free(octseg_net *net) {
   for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); cudaFree(t.wpack_dgrad); cudaFree(t.wpack_dgrad2); }
   cudaFree(S->d_class_w); cudaFree(S->d_grads); cudaFree(S->d_m); cudaFree(S->d_v); cudaFree(S->d_ones); cudaFree(S->d_zeros);
   cudaFree(S->d_sums); cudaFree(S->d_loss); cudaFree(S->d_stem_tmp); cudaFree(S->ws); cudaFree(S->d_img);
-  cudaFree(S->d_labels); cudaFree(S->d_mask_in); cudaFree(S->d_pack_jobs); cudaFree(S->d_state);
+  cudaFree(S->d_labels); cudaFree(S->d_mask_in); cudaFree(S->d_pack_jobs); cudaFree(S->d_state); cudaFree(S->d_wg_scratch);
   if (S->graph_exec) cudaGraphExecDestroy(S->graph_exec);
   if (S->h_loss) cudaFreeHost(S->h_loss);
   delete S;
@@ -880,6 +917,7 @@ int32_t octseg_train_step_device(octseg_net *net, const void *images, int32_t dt
   if (n <= 0 || h <= 0 || w <= 0) { set_error("bad batch shape"); return 1; }
   OCTSEG_CUDA(cudaSetDevice(net->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : net->stream;
+  net->last_train_stream = st;
   if (ensure_train_workspace(net, n, h, w)) return 1;
   auto run_eager = [&](bool with_tail) -> int {
     int rc = net->precision == OCTSEG_BF16

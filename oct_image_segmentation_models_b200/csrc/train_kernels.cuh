@@ -78,6 +78,14 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
                      int pad_left, int ups, int cin, int cout, float *dW, float *db, int *status,
                      cudaStream_t st);
 
+// tcgen05 weight gradient for dense layers with >= 64 input channels (csrc/wgrad_tc.cu): MN-major UMMA operands straight
+// from the blocked tiles, accumulators in TMEM, deterministic split-K reduction through `scratch`
+bool wgrad_tc_applicable(int kh, int kw, int cin, int cout, int ups, int h, int w);
+size_t wgrad_tc_scratch_floats(int kh, int kw, int cin, int cout, int n, int h, int w);
+int launch_wgrad_tc(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> dz, int kh, int kw, int pad_top, int pad_left,
+                    int cin, int cout, float *dW, float *db, float *scratch, size_t scratch_floats, int *status,
+                    cudaStream_t st);
+
 // raw image -> blocked T tensor with 8 channels (channel c < cin = x/255, rest 0)
 template <typename T>
 int launch_image_to_blocked(const void *img, int img_dtype, int n, int h, int w, int cin, T *out,

@@ -111,6 +111,22 @@ class UNetEngine:
                                                      int(transposed), _ptr(labels), _ptr(maps)))
         return labels, maps
 
+    def predict_maps_submit(self, images: np.ndarray, labels_out: np.ndarray, maps_out: np.ndarray, bg_ilm: bool = True,
+                            bg_csi: bool = False, transposed: bool = False) -> int:
+        """Asynchronous predict_maps on PINNED, C-contiguous host arrays (uint8 images [N,H,W,C]): enqueues the call and
+        returns a ticket for predict_wait().  Submit batch i+1 before waiting for batch i to overlap its upload with the
+        forward and the download of batch i; at most two calls in flight; the arrays must stay alive until the wait."""
+        if images.dtype != np.uint8 or not images.flags.c_contiguous or not labels_out.flags.c_contiguous or not maps_out.flags.c_contiguous:
+            raise ValueError("predict_maps_submit needs C-contiguous uint8 arrays")
+        n, h, w, _ = images.shape
+        t = C.c_int32()
+        nat.check(self._lib.octseg_predict_maps_submit(self._h, _ptr(images), nat.U8, n, h, w, int(bg_ilm), int(bg_csi),
+                                                       int(transposed), _ptr(labels_out), _ptr(maps_out), C.byref(t)))
+        return int(t.value)
+
+    def predict_wait(self, ticket: int):
+        nat.check(self._lib.octseg_predict_wait(self._h, int(ticket)))
+
     def predict_preprocessed(self, x32: np.ndarray) -> np.ndarray:
         """x32: float32 [N,H,W,C] already divided by 255 on the host (the reference's
         preprocess_input_fn output after Keras' float32 cast)."""

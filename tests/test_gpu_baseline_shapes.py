@@ -142,3 +142,25 @@ def test_two_gpu_data_parallel_training_parity():
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "PASS" in out.stdout, out.stdout[-2000:]
+
+
+def test_two_handles_in_one_process_on_two_devices():
+    """include/octseg.h allows one process to drive several GPUs (one handle per device): kernel attributes such as
+    the dynamic shared-memory limit are per-device settings and must be applied on each.  Skips with one GPU."""
+    from oct_image_segmentation_models_b200 import _native as nat
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    if nat.load().octseg_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    w = synthetic_weights(seed=42, **CFG)
+    imgs, labs = synthetic_batch(3, 2, 256, 128)
+    outs = []
+    for dev in (1, 0):                   # device 1 FIRST: a process-wide "attribute already set" flag would break it
+        eng = UNetEngine(precision="bf16", device=dev, **CFG)
+        eng.set_weights(w)
+        p, _ = eng.predict(imgs)
+        eng.train_begin([0.5, 1.0, 2.0, 1.0], dropout_rate=0.0, global_batch=2)
+        loss = eng.train_step(imgs, labs)
+        outs.append((p, loss))
+        eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert abs(outs[0][1] - outs[1][1]) <= 1e-3 * abs(outs[1][1])

@@ -333,3 +333,31 @@ def test_config_sweep_all_precisions_vs_oracle(cfg, n, h, w):
         _, cat = postproc.perform_argmax(p)
         assert np.array_equal(maps, postproc.convert_predictions_to_maps_semantic(cat, bg_ilm=True, bg_csi=False))
         eng.close()
+
+
+def test_predict_maps_submit_wait_pipeline_equals_blocking_call(engines):
+    """octseg_predict_maps_submit / octseg_predict_wait (two staging slots, up to two batches in flight) must return the
+    bytes of the blocking call, in any interleaving, incl. a third submit that has to drain the oldest slot first."""
+    import torch
+    _, e32, e16 = engines
+    batches = [synthetic_batch(60 + 7 * i, 5, 64, 96)[0] for i in range(4)]
+    for eng in (e16, e32):
+        want = [eng.predict_maps(b) for b in batches]
+        pins = [torch.from_numpy(b).pin_memory() for b in batches]
+        labs = [torch.empty((5, 64, 96), dtype=torch.uint8).pin_memory() for _ in batches]
+        maps = [torch.empty((5, 3, 64, 96), dtype=torch.uint8).pin_memory() for _ in batches]
+        tickets = []
+        for i in range(4):
+            tickets.append(eng.predict_maps_submit(pins[i].numpy(), labs[i].numpy(), maps[i].numpy()))
+            if i >= 1:
+                eng.predict_wait(tickets[i - 1])
+        eng.predict_wait(tickets[-1])
+        eng.predict_wait(tickets[-1])                       # waiting twice is harmless
+        for i in range(4):
+            assert np.array_equal(labs[i].numpy(), want[i][0]) and np.array_equal(maps[i].numpy(), want[i][1]), i
+        # three submits without a wait: the third drains slot 0 internally
+        t = [eng.predict_maps_submit(pins[i].numpy(), labs[i].numpy(), maps[i].numpy()) for i in range(3)]
+        eng.synchronize()
+        assert t[0] == t[2] != t[1]
+        for i in range(3):
+            assert np.array_equal(maps[i].numpy(), want[i][1])
