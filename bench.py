@@ -124,6 +124,25 @@ def bench_config(n):
             "sharding": "B-scans sharded across ranks, no collective"}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `index`, so that the pinned staging buffers it
+    allocates next live on that GPU's NUMA node (with 8 ranks, 8 x 84 MB per step through ONE node's memory
+    controller and PCIe root was what capped the round-1 host-buffer numbers).  Best effort: returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, wv in enumerate(words) for b in range(64) if (wv >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} cores local to GPU {index}"
+        return "no local cores inside the allowed set"
+    except Exception as ex:  # noqa: BLE001
+        return f"not bound ({type(ex).__name__})"
+
+
 def host_threads():
     """Host cores this process may use (affinity mask, not the machine total: containers are often pinned)."""
     try:
@@ -298,6 +317,82 @@ def bench_wide(args, rank, local_rank, world, torch, dist, stream):
     return res
 
 
+def bench_cfg5(args, rank, local_rank, world, torch, dist):
+    """BASELINE configs[4]: end-to-end evaluation -- GPU predict (exact fp32 mode) + argmax + boundary maps on the device,
+    then the reference's min-path boundary extraction (native C++, host cores) on 10 000 synthetic 512x512 B-scans
+    sharded over the ranks; boundary agreement with the CPU oracle chain on the 256 golden B-scans.  The 10 000
+    B-scans are the 256 DISTINCT golden B-scans repeated (generating 10 000 distinct ones costs ~2 minutes of host
+    time); every one is uploaded, predicted, downloaded and searched."""
+    import concurrent.futures as cf
+    from oct_image_segmentation_models_b200.common.synthetic import synthetic_batch
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    from oct_image_segmentation_models_b200.min_path_processing import graph_search
+    gdir = ROOT / "tests" / "golden"
+    wz = np.load(gdir / "trained_default_unet_weights.npz")
+    gold = np.load(gdir / "trained_default_unet_golden.npz")
+    weights = [wz[f"w{i:03d}"] for i in range(len(wz.files))]
+    total, distinct, bs = int(os.environ.get("OCTSEG_CFG5_N", "10000")), 256, 64
+    per_rank = (total + world - 1) // world
+    n_batches = (per_rank + bs - 1) // bs
+    imgs, _ = synthetic_batch(0, distinct, H, W)
+    pin = [torch.from_numpy(imgs[i:i + bs]).pin_memory() for i in range(0, distinct, bs)]
+    labs = [torch.empty((bs, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    maps = [torch.empty((bs, K_CLASSES - 1, W, H), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    eng = UNetEngine(precision="fp32", device=local_rank, **CFG)
+    eng.set_weights(weights)
+    threads = max(1, host_threads() if world == 1 else (os.cpu_count() or 1) // world)
+    seg_first = {}          # boundaries / labels of the first pass over the distinct B-scans (rank 0 checks them)
+
+    def search(b, m, l):
+        segs = graph_search.segment_maps(m.reshape(-1, W, H), None, None, n_threads=threads)[0].reshape(bs, K_CLASSES - 1, W)
+        if b < len(pin):
+            seg_first[b] = (segs, l.copy())
+        return segs.shape[0]
+
+    for b in range(2):      # warm-up (plans, pinned staging)
+        eng.predict_wait(eng.predict_maps_submit(pin[b % len(pin)].numpy(), labs[b % 2].numpy(), maps[b % 2].numpy(), transposed=True))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(max_workers=1) as pool:
+        futs, tickets = {}, {}
+
+        def finish(b):      # download of batch b complete -> boundary search on the host while the GPU runs b+1
+            eng.predict_wait(tickets[b])
+            futs[b] = pool.submit(search, b, maps[b % 2].numpy(), labs[b % 2].numpy() if b < len(pin) else None)
+
+        for b in range(n_batches):
+            if b >= 2:
+                futs.pop(b - 2).result()        # its host buffers (b % 2) are free again
+            tickets[b] = eng.predict_maps_submit(pin[b % len(pin)].numpy(), labs[b % 2].numpy(), maps[b % 2].numpy(),
+                                                 transposed=True)
+            if b >= 1:
+                finish(b - 1)
+        finish(n_batches - 1)
+        for f in futs.values():
+            f.result()
+    dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    done = world * n_batches * bs
+    out = {"metric": "e2e_eval_bscans_per_sec", "value": done / float(dt.item()), "unit": UNIT, "bscans": done,
+           "seconds": float(dt.item()), "dtype": "fp32", "min_path_threads_per_rank": threads,
+           "config": {"workload": "BASELINE configs[4]: predict (fp32 mode on tcgen05) + device argmax / boundary maps + "
+                                  "reference min-path (native C++) on 10 000 synthetic 512x512 B-scans (256 distinct, "
+                                  "repeated), sharded over the ranks; every B-scan uploaded, predicted, downloaded, searched",
+                      "scaling": "strong"}}
+    if rank == 0 and len(seg_first) == len(pin):
+        segs = np.concatenate([seg_first[b][0] for b in range(len(pin))])
+        labels = np.concatenate([seg_first[b][1] for b in range(len(pin))])
+        d = np.abs(segs.astype(np.int32) - gold["segs"].astype(np.int32))
+        out["vs_cpu_oracle_chain"] = {"bscans": distinct, "argmax_agreement": float((labels == gold["labels"]).mean()),
+                                      "boundary_positions_identical": float((d == 0).mean()), "max_row_delta": int(d.max()),
+                                      "bscans_fully_identical": int((d.reshape(distinct, -1).max(1) == 0).sum())}
+    eng.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -310,6 +405,7 @@ def main():
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-wide", action="store_true")
     ap.add_argument("--no-fp32", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true")
     ap.add_argument("--train-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -329,6 +425,8 @@ def main():
     from oct_image_segmentation_models_b200.engine import UNetEngine
 
     torch.cuda.set_device(local_rank)
+    all_cores = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation: first touch decides the NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -557,9 +655,18 @@ def main():
         except Exception as ex:  # noqa: BLE001
             wide = {"error": str(ex)[:300]}
 
+    # ---------------- end-to-end evaluation with boundary extraction (BASELINE configs[4]) ----------------
+    cfg5 = None
+    if not args.no_cfg5:
+        try:
+            cfg5 = bench_cfg5(args, rank, local_rank, world, torch, dist)
+        except Exception as ex:  # noqa: BLE001
+            cfg5 = {"error": str(ex)[:300]}
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cores)          # the CPU arm gets every host core again
         threads = host_threads()
         v, secs, done = CpuReference(4, threads).run(480)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
@@ -570,7 +677,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": bench_config(n),
+                "config": bench_config(n), "numa_binding": numa,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_np.nbytes),
                         "d2h_bytes_per_step": int(l_np.nbytes + m_np.nbytes), "steps": e2e_steps,
                         "api": "octseg_predict_maps_submit / octseg_predict_wait, two batches in flight: uint8 B-scans in "
@@ -583,7 +690,7 @@ def main():
                               "d2h_bytes_per_step": int(p_np.nbytes), "steps": e2e_steps, "checksum": checksum,
                               "api": "octseg_predict_host: model.predict() drop-in, fp32 probabilities out"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "roofline_step": roofline_step, "fp32": fp32, "cpu_baseline": cpu, "train": train, "wide_net": wide,
+                "roofline_step": roofline_step, "fp32": fp32, "cpu_baseline": cpu, "train": train, "wide_net": wide, "cfg5": cfg5,
                 "block_ms": [round(float(x), 4) for x in per_block]}
         print(json.dumps(line))
     eng.close()
