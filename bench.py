@@ -317,6 +317,56 @@ def bench_wide(args, rank, local_rank, world, torch, dist, stream):
     return res
 
 
+def bench_wide_train(args, rank, local_rank, world, torch, dist, stream):
+    """Train step of the BASELINE configs[3] network (wide U-Net, 64..1024 channels) on 1024x512x1 B-scans, 4 per GPU:
+    forward, data gradient and weight gradient of every conv after the stem on tcgen05."""
+    from oct_image_segmentation_models_b200 import _native as nat
+    from oct_image_segmentation_models_b200 import parallel
+    from oct_image_segmentation_models_b200.common.synthetic import fast_random_batch, synthetic_weights
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    from oct_image_segmentation_models_b200.models.unet_spec import unet_blocks
+    cfg = dict(input_channels=1, num_classes=K_CLASSES, start_neurons=64)
+    n, h, w = 4, 1024, 512
+    eng = UNetEngine(precision="bf16", device=local_rank, **cfg)
+    eng.set_weights(synthetic_weights(seed=4, random_bn_stats=False, **cfg))
+    eng.train_begin([0.5, 1.0, 2.0, 1.0], learning_rate=1e-3, dropout_rate=0.5, dropout_seed=77 + rank, global_batch=n * world)
+    parallel.init_training_comm(eng, dist)
+    imgs = torch.from_numpy(fast_random_batch(31 + rank, n, h, w)).cuda()
+    labs = torch.from_numpy(np.random.default_rng(3 + rank).integers(0, K_CLASSES, size=(n, h, w), dtype=np.uint8)).cuda()
+    loss = torch.zeros(1, dtype=torch.float32, device="cuda")
+
+    def step():
+        eng.train_step_device(imgs.data_ptr(), nat.U8, labs.data_ptr(), n, h, w, loss.data_ptr(), stream)
+    for _ in range(3):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    blocks = unet_blocks(**cfg)
+    fwd = sum(2.0 * (h >> b.level) * (w >> b.level) * b.cin * b.cout * b.kh * b.kw for b in blocks)
+    flops = (3.0 * fwd - 2.0 * h * w * blocks[0].cin * blocks[0].cout * 9) * n      # fwd + dgrad + wgrad, no dgrad for the stem
+    eng.synchronize()
+    out = {"metric": "wide_unet_train_samples_per_sec", "value": world * n / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms,
+           "tflops": flops / (ms / 1e3) / 1e12, "final_loss": float(loss.item()),
+           "config": {"workload": "wide U-Net (base 64 filters, 5 levels) train step (fwd+bwd+Adam, weighted CE), 1024x512x1, "
+                                  "4 samples per GPU", "scaling": "weak"}}
+    eng.close()
+    return out
+
+
 def bench_cfg5(args, rank, local_rank, world, torch, dist):
     """BASELINE configs[4]: end-to-end evaluation -- GPU predict (exact fp32 mode) + argmax + boundary maps on the device,
     then the reference's min-path boundary extraction (native C++, host cores) on 10 000 synthetic 512x512 B-scans
@@ -655,6 +705,13 @@ def main():
         except Exception as ex:  # noqa: BLE001
             wide = {"error": str(ex)[:300]}
 
+    wide_train = None
+    if not args.no_wide:
+        try:
+            wide_train = bench_wide_train(args, rank, local_rank, world, torch, dist, stream)
+        except Exception as ex:  # noqa: BLE001
+            wide_train = {"error": str(ex)[:300]}
+
     # ---------------- end-to-end evaluation with boundary extraction (BASELINE configs[4]) ----------------
     cfg5 = None
     if not args.no_cfg5:
@@ -690,7 +747,7 @@ def main():
                               "d2h_bytes_per_step": int(p_np.nbytes), "steps": e2e_steps, "checksum": checksum,
                               "api": "octseg_predict_host: model.predict() drop-in, fp32 probabilities out"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "roofline_step": roofline_step, "fp32": fp32, "cpu_baseline": cpu, "train": train, "wide_net": wide, "cfg5": cfg5,
+                "roofline_step": roofline_step, "fp32": fp32, "cpu_baseline": cpu, "train": train, "wide_net": wide, "wide_net_train": wide_train, "cfg5": cfg5,
                 "block_ms": [round(float(x), 4) for x in per_block]}
         print(json.dumps(line))
     eng.close()

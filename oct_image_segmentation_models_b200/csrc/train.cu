@@ -116,6 +116,8 @@ struct TrainState {
   TcPackJob *d_pack_jobs = nullptr; // all tensor-core weight images of the net, packed in one launch per step
   int n_pack_jobs = 0;
   void *img_blocked = nullptr;      // stem input as a 1-plane blocked tensor
+  float *d_dlog = nullptr;          // [n*h*w][K] dlogits of heads with more than 16 input channels (two-pass head)
+  size_t dlog_floats = 0;
   float *d_wg_scratch = nullptr;    // split-K partial sums of the tcgen05 weight gradient (wgrad_tc.cu)
   size_t wg_scratch_floats = 0;
   void *up_scratch = nullptr;       // materialised x2-upsampled input of an up-conv (weight-gradient stream)
@@ -270,6 +272,15 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
   S->dup_scratch = base + o_dup;
   S->mask = base + o_mask;
   S->n = n; S->h = h; S->w = w;
+  if (net->blocks.back().cin > 16 || (net->blocks.back().cin == 16 && net->cfg.num_classes > 8)) {
+    const size_t need = (size_t)n * h * w * net->cfg.num_classes;
+    if (need > S->dlog_floats) {
+      if (S->d_dlog) OCTSEG_CUDA(cudaFree(S->d_dlog));
+      S->d_dlog = nullptr;
+      OCTSEG_CUDA(cudaMalloc(&S->d_dlog, need * sizeof(float)));
+      S->dlog_floats = need;
+    }
+  }
   if (net->precision == OCTSEG_BF16 && !net->disable_tc) {
     size_t need = 0;
     for (auto &b : net->blocks) {
@@ -495,7 +506,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     const float inv_den = 1.0f / ((float)S->tc.global_batch * (float)h * (float)w);
     if (launch_head_loss<T>(a, P + net->params[head.p_kernel].offset, P + net->params[head.p_bias].offset, head.cin,
                             head.cout, d_labels, S->d_class_w, inv_den, da, G + net->params[head.p_kernel].offset,
-                            G + net->params[head.p_bias].offset, S->d_loss, st))
+                            G + net->params[head.p_bias].offset, S->d_loss, S->d_dlog, st))
       return 1;
     ++net->launches;
   }
@@ -797,7 +808,7 @@ void octseg_train_free(octseg_net *net) {
   for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); cudaFree(t.wpack_dgrad); cudaFree(t.wpack_dgrad2); }
   cudaFree(S->d_class_w); cudaFree(S->d_grads); cudaFree(S->d_m); cudaFree(S->d_v); cudaFree(S->d_ones); cudaFree(S->d_zeros);
   cudaFree(S->d_sums); cudaFree(S->d_loss); cudaFree(S->d_stem_tmp); cudaFree(S->ws); cudaFree(S->d_img);
-  cudaFree(S->d_labels); cudaFree(S->d_mask_in); cudaFree(S->d_pack_jobs); cudaFree(S->d_state); cudaFree(S->d_wg_scratch);
+  cudaFree(S->d_labels); cudaFree(S->d_mask_in); cudaFree(S->d_pack_jobs); cudaFree(S->d_state); cudaFree(S->d_wg_scratch); cudaFree(S->d_dlog);
   if (S->graph_exec) cudaGraphExecDestroy(S->graph_exec);
   if (S->h_loss) cudaFreeHost(S->h_loss);
   delete S;

@@ -154,12 +154,16 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(
   const T *zb = z.ptr + (long long)img * z.img_stride + (long long)pl * hw * 8;
   T *ab = a.ptr + (long long)img * a.img_stride + (long long)pl * hw * 8;
   const T *mb = mask ? mask + ((long long)img * z.planes + pl) * hw * 8 : nullptr;
+  // the 8 channels of this plane: computed once per block (double math + rsqrt), broadcast through shared memory
+  __shared__ float s_sc[8], s_sh[8];
+  if (threadIdx.x < 8) {
+    const BnChan b = bn_channel(sums, c, pl * 8 + threadIdx.x, inv_count, eps, gamma, beta);
+    s_sc[threadIdx.x] = b.scale; s_sh[threadIdx.x] = b.shift;
+  }
+  __syncthreads();
   float sc[8], sh[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const BnChan b = bn_channel(sums, c, pl * 8 + k, inv_count, eps, gamma, beta);
-    sc[k] = b.scale; sh[k] = b.shift;
-  }
+  for (int k = 0; k < 8; ++k) { sc[k] = s_sc[k]; sh[k] = s_sh[k]; }
   if constexpr (POOL == 0) {
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < hw; v += gridDim.x * blockDim.x) {
       Vec8f x = load8(zb + (long long)v * 8);
@@ -202,11 +206,11 @@ int launch_bn_finalize_apply(View<const T> z, const double *sums, long long coun
   const int hw = z.h * z.w;
   if (pooled.ptr) {
     if (mask || (z.h & 1) || (z.w & 1)) { set_error("bn_finalize_apply: pooled variant needs even dims and no dropout"); return 1; }
-    dim3 grid(std::max(1, std::min((hw / 4 + 255) / 256, 64)), z.planes, z.n);
+    dim3 grid(std::max(1, std::min((hw / 4 + 2047) / 2048, 64)), z.planes, z.n);     // >= 8 windows (32 vectors) per thread
     bn_finalize_apply_kernel<T, 1><<<grid, 256, 0, st>>>(z, sums, count, eps, momentum, gamma, beta, moving_mean, moving_var,
                                                          mean, invstd, scale, shift, mask, a, pooled);
   } else {
-    dim3 grid(std::max(1, std::min((hw + 1023) / 1024, 64)), z.planes, z.n);
+    dim3 grid(std::max(1, std::min((hw + 4095) / 4096, 64)), z.planes, z.n);         // >= 16 vectors per thread
     bn_finalize_apply_kernel<T, 0><<<grid, 256, 0, st>>>(z, sums, count, eps, momentum, gamma, beta, moving_mean, moving_var,
                                                          mean, invstd, scale, shift, mask, a, pooled);
   }
@@ -410,22 +414,169 @@ static int launch_head_loss_kp(View<const T> a, const float *wgt, const float *b
   return 0;
 }
 
+// ---------------------------------------------------------------------------------
+// Generic head (any channel count): the register-resident d(head weights) of head_loss_kernel does not scale past 16
+// input channels, so wide heads run two passes: (A) logits / softmax / loss / dlogits -> scratch, d(input), d(bias);
+// (B) d(weights)[ci][k] = sum_px a[px][ci] * dlogit[px][k], one block column per input plane.
+// ---------------------------------------------------------------------------------
+template <typename T, int K>
+__global__ void __launch_bounds__(256) head_loss_wide_kernel(View<const T> a, const float *__restrict__ wgt,
+                                                             const float *__restrict__ bias, int cin,
+                                                             const uint8_t *__restrict__ labels,
+                                                             const float *__restrict__ class_w, float inv_den, View<T> da,
+                                                             float *__restrict__ dlog, float *__restrict__ d_bias,
+                                                             double *loss_acc) {
+  extern __shared__ float s_w[];      // [cin][K] + bias[K] + class_w[K]
+  for (int i = threadIdx.x; i < cin * K; i += blockDim.x) s_w[i] = wgt[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) { s_w[cin * K + i] = bias[i]; s_w[cin * K + K + i] = class_w[i]; }
+  __syncthreads();
+  const float *s_b = s_w + cin * K, *s_cw = s_b + K;
+  const int planes = cin / 8;
+  const long long hw = (long long)a.h * a.w, total = (long long)a.n * hw;
+  float p_db[K], p_loss = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) p_db[k] = 0.f;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+    const long long off = pix % hw;
+    const int b = (int)(pix / hw);
+    float z[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) z[k] = s_b[k];
+    for (int pl = 0; pl < planes; ++pl) {
+      const Vec8f v = load8(a.ptr + b * a.img_stride + ((long long)pl * hw + off) * 8);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int k = 0; k < K; ++k) z[k] = fmaf(v.v[c], s_w[(pl * 8 + c) * K + k], z[k]);
+    }
+    float mx = z[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) mx = fmaxf(mx, z[k]);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { z[k] = expf(z[k] - mx); s += z[k]; }
+    const float inv = 1.f / s;
+    float S = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { z[k] *= inv; S += z[k]; }
+    const int t = labels[pix];
+    float pt = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { z[k] = z[k] / S; if (k == t) pt = z[k]; }
+    const float wt = (t < K) ? s_cw[t] : 0.f;
+    const bool active = (pt >= 1e-7f) && (pt <= 1.f - 1e-7f);
+    p_loss += -wt * logf(fminf(fmaxf(pt, 1e-7f), 1.f - 1e-7f)) * inv_den;
+    float dl[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      dl[k] = active ? wt * (z[k] - (k == t ? 1.f : 0.f)) * inv_den : 0.f;
+      p_db[k] += dl[k];
+      dlog[pix * K + k] = dl[k];
+    }
+    for (int pl = 0; pl < planes; ++pl) {
+      Vec8f g;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc = fmaf(dl[k], s_w[(pl * 8 + c) * K + k], acc);
+        g.v[c] = acc;
+      }
+      store8(da.ptr + b * da.img_stride + ((long long)pl * hw + off) * 8, g);
+    }
+  }
+  __shared__ float s_red[8][K + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float r = warp_sum(p_db[k]);
+    if (lane == 0) s_red[warp][k] = r;
+  }
+  p_loss = warp_sum(p_loss);
+  if (lane == 0) s_red[warp][K] = p_loss;
+  __syncthreads();
+  if (threadIdx.x <= K) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += s_red[w][threadIdx.x];
+    if (threadIdx.x < K) atomicAdd(&d_bias[threadIdx.x], r);
+    else atomicAdd(loss_acc, (double)r);
+  }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(256) head_wgrad_wide_kernel(View<const T> a, const float *__restrict__ dlog,
+                                                              float *__restrict__ d_wgt) {
+  const int pl = blockIdx.y;
+  const long long hw = (long long)a.h * a.w, total = (long long)a.n * hw;
+  float p[8][K];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[c][k] = 0.f;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+    const long long off = pix % hw;
+    const int b = (int)(pix / hw);
+    const Vec8f v = load8(a.ptr + b * a.img_stride + ((long long)pl * hw + off) * 8);
+    float dl[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) dl[k] = dlog[pix * K + k];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int k = 0; k < K; ++k) p[c][k] = fmaf(v.v[c], dl[k], p[c][k]);
+  }
+  __shared__ float s_red[8][8 * K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float r = warp_sum(p[c][k]);
+      if (lane == 0) s_red[warp][c * K + k] = r;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += s_red[w][i];
+    atomicAdd(&d_wgt[(pl * 8) * K + i], r);
+  }
+}
+
+template <typename T, int K>
+static int launch_head_loss_wide(View<const T> a, const float *wgt, const float *bias, int cin, const uint8_t *labels,
+                                 const float *class_w, float inv_den, View<T> da, float *d_wgt, float *d_bias,
+                                 double *loss_acc, float *dlog_scratch, cudaStream_t st) {
+  if (!dlog_scratch) { set_error("training head with more than 16 input channels needs the dlogits scratch buffer"); return 1; }
+  const long long total = (long long)a.n * a.h * a.w;
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
+  const size_t smem = (size_t)(cin * K + 2 * K) * sizeof(float);
+  if (smem > 48 * 1024) { set_error("training head: cin * num_classes too large"); return 1; }
+  head_loss_wide_kernel<T, K><<<grid, 256, smem, st>>>(a, wgt, bias, cin, labels, class_w, inv_den, da, dlog_scratch, d_bias,
+                                                       loss_acc);
+  OCTSEG_CUDA(cudaGetLastError());
+  dim3 g2((unsigned)std::min<long long>((total + 255) / 256, 148), cin / 8);
+  head_wgrad_wide_kernel<T, K><<<g2, 256, 0, st>>>(a, dlog_scratch, d_wgt);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <typename T, int K>
 static int launch_head_loss_k(View<const T> a, const float *wgt, const float *bias, int cin, const uint8_t *labels,
                               const float *class_w, float inv_den, View<T> da, float *d_wgt, float *d_bias,
-                              double *loss_acc, cudaStream_t st) {
+                              double *loss_acc, float *dlog_scratch, cudaStream_t st) {
   if (cin == 8) return launch_head_loss_kp<T, K, 1>(a, wgt, bias, labels, class_w, inv_den, da, d_wgt, d_bias, loss_acc, st);
   if (cin == 16 && K <= 8) return launch_head_loss_kp<T, K, 2>(a, wgt, bias, labels, class_w, inv_den, da, d_wgt, d_bias, loss_acc, st);
-  set_error("training head supports start_neurons 8 (any K<=16) or 16 (K<=8); wider heads: not built yet");
-  return 1;
+  return launch_head_loss_wide<T, K>(a, wgt, bias, cin, labels, class_w, inv_den, da, d_wgt, d_bias, loss_acc, dlog_scratch, st);
 }
 
 template <typename T>
 int launch_head_loss(View<const T> a, const float *wgt, const float *bias, int cin, int K,
                      const uint8_t *labels, const float *class_w, float inv_denominator, View<T> da,
-                     float *d_wgt, float *d_bias, double *loss_acc, cudaStream_t st) {
+                     float *d_wgt, float *d_bias, double *loss_acc, float *dlog_scratch, cudaStream_t st) {
   switch (K) {
-#define HK(k) case k: return launch_head_loss_k<T, k>(a, wgt, bias, cin, labels, class_w, inv_denominator, da, d_wgt, d_bias, loss_acc, st);
+#define HK(k) case k: return launch_head_loss_k<T, k>(a, wgt, bias, cin, labels, class_w, inv_denominator, da, d_wgt, d_bias, loss_acc, dlog_scratch, st);
     HK(2) HK(3) HK(4) HK(5) HK(6) HK(7) HK(8)
 #undef HK
   }
@@ -498,12 +649,18 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
   T *ob = dz.ptr + (long long)img * dz.img_stride + (long long)pl * hw * 8;
   const T *mb = mask ? mask + ((long long)img * z.planes + pl) * hw * 8 : nullptr;
   const float inv_m = 1.f / (float)count;
+  __shared__ float s_par[6][8];
+  if (threadIdx.x < 8) {
+    const int ch = pl * 8 + threadIdx.x;
+    s_par[0][threadIdx.x] = mean[ch]; s_par[1][threadIdx.x] = invstd[ch]; s_par[2][threadIdx.x] = gamma[ch];
+    s_par[3][threadIdx.x] = beta[ch];
+    s_par[4][threadIdx.x] = (float)sums[ch] * inv_m; s_par[5][threadIdx.x] = (float)sums[c + ch] * inv_m;
+  }
+  __syncthreads();
   float mu[8], is[8], ga[8], be[8], sdy[8], sdyz[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int ch = pl * 8 + k;
-    mu[k] = mean[ch]; is[k] = invstd[ch]; ga[k] = gamma[ch]; be[k] = beta[ch];
-    sdy[k] = (float)sums[ch] * inv_m; sdyz[k] = (float)sums[c + ch] * inv_m;
+    mu[k] = s_par[0][k]; is[k] = s_par[1][k]; ga[k] = s_par[2][k]; be[k] = s_par[3][k]; sdy[k] = s_par[4][k]; sdyz[k] = s_par[5][k];
   }
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < hw; v += gridDim.x * blockDim.x) {
     const Vec8f zz = load8(zb + (long long)v * 8);
@@ -529,7 +686,7 @@ int launch_bn_bwd_apply(View<const T> da, View<const T> z, const float *mean, co
                         const float *gamma, const float *beta, const T *mask, const double *sums,
                         long long count, View<T> dz, float *d_gamma, float *d_beta, cudaStream_t st) {
   const int hw = z.h * z.w;
-  dim3 grid(std::max(1, std::min((hw + 1023) / 1024, 64)), z.planes, z.n);
+  dim3 grid(std::max(1, std::min((hw + 4095) / 4096, 64)), z.planes, z.n);           // >= 16 vectors per thread
   bn_bwd_apply_kernel<T><<<grid, 256, 0, st>>>(da, z, mean, invstd, gamma, beta, mask, sums, count, dz, d_gamma,
                                                d_beta, z.planes * 8);
   OCTSEG_CUDA(cudaGetLastError());
@@ -866,7 +1023,7 @@ int launch_adam(float *p, const float *g, float *m, float *v, long long n, const
   template int launch_dropout_mask<T>(const uint8_t *, unsigned long long, const StepState *, float, int, int, \
                                       int, int, T *, cudaStream_t);                                         \
   template int launch_head_loss<T>(View<const T>, const float *, const float *, int, int, const uint8_t *,  \
-                                   const float *, float, View<T>, float *, float *, double *, cudaStream_t); \
+                                   const float *, float, View<T>, float *, float *, double *, float *, cudaStream_t); \
   template int launch_bn_bwd_reduce<T>(View<const T>, View<const T>, const float *, const float *,          \
                                        const float *, const float *, const T *, double *, cudaStream_t);    \
   template int launch_bn_bwd_apply<T>(View<const T>, View<const T>, const float *, const float *,           \

@@ -44,7 +44,8 @@ int launch_dropout_mask(const uint8_t *mask_nhwc, unsigned long long seed, const
 template <typename T>
 int launch_head_loss(View<const T> a, const float *wgt, const float *bias, int cin, int K,
                      const uint8_t *labels, const float *class_w, float inv_denominator, View<T> da,
-                     float *d_wgt, float *d_bias, double *loss_acc, cudaStream_t st);
+                     float *d_wgt, float *d_bias, double *loss_acc, float *dlog_scratch /* [n*h*w][K], heads wider than 16 channels */,
+                     cudaStream_t st);
 
 // BN+ReLU backward, pass 1: sums of dy and dy*zhat per channel ([2*C] doubles)
 template <typename T>
