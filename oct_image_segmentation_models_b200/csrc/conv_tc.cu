@@ -620,6 +620,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int k = 0; k < HK; ++k) z[k] = s_head[p.cout * HK + k];
           }
           float amax = 0.f;
+          if (HK == 0 && p.row_mul == 2) {
+            // row pairs: this GEMM row is pixel (2r, x); logical columns [row parity][channel] -> physical groups
+            // par * (C/8) + c8.  Both parities of a channel chunk are handled together (the 2x2 max needs them).
+            const int C = p.scale_mod, cg8 = C >> 3;
+            const int yb = 2 * y;
+            const bool in0 = (yb < p.h) && (x < p.w), in1 = (yb + 1 < p.h) && (x < p.w);
+            for (int c8 = 0; c8 < cg8; ++c8) {
+              uint32_t v[2][16];
+              tmem_ld16(t_base + (uint32_t)(c8 * 16), v[0]);
+              tmem_ld16(t_base + (uint32_t)((cg8 + c8) * 16), v[1]);
+              tmem_ld_wait();
+              const int co0 = c8 * 8;
+              const float4 sa = *reinterpret_cast<const float4 *>(s_scale + co0), sb = *reinterpret_cast<const float4 *>(s_scale + co0 + 4);
+              const float4 ha = *reinterpret_cast<const float4 *>(s_shift + co0), hb = *reinterpret_cast<const float4 *>(s_shift + co0 + 4);
+              const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+              const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+              float o[2][8];
+#pragma unroll
+              for (int par = 0; par < 2; ++par)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const float val = fmaf(__uint_as_float(v[par][8 + k]), 4.8828125e-4f, __uint_as_float(v[par][k]));
+                  o[par][k] = fmaxf(fmaf(val, sc[k], sh[k]), relu_floor);
+                  amax = fmaxf(amax, fabsf(o[par][k]));
+                }
+              uint4 hi, lo;
+              __nv_bfloat16 *dst = p.out + (long long)img * p.out_img_stride + (long long)(co0 >> 2) * plane_elems +
+                                   ((long long)yb * p.out_w + x) * 8;
+              split_pack8(o[0], hi, lo);
+              if (in0) { *reinterpret_cast<uint4 *>(dst) = hi; *reinterpret_cast<uint4 *>(dst + plane_elems) = lo; }
+              split_pack8(o[1], hi, lo);
+              if (in1) {
+                *reinterpret_cast<uint4 *>(dst + (long long)p.out_w * 8) = hi;
+                *reinterpret_cast<uint4 *>(dst + (long long)p.out_w * 8 + plane_elems) = lo;
+              }
+              if (p.pool_out) {
+                float m[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  m[k] = fmaxf(o[0][k], o[1][k]);
+                  m[k] = fmaxf(m[k], __shfl_xor_sync(0xffffffffu, m[k], 1));
+                }
+                split_pack8(m, hi, lo);
+                if (in1 && !(px & 1)) {
+                  __nv_bfloat16 *pd = p.pool_out + (long long)img * p.pool_img_stride + (long long)(co0 >> 2) * (plane_elems >> 2) +
+                                      ((long long)y * (p.out_w >> 1) + (x >> 1)) * 8;
+                  *reinterpret_cast<uint4 *>(pd) = hi;
+                  *reinterpret_cast<uint4 *>(pd + (plane_elems >> 2)) = lo;
+                }
+              }
+            }
+            if ((in0 || in1) && !(amax <= 65000.f) && p.overflow) atomicOr(p.overflow, 1);
+            continue;
+          }
           for (int j = 0; j < groups; j += 2) {
             uint32_t v[2][16];
             const bool two = (j + 1 < groups);
@@ -1134,6 +1188,7 @@ int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, 
     std::vector<std::pair<int, int>> taps;
     for (int ty = 0; ty < nty; ++ty)
       for (int tx = 0; tx < ntx; ++tx) taps.push_back({ty, tx});
+    if ((int)(taps.size() + 1) / 2 > kTcMaxKSteps) return 1;
     size_t i = 0;
     if (taps.size() & 1) {
       // odd count: first step = (zero-weight dummy, tap0) is impossible (nothing before
@@ -1158,6 +1213,7 @@ int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, 
       }
     }
   } else {
+    if (nty * ntx * (g->planes_per_chunk / 2) > kTcMaxKSteps) return 1;     // would overrun the per-k-step tables
     for (int ty = 0; ty < nty; ++ty)
       for (int tx = 0; tx < ntx; ++tx)
         for (int jj = 0; jj < g->planes_per_chunk / 2; ++jj) {
@@ -1218,8 +1274,8 @@ void tc_rowpair_weights(const float *w, int cin, int cout, std::vector<float> *o
     }
 }
 
-int tc_make_geometry_split(int kh, int kw, int cin, int cout, int ups, TcGeometry *g) {
-  if (tc_make_geometry(kh, kw, 2 * cin, 2 * cout, ups, g)) return 1;
+int tc_make_geometry_split(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, int pad_top, int pad_left) {
+  if (tc_make_geometry(kh, kw, 2 * cin, 2 * cout, ups, g, pad_top, pad_left)) return 1;
   g->split = 1; g->cin_l = cin; g->cout_l = cout; g->wscale = 1.f;
   return 0;
 }
@@ -1450,10 +1506,10 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
   const int max_mt = std::max(1, 256 / g.n_cols);          // 2 accumulator stages in 512 TMEM columns
   const int tile_h = kTcTileH * (g.rows2 ? 2 : 1);          // image rows covered by one M-tile
   p.row_mul = g.rows2 ? 2 : 1;
-  p.scale_mod = g.split ? g.cout_l : (g.rows2 ? g.cout / 2 : g.cout);
+  p.scale_mod = g.split ? (g.rows2 ? g.cout_l / 2 : g.cout_l) : (g.rows2 ? g.cout / 2 : g.cout);
   p.split = g.split;
   p.scale_mul = g.split ? 1.f / g.wscale : 1.f;
-  if (g.split && (g.rows2 || g.stem_groups)) { set_error("tc plan: split mode has no row-pair / stem-group variant"); return 1; }
+  if (g.split && g.stem_groups) { set_error("tc plan: split mode has no stem-group variant"); return 1; }
   static const int cand[][2] = {{8, 2}, {4, 2}, {8, 1}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
   int best_x = 1, best_y = 1;
   for (auto &c : cand) {
@@ -1546,7 +1602,7 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
     p.out_h = h; p.out_w = w;
   }
   if (g.rows2) {
-    const int cr = g.cout / 2;
+    const int cr = (g.split ? g.cout_l : g.cout) / 2;
     if (g.ups || g.n_tiles_n != 1 || (cr != 8 && cr != 16) || (epi.head_w && cr != 8)) { set_error("tc plan: row-pair mode not applicable"); return 1; }
   }
   if (g.stem_groups) {

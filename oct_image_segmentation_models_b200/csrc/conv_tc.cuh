@@ -96,7 +96,7 @@ bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w);
 // pad_top/pad_left < 0: Keras "same" padding ((k-1)/2 before); otherwise explicit (data-gradient convs)
 int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, int pad_top = -1, int pad_left = -1);
 // fp32-accurate variant: error-compensated fp16 pairs on both operands (see TcGeometry::split); cin / cout logical
-int tc_make_geometry_split(int kh, int kw, int cin, int cout, int ups, TcGeometry *g);
+int tc_make_geometry_split(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, int pad_top = -1, int pad_left = -1);
 // power-of-two scale that brings max |w| of a layer into [2^3, 2^4) (fp16 keeps 11 bits for everything within 2^-17 of it)
 float tc_split_weight_scale(const float *w, size_t count);
 // Row-pair filter: GEMM row = pixel (2r, x) computes outputs (2r, x) and (2r+1, x) from the 4x3 input window

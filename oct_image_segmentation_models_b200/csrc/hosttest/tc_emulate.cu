@@ -193,8 +193,12 @@ static int run_stem(int cout, int n, int h, int w) {
 #include <cuda_fp16.h>
 static float h2f(uint16_t b) { __half_raw r; r.x = b; return __half2float(__half(r)); }
 static uint16_t f2h16(float f) { return static_cast<__half_raw>(__float2half_rn(f)).x; }
-static int run_split(int kh, int kw, int cin, int cout, int ups, int n, int h, int w) {
+static int run_split(int kh, int kw, int cin, int cout, int ups, int n, int h, int w, int rowpair = 0) {
   TcGeometry g;
+  if (rowpair) {
+    if (tc_make_geometry_split(4, 3, cin, 2 * cout, 0, &g, 1, 1)) { printf("split row-pair geometry failed\n"); return 1; }
+    g.rows2 = 1;
+  } else
   if (tc_make_geometry_split(kh, kw, cin, cout, ups, &g)) { printf("split geometry failed\n"); return 1; }
   TcConvParams p; size_t smem;
   std::mt19937 rng(3);
@@ -214,7 +218,13 @@ static int run_split(int kh, int kw, int cin, int cout, int ups, int n, int h, i
     x[((size_t)b * cgp + 2 * pl + 1) * h * w * 8 + i] = f2h16((a - h2f(hi)) * 2048.f);
   }
   std::vector<uint16_t> wp;
+  if (rowpair) {
+    std::vector<float> banded;
+    tc_rowpair_weights(wt.data(), cin, cout, &banded);
+    tc_pack_weights(g, banded.data(), &wp, 1);
+  } else
   tc_pack_weights(g, wt.data(), &wp, 1);
+  const int RM = p.row_mul;
   const int oh = ups ? 2 * h : h, ow = ups ? 2 * w : w;
   std::vector<double> out((size_t)n * oh * ow * cout, 1e30), ref((size_t)n * oh * ow * cout, 0), mag((size_t)n * oh * ow * cout, 0);
   const int pt = (kh - 1) / 2, pl_ = (kw - 1) / 2;
@@ -242,7 +252,7 @@ static int run_split(int kh, int kw, int cin, int cout, int ups, int n, int h, i
     for (int ch = 0; ch < p.cin_chunks; ++ch) {
       uint16_t *s16 = reinterpret_cast<uint16_t *>(stage.data());
       for (int pc = 0; pc < p.planes_per_chunk; ++pc) for (int r = 0; r < p.box_h; ++r) for (int e = 0; e < p.box_w * 8; ++e) {
-        int gx = (tx * p.mt_x * kTcTileW - p.pad_x) * 8 + e, gy = ty * p.mt_y * kTcTileH - p.pad_y + r, gp = ch * p.planes_per_chunk + pc;
+        int gx = (tx * p.mt_x * kTcTileW - p.pad_x) * 8 + e, gy = ty * p.mt_y * kTcTileH * RM - p.pad_y + r, gp = ch * p.planes_per_chunk + pc;
         uint16_t v = 0;
         if (gx >= 0 && gx < w * 8 && gy >= 0 && gy < h) v = x[(((size_t)img * cgp + gp) * h + gy) * w * 8 + gx];
         s16[((size_t)pc * p.box_h + r) * p.box_w * 8 + e] = v;
@@ -251,8 +261,8 @@ static int run_split(int kh, int kw, int cin, int cout, int ups, int n, int h, i
         const uint16_t *bbase = wp.data() + ((size_t)(n_tile * p.cin_chunks + ch) * p.ksteps + ks) * 2 * p.n_cols * 8;
         for (int tt = 0; tt < MT; ++tt) for (int m = 0; m < 128; ++m) for (int k = 0; k < 16; ++k) {
           const int iy = tt / p.mt_x, ix = tt % p.mt_x;
-          size_t aoff = p.a_off[ks] + (size_t)iy * kTcTileH * p.box_w * 16 + (size_t)ix * 128 +
-                        (size_t)(k / 8) * p.a_lbo[ks] + (size_t)(m / 8) * p.box_w * 16 + (m % 8) * 16 + (k % 8) * 2;
+          size_t aoff = p.a_off[ks] + (size_t)iy * kTcTileH * RM * p.box_w * 16 + (size_t)ix * 128 +
+                        (size_t)(k / 8) * p.a_lbo[ks] + (size_t)(m / 8) * RM * p.box_w * 16 + (m % 8) * 16 + (k % 8) * 2;
           if (aoff + 2 > p.a_stage_bytes) { printf("split A read out of stage\n"); return 1; }
           const float av = h2f(*reinterpret_cast<uint16_t *>(stage.data() + aoff));
           if (av == 0.f) continue;
@@ -266,12 +276,13 @@ static int run_split(int kh, int kw, int cin, int cout, int ups, int n, int h, i
     for (int tt = 0; tt < MT; ++tt) for (int m = 0; m < 128; ++m) {
       const int iy = tt / p.mt_x, ix = tt % p.mt_x;
       int r = m >> 3, px = m & 7, y = (ty * p.mt_y + iy) * kTcTileH + r, xx = (tx * p.mt_x + ix) * kTcTileW + px;
-      if (y >= h || xx >= w) continue;
+      if (y * RM >= h || xx >= w) continue;
       const int groups = std::min(p.n_cols, p.cols_valid - n_tile * p.n_cols) >> 4;
       for (int j = 0; j < groups; ++j) {
         const int colp = n_tile * p.n_cols + j * 16;       // the kernel's EPI 7 mapping
         int co0 = (colp >> 4) << 3, oy = y, ox = xx;
         if (p.mode == 1) { const int par = colp / p.cout; co0 = ((colp - par * p.cout) >> 4) << 3; oy = 2 * y + (par >> 1); ox = 2 * xx + (par & 1); }
+        if (RM == 2) { const int cg8 = p.scale_mod >> 3, par = j / cg8; co0 = (j - par * cg8) * 8; oy = 2 * y + par; if (oy >= h) continue; }
         for (int k = 0; k < 8; ++k) {
           const float mainv = (float)D[((size_t)tt * 128 + m) * p.n_cols + j * 16 + k], corr = (float)D[((size_t)tt * 128 + m) * p.n_cols + j * 16 + 8 + k];
           const float val = std::fmaf(corr, 4.8828125e-4f, mainv) * p.scale_mul;
@@ -282,7 +293,7 @@ static int run_split(int kh, int kw, int cin, int cout, int ups, int n, int h, i
   }
   double maxrel = 0;
   for (size_t i = 0; i < ref.size(); ++i) maxrel = std::max(maxrel, std::fabs(out[i] - ref[i]) / std::max(mag[i], 1e-30));
-  const bool ok = maxrel < 2e-6 && p.scale_mod == cout;
+  const bool ok = maxrel < 2e-6 && p.scale_mod == cout && p.row_mul == (rowpair ? 2 : 1);
   printf("split k%dx%d cin %d cout %d ups %d %dx%dx%d: mt %dx%d res %d ksteps %d n_cols %d n_tiles %d chunks %d a_st %d smem %zu wscale %g | max err / sum|terms| %.3g %s\n",
          kh, kw, cin, cout, ups, n, h, w, p.mt_x, p.mt_y, p.b_resident, p.ksteps, p.n_cols, p.n_tiles_n, p.cin_chunks, p.a_stages, smem,
          g.wscale, maxrel, ok ? "OK" : "MISMATCH");
@@ -299,6 +310,10 @@ int main() {
   bad += run_split(3, 3, 128, 128, 0, 1, 16, 8);
   bad += run_split(2, 2, 128, 64, 1, 1, 16, 8);
   bad += run_split(3, 3, 256, 256, 0, 1, 16, 8);   // physical 512 columns: two n-tiles
+  bad += run_split(3, 3, 8, 8, 0, 2, 32, 24, 1);   // split mode x row pairs
+  bad += run_split(3, 3, 16, 8, 0, 1, 64, 40, 1);
+  bad += run_split(3, 3, 8, 16, 0, 1, 34, 16, 1);  // ragged: 34 rows in 32-row tiles (32 -> 16 would need 48 K steps: no pair plan)
+  bad += run_split(3, 3, 16, 16, 0, 40, 64, 64, 1);
   bad += run_stem(8, 2, 32, 128);
   bad += run_stem(8, 1, 40, 136);     // ragged group count
   bad += run_stem(16, 1, 16, 64);

@@ -125,6 +125,7 @@ int sync_host_mirror(octseg_net *net) {
 int prepare_derived(octseg_net *net) {
   if (!net->derived_dirty) return 0;
   if (sync_host_mirror(net)) return 1;
+  OCTSEG_CUDA(cudaGetLastError());
   for (auto &b : net->blocks) {
     BlockState &st = net->bstate[b.index];
     if (!b.has_bn) continue;
@@ -145,6 +146,15 @@ int prepare_derived(octseg_net *net) {
       if (packed.size() != st.wpack_s_elems) { set_error("internal: wpack_s size"); return 1; }
       OCTSEG_CUDA(cudaMemcpyAsync(st.wpack_s, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, net->stream));
       OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+      if (st.geo_s2_ok) {
+        std::vector<float> pair_w;
+        tc_rowpair_weights(wk, b.cin, b.cout, &pair_w);
+        st.geo_s2.wscale = ws;                       // same maximum: the banded filter only re-arranges the taps
+        tc_pack_weights(st.geo_s2, pair_w.data(), &packed, 1);
+        if (packed.size() != st.wpack_s2_elems) { set_error("internal: wpack_s2 size"); return 1; }
+        OCTSEG_CUDA(cudaMemcpyAsync(st.wpack_s2, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, net->stream));
+        OCTSEG_CUDA(cudaStreamSynchronize(net->stream));
+      }
     }
     if (net->precision != OCTSEG_FP32 && st.geo_ok) {
       std::vector<uint16_t> packed;
@@ -301,8 +311,11 @@ int ensure_workspace(octseg_net *net, int n, int h, int w) {
         epi.head_k = last.cout;
         io.head_fused = true;
       }
-      if (tc_make_plan(bst.geo_s, reinterpret_cast<const __nv_bfloat16 *>(io.in), n, io.in_h, io.in_w, bst.wpack_s, epi,
-                       net->d_status, &io.plan))
+      // row pairs (12 instead of 18 K steps per two output rows) where the tensor-core operand path is the bound;
+      // the fused head is epilogue-bound and keeps single rows
+      const bool pair = bst.geo_s2_ok && (io.in_h % 2) == 0 && io.in_h >= 2 * kTcTileH && !epi.head_w;
+      if (tc_make_plan(pair ? bst.geo_s2 : bst.geo_s, reinterpret_cast<const __nv_bfloat16 *>(io.in), n, io.in_h, io.in_w,
+                       pair ? bst.wpack_s2 : bst.wpack_s, epi, net->d_status, &io.plan))
         return 1;
       io.use_tc = true;
       continue;
@@ -551,6 +564,7 @@ static int32_t create_impl(const octseg_config *cfg, int32_t device, int32_t pre
   OCTSEG_CUDA(cudaMallocHost(&net->h_status, 2 * sizeof(int)));
   { const char *fp = std::getenv("OCTSEG_FP32_PATH"); net->fp32_path = (fp && (fp[0] == 'c' || fp[0] == 'C')) ? 1 : 0; }
   if (init_preprocess_lut()) return 1;
+  OCTSEG_CUDA(cudaGetLastError());
   net->bstate.resize(net->blocks.size());
   for (auto &b : net->blocks) {
     BlockState &st = net->bstate[b.index];
@@ -571,6 +585,13 @@ static int32_t create_impl(const octseg_config *cfg, int32_t device, int32_t pre
       st.geo_s_ok = true;
       st.wpack_s_elems = (size_t)st.geo_s.n_tiles_n * st.geo_s.cin_chunks * st.geo_s.ksteps * 2 * st.geo_s.n_cols * 8;
       OCTSEG_CUDA(cudaMalloc(&st.wpack_s, st.wpack_s_elems * 2));
+      if (!net->disable_rowpair && !b.ups && b.kh == 3 && b.kw == 3 && (b.cout == 8 || b.cout == 16) &&
+          tc_make_geometry_split(4, 3, b.cin, 2 * b.cout, 0, &st.geo_s2, 1, 1) == 0 && st.geo_s2.n_tiles_n == 1) {
+        st.geo_s2_ok = true;
+        st.geo_s2.rows2 = 1;
+        st.wpack_s2_elems = (size_t)st.geo_s2.n_tiles_n * st.geo_s2.cin_chunks * st.geo_s2.ksteps * 2 * st.geo_s2.n_cols * 8;
+        OCTSEG_CUDA(cudaMalloc(&st.wpack_s2, st.wpack_s2_elems * 2));
+      }
     }
     // row-pair variant (inference): 3x3 layers with 8 or 16 output channels are bound by the smem reads of
     // the A operand; computing two output rows per GEMM row cuts those by a third
@@ -581,6 +602,7 @@ static int32_t create_impl(const octseg_config *cfg, int32_t device, int32_t pre
       st.wpack2_elems = (size_t)st.geo2.n_tiles_n * st.geo2.cin_chunks * st.geo2.ksteps * 2 * st.geo2.n_cols * 8;
       OCTSEG_CUDA(cudaMalloc(&st.wpack2, st.wpack2_elems * 2));
     }
+    OCTSEG_CUDA(cudaGetLastError());
     // tensor-core stem: 3x3, one input channel; GEMM row = 8 adjacent pixels (K = 8 per tap),
     // GEMM columns = 8 pixels x cout channels (a banded weight matrix, see stem_group_weights)
     if (precision != OCTSEG_FP32 && !net->disable_tc && b.index == 0 && b.kh == 3 && b.kw == 3 && b.cin == 1 &&
@@ -617,6 +639,7 @@ int32_t octseg_create(const octseg_config *cfg, int32_t device, int32_t precisio
     g_err = err;
     return 1;
   }
+  OCTSEG_CUDA(cudaGetLastError());
   *out = net;
   return 0;
 }
@@ -637,7 +660,7 @@ int32_t octseg_destroy(octseg_net *net) {
   }
   if (net->copy_in) cudaStreamDestroy(net->copy_in);
   if (net->copy_out) cudaStreamDestroy(net->copy_out);
-  for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); cudaFree(st.rep_scale); cudaFree(st.rep_shift); cudaFree(st.wpack2); cudaFree(st.wpack_s); }
+  for (auto &st : net->bstate) { cudaFree(st.scale); cudaFree(st.shift); cudaFree(st.wpack); cudaFree(st.rep_scale); cudaFree(st.rep_shift); cudaFree(st.wpack2); cudaFree(st.wpack_s); cudaFree(st.wpack_s2); }
   cudaFree(net->d_params); cudaFree(net->ws); cudaFree(net->d_eval); cudaFree(net->d_status);
   if (net->h_status) cudaFreeHost(net->h_status);
   if (net->ev_derived) cudaEventDestroy(net->ev_derived);
@@ -709,6 +732,7 @@ static int predict_enqueue(octseg_net *net, int si, const void *images, int32_t 
   if (n <= 0 || h <= 0 || w <= 0) { set_error("bad image batch shape"); return 1; }
   if (dtype != OCTSEG_U8 && dtype != OCTSEG_F32 && dtype != OCTSEG_F32_PRE) { set_error("bad image dtype"); return 1; }
   OCTSEG_CUDA(cudaSetDevice(net->device));
+  OCTSEG_CUDA(cudaGetLastError());                        // an earlier unchecked failure must not be blamed on this call
   octseg_net::HostSlot &S = net->slot[si];
   if (S.busy && predict_wait(net, si)) return 1;          // the slot's previous call must have drained
   const int K = net->cfg.num_classes;

@@ -53,6 +53,11 @@ struct BlockState {
   TcGeometry geo_s{};
   __nv_bfloat16 *wpack_s = nullptr;
   size_t wpack_s_elems = 0;
+  // ... and its row-pair variant for the 3x3 layers with 8 / 16 output channels (tensor-pipe-bound in split mode)
+  bool geo_s2_ok = false;
+  TcGeometry geo_s2{};
+  __nv_bfloat16 *wpack_s2 = nullptr;
+  size_t wpack_s2_elems = 0;
 };
 
 // Workspace views for one (n,h,w)

@@ -242,32 +242,24 @@ def test_cfg3_shape_train_step_fp32_and_bf16_vs_oracle():
 def test_wide_net_bf16_train_step_runs_on_tcgen05_and_tracks_oracle():
     """BASELINE configs[3] network in training (start_neurons 64: every conv after the stem has >= 64 input channels, so
     forward, data gradient AND weight gradient are tcgen05 kernels; 64-channel head through the two-pass head kernels):
-    loss within 2e-2 of the oracle, whole-gradient cosine >= 0.97, and the gradient is bit-reproducible run to run for
-    the tensors the deterministic tcgen05 weight-gradient path produces."""
+    loss within 2e-2 of the oracle, whole-gradient cosine >= 0.97.  (Bit-reproducibility of the tcgen05 weight gradient
+    itself is checked on identical inputs in tests/test_gpu_backward_kernels.py; a whole step also contains the
+    order-dependent double atomics of the BatchNorm reductions.)"""
     from oct_image_segmentation_models_b200.engine import UNetEngine
     cfg = dict(input_channels=1, num_classes=4, start_neurons=64, pool_layers=2, conv_layers=2)
     weights, imgs, labs, mask = _setup(cfg, 2, 64, 64)
     names = [nm for nm, _ in unet_param_specs(**cfg)]
     ora = OracleUNet(weights, **cfg)
     loss_ref, grads_ref, _, _ = ora.loss_and_grads(imgs, labs, CW, dropout_mask=mask)
-    runs = []
-    for _ in range(2):
-        eng = UNetEngine(precision="bf16", **cfg)
-        eng.set_weights(weights)
-        eng.train_begin(CW, global_batch=2)
-        loss = eng.train_step(imgs, labs, dropout_mask=mask)
-        runs.append((loss, eng.get_grads()))
-        eng.close()
-    loss, got = runs[0]
+    eng = UNetEngine(precision="bf16", **cfg)
+    eng.set_weights(weights)
+    eng.train_begin(CW, global_batch=2)
+    loss = eng.train_step(imgs, labs, dropout_mask=mask)
+    got = eng.get_grads()
+    eng.close()
     assert abs(loss - loss_ref) <= 2e-2 * max(1.0, abs(loss_ref)), (loss, loss_ref)
     keep = [i for i, nm in enumerate(names) if grads_ref[i] is not None and not (nm.endswith("bias:0") and nm != names[-1])]
     a = np.concatenate([got[i].ravel() for i in keep])
     b = np.concatenate([grads_ref[i].numpy().ravel() for i in keep])
     cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
     assert cos >= 0.97, cos
-    # conv kernels with >= 64 input and output channels: split-K partials are added in a fixed order -> same bits twice
-    det = [i for i, (nm, shp) in enumerate(unet_param_specs(**cfg)) if nm.endswith("kernel:0") and len(shp) == 4
-           and shp[2] >= 64 and shp[3] >= 64 and shp[0] == 3]
-    assert det
-    for i in det:
-        assert np.array_equal(runs[0][1][i], runs[1][1][i]), names[i]
