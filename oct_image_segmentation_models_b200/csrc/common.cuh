@@ -107,6 +107,36 @@ __device__ __forceinline__ void store_plane8<SplitHalf>(SplitHalf *p, long long 
   *reinterpret_cast<uint4 *>(p + plane_elems) = lo;
 }
 
+// Raw (unconverted) 8-channel vector: lets a streaming kernel keep several loads in flight without paying 8 fp32
+// registers per vector before the data is needed.
+template <typename T> struct Raw8 { uint4 u; };
+template <> struct Raw8<float> { float4 a, b; };
+template <typename T>
+__device__ __forceinline__ Raw8<T> load_raw8(const T *p) { Raw8<T> r; r.u = *reinterpret_cast<const uint4 *>(p); return r; }
+template <>
+__device__ __forceinline__ Raw8<float> load_raw8<float>(const float *p) {
+  Raw8<float> r; r.a = *reinterpret_cast<const float4 *>(p); r.b = *reinterpret_cast<const float4 *>(p + 4); return r;
+}
+__device__ __forceinline__ Vec8f cvt8(const Raw8<__nv_bfloat16> &r) {
+  Vec8f o;
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); o.v[2 * i] = f.x; o.v[2 * i + 1] = f.y; }
+  return o;
+}
+__device__ __forceinline__ Vec8f cvt8(const Raw8<__half> &r) {
+  Vec8f o;
+  const __half2 *h = reinterpret_cast<const __half2 *>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); o.v[2 * i] = f.x; o.v[2 * i + 1] = f.y; }
+  return o;
+}
+__device__ __forceinline__ Vec8f cvt8(const Raw8<float> &r) {
+  Vec8f o;
+  o.v[0] = r.a.x; o.v[1] = r.a.y; o.v[2] = r.a.z; o.v[3] = r.a.w; o.v[4] = r.b.x; o.v[5] = r.b.y; o.v[6] = r.b.z; o.v[7] = r.b.w;
+  return o;
+}
+
 __device__ __forceinline__ Vec8f zero8() {
   Vec8f r;
 #pragma unroll

@@ -165,16 +165,32 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(
 #pragma unroll
   for (int k = 0; k < 8; ++k) { sc[k] = s_sc[k]; sh[k] = s_sh[k]; }
   if constexpr (POOL == 0) {
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < hw; v += gridDim.x * blockDim.x) {
-      Vec8f x = load8(zb + (long long)v * 8);
+    constexpr int kU = 4;
+    const int stride = gridDim.x * blockDim.x;
+    for (int v0 = blockIdx.x * blockDim.x + threadIdx.x; v0 < hw; v0 += stride * kU) {
+      Raw8<T> rx[kU], rm[kU];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x.v[k] = fmaxf(fmaf(x.v[k], sc[k], sh[k]), 0.f);
-      if (mb) {
-        const Vec8f mk = load8(mb + (long long)v * 8);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) x.v[k] *= mk.v[k];
+      for (int u = 0; u < kU; ++u) {
+        const int v = v0 + u * stride;
+        if (v < hw) {
+          rx[u] = load_raw8(zb + (long long)v * 8);
+          if (mb) rm[u] = load_raw8(mb + (long long)v * 8);
+        }
       }
-      store8(ab + (long long)v * 8, x);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int v = v0 + u * stride;
+        if (v >= hw) break;
+        Vec8f x = cvt8(rx[u]);
+        Vec8f mk = zero8();
+        if (mb) mk = cvt8(rm[u]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          x.v[k] = fmaxf(fmaf(x.v[k], sc[k], sh[k]), 0.f);
+          if (mb) x.v[k] *= mk.v[k];
+        }
+        store8(ab + (long long)v * 8, x);
+      }
     }
   } else {
     // one thread = one 2x2 window: four activations out, their maximum to the pooled tensor
@@ -588,7 +604,7 @@ int launch_head_loss(View<const T> a, const float *wgt, const float *bias, int c
 // BN + ReLU (+dropout multiplier) backward
 // ---------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
+__global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_reduce_kernel(
     View<const T> da, View<const T> z, const float *__restrict__ mean, const float *__restrict__ invstd,
     const float *__restrict__ gamma, const float *__restrict__ beta, const T *__restrict__ mask, double *sums,
     int c) {
@@ -604,20 +620,35 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int v = blockIdx.x * kSpanVecs + threadIdx.x; v < v_end; v += kRedThreads) {
-    const Vec8f zz = load8(zb + (long long)v * 8);
-    Vec8f g = load8(gb + (long long)v * 8);
-    if (mb) {
-      const Vec8f mk = load8(mb + (long long)v * 8);
+  // 4 vectors per iteration with every load issued before the first use: the kernel runs at ~37 % occupancy (78
+  // registers), so memory-level parallelism has to come from the instruction stream (ncu: DRAM 44 % -> see profiles/)
+  constexpr int kU = 4;
+  for (int v0 = blockIdx.x * kSpanVecs + threadIdx.x; v0 < v_end; v0 += kRedThreads * kU) {
+    Raw8<T> rz[kU], rg[kU], rm[kU];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g.v[i] *= mk.v[i];
+    for (int u = 0; u < kU; ++u) {
+      const int v = v0 + u * kRedThreads;
+      if (v < v_end) {
+        rz[u] = load_raw8(zb + (long long)v * 8);
+        rg[u] = load_raw8(gb + (long long)v * 8);
+        if (mb) rm[u] = load_raw8(mb + (long long)v * 8);
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float zh = (zz.v[i] - mu[i]) * is[i];
-      const float dy = (fmaf(ga[i], zh, be[i]) > 0.f) ? g.v[i] : 0.f;
-      acc[i] += dy;
-      acc[8 + i] = fmaf(dy, zh, acc[8 + i]);
+    for (int u = 0; u < kU; ++u) {
+      const int v = v0 + u * kRedThreads;
+      if (v >= v_end) break;
+      const Vec8f zz = cvt8(rz[u]), g = cvt8(rg[u]);
+      Vec8f mk = zero8();
+      if (mb) mk = cvt8(rm[u]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float gi = mb ? g.v[i] * mk.v[i] : g.v[i];
+        const float zh = (zz.v[i] - mu[i]) * is[i];
+        const float dy = (fmaf(ga[i], zh, be[i]) > 0.f) ? gi : 0.f;
+        acc[i] += dy;
+        acc[8 + i] = fmaf(dy, zh, acc[8 + i]);
+      }
     }
   }
   block_reduce16_to_double(acc, sums, sums + c, pl * 8);
@@ -636,7 +667,7 @@ int launch_bn_bwd_reduce(View<const T> da, View<const T> z, const float *mean, c
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(
     View<const T> da, View<const T> z, const float *__restrict__ mean, const float *__restrict__ invstd,
     const float *__restrict__ gamma, const float *__restrict__ beta, const T *__restrict__ mask,
     const double *__restrict__ sums, long long count, View<T> dz, float *d_gamma, float *d_beta, int c) {
@@ -662,22 +693,36 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
   for (int k = 0; k < 8; ++k) {
     mu[k] = s_par[0][k]; is[k] = s_par[1][k]; ga[k] = s_par[2][k]; be[k] = s_par[3][k]; sdy[k] = s_par[4][k]; sdyz[k] = s_par[5][k];
   }
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < hw; v += gridDim.x * blockDim.x) {
-    const Vec8f zz = load8(zb + (long long)v * 8);
-    Vec8f g = load8(gb + (long long)v * 8);
-    if (mb) {
-      const Vec8f mk = load8(mb + (long long)v * 8);
+  constexpr int kU = 4;      // see bn_bwd_reduce_kernel: loads of 4 vectors in flight per thread
+  const int stride = gridDim.x * blockDim.x;
+  for (int v0 = blockIdx.x * blockDim.x + threadIdx.x; v0 < hw; v0 += stride * kU) {
+    Raw8<T> rz[kU], rg[kU], rm[kU];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g.v[k] *= mk.v[k];
+    for (int u = 0; u < kU; ++u) {
+      const int v = v0 + u * stride;
+      if (v < hw) {
+        rz[u] = load_raw8(zb + (long long)v * 8);
+        rg[u] = load_raw8(gb + (long long)v * 8);
+        if (mb) rm[u] = load_raw8(mb + (long long)v * 8);
+      }
     }
-    Vec8f o;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float zh = (zz.v[k] - mu[k]) * is[k];
-      const float dy = (fmaf(ga[k], zh, be[k]) > 0.f) ? g.v[k] : 0.f;
-      o.v[k] = ga[k] * is[k] * (dy - sdy[k] - zh * sdyz[k]);
+    for (int u = 0; u < kU; ++u) {
+      const int v = v0 + u * stride;
+      if (v >= hw) break;
+      const Vec8f zz = cvt8(rz[u]), g = cvt8(rg[u]);
+      Vec8f mk = zero8();
+      if (mb) mk = cvt8(rm[u]);
+      Vec8f o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float gk = mb ? g.v[k] * mk.v[k] : g.v[k];
+        const float zh = (zz.v[k] - mu[k]) * is[k];
+        const float dy = (fmaf(ga[k], zh, be[k]) > 0.f) ? gk : 0.f;
+        o.v[k] = ga[k] * is[k] * (dy - sdy[k] - zh * sdyz[k]);
+      }
+      store8(ob + (long long)v * 8, o);
     }
-    store8(ob + (long long)v * 8, o);
   }
 }
 

@@ -109,9 +109,11 @@ def test_train_model_api_learns(tmp_path):
         train_model(tp_bad)
 
 
-def test_fit_callback_protocol_and_resume_from_checkpoint(tmp_path):
+def test_fit_callback_protocol_and_resume_from_checkpoint(tmp_path, monkeypatch):
     """Keras protocol of B200Model.fit (reference training.py:401-407, training_callbacks.py:35-64) and
-    `initial_model` resume: 2 + 2 epochs through a checkpoint (weights + Adam m, v, iterations) == 4 epochs."""
+    `initial_model` resume: 2 + 2 epochs through a checkpoint (weights + Adam m, v, iterations) == 4 epochs.
+    (Trained on the fp32 kernels so that the two trajectories can be compared tightly; the default trains in bf16.)"""
+    monkeypatch.setenv("OCTSEG_TRAIN_PRECISION", "fp32")
     from oct_image_segmentation_models_b200.common.custom_losses import custom_loss_objects
     from oct_image_segmentation_models_b200.common.data_generator import DataGenerator
     from oct_image_segmentation_models_b200.common.synthetic import synthetic_batch
