@@ -495,6 +495,40 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(View<const T> in, View<T>
   }
 }
 
+// fp32 mode on tensor cores: activations are fp16 (hi, lo') plane pairs; the pool acts on hi + lo' * 2^-11
+__global__ void __launch_bounds__(256) maxpool2_split_kernel(View<const SplitHalf> in, View<SplitHalf> out) {
+  const int Ho = out.h, Wo = out.w, lp = out.planes >> 1;          // logical planes
+  const long long total = (long long)out.n * lp * Ho * Wo;
+  const long long ipe = (long long)in.h * in.w * 8, ope = (long long)Ho * Wo * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wo);
+    const int y = (int)((i / Wo) % Ho);
+    const int pl = (int)((i / ((long long)Wo * Ho)) % lp);
+    const int b = (int)(i / ((long long)Wo * Ho * lp));
+    const __half *src = reinterpret_cast<const __half *>(in.ptr) + b * in.img_stride + (2LL * pl) * ipe + ((long long)(2 * y) * in.w + 2 * x) * 8;
+    Vec8f m;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m.v[k] = -3.0e38f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long o = (long long)(q >> 1) * in.w * 8 + (q & 1) * 8;
+      const Vec8f hi = load8(src + o), lo = load8(src + ipe + o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m.v[k] = fmaxf(m.v[k], fmaf(lo.v[k], 4.8828125e-4f, hi.v[k]));
+    }
+    SplitHalf *dst = out.ptr + b * out.img_stride + (2LL * pl) * ope + ((long long)y * Wo + x) * 8;
+    store_plane8(dst, ope, m);
+  }
+}
+template <>
+int launch_maxpool2<SplitHalf>(View<const SplitHalf> in, View<SplitHalf> out, cudaStream_t st) {
+  const long long total = (long long)out.n * (out.planes >> 1) * out.h * out.w;
+  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  maxpool2_split_kernel<<<grid, 256, 0, st>>>(in, out);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <typename T>
 int launch_maxpool2(View<const T> in, View<T> out, cudaStream_t st) {
   const long long total = (long long)out.n * out.planes * out.h * out.w;

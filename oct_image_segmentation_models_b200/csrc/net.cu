@@ -430,8 +430,8 @@ static int forward_t(octseg_net *net, const void *d_img, int dtype, int n, int h
         return 1;
     }
     ++net->launches;
-    if constexpr (!kSplit) {
-    if (io.pool && !io.pool_fused) {
+    {
+    if (io.pool && !io.pool_fused) {      // split mode: only the stem of a conv_layers == 1 net gets here (FFMA stem, no fused pool)
       View<const T> pin = make_view(reinterpret_cast<const T *>(io.out), n, io.out_planes_total,
                                     io.out_plane0, io.out_planes, io.out_h, io.out_w);
       View<T> pout = make_view(reinterpret_cast<T *>(io.pool), n, io.out_planes, 0, io.out_planes, io.pool_h,

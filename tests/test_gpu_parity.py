@@ -310,6 +310,10 @@ SWEEP = [
     (dict(input_channels=3, num_classes=4, start_neurons=8, pool_layers=2, conv_layers=2), 2, 48, 64),
     (dict(input_channels=1, num_classes=4, start_neurons=32, pool_layers=2, conv_layers=2), 1, 64, 128),   # 256-column TC stem
     (dict(input_channels=1, num_classes=6, start_neurons=16, pool_layers=4, conv_layers=2), 1, 32, 96),
+    # conv_layers == 1: the stem itself is followed by the pool (found by tools/stress_parity.py: the fp32 tensor-core
+    # mode runs the stem on the FFMA kernel and needs the split-layout max-pool kernel behind it); odd level-1 width
+    (dict(input_channels=1, num_classes=7, start_neurons=32, pool_layers=1, conv_layers=1), 2, 72, 174),
+    (dict(input_channels=1, num_classes=4, start_neurons=8, pool_layers=2, conv_layers=1), 2, 64, 96),
 ]
 
 
