@@ -394,7 +394,7 @@ def bench_cfg5(args, rank, local_rank, world, torch, dist):
     seg_first = {}          # boundaries / labels of the first pass over the distinct B-scans (rank 0 checks them)
 
     def search(b, m, l):
-        segs = graph_search.segment_maps(m.reshape(-1, W, H), None, None, n_threads=threads)[0].reshape(bs, K_CLASSES - 1, W)
+        segs = graph_search.segment_maps(m.reshape(-1, W, H), None, None, n_threads=threads, return_prob_maps=False)[0].reshape(bs, K_CLASSES - 1, W)
         if b < len(pin):
             seg_first[b] = (segs, l.copy())
         return segs.shape[0]

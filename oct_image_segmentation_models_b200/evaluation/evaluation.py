@@ -70,7 +70,7 @@ def evaluate_model(eval_params: EvaluationParameters, batch_size: int = 64) -> L
         if eval_params.graph_search:
             maps_t = np.ascontiguousarray(np.transpose(maps, (0, 1, 3, 2)))
             n, km1, W, H = maps_t.shape
-            segs = graph_search.segment_maps(maps_t.reshape(-1, W, H), None, None)[0].reshape(n, km1, W)
+            segs = graph_search.segment_maps(maps_t.reshape(-1, W, H), None, None, return_prob_maps=False)[0].reshape(n, km1, W)
         for k in range(len(chunk)):
             i = i0 + k
             cat = np.transpose(utils.to_categorical(labels[k], K), (2, 0, 1))          # [K,H,W], binarised

@@ -75,7 +75,7 @@ def predict(predict_params: PredictionParams, batch_size: int = 64) -> List[Pred
             if predict_params.graph_search:
                 from ..min_path_processing import graph_search
                 boundary_maps_t = np.transpose(boundary_maps, axes=[0, 2, 1])
-                gs_pred_segs, _, _ = graph_search.segment_maps(boundary_maps_t, None, None)
+                gs_pred_segs, _, _ = graph_search.segment_maps(boundary_maps_t, None, None, return_prob_maps=False)
             _save_image_prediction_results(predict_params, dataset.image_output_dirs[i], predicted_labels,
                                            categorical_pred, boundary_maps, gs_pred_segs, predict_time)
             outputs.append(PredictionOutput(image=images[i], image_name=dataset.image_names[i],

@@ -19,7 +19,7 @@ on torch-CPU (oneDNN, the same kernel-library family TF uses on CPU):
   * Keras optimizer_v2 Adam (eps outside the bias correction).
 
 What *is* pinned: the min-path comparator (oracle/min_path.py) is checked against
-the unmodified reference file in tests/test_oracle_minpath.py.
+the unmodified reference file in tests/test_oracle_golden.py (goldens made by tests/golden/make_minpath_golden.py).
 """
 from __future__ import annotations
 

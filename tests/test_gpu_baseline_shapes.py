@@ -74,7 +74,7 @@ def _predict_boundaries(eng, imgs, threads):
         l, m = eng.predict_maps(imgs[i0:i0 + 64], transposed=True)
         labels[i0:i0 + len(l)] = l
         maps_t[i0:i0 + len(l)] = m
-    segs = graph_search.segment_maps(maps_t.reshape(-1, w, h), None, None, n_threads=threads)[0].reshape(n, 3, w)
+    segs = graph_search.segment_maps(maps_t.reshape(-1, w, h), None, None, n_threads=threads, return_prob_maps=False)[0].reshape(n, 3, w)
     return labels, segs
 
 

@@ -28,7 +28,7 @@ def boundaries(labels_u8, K=4, threads=16):
         cat = np.transpose(utils.to_categorical(lab, K), (0, 3, 1, 2))
         maps = utils.convert_predictions_to_maps_semantic(cat, bg_ilm=True, bg_csi=False)      # [m,K-1,H,W]
         maps_t = np.ascontiguousarray(np.transpose(maps, (0, 1, 3, 2))).reshape(-1, W, H)
-        seg = graph_search.segment_maps(maps_t, None, None, n_threads=threads)[0]
+        seg = graph_search.segment_maps(maps_t, None, None, n_threads=threads, return_prob_maps=False)[0]
         out[i0:i0 + len(lab)] = seg.reshape(len(lab), K - 1, W)
     return out
 
@@ -72,8 +72,8 @@ def main():
             maps_t[i0:i0 + len(l)] = m
         t_pred = time.time() - t1
         t2 = time.time()
-        segs = graph_search.segment_maps(maps_t.reshape(-1, W, H), None, None,
-                                         n_threads=os.cpu_count() or 1)[0].reshape(args.n, 3, W)
+        segs = graph_search.segment_maps(maps_t.reshape(-1, W, H), None, None, n_threads=os.cpu_count() or 1,
+                                         return_prob_maps=False)[0].reshape(args.n, 3, W)
         t_path = time.time() - t2
         if prec == "bf16":   # the numpy chain on the same labels gives the same boundaries (first 64 images)
             assert np.array_equal(segs[:64], boundaries(labels[:64], threads=os.cpu_count() or 1))
