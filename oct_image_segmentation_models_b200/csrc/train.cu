@@ -563,7 +563,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
       net->launches += 4;
       break;
     }
-    if (b.ups && sizeof(T) == 2 && !net->disable_tc) {
+    if (b.ups && sizeof(T) == 2 && !net->disable_tc && !wgrad_rows_applicable(b.kh, b.kw, b.cin, 1)) {
       // tensor-core path wants a real tensor: materialise the x2-upsampled input once (1 write + 1 read
       // of a tensor the forward pass never stores) and run the plain 2x2 weight gradient on it
       View<T> up = make_view((T *)S->up_scratch, n, b.cin / 8, 0, b.cin / 8, t.h, t.w);
@@ -705,7 +705,7 @@ static int debug_backward_t(octseg_net *net, const BlockSpec &b, const float *a_
     }
   }
   // ---- weight gradient (same dispatch as train_step_t)
-  if (b.ups && sizeof(T) == 2 && !net->disable_tc) {
+  if (b.ups && sizeof(T) == 2 && !net->disable_tc && !wgrad_rows_applicable(b.kh, b.kw, b.cin, 1)) {
     OCTSEG_CUDA(cudaMalloc(&d_up, (size_t)n * b.cin * oh * ow * sizeof(T)));
     View<T> up = make_view(d_up, n, b.cin / 8, 0, b.cin / 8, oh, ow);
     rc = launch_upsample2x<T>(in, up, st);

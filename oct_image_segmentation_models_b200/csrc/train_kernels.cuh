@@ -79,6 +79,10 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
                      int pad_left, int ups, int cin, int cout, float *dW, float *db, int *status,
                      cudaStream_t st);
 
+// narrow layers (Cin <= 16) run the row-walking kernel, which also reads the LOW-res input of the up-conv directly
+// (ups = 1, 2x2 kernel): the caller does not materialise the up-sampled tensor when this returns true
+bool wgrad_rows_applicable(int kh, int kw, int cin, int ups);
+
 // tcgen05 weight gradient for dense layers with >= 64 input channels (csrc/wgrad_tc.cu): MN-major UMMA operands straight
 // from the blocked tiles, accumulators in TMEM, deterministic split-K reduction through `scratch`
 bool wgrad_tc_applicable(int kh, int kw, int cin, int cout, int ups, int h, int w);

@@ -583,6 +583,236 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16 *__r
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Row-walking kernel for the narrow layers (Cin = 8 / 16: the full-resolution layers that carry most of the bytes).
+// The TMA kernel above gives every warp single tile rows, so each of the kh*kw taps of a row is its own ldmatrix.x4
+// plus address arithmetic: ~26 instructions per MMA, issue-bound at IPC 2.5 with DRAM at 33-45 % (profiles/r1_wgrad_*).
+// Here a warp owns a band of R consecutive output rows of one 16-pixel column and ONE output plane, and walks the
+// INPUT rows of its band: the fragments of input row j (one ldmatrix.x4 per pair of (dx, plane) column groups) feed
+// the taps dy = 0..kh-1 of output rows j, j-1, j-2, whose dz fragments sit in a rolling register window.  Everything
+// is compile-time (PC planes, NB output planes per CTA, KS = kernel size, band height), the loop over the band is
+// fully unrolled and every shared-memory address is `base + immediate`: ~1.4 instructions per MMA.  The bias gradient
+// is one more MMA per dz fragment against an all-ones A fragment held in registers.
+// UPS = 1: the decoder's 2x2 convolution reads the x2-upsampled tensor; ldmatrix takes one row address per lane, so
+// the virtual pixel (y, x) is simply the low-res smem pixel (y >> 1, x >> 1) -- the up-sampled tensor is never built.
+// ---------------------------------------------------------------------------------
+constexpr int kWrCW = 16;                          // compute warps: (8 / NB bands) x 2 k-steps x NB output planes
+constexpr int kWrThreads = 32 * (1 + kWrCW);
+constexpr int kWrTH = 32;                          // tile rows
+
+template <int PC, int NB, int KS, int UPS>
+struct WrGeo {
+  static constexpr int TH = kWrTH, TW = kWmTW;
+  static constexpr int AW = UPS ? (TW / 2 + 1) : (TW + KS - 1);
+  static constexpr int AH = UPS ? (TH / 2 + 1) : (TH + KS - 1);
+  static constexpr int U = KS * PC, L = (U + 1) / 2;       // (dx, plane) column groups, m16 loads (pairs of groups)
+  static constexpr int BANDS = 8 / NB, R = TH / BANDS;
+  static constexpr uint32_t A_BYTES = PC * AH * AW * 16, D_BYTES = NB * TH * TW * 16;
+  static constexpr uint32_t A_PAD = (A_BYTES + 127u) & ~127u;
+  static constexpr uint32_t STAGE = A_PAD + ((D_BYTES + 127u) & ~127u);
+  static constexpr int ACC_FLOATS = KS * KS * PC * 8 * NB * 8 + NB * 8;
+};
+
+template <int PC, int NB, int KS, int UPS>
+__global__ void __launch_bounds__(kWrThreads, 1) wgrad_rows_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                   const __grid_constant__ CUtensorMap map_d,
+                                                                   const WgParams p, int n_stages, int *status) {
+  using G = WrGeo<PC, NB, KS, UPS>;
+  constexpr int TH = G::TH, TW = G::TW, AW = G::AW, AH = G::AH, U = G::U, L = G::L, R = G::R;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *s_stage = smem_raw;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * G::STAGE);   // full[S], empty[S]
+  float *s_acc = reinterpret_cast<float *>(bars + 2 * n_stages);                           // [tap][ci][NB*8] + bias[NB*8]
+  for (int i = threadIdx.x; i < G::ACC_FLOATS; i += blockDim.x) s_acc[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[i])), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(&bars[n_stages + i])), "r"(kWrCW) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int nb0 = blockIdx.y * NB;                  // first output plane of this CTA
+
+  if (warp == 0) {
+    // ---------------- producer ----------------
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xFFFFFFFFu));
+    int st = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int txi = tile % p.tiles_x;
+      const int tyi = (tile / p.tiles_x) % p.tiles_y;
+      const int img = tile / (p.tiles_x * p.tiles_y);
+      if (!wm_wait(wm_smem_u32(&bars[n_stages + st]), ph ^ 1u)) { if (pred) atomicCAS(status, 0, 25); break; }
+      if (pred) {
+        const uint32_t full = wm_smem_u32(&bars[st]);
+        const uint32_t dst_a = wm_smem_u32(s_stage + (size_t)st * G::STAGE);
+        const uint32_t dst_d = dst_a + G::A_PAD;
+        const int ax = UPS ? txi * (TW / 2) : txi * TW - p.pl, ay = UPS ? tyi * (TH / 2) : tyi * TH - p.pt;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(G::A_BYTES + G::D_BYTES) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(dst_a), "l"(&map_a), "r"(full), "r"(ax * 2), "r"(ay), "r"(0), "r"(img) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(dst_d), "l"(&map_d), "r"(full), "r"(txi * TW * 2), "r"(tyi * TH), "r"(nb0), "r"(img) : "memory");
+      }
+      if (++st == n_stages) { st = 0; ph ^= 1u; }
+    }
+  } else {
+    // ---------------- consumers: warp = (band, k-step, output plane) ----------------
+    const int cwi = warp - 1;
+    const int nbp = cwi % NB, ks = (cwi / NB) & 1, band = cwi / (2 * NB);
+    const int y0 = band * R;
+    const bool live = (nb0 + nbp) < p.cout_planes;
+    // per-lane ldmatrix row addresses (bytes inside a stage): matrix i = lane >> 3 (group half i & 1, pixel octet i >> 1),
+    // row r = lane & 7 = pixel inside the octet
+    uint32_t a_lane[L];
+    {
+      const int i = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        int u = 2 * l + (i & 1);
+        if (u >= U) u = U - 1;                      // odd group count: the dummy half re-reads the last group, result dropped
+        const int dx = u / PC, c = u - dx * PC;
+        const int px = ks * 16 + dx + r + 8 * (i >> 1);
+        const int row0 = UPS ? (y0 >> 1) : y0;
+        a_lane[l] = (uint32_t)(((c * AH + row0) * AW + (UPS ? (px >> 1) : px)) * 16);
+      }
+    }
+    const uint32_t b_lane = G::A_PAD + (uint32_t)((((nbp * TH + y0) * TW) + ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * 16);
+    const uint32_t ones[4] = {0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u};     // bf16 1.0 pairs
+    float acc[L][KS][4], accb[4];
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+#pragma unroll
+      for (int d = 0; d < KS; ++d)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[l][d][k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) accb[k] = 0.f;
+    int st = 0;
+    uint32_t ph = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; ok && tile < p.num_tiles; tile += gridDim.x) {
+      ok = wm_wait(wm_smem_u32(&bars[st]), ph);
+      if (!ok) { if (lane == 0) atomicCAS(status, 0, 26); break; }
+      if (live) {
+        const uint32_t base = wm_smem_u32(s_stage + (size_t)st * G::STAGE);
+        uint32_t bw[KS][2];
+        uint32_t af[L][4];
+#pragma unroll
+        for (int d = 0; d < KS; ++d) { bw[d][0] = 0u; bw[d][1] = 0u; }
+#pragma unroll
+        for (int jj = 0; jj < R + KS - 1; ++jj) {
+          // input row y0 + jj serves output rows y0 + jj - dy; dz fragments of the last KS rows in a rolling window
+#pragma unroll
+          for (int d = KS - 1; d > 0; --d) { bw[d][0] = bw[d - 1][0]; bw[d][1] = bw[d - 1][1]; }
+          if (jj < R) {
+            ldmatrix_x2_trans(base + b_lane + (uint32_t)(jj * TW * 16), bw[0]);
+            mma_bf16_16816(accb, ones, bw[0]);
+          }
+          if (!UPS || (jj & 1) == 0) {
+#pragma unroll
+            for (int l = 0; l < L; ++l) ldmatrix_x4_trans(base + a_lane[l] + (uint32_t)((UPS ? (jj >> 1) : jj) * AW * 16), af[l]);
+          }
+#pragma unroll
+          for (int d = 0; d < KS; ++d) {
+            if (jj - d >= 0 && jj - d < R) {
+#pragma unroll
+              for (int l = 0; l < L; ++l) mma_bf16_16816(acc[l][d], af[l], bw[d]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wm_smem_u32(&bars[n_stages + st])) : "memory");
+      if (++st == n_stages) { st = 0; ph ^= 1u; }
+    }
+    // ---- the CTA's dW block: shared-memory accumulation over the 16 / NB warps of each output plane
+    if (live) {
+      const int ci = lane >> 2, co = nbp * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int u = 2 * l + hf;
+          if (u < U) {
+            const int dx = u / PC, c = u - dx * PC;
+#pragma unroll
+            for (int d = 0; d < KS; ++d) {
+              float *dst = s_acc + (((d * KS + dx) * PC + c) * 8 + ci) * (NB * 8) + co;
+              atomicAdd(dst, acc[l][d][2 * hf]);
+              atomicAdd(dst + 1, acc[l][d][2 * hf + 1]);
+            }
+          }
+        }
+      }
+      if (lane < 4) {      // every row of the ones-MMA holds sum(dz): take row 0
+        atomicAdd(s_acc + KS * KS * PC * 8 * NB * 8 + co, accb[0]);
+        atomicAdd(s_acc + KS * KS * PC * 8 * NB * 8 + co + 1, accb[1]);
+      }
+    }
+  }
+  __syncthreads();
+  const int nb_cur = min(NB, p.cout_planes - nb0);
+  for (int i = threadIdx.x; i < KS * KS * PC * 8 * NB * 8; i += blockDim.x) {
+    const int co = i % (NB * 8);
+    if (co >= nb_cur * 8) continue;
+    const int row = i / (NB * 8);                   // (tap * PC + c) * 8 + ci
+    const int t = row / (PC * 8), cc = row - t * (PC * 8);
+    atomicAdd(&p.dW[((long long)t * p.cin + cc) * p.cout + nb0 * 8 + co], s_acc[i]);
+  }
+  if (p.db && threadIdx.x < nb_cur * 8) atomicAdd(&p.db[nb0 * 8 + threadIdx.x], s_acc[KS * KS * PC * 8 * NB * 8 + threadIdx.x]);
+}
+
+template <int PC, int NB, int KS, int UPS>
+static int launch_wgrad_rows_t(const CUtensorMap &map_a, const CUtensorMap &map_d, const WgParams &p, int *status, cudaStream_t st) {
+  using G = WrGeo<PC, NB, KS, UPS>;
+  const size_t fixed = 2 * kWmMaxStages * 8 + (size_t)G::ACC_FLOATS * sizeof(float) + 1024;
+  int n_stages = (int)std::min<size_t>(kWmMaxStages, (220 * 1024 - fixed) / G::STAGE);
+  if (n_stages < 2) { set_error("wgrad_rows: smem budget exceeded"); return 1; }
+  const size_t smem = (size_t)n_stages * G::STAGE + fixed;
+  static PerDeviceOnce attr;
+  if (const int dev_ = attr.pending(); dev_ >= 0) {
+    OCTSEG_CUDA(cudaFuncSetAttribute(wgrad_rows_kernel<PC, NB, KS, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    attr.mark(dev_);
+  }
+  const int blocks_y = p.n_nchunks;
+  const int gx = std::max(1, std::min(p.num_tiles, (148 + blocks_y - 1) / blocks_y));
+  wgrad_rows_kernel<PC, NB, KS, UPS><<<dim3(gx, blocks_y), kWrThreads, smem, st>>>(map_a, map_d, p, n_stages, status);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+bool wgrad_rows_applicable(int kh, int kw, int cin, int ups) {
+  static const bool off = []() { const char *e = std::getenv("OCTSEG_WGRAD_ROWS"); return e && e[0] == '0'; }();
+  if (off || kh != kw || cin % 8 || cin > 16) return false;
+  return ups ? kh == 2 : (kh == 2 || kh == 3);
+}
+
+// a_in: the conv's input (low-res for ups = 1), dz on the output grid; both dense
+static int launch_wgrad_rows(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> dz, WgParams p, int *status, cudaStream_t st) {
+  const int nb = std::min(2, p.cout_planes), ks = p.kh, pc = p.cin_planes, ups = p.ups;
+  p.n_nchunks = (p.cout_planes + nb - 1) / nb;
+  p.tiles_y = (dz.h + kWrTH - 1) / kWrTH;
+  p.num_tiles = dz.n * p.tiles_x * p.tiles_y;
+  p.d_planes = nb;
+  const int aw = ups ? kWmTW / 2 + 1 : kWmTW + ks - 1, ah = ups ? kWrTH / 2 + 1 : kWrTH + ks - 1;
+  CUtensorMap map_a, map_d;
+  if (tc_encode_map_4d(a_in.ptr, a_in.w, a_in.h, p.cin_planes, a_in.n, aw, ah, pc, &map_a)) return 1;
+  if (tc_encode_map_4d(dz.ptr, dz.w, dz.h, p.cout_planes, dz.n, kWmTW, kWrTH, nb, &map_d)) return 1;
+#define OCTSEG_WR(PC_, NB_, KS_, UPS_) \
+  if (pc == PC_ && nb == NB_ && ks == KS_ && ups == UPS_) return launch_wgrad_rows_t<PC_, NB_, KS_, UPS_>(map_a, map_d, p, status, st);
+  OCTSEG_WR(1, 1, 3, 0) OCTSEG_WR(1, 2, 3, 0) OCTSEG_WR(2, 1, 3, 0) OCTSEG_WR(2, 2, 3, 0)
+  OCTSEG_WR(1, 1, 2, 0) OCTSEG_WR(1, 2, 2, 0) OCTSEG_WR(2, 1, 2, 0) OCTSEG_WR(2, 2, 2, 0)
+  OCTSEG_WR(1, 1, 2, 1) OCTSEG_WR(1, 2, 2, 1) OCTSEG_WR(2, 1, 2, 1) OCTSEG_WR(2, 2, 2, 1)
+#undef OCTSEG_WR
+  set_error("wgrad_rows: no instantiation");
+  return 1;
+}
+
 int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> dz, int kh, int kw, int pad_top,
                      int pad_left, int ups, int cin, int cout, float *dW, float *db, int *status,
                      cudaStream_t st) {
@@ -602,6 +832,9 @@ int launch_wgrad_mma(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> d
   p.dW = dW; p.db = db;
   const bool dense = a_in.img_stride == (long long)a_in.planes * a_in.h * a_in.w * 8 &&
                      dz.img_stride == (long long)dz.planes * dz.h * dz.w * 8 && a_in.planes == p.cin_planes;
+  if (dense && status && wgrad_rows_applicable(kh, kw, cin, ups) &&
+      (ups ? (pad_top == 0 && pad_left == 0 && dz.h == 2 * a_in.h && dz.w == 2 * a_in.w) : (dz.h == a_in.h && dz.w == a_in.w)))
+    return launch_wgrad_rows(a_in, dz, p, status, st);
   static const bool no_deep = []() { const char *e = std::getenv("OCTSEG_NO_DEEP_WGRAD"); return e && e[0] == '1'; }();
   if (!ups && dense && status && !no_deep && p.cin_planes >= 4) {
     // ---- deep-layer kernel: pick the warp tiling MP x NP (3 m16 tiles x NBW n8 tiles per warp)

@@ -51,7 +51,11 @@ def engines():
 CASES = [(1, 2, 32, 24), (2, 2, 32, 16), (3, 1, 32, 32), (4, 2, 16, 16), (5, 2, 32, 16), (6, 2, 16, 16), (7, 3, 16, 16),
          (8, 4, 16, 8), (9, 4, 16, 16), (10, 2, 16, 8), (11, 2, 32, 16), (12, 2, 16, 32), (13, 2, 16, 16), (14, 1, 32, 32),
          (15, 2, 32, 16), (16, 2, 16, 16), (17, 1, 32, 32), (18, 2, 32, 16), (19, 2, 32, 24), (20, 2, 32, 24), (21, 2, 48, 40),
-         (9, 8, 32, 16), (11, 1, 64, 32)]
+         (9, 8, 32, 16), (11, 1, 64, 32),
+         # row-walking weight gradient of the narrow layers: enough tiles per persistent CTA to wrap its TMA stage ring
+         # (8 -> 8: 960 tiles of 32x32 over 148 CTAs, 6 stages), the 16 -> 16 variant, and the up-conv read from the
+         # LOW-res tensor over several tiles with a partial one
+         (1, 30, 256, 128), (3, 6, 128, 64), (19, 4, 64, 40)]
 
 
 @pytest.mark.parametrize("idx,n,h,w", CASES)
