@@ -6,7 +6,6 @@
 #include <stdint.h>
 #include <atomic>
 #include <string>
-#include <utility>
 
 namespace octseg {
 
@@ -160,27 +159,6 @@ struct PerDeviceOnce {
 
 // error plumbing -------------------------------------------------------------------
 void set_error(const std::string &msg);
-
-// Programmatic dependent launch for the streaming kernels of the train step.  A kernel launched through launch_pdl
-// may be scheduled while the previous kernel of the stream drains (its CTAs take the SM slots that free up), so it must
-// call pdl_sync() before it touches global memory: that waits until the previous kernel has completed and its writes
-// are visible, then lets the NEXT kernel of the stream be scheduled the same way.  Inside a captured CUDA graph the
-// attribute becomes a programmatic dependency edge between the two kernel nodes.  OCTSEG_NO_PDL=1 switches it off.
-__device__ __forceinline__ void pdl_sync() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-bool pdl_enabled();
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
-}
 #define OCTSEG_CUDA(expr)                                                              \
   do {                                                                                 \
     cudaError_t _e = (expr);                                                           \

@@ -13,10 +13,6 @@ namespace octseg {
 
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
-bool pdl_enabled() {
-  static const bool on = []() { const char *e = std::getenv("OCTSEG_NO_PDL"); return !(e && e[0] == '1'); }();
-  return on;
-}
 
 static const float kBnEps = 1e-3f;   // Keras BatchNormalization() default
 

@@ -176,7 +176,7 @@ struct PhaseProf {
       float ms = 0;
       cudaEventElapsedTime(&ms, s.second.first, s.second.second);
       tot[s.first % 100] += ms;
-      if (detail && ms > 0.05f) fprintf(stderr, "[train detail] block %d %s %.3f ms\n", s.first / 100, names[s.first % 100], ms);
+      if (detail && ms > 0.002f) fprintf(stderr, "[train detail] block %d %s %.3f ms\n", s.first / 100, names[s.first % 100], ms);
       cudaEventDestroy(s.second.first);
       cudaEventDestroy(s.second.second);
     }

@@ -56,7 +56,6 @@ constexpr int kSpanVecs = 8192;   // vectors per block span
 
 template <typename T>
 __global__ void __launch_bounds__(kRedThreads) bn_stats_kernel(View<const T> z, double *sums, int c) {
-  pdl_sync();
   const int pl = blockIdx.y, img = blockIdx.z;
   const int hw = z.h * z.w;
   const T *base = z.ptr + (long long)img * z.img_stride + (long long)pl * hw * 8;
@@ -77,7 +76,8 @@ int launch_bn_stats(View<const T> z, double *sums, cudaStream_t st) {
   const int c = z.planes * 8;   // `sums` is zeroed by the caller (one memset per train step)
   const int hw = z.h * z.w;
   dim3 grid((hw + kSpanVecs - 1) / kSpanVecs, z.planes, z.n);
-  OCTSEG_CUDA(launch_pdl(bn_stats_kernel<T>, grid, dim3(kRedThreads), 0, st, z, sums, c));
+  bn_stats_kernel<T><<<grid, kRedThreads, 0, st>>>(z, sums, c);
+  OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -137,7 +137,6 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(
     View<const T> z, const double *__restrict__ sums, long long count, float eps, float momentum,
     const float *__restrict__ gamma, const float *__restrict__ beta, float *moving_mean, float *moving_var,
     float *mean, float *invstd, float *scale, float *shift, const T *__restrict__ mask, View<T> a, View<T> pooled) {
-  pdl_sync();
   const int c = z.planes * 8;
   const double inv_count = 1.0 / (double)count;
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
@@ -224,12 +223,12 @@ int launch_bn_finalize_apply(View<const T> z, const double *sums, long long coun
   if (pooled.ptr) {
     if (mask || (z.h & 1) || (z.w & 1)) { set_error("bn_finalize_apply: pooled variant needs even dims and no dropout"); return 1; }
     dim3 grid(std::max(1, std::min((hw / 4 + 2047) / 2048, 64)), z.planes, z.n);     // >= 8 windows (32 vectors) per thread
-    OCTSEG_CUDA(launch_pdl(bn_finalize_apply_kernel<T, 1>, grid, dim3(256), 0, st, z, sums, count, eps, momentum, gamma, beta,
-                           moving_mean, moving_var, mean, invstd, scale, shift, mask, a, pooled));
+    bn_finalize_apply_kernel<T, 1><<<grid, 256, 0, st>>>(z, sums, count, eps, momentum, gamma, beta, moving_mean, moving_var,
+                                                         mean, invstd, scale, shift, mask, a, pooled);
   } else {
     dim3 grid(std::max(1, std::min((hw + 4095) / 4096, 64)), z.planes, z.n);         // >= 16 vectors per thread
-    OCTSEG_CUDA(launch_pdl(bn_finalize_apply_kernel<T, 0>, grid, dim3(256), 0, st, z, sums, count, eps, momentum, gamma, beta,
-                           moving_mean, moving_var, mean, invstd, scale, shift, mask, a, pooled));
+    bn_finalize_apply_kernel<T, 0><<<grid, 256, 0, st>>>(z, sums, count, eps, momentum, gamma, beta, moving_mean, moving_var,
+                                                         mean, invstd, scale, shift, mask, a, pooled);
   }
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
@@ -328,7 +327,6 @@ __global__ void __launch_bounds__(256) head_loss_kernel(View<const T> a, const f
                                                         const float *__restrict__ class_w, float inv_den,
                                                         View<T> da, float *__restrict__ d_wgt,
                                                         float *__restrict__ d_bias, double *loss_acc) {
-  pdl_sync();
   constexpr int CIN = PL * 8;
   __shared__ float s_w[CIN * K], s_b[K], s_cw[K];
   __shared__ float s_red[8][CIN * K + K + 1];
@@ -426,8 +424,9 @@ static int launch_head_loss_kp(View<const T> a, const float *wgt, const float *b
                                double *loss_acc, cudaStream_t st) {
   const long long total = (long long)a.n * a.h * a.w;
   unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 4);
-  OCTSEG_CUDA(launch_pdl(head_loss_kernel<T, K, PL>, dim3(grid), dim3(256), 0, st, a, wgt, bias, labels, class_w, inv_den, da,
-                         d_wgt, d_bias, loss_acc));
+  head_loss_kernel<T, K, PL><<<grid, 256, 0, st>>>(a, wgt, bias, labels, class_w, inv_den, da, d_wgt, d_bias,
+                                                   loss_acc);
+  OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -609,7 +608,6 @@ __global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_reduce_kernel(
     View<const T> da, View<const T> z, const float *__restrict__ mean, const float *__restrict__ invstd,
     const float *__restrict__ gamma, const float *__restrict__ beta, const T *__restrict__ mask, double *sums,
     int c) {
-  pdl_sync();
   const int pl = blockIdx.y, img = blockIdx.z;
   const int hw = z.h * z.w;
   const T *zb = z.ptr + (long long)img * z.img_stride + (long long)pl * hw * 8;
@@ -663,7 +661,8 @@ int launch_bn_bwd_reduce(View<const T> da, View<const T> z, const float *mean, c
   const int c = z.planes * 8;   // `sums` is zeroed by the caller
   const int hw = z.h * z.w;
   dim3 grid((hw + kSpanVecs - 1) / kSpanVecs, z.planes, z.n);
-  OCTSEG_CUDA(launch_pdl(bn_bwd_reduce_kernel<T>, grid, dim3(kRedThreads), 0, st, da, z, mean, invstd, gamma, beta, mask, sums, c));
+  bn_bwd_reduce_kernel<T><<<grid, kRedThreads, 0, st>>>(da, z, mean, invstd, gamma, beta, mask, sums, c);
+  OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -672,7 +671,6 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(
     View<const T> da, View<const T> z, const float *__restrict__ mean, const float *__restrict__ invstd,
     const float *__restrict__ gamma, const float *__restrict__ beta, const T *__restrict__ mask,
     const double *__restrict__ sums, long long count, View<T> dz, float *d_gamma, float *d_beta, int c) {
-  pdl_sync();
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
     for (int i = threadIdx.x; i < c; i += blockDim.x) { d_beta[i] = (float)sums[i]; d_gamma[i] = (float)sums[c + i]; }
   const int pl = blockIdx.y, img = blockIdx.z;
@@ -734,8 +732,9 @@ int launch_bn_bwd_apply(View<const T> da, View<const T> z, const float *mean, co
                         long long count, View<T> dz, float *d_gamma, float *d_beta, cudaStream_t st) {
   const int hw = z.h * z.w;
   dim3 grid(std::max(1, std::min((hw + 4095) / 4096, 64)), z.planes, z.n);           // >= 16 vectors per thread
-  OCTSEG_CUDA(launch_pdl(bn_bwd_apply_kernel<T>, grid, dim3(256), 0, st, da, z, mean, invstd, gamma, beta, mask, sums, count, dz,
-                         d_gamma, d_beta, z.planes * 8));
+  bn_bwd_apply_kernel<T><<<grid, 256, 0, st>>>(da, z, mean, invstd, gamma, beta, mask, sums, count, dz, d_gamma,
+                                               d_beta, z.planes * 8);
+  OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -745,7 +744,6 @@ int launch_bn_bwd_apply(View<const T> da, View<const T> z, const float *mean, co
 template <typename T>
 __global__ void __launch_bounds__(256) pool_bwd_add_kernel(View<const T> a, View<const T> d_pooled,
                                                            View<const T> d_skip, View<T> out, int has_skip) {
-  pdl_sync();
   const int Ho = d_pooled.h, Wo = d_pooled.w;
   const int pl = blockIdx.y, b = blockIdx.z;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Ho * Wo; i += gridDim.x * blockDim.x) {
@@ -782,8 +780,8 @@ int launch_pool_bwd_add(View<const T> a, View<const T> d_pooled, View<const T> d
                         cudaStream_t st) {
   const int hw = d_pooled.h * d_pooled.w;
   dim3 grid(std::max(1, std::min((hw + 255) / 256, 64)), d_pooled.planes, d_pooled.n);
-  OCTSEG_CUDA(launch_pdl(pool_bwd_add_kernel<T>, grid, dim3(256), 0, st, a, d_pooled, d_skip, da_total,
-                         (int)(d_skip.ptr != nullptr)));
+  pool_bwd_add_kernel<T><<<grid, 256, 0, st>>>(a, d_pooled, d_skip, da_total, d_skip.ptr != nullptr);
+  OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -820,7 +818,6 @@ int launch_upsample2x(View<const T> in, View<T> out, cudaStream_t st) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) sumpool2x_kernel(View<const T> in, View<T> out) {
-  pdl_sync();
   const int pl = blockIdx.y, b = blockIdx.z;
   const int h = out.h, w = out.w;
   const T *ib = in.ptr + b * in.img_stride + (long long)pl * (4LL * h * w) * 8;
@@ -838,7 +835,8 @@ __global__ void __launch_bounds__(256) sumpool2x_kernel(View<const T> in, View<T
 template <typename T>
 int launch_sumpool2x(View<const T> in, View<T> out, cudaStream_t st) {
   dim3 grid(std::max(1, std::min((out.h * out.w + 255) / 256, 64)), out.planes, out.n);
-  OCTSEG_CUDA(launch_pdl(sumpool2x_kernel<T>, grid, dim3(256), 0, st, in, out));
+  sumpool2x_kernel<T><<<grid, 256, 0, st>>>(in, out);
+  OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }
 
