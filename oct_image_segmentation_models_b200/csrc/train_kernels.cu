@@ -321,7 +321,7 @@ constexpr int kHeadMaxK = 16;
 // (d_wgt[cin][K], d_bias[K], loss) lives in registers for the whole grid-stride loop and is
 // reduced ONCE per block (warp shuffles -> smem -> one global atomic per value per block).
 template <typename T, int K, int PL>
-__global__ void __launch_bounds__(256) head_loss_kernel(View<const T> a, const float *__restrict__ wgt,
+__global__ void __launch_bounds__(256, (PL * 8 * K <= 32) ? 2 : 1) head_loss_kernel(View<const T> a, const float *__restrict__ wgt,
                                                         const float *__restrict__ bias,
                                                         const uint8_t *__restrict__ labels,
                                                         const float *__restrict__ class_w, float inv_den,
@@ -333,65 +333,87 @@ __global__ void __launch_bounds__(256) head_loss_kernel(View<const T> a, const f
   for (int i = threadIdx.x; i < CIN * K; i += blockDim.x) s_w[i] = wgt[i];
   for (int i = threadIdx.x; i < K; i += blockDim.x) { s_b[i] = bias[i]; s_cw[i] = class_w[i]; }
   __syncthreads();
-  const long long hw = (long long)a.h * a.w, total = (long long)a.n * hw;
+  // grid = (blocks per image, images): no 64-bit division per pixel (it cost more than the softmax)
+  const int hw = a.h * a.w;
+  const long long b = blockIdx.y;
+  const uint8_t *lab = labels + b * hw;
   float p_dw[CIN * K], p_db[K], p_loss = 0.f;
 #pragma unroll
   for (int i = 0; i < CIN * K; ++i) p_dw[i] = 0.f;
 #pragma unroll
   for (int k = 0; k < K; ++k) p_db[k] = 0.f;
-  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
-       pix += (long long)gridDim.x * blockDim.x) {
-    const long long off = pix % hw;
-    const int b = (int)(pix / hw);
-    Vec8f v[PL];
-    float z[K];
+  // kU pixels per thread and iteration with every load issued before the first use: at 128 registers the kernel runs 16
+  // warps per SM, and one 16-byte load in flight per thread left the memory system idle (ncu: DRAM 16 %)
+  constexpr int kU = (PL == 1) ? 4 : 2;
+  const int stride = gridDim.x * blockDim.x;
+  for (int off0 = blockIdx.x * blockDim.x + threadIdx.x; off0 < hw; off0 += stride * kU) {
+    Raw8<T> rv[kU][PL];
+    int tt[kU];
 #pragma unroll
-    for (int k = 0; k < K; ++k) z[k] = s_b[k];
+    for (int u = 0; u < kU; ++u) {
+      const int off = off0 + u * stride;
+      tt[u] = 0;
+      if (off < hw) {
 #pragma unroll
-    for (int pl = 0; pl < PL; ++pl) {
-      v[pl] = load8(a.ptr + b * a.img_stride + ((long long)pl * hw + off) * 8);
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-#pragma unroll
-        for (int k = 0; k < K; ++k) z[k] = fmaf(v[pl].v[c], s_w[(pl * 8 + c) * K + k], z[k]);
-    }
-    float mx = z[0];
-#pragma unroll
-    for (int k = 1; k < K; ++k) mx = fmaxf(mx, z[k]);
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) { z[k] = expf(z[k] - mx); s += z[k]; }
-    const float inv = 1.f / s;
-    float S = 0.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) { z[k] *= inv; S += z[k]; }
-    const int t = labels[pix];
-    float pt = 0.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) { z[k] = z[k] / S; if (k == t) pt = z[k]; }
-    const float wt = (t < K) ? s_cw[t] : 0.f;
-    const bool active = (pt >= 1e-7f) && (pt <= 1.f - 1e-7f);
-    p_loss += -wt * logf(fminf(fmaxf(pt, 1e-7f), 1.f - 1e-7f)) * inv_den;
-    float dl[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      dl[k] = active ? wt * (z[k] - (k == t ? 1.f : 0.f)) * inv_den : 0.f;
-      p_db[k] += dl[k];
-    }
-#pragma unroll
-    for (int pl = 0; pl < PL; ++pl) {
-      Vec8f g;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          acc = fmaf(dl[k], s_w[(pl * 8 + c) * K + k], acc);
-          p_dw[(pl * 8 + c) * K + k] = fmaf(v[pl].v[c], dl[k], p_dw[(pl * 8 + c) * K + k]);
-        }
-        g.v[c] = acc;
+        for (int pl = 0; pl < PL; ++pl) rv[u][pl] = load_raw8(a.ptr + b * a.img_stride + ((long long)pl * hw + off) * 8);
+        tt[u] = lab[off];
       }
-      store8(da.ptr + b * da.img_stride + ((long long)pl * hw + off) * 8, g);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int off = off0 + u * stride;
+      if (off >= hw) break;
+      Vec8f v[PL];
+      float z[K];
+#pragma unroll
+      for (int pl = 0; pl < PL; ++pl) v[pl] = cvt8(rv[u][pl]);
+      const int t = tt[u];
+#pragma unroll
+      for (int k = 0; k < K; ++k) z[k] = s_b[k];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int k = 0; k < K; ++k) z[k] = fmaf(v[c >> 3].v[c & 7], s_w[c * K + k], z[k]);
+      float mx = z[0];
+#pragma unroll
+      for (int k = 1; k < K; ++k) mx = fmaxf(mx, z[k]);
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) { z[k] = expf(z[k] - mx); s += z[k]; }
+      const float inv = 1.f / s;
+      float S = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) { z[k] *= inv; S += z[k]; }
+      // the loss renormalises its input (custom_losses.py:30): S = 1 +- a few ulp, so one reciprocal serves all classes
+      const float rS = 1.f / S;
+      float pt = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) { z[k] *= rS; if (k == t) pt = z[k]; }
+      const float wt = (t < K) ? s_cw[t] : 0.f;
+      const bool active = (pt >= 1e-7f) && (pt <= 1.f - 1e-7f);
+      p_loss += -wt * logf(fminf(fmaxf(pt, 1e-7f), 1.f - 1e-7f)) * inv_den;
+      const float gs = active ? wt * inv_den : 0.f;
+      float dl[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        dl[k] = gs * (z[k] - (k == t ? 1.f : 0.f));
+        p_db[k] += dl[k];
+      }
+#pragma unroll
+      for (int pl = 0; pl < PL; ++pl) {
+        Vec8f g;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            acc = fmaf(dl[k], s_w[(pl * 8 + c) * K + k], acc);
+            p_dw[(pl * 8 + c) * K + k] = fmaf(v[pl].v[c], dl[k], p_dw[(pl * 8 + c) * K + k]);
+          }
+          g.v[c] = acc;
+        }
+        store8(da.ptr + b * da.img_stride + ((long long)pl * hw + off) * 8, g);
+      }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -422,8 +444,10 @@ template <typename T, int K, int PL>
 static int launch_head_loss_kp(View<const T> a, const float *wgt, const float *bias, const uint8_t *labels,
                                const float *class_w, float inv_den, View<T> da, float *d_wgt, float *d_bias,
                                double *loss_acc, cudaStream_t st) {
-  const long long total = (long long)a.n * a.h * a.w;
-  unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 4);
+  // ~148 * 4 blocks in total (every block reduces its partial sums once: few, long-lived blocks)
+  const int hw = a.h * a.w;
+  const int per_img = std::max(1, std::min((hw + 255) / 256, (148 * 4 + a.n - 1) / a.n));
+  dim3 grid(per_img, a.n);
   head_loss_kernel<T, K, PL><<<grid, 256, 0, st>>>(a, wgt, bias, labels, class_w, inv_den, da, d_wgt, d_bias,
                                                    loss_acc);
   OCTSEG_CUDA(cudaGetLastError());

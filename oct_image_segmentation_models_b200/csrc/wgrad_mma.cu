@@ -598,11 +598,11 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16 *__r
 // ---------------------------------------------------------------------------------
 constexpr int kWrCW = 16;                          // compute warps: (8 / NB bands) x 2 k-steps x NB output planes
 constexpr int kWrThreads = 32 * (1 + kWrCW);
-constexpr int kWrTH = 32;                          // tile rows
+constexpr int kWrTH = 32;                          // tile rows (16 for Cin = 32)
 
 template <int PC, int NB, int KS, int UPS>
 struct WrGeo {
-  static constexpr int TH = kWrTH, TW = kWmTW;
+  static constexpr int TH = PC > 2 ? kWrTH / 2 : kWrTH, TW = kWmTW;      // 32 input channels: half-height tiles (smem)
   static constexpr int AW = UPS ? (TW / 2 + 1) : (TW + KS - 1);
   static constexpr int AH = UPS ? (TH / 2 + 1) : (TH + KS - 1);
   static constexpr int U = KS * PC, L = (U + 1) / 2;       // (dx, plane) column groups, m16 loads (pairs of groups)
@@ -788,26 +788,29 @@ static int launch_wgrad_rows_t(const CUtensorMap &map_a, const CUtensorMap &map_
 
 bool wgrad_rows_applicable(int kh, int kw, int cin, int ups) {
   static const bool off = []() { const char *e = std::getenv("OCTSEG_WGRAD_ROWS"); return e && e[0] == '0'; }();
-  if (off || kh != kw || cin % 8 || cin > 16) return false;
+  if (off || kh != kw || (cin != 8 && cin != 16 && cin != 32)) return false;
   return ups ? kh == 2 : (kh == 2 || kh == 3);
 }
 
 // a_in: the conv's input (low-res for ups = 1), dz on the output grid; both dense
 static int launch_wgrad_rows(View<const __nv_bfloat16> a_in, View<const __nv_bfloat16> dz, WgParams p, int *status, cudaStream_t st) {
-  const int nb = std::min(2, p.cout_planes), ks = p.kh, pc = p.cin_planes, ups = p.ups;
+  const int ks = p.kh, pc = p.cin_planes, ups = p.ups;
+  const int nb = pc > 2 ? 2 : std::min(2, p.cout_planes);
+  const int th = pc > 2 ? kWrTH / 2 : kWrTH;
   p.n_nchunks = (p.cout_planes + nb - 1) / nb;
-  p.tiles_y = (dz.h + kWrTH - 1) / kWrTH;
+  p.tiles_y = (dz.h + th - 1) / th;
   p.num_tiles = dz.n * p.tiles_x * p.tiles_y;
   p.d_planes = nb;
-  const int aw = ups ? kWmTW / 2 + 1 : kWmTW + ks - 1, ah = ups ? kWrTH / 2 + 1 : kWrTH + ks - 1;
+  const int aw = ups ? kWmTW / 2 + 1 : kWmTW + ks - 1, ah = ups ? th / 2 + 1 : th + ks - 1;
   CUtensorMap map_a, map_d;
   if (tc_encode_map_4d(a_in.ptr, a_in.w, a_in.h, p.cin_planes, a_in.n, aw, ah, pc, &map_a)) return 1;
-  if (tc_encode_map_4d(dz.ptr, dz.w, dz.h, p.cout_planes, dz.n, kWmTW, kWrTH, nb, &map_d)) return 1;
+  if (tc_encode_map_4d(dz.ptr, dz.w, dz.h, p.cout_planes, dz.n, kWmTW, th, nb, &map_d)) return 1;
 #define OCTSEG_WR(PC_, NB_, KS_, UPS_) \
   if (pc == PC_ && nb == NB_ && ks == KS_ && ups == UPS_) return launch_wgrad_rows_t<PC_, NB_, KS_, UPS_>(map_a, map_d, p, status, st);
   OCTSEG_WR(1, 1, 3, 0) OCTSEG_WR(1, 2, 3, 0) OCTSEG_WR(2, 1, 3, 0) OCTSEG_WR(2, 2, 3, 0)
   OCTSEG_WR(1, 1, 2, 0) OCTSEG_WR(1, 2, 2, 0) OCTSEG_WR(2, 1, 2, 0) OCTSEG_WR(2, 2, 2, 0)
   OCTSEG_WR(1, 1, 2, 1) OCTSEG_WR(1, 2, 2, 1) OCTSEG_WR(2, 1, 2, 1) OCTSEG_WR(2, 2, 2, 1)
+  OCTSEG_WR(4, 2, 3, 0) OCTSEG_WR(4, 2, 2, 0) OCTSEG_WR(4, 2, 2, 1)
 #undef OCTSEG_WR
   set_error("wgrad_rows: no instantiation");
   return 1;
