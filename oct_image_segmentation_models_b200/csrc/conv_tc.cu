@@ -218,11 +218,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (!ok) break;
           const uint32_t afull = smem_u32(&bars->a_full[as]);
           if (leader) {
-            mbar_expect_tx(afull, p.a_stage_bytes);
-            // tensor map is declared in 8-byte elements: x coordinate = px * 2
-            tma_load_4d(smem_u32(a_smem + (size_t)as * a_stride), &tmap_a, afull,
-                        (tx * p.mt_x * kTcTileW - p.pad_x) * 2, ty * p.mt_y * kTcTileH * p.row_mul - p.pad_y,
-                        ch * p.planes_per_chunk, img);
+            mbar_expect_tx(afull, p.a_tx_bytes);
+            if (p.s2d) {
+              // four pixel parities of the high-res input, each a [plane][row][px] sub-tile of low-res coordinates
+#pragma unroll
+              for (int par = 0; par < 4; ++par)
+                tma_load_5d(smem_u32(a_smem + (size_t)as * a_stride) + (uint32_t)par * p.s2d_part_bytes, p.s2d_maps + par, afull,
+                            0, tx * p.mt_x * kTcTileW - p.pad_x, ty * p.mt_y * kTcTileH - p.pad_y, 0, img);
+            } else {
+              // tensor map is declared in 8-byte elements: x coordinate = px * 2
+              tma_load_4d(smem_u32(a_smem + (size_t)as * a_stride), &tmap_a, afull,
+                          (tx * p.mt_x * kTcTileW - p.pad_x) * 2, ty * p.mt_y * kTcTileH * p.row_mul - p.pad_y,
+                          ch * p.planes_per_chunk, img);
+            }
           }
           if (++as == p.a_stages) { as = 0; aph ^= 1u; }
           if (p.b_resident) continue;
@@ -867,6 +875,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
               uint4 pk;
               uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk);
+              if constexpr (ST == 0) {
+                if (p.pool_sum) {
+                  // data gradient of the up-conv: only the 2x2 sums of the fp32 outputs are stored (partners: lanes ^1, ^8)
+                  float o[8];
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    o[k] = fmaxf(fmaf(__uint_as_float(v[bb][u][k]), sc[k], sh[k]), relu_floor);
+                    o[k] += __shfl_xor_sync(0xffffffffu, o[k], 1);
+                    o[k] += __shfl_xor_sync(0xffffffffu, o[k], 8);
+                  }
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) h2[k] = pack2(o[2 * k], o[2 * k + 1], p.fp16);
+                  if (inside && !(px & 1) && !(r & 1))
+                    *reinterpret_cast<uint4 *>(p.pool_out + (long long)img * p.pool_img_stride +
+                                               (long long)(co0 >> 3) * (plane_elems >> 2) +
+                                               ((long long)(y >> 1) * (p.out_w >> 1) + (x >> 1)) * 8) = pk;
+                  continue;
+                }
+              }
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 h2[k] = bn_relu_pack2(v[bb][u][2 * k], v[bb][u][2 * k + 1], sc[2 * k], sc[2 * k + 1], sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
@@ -1074,6 +1101,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
               uint4 pk;
               uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk);
+              if (p.pool_sum) {
+                // data gradient of the up-conv: only the 2x2 sums of the fp32 outputs are stored (partners: lanes ^1, ^8)
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  o[k] = fmaxf(fmaf(__uint_as_float(v[u][k]), sc[k], sh[k]), relu_floor);
+                  o[k] += __shfl_xor_sync(0xffffffffu, o[k], 1);
+                  o[k] += __shfl_xor_sync(0xffffffffu, o[k], 8);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h2[k] = pack2(o[2 * k], o[2 * k + 1], p.fp16);
+                if (inside && !(px & 1) && !(r & 1))
+                  *reinterpret_cast<uint4 *>(p.pool_out + (long long)img * p.pool_img_stride +
+                                             (long long)(co0 >> 3) * (plane_elems >> 2) +
+                                             ((long long)(y >> 1) * (p.out_w >> 1) + (x >> 1)) * 8) = pk;
+                continue;
+              }
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 h2[k] = bn_relu_pack2(v[u][2 * k], v[u][2 * k + 1], sc[2 * k], sc[2 * k + 1], sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
@@ -1230,6 +1274,66 @@ int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, 
   return 0;
 }
 
+int tc_make_geometry_s2d(int cz, int cout, TcGeometry *g) {
+  std::memset(g, 0, sizeof(*g));
+  if (cz % 8 || cout % 8 || cz > 32 || (cz != 8 && (cz / 8) % 2)) return 1;
+  g->kh = 3; g->kw = 3; g->cin = cz; g->cout = cout; g->ups = 0; g->s2d = 1;
+  g->cin_l = cz; g->cout_l = cout; g->wscale = 1.f;
+  g->pt = 1; g->pl = 1;
+  g->dy_min = -1; g->dy_max = 0; g->dx_min = -1; g->dx_max = 0;     // one halo row / px BEFORE the tile (taps a, b = -1)
+  g->box_h = 1; g->box_w = 1;
+  const int P = cz / 8;
+  g->planes_per_chunk = 4 * P;       // "planes" of the stage: [parity][plane]
+  g->cin_chunks = 1;
+  g->cols_valid = cout;
+  const int cols_pad = (cout + 15) / 16 * 16;
+  int nc = 256;
+  while (cols_pad % nc) nc >>= 1;
+  g->n_cols = nc;
+  g->n_tiles_n = cols_pad / nc;
+  struct Half { int v, ty, tx; };
+  std::vector<Half> halves;
+  for (int par = 0; par < 4; ++par) {              // ascending smem offset: (parity, plane, row, px)
+    const int py = par >> 1, px = par & 1;
+    for (int pl8 = 0; pl8 < P; ++pl8)
+      for (int ty = (py ? 0 : 1); ty < 2; ++ty)     // parity 0 rows / columns carry only the tap a = 0 (box offset 1)
+        for (int tx = (px ? 0 : 1); tx < 2; ++tx) halves.push_back({par * P + pl8, ty, tx});
+  }
+  int ks = 0;
+  if (P == 1) {
+    // 9 single-plane halves: consecutive pairs (LBO = offset difference > 0); the odd one gets a zero-weight dummy in front
+    size_t i = 0;
+    for (; i + 2 < halves.size() || (halves.size() % 2 == 0 && i < halves.size()); i += 2) {
+      for (int hf = 0; hf < 2; ++hf) {
+        g->half_ty[ks][hf] = halves[i + hf].ty; g->half_tx[ks][hf] = halves[i + hf].tx; g->half_pl[ks][hf] = halves[i + hf].v;
+      }
+      ++ks;
+    }
+    if (halves.size() % 2) {
+      const Half &d = halves[halves.size() - 2], &l = halves.back();
+      g->half_ty[ks][0] = -1 - d.ty; g->half_tx[ks][0] = d.tx; g->half_pl[ks][0] = d.v;     // dummy (encoded ty < 0)
+      g->half_ty[ks][1] = l.ty; g->half_tx[ks][1] = l.tx; g->half_pl[ks][1] = l.v;
+      ++ks;
+    }
+  } else {
+    // plane pairs (2j, 2j+1) of one parity at one tap: LBO = plane pitch
+    for (int par = 0; par < 4; ++par) {
+      const int py = par >> 1, px = par & 1;
+      for (int ty = (py ? 0 : 1); ty < 2; ++ty)
+        for (int tx = (px ? 0 : 1); tx < 2; ++tx)
+          for (int j = 0; j < P / 2; ++j) {
+            for (int hf = 0; hf < 2; ++hf) { g->half_ty[ks][hf] = ty; g->half_tx[ks][hf] = tx; g->half_pl[ks][hf] = par * P + 2 * j + hf; }
+            ++ks;
+          }
+    }
+  }
+  if (ks > kTcMaxKSteps) return 1;
+  g->ksteps = ks;
+  g->bgroup = ks;
+  if ((size_t)ks * 32 * nc > 80 * 1024) return 1;      // the plan keeps these weights resident
+  return 0;
+}
+
 static inline uint16_t f2h(float f) {
   const __half_raw r = static_cast<__half_raw>(__float2half_rn(f));   // host-callable, round to nearest even
   return r.x;
@@ -1346,6 +1450,23 @@ void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> 
 
 // Device-side twin of tc_pack_weights (training: the weights change every step).
 // transposed=1 packs the data-gradient operator: W'[a][b][ci'][co'] = w[kh-1-a][kw-1-b][co'][ci']
+// s2d geometry (tc_make_geometry_s2d): weight of K half (s, hf), input channel kk of its plane, output column col, summed
+// from the up-conv's FORWARD kernel w[2][2][g.cout][g.cin]
+__device__ __forceinline__ float s2d_weight(const TcGeometry &g, const float *__restrict__ w, int s, int hf, int kk, int col) {
+  const int P = g.cin / 8, v = g.half_pl[s][hf], par = v / P, cz = (v - par * P) * 8 + kk;
+  const int py = par >> 1, px = par & 1;
+  const int a = py ? (g.half_ty[s][hf] ? 1 : -1) : 0, b = px ? (g.half_tx[s][hf] ? 1 : -1) : 0;
+  float val = 0.f;
+  for (int ky = 0; ky < 2; ++ky) {
+    if ((a == -1 && ky != 1) || (a == 1 && ky != 0)) continue;
+    for (int kx = 0; kx < 2; ++kx) {
+      if ((b == -1 && kx != 1) || (b == 1 && kx != 0)) continue;
+      val += w[(((long long)ky * 2 + kx) * g.cout + col) * g.cin + cz];
+    }
+  }
+  return val;
+}
+
 // where w is the forward kernel [kh][kw][g.cout][g.cin] (g describes the dgrad conv).
 __global__ void tc_pack_kernel(TcGeometry g, const float *__restrict__ w, int transposed,
                                __nv_bfloat16 *__restrict__ out, long long total) {
@@ -1364,7 +1485,9 @@ __global__ void tc_pack_kernel(TcGeometry g, const float *__restrict__ w, int tr
     if (g.half_ty[s][hf] >= 0 && col < g.cols_valid) {
       const int dy = g.half_ty[s][hf] + g.dy_min, dx = g.half_tx[s][hf] + g.dx_min;
       const int ci = (ch * g.planes_per_chunk + g.half_pl[s][hf]) * 8 + kk;
-      if (g.rows2) {
+      if (g.s2d) {
+        val = s2d_weight(g, w, s, hf, kk, col);
+      } else if (g.rows2) {
         // banded 4x3 row-pair filter built on the fly from the 3x3 kernel (tc_rowpair_weights)
         const int cr = g.cout >> 1, par = col / cr, co = col - par * cr;
         const int a = dy + pt - par, b = dx + pl;
@@ -1410,7 +1533,9 @@ __global__ void tc_pack_all_kernel(const TcPackJob *__restrict__ jobs) {
     if (g.half_ty[s][hf] >= 0 && col < g.cols_valid) {
       const int dy = g.half_ty[s][hf] + g.dy_min, dx = g.half_tx[s][hf] + g.dx_min;
       const int ci = (ch * g.planes_per_chunk + g.half_pl[s][hf]) * 8 + kk;
-      if (g.rows2) {
+      if (g.s2d) {
+        val = s2d_weight(g, j.w, s, hf, kk, col);
+      } else if (g.rows2) {
         const int cr = g.cout >> 1, par = col / cr, co = col - par * cr;
         const int a = dy + pt - par, b = dx + pl;
         if (a >= 0 && a <= 2) {
@@ -1538,11 +1663,21 @@ int tc_fill_params(const TcGeometry &g, int n, int h, int w, TcConvParams *pp, s
   const uint32_t pitch = (uint32_t)p.box_w * 16u;
   const uint32_t plane = pitch * (uint32_t)p.box_h;
   p.a_stage_bytes = plane * (uint32_t)g.planes_per_chunk;
+  p.a_tx_bytes = p.a_stage_bytes;
+  p.s2d = g.s2d;
+  if (g.s2d) {
+    p.s2d_part_bytes = (plane * (uint32_t)(g.cin / 8) + 127u) & ~127u;     // TMA destinations are 128-byte aligned
+    p.a_stage_bytes = 4u * p.s2d_part_bytes;
+  }
   for (int s = 0; s < g.ksteps; ++s) {
     uint32_t off[2];
     for (int hf = 0; hf < 2; ++hf) {
       int ty = g.half_ty[s][hf];
       if (ty < 0) ty = -1 - ty;   // dummy half: valid in-tile address, zero weights
+      if (g.s2d) {
+        const uint32_t P = (uint32_t)g.cin / 8u, v = (uint32_t)g.half_pl[s][hf];
+        off[hf] = (v / P) * p.s2d_part_bytes + (v % P) * plane + (uint32_t)ty * pitch + (uint32_t)g.half_tx[s][hf] * 16u;
+      } else
       off[hf] = (uint32_t)g.half_pl[s][hf] * plane + (uint32_t)ty * pitch + (uint32_t)g.half_tx[s][hf] * 16u;
     }
     if (off[1] <= off[0]) { set_error("tc plan: non-positive LBO"); return 1; }
@@ -1593,7 +1728,11 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
   if (g.split && !epi.fp16) { set_error("tc plan: split mode stores fp16 pairs"); return 1; }
   p.scale = epi.scale; p.shift = epi.shift;
   p.out = epi.out.ptr; p.out_img_stride = epi.out.img_stride; p.out_h = epi.out.h; p.out_w = epi.out.w;
-  p.pool_out = epi.pool_out; p.pool_img_stride = epi.pool_img_stride;
+  p.pool_out = epi.pool_out; p.pool_img_stride = epi.pool_img_stride; p.pool_sum = epi.pool_sum;
+  if (epi.pool_sum && (!epi.pool_out || epi.head_w || epi.stats || g.split || g.rows2 || g.stem_groups)) {
+    set_error("tc plan: sum-pool epilogue not applicable");
+    return 1;
+  }
   if (epi.head_w) {
     if (g.ups || g.n_tiles_n != 1 || !tc_head_fusable(epi.head_k)) { set_error("tc plan: head fusion not applicable"); return 1; }
     p.mode = 2;
@@ -1615,7 +1754,29 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
 
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return 1; }
-  const int cg = g.cin / 8;
+  if (g.s2d) {
+    // `in` = dz on the HIGH-res grid [n][cz/8][2h][2w][8]; (h, w) = the low-res GEMM-row grid.  One 5-D map per pixel
+    // parity: (8-byte half, X stride 32 B, Y stride 2 rows, plane, image), base shifted by the parity.
+    if (epi.head_w || epi.pool_out || epi.stats) { set_error("tc plan: s2d data gradient takes the plain epilogue"); return 1; }
+    const int P = g.cin / 8, H = 2 * h, W = 2 * w;
+    CUtensorMap maps[4];
+    for (int par = 0; par < 4; ++par) {
+      const int py = par >> 1, px = par & 1;
+      const uint8_t *base = reinterpret_cast<const uint8_t *>(in) + ((size_t)py * W + px) * 16;
+      cuuint64_t dims5[5] = {2, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)P, (cuuint64_t)n};
+      cuuint64_t str5[4] = {32, (cuuint64_t)2 * W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)P * H * W * 16};
+      cuuint32_t box5[5] = {2, (cuuint32_t)p.box_w, (cuuint32_t)p.box_h, (cuuint32_t)P, 1};
+      cuuint32_t es5[5] = {1, 1, 1, 1, 1};
+      CUresult r5 = enc(&maps[par], CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<uint8_t *>(base), dims5, str5, box5, es5,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r5 != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (s2d) failed: " + std::to_string((int)r5)); return 1; }
+    }
+    if (!plan->dev_maps) OCTSEG_CUDA(cudaMalloc(&plan->dev_maps, sizeof(maps)));
+    OCTSEG_CUDA(cudaMemcpy(plan->dev_maps, maps, sizeof(maps), cudaMemcpyHostToDevice));
+    p.s2d_maps = reinterpret_cast<const CUtensorMap *>(plan->dev_maps);
+  }
+  const int cg = g.s2d ? 4 * (g.cin / 8) : g.cin / 8;
   // declared as 8-byte elements (2 per pixel-plane vector) so that one box row may span up to 128 px
   cuuint64_t dims[4] = {(cuuint64_t)w * 2, (cuuint64_t)h, (cuuint64_t)cg, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)cg * h * w * 16};
@@ -1642,6 +1803,12 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
   }
   plan->valid = true;
   return 0;
+}
+
+void tc_release_plan(TcPlan *plan) {
+  if (plan->dev_maps) cudaFree(plan->dev_maps);
+  plan->dev_maps = nullptr;
+  plan->valid = false;
 }
 
 template <int HK, int EPI, int ST = 0>
@@ -1698,6 +1865,10 @@ int tc_launch(const TcPlan &plan, cudaStream_t st) {
       case 6: return tc_launch_k<0, 6, 1>(plan, st);
     }
     return tc_launch_k<0, 8>(plan, st);
+  }
+  if (plan.p.pool_sum && (plan.p.mode != 0 || (tc_epi_kind(plan.p) != 0 && tc_epi_kind(plan.p) != 2))) {
+    set_error("tc launch: sum-pool epilogue exists for the plain 16-column and generic epilogues only");
+    return 1;
   }
   if (plan.p.mode != 2) {
     switch (tc_epi_kind(plan.p)) {

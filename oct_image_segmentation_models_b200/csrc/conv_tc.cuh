@@ -44,6 +44,13 @@ struct TcConvParams {
   int out_h, out_w;
   __nv_bfloat16 *pool_out;     // mode 0: also write the 2x2 max-pooled tensor (NULL = off)
   long long pool_img_stride;
+  int s2d;                     // data gradient of the up-conv on the LOW-res grid: the A stage holds the four pixel parities of dz
+                               // as separate sub-tiles, fetched through four stride-2 tensor maps (s2d_maps, device memory)
+  uint32_t s2d_part_bytes;     // smem distance between parity sub-tiles (128-byte aligned); a_tx_bytes = bytes TMA delivers per stage
+  uint32_t a_tx_bytes;
+  const CUtensorMap *s2d_maps;
+  int pool_sum;                // 1: pool_out receives the 2x2 SUM of the fp32 outputs and the full-resolution tensor is not
+                               // stored at all (data gradient of the up-conv: adjoint of the nearest x2 up-sampling)
   const float *head_w, *head_b; // mode 2: [cout][K] and [K]
   int head_k;
   float *probs;                // mode 2 outputs (NHWC fp32 / u8), either may be NULL
@@ -69,7 +76,9 @@ struct TcPlan {
   CUtensorMap tmap{};
   size_t smem_bytes = 0;
   int grid = 0;
+  void *dev_maps = nullptr;    // s2d plans: the four parity tensor maps in device memory (owned; tc_release_plan)
 };
+void tc_release_plan(TcPlan *plan);
 
 // Describes how GEMM K and N map to taps / channels; shared by the weight packer and
 // the kernel's A-descriptor table.
@@ -82,6 +91,7 @@ struct TcGeometry {
   int rows2;                           // set by the caller: every GEMM row yields TWO vertically adjacent output pixels
                                        // (geometry built for the 4x3 banded filter of tc_rowpair_weights)
   int stem_groups;                     // set by the caller: GEMM row = 8 adjacent pixels, columns = [plane][pixel][8 ch]
+  int s2d;                             // tc_make_geometry_s2d: stride-2 3x3 conv over the pixel parities of the input (see there)
   // fp32-accurate split mode (tc_make_geometry_split): cin / cout above are PHYSICAL (2x logical).  Every logical
   // 8-channel input plane is a pair of fp16 planes (hi, lo' = (a - hi) * 2^11) and every logical 8-column output
   // group is the 16 GEMM columns [main 8 | corr 8]; the epilogue computes main + corr * 2^-11.
@@ -95,6 +105,13 @@ struct TcGeometry {
 bool tc_supported(int kh, int kw, int cin, int cout, int ups, int h, int w);
 // pad_top/pad_left < 0: Keras "same" padding ((k-1)/2 before); otherwise explicit (data-gradient convs)
 int tc_make_geometry(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, int pad_top = -1, int pad_left = -1);
+// Data gradient of the decoder's up-conv (x2 nearest up-sampling + 2x2 conv, reference models/unet.py:41-44) computed on
+// the LOW-res grid: d(a)[Y][X] = sum_{a,b in {-1,0,1}} Weff[a][b]^T dz[2Y+a][2X+b], Weff[a][b] = sum of the forward taps
+// (ky, kx) with ky in S(a), kx in S(b), S(-1) = {1}, S(0) = {0,1}, S(1) = {0}.  A stride-2 read is not a UMMA operand (rows
+// of a core matrix are 16 B apart), so the four pixel parities of dz are fetched as four sub-tiles through stride-2 tensor
+// maps; tap (a, b) is then parity (a != 0, b != 0) at box offset (a >= 0, b >= 0).  cz = channels of dz (<= 32), cout = the
+// up-conv's input channels.  The packer reads the FORWARD kernel [2][2][cout][cz].
+int tc_make_geometry_s2d(int cz, int cout, TcGeometry *g);
 // fp32-accurate variant: error-compensated fp16 pairs on both operands (see TcGeometry::split); cin / cout logical
 int tc_make_geometry_split(int kh, int kw, int cin, int cout, int ups, TcGeometry *g, int pad_top = -1, int pad_left = -1);
 // power-of-two scale that brings max |w| of a layer into [2^3, 2^4) (fp16 keeps 11 bits for everything within 2^-17 of it)
@@ -130,6 +147,7 @@ struct TcEpilogue {
   View<__nv_bfloat16> out{};                 // unused when the head is fused
   __nv_bfloat16 *pool_out = nullptr;         // fused 2x2 max-pool (encoder-final blocks)
   long long pool_img_stride = 0;
+  int pool_sum = 0;                          // pool_out = 2x2 sum instead of max, `out` is not written (out.ptr may be null)
   const float *head_w = nullptr, *head_b = nullptr;   // fused 1x1 conv + softmax head
   int head_k = 0;
   int static_weights = 0;                    // weights final before the stream's preceding kernels ran (inference)

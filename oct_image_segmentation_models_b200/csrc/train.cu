@@ -81,6 +81,7 @@ struct TrainBlock {
   // row-pair variants (conv_tc.cuh: tc_rowpair_weights) for narrow 3x3 layers
   TcGeometry geo_dgrad2{};
   bool geo_dgrad2_ok = false, fwd_pair = false, dgrad_pair = false;
+  bool dgrad_s2d = false;         // up-conv with <= 32 output channels: data gradient on the low-res grid (tc_make_geometry_s2d)
   __nv_bfloat16 *wpack_dgrad2 = nullptr;
   TcPlan plan_fwd, plan_dgrad;
 };
@@ -121,7 +122,6 @@ struct TrainState {
   float *d_wg_scratch = nullptr;    // split-K partial sums of the tcgen05 weight gradient (wgrad_tc.cu)
   size_t wg_scratch_floats = 0;
   void *up_scratch = nullptr;       // materialised x2-upsampled input of an up-conv (weight-gradient stream)
-  void *dup_scratch = nullptr;      // gradient wrt the upsampled tensor (main stream), then 2x2 sum-pooled
   void *mask = nullptr;             // dropout multiplier tensor at the bottleneck
   void *d_img = nullptr; size_t d_img_bytes = 0;
   uint8_t *d_labels = nullptr; size_t d_labels_bytes = 0;
@@ -241,8 +241,11 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
     o_pool[b.index] = b.pool_after ? bump.take(bytes(b.cout, b.level + 1)) : (size_t)-1;
   }
   size_t up_bytes = 1024;
-  for (auto &b : net->blocks) if (b.ups) up_bytes = std::max(up_bytes, bytes(b.cin, b.level));
-  const size_t o_up = bump.take(up_bytes), o_dup = bump.take(up_bytes);
+  // x2-upsampled input of the up-convs whose weight gradient needs a real tensor (>= 64 input channels); the narrow ones
+  // read the low-res tensor, and the data gradient stores 2x2 sums straight from its epilogue
+  for (auto &b : net->blocks)
+    if (b.ups && !wgrad_rows_applicable(b.kh, b.kw, b.cin, 1)) up_bytes = std::max(up_bytes, bytes(b.cin, b.level));
+  const size_t o_up = bump.take(up_bytes);
   const size_t o_img = bump.take((size_t)n * h * w * 8 * es);
   const size_t o_mask = bump.take(bytes(s << P, P));
   if (bump.off > S->ws_bytes) {
@@ -269,7 +272,6 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
   }
   S->img_blocked = base + o_img;
   S->up_scratch = base + o_up;
-  S->dup_scratch = base + o_dup;
   S->mask = base + o_mask;
   S->n = n; S->h = h; S->w = w;
   if (net->blocks.back().cin > 16 || (net->blocks.back().cin == 16 && net->cfg.num_classes > 8)) {
@@ -326,7 +328,7 @@ static int ensure_train_workspace(octseg_net *net, int n, int h, int w) {
         return 1;
       t.tc_fwd = true;
     }
-    if (t.geo_dgrad_ok && tc_supported(b.kh, b.kw, b.cout, b.cin, 0, t.h, t.w)) {
+    if (t.geo_dgrad_ok && tc_supported(b.kh, b.kw, b.cout, b.cin, 0, t.dgrad_s2d ? t.h / 2 : t.h, t.dgrad_s2d ? t.w / 2 : t.w)) {
       // destination of the data gradient: fixed per block (see the buffer walk in train_step_t)
       t.tc_dgrad = true;
       t.dgrad_pair = t.geo_dgrad2_ok && !b.ups && (t.h % 2) == 0 && t.h >= 2 * kTcTileH;
@@ -607,19 +609,32 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     } else {
       void *dst = S->gA[b.level + 1];
       View<T> din = make_view((T *)dst, n, b.cin / 8, 0, b.cin / 8, t.h / 2, t.w / 2);
-      if (t.tc_dgrad) {
-        // d(upsampled input) on the high-res grid with the flipped kernel, then its 2x2 sum-pool
+      if (t.tc_dgrad && t.dgrad_s2d) {
+        // stride-2 3x3 conv over the four pixel parities of dz, straight on the low-res grid
         TcEpilogue epi;
         epi.relu = 0; epi.scale = S->d_ones; epi.shift = S->d_zeros;
-        epi.out = make_view((__nv_bfloat16 *)S->dup_scratch, n, b.cin / 8, 0, b.cin / 8, t.h, t.w);
+        epi.out = make_view((__nv_bfloat16 *)dst, n, b.cin / 8, 0, b.cin / 8, t.h / 2, t.w / 2);
         if (!t.plan_dgrad.valid || t.plan_dgrad.p.out != epi.out.ptr) {
+          if (tc_make_plan(t.geo_dgrad, (const __nv_bfloat16 *)t.dz, n, t.h / 2, t.w / 2, t.wpack_dgrad, epi, net->d_status,
+                           &t.plan_dgrad))
+            return 1;
+        }
+        if (tc_launch(t.plan_dgrad, st)) return 1;
+      } else if (t.tc_dgrad) {
+        // d(upsampled input) on the high-res grid with the flipped kernel; the epilogue stores only its 2x2 sums
+        // (the adjoint of the nearest up-sampling), so the 4x larger tensor is neither written nor re-read
+        TcEpilogue epi;
+        epi.relu = 0; epi.scale = S->d_ones; epi.shift = S->d_zeros;
+        epi.out = make_view((__nv_bfloat16 *)nullptr, n, b.cin / 8, 0, b.cin / 8, t.h, t.w);
+        epi.pool_out = (__nv_bfloat16 *)dst;
+        epi.pool_img_stride = din.img_stride;
+        epi.pool_sum = 1;
+        if (!t.plan_dgrad.valid || t.plan_dgrad.p.pool_out != epi.pool_out) {
           if (tc_make_plan(t.geo_dgrad, (const __nv_bfloat16 *)t.dz, n, t.h, t.w, t.wpack_dgrad, epi, net->d_status,
                            &t.plan_dgrad))
             return 1;
         }
         if (tc_launch(t.plan_dgrad, st)) return 1;
-        View<const T> dup = make_view((const T *)S->dup_scratch, n, b.cin / 8, 0, b.cin / 8, t.h, t.w);
-        if (launch_sumpool2x<T>(dup, din, st)) return 1;
       } else {
         // up-conv: d(prev) on the low-res grid = stride-2 (kh+1)x(kw+1) conv over dz
         if (launch_upconv_dgrad_weights(P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout, t.w_t, st)) return 1;
@@ -676,7 +691,7 @@ static int debug_backward_t(octseg_net *net, const BlockSpec &b, const float *a_
   std::vector<T> hin, hdz;
   to_blocked(a_in, b.cin, h, w, &hin);
   to_blocked(dz, b.cout, oh, ow, &hdz);
-  T *d_in = nullptr, *d_dz = nullptr, *d_din = nullptr, *d_up = nullptr, *d_dup = nullptr;
+  T *d_in = nullptr, *d_dz = nullptr, *d_din = nullptr, *d_up = nullptr;
   float *d_dW = nullptr, *d_db = nullptr;
   const size_t w_count = (size_t)b.kh * b.kw * b.cin * b.cout;
   OCTSEG_CUDA(cudaMalloc(&d_in, in_elems * sizeof(T)));
@@ -715,7 +730,8 @@ static int debug_backward_t(octseg_net *net, const BlockSpec &b, const float *a_
     rc = wgrad_dispatch<T>(net, in, dzc, b.kh, b.kw, pt, pl, b.ups ? 1 : 0, b.cin, b.cout, d_dW, d_db, st);
   }
   // ---- data gradient
-  const bool tc_dgrad = sizeof(T) == 2 && !net->disable_tc && t.geo_dgrad_ok && tc_supported(b.kh, b.kw, b.cout, b.cin, 0, oh, ow);
+  const bool tc_dgrad = sizeof(T) == 2 && !net->disable_tc && t.geo_dgrad_ok &&
+                        tc_supported(b.kh, b.kw, b.cout, b.cin, 0, t.dgrad_s2d ? h : oh, t.dgrad_s2d ? w : ow);
   if (!rc && tc_dgrad) {
     const bool pair = t.geo_dgrad2_ok && !b.ups && (oh % 2) == 0 && oh >= 2 * kTcTileH;
     const TcGeometry &gd = pair ? t.geo_dgrad2 : t.geo_dgrad;
@@ -728,15 +744,20 @@ static int debug_backward_t(octseg_net *net, const BlockSpec &b, const float *a_
       epi.out = make_view((__nv_bfloat16 *)d_din, n, b.cin / 8, 0, b.cin / 8, h, w);
       if (!rc) rc = tc_make_plan(gd, (const __nv_bfloat16 *)d_dz, n, oh, ow, wp, epi, net->d_status, &plan);
       if (!rc) rc = tc_launch(plan, st);
+    } else if (t.dgrad_s2d) {
+      epi.out = make_view((__nv_bfloat16 *)d_din, n, b.cin / 8, 0, b.cin / 8, h, w);
+      if (!rc) rc = tc_make_plan(gd, (const __nv_bfloat16 *)d_dz, n, h, w, wp, epi, net->d_status, &plan);
+      if (!rc) rc = tc_launch(plan, st);
     } else {
-      OCTSEG_CUDA(cudaMalloc(&d_dup, (size_t)n * b.cin * oh * ow * sizeof(T)));
-      epi.out = make_view((__nv_bfloat16 *)d_dup, n, b.cin / 8, 0, b.cin / 8, oh, ow);
+      epi.out = make_view((__nv_bfloat16 *)nullptr, n, b.cin / 8, 0, b.cin / 8, oh, ow);
+      epi.pool_out = (__nv_bfloat16 *)d_din;
+      epi.pool_img_stride = (long long)b.cin * h * w;
+      epi.pool_sum = 1;
       if (!rc) rc = tc_make_plan(gd, (const __nv_bfloat16 *)d_dz, n, oh, ow, wp, epi, net->d_status, &plan);
       if (!rc) rc = tc_launch(plan, st);
-      View<const T> dup = make_view((const T *)d_dup, n, b.cin / 8, 0, b.cin / 8, oh, ow);
-      View<T> din = make_view(d_din, n, b.cin / 8, 0, b.cin / 8, h, w);
-      if (!rc) rc = launch_sumpool2x<T>(dup, din, st);
     }
+    cudaStreamSynchronize(st);
+    tc_release_plan(&plan);
   } else if (!rc) {
     View<T> din = make_view(d_din, n, b.cin / 8, 0, b.cin / 8, h, w);
     if (!b.ups) {
@@ -765,7 +786,7 @@ static int debug_backward_t(octseg_net *net, const BlockSpec &b, const float *a_
             din_out[(((size_t)i * h + y) * w + x) * b.cin + k] = f;
           }
   }
-  cudaFree(d_in); cudaFree(d_dz); cudaFree(d_din); cudaFree(d_dW); cudaFree(d_db); cudaFree(d_up); cudaFree(d_dup);
+  cudaFree(d_in); cudaFree(d_dz); cudaFree(d_din); cudaFree(d_dW); cudaFree(d_db); cudaFree(d_up);
   return rc;
 }
 
@@ -805,7 +826,7 @@ void octseg_train_free(octseg_net *net) {
   if (S->wg_stream) cudaStreamDestroy(S->wg_stream);
   if (S->comm_stream) cudaStreamDestroy(S->comm_stream);
   for (cudaEvent_t e : {S->ev_tail_main, S->ev_tail_wg, S->ev_head_main, S->ev_comm_done}) if (e) cudaEventDestroy(e);
-  for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); cudaFree(t.wpack_dgrad); cudaFree(t.wpack_dgrad2); }
+  for (auto &t : S->tb) { cudaFree(t.mean); cudaFree(t.invstd); cudaFree(t.scale); cudaFree(t.shift); cudaFree(t.w_t); cudaFree(t.wpack_dgrad); cudaFree(t.wpack_dgrad2); tc_release_plan(&t.plan_dgrad); }
   cudaFree(S->d_class_w); cudaFree(S->d_grads); cudaFree(S->d_m); cudaFree(S->d_v); cudaFree(S->d_ones); cudaFree(S->d_zeros);
   cudaFree(S->d_sums); cudaFree(S->d_loss); cudaFree(S->d_stem_tmp); cudaFree(S->ws); cudaFree(S->d_img);
   cudaFree(S->d_labels); cudaFree(S->d_mask_in); cudaFree(S->d_pack_jobs); cudaFree(S->d_state); cudaFree(S->d_wg_scratch); cudaFree(S->d_dlog);
@@ -861,10 +882,13 @@ int32_t octseg_train_begin(octseg_net *net, const octseg_train_config *tc, const
       OCTSEG_CUDA(cudaMalloc(&t.scale, b.cout * sizeof(float)));
       OCTSEG_CUDA(cudaMalloc(&t.shift, b.cout * sizeof(float)));
       OCTSEG_CUDA(cudaMalloc(&t.w_t, (size_t)(b.kh + 1) * (b.kw + 1) * b.cin * b.cout * sizeof(float)));
+      static const bool s2d_off = []() { const char *e = std::getenv("OCTSEG_DGRAD_S2D"); return e && e[0] == '0'; }();
+      t.dgrad_s2d = net->precision == OCTSEG_BF16 && !net->disable_tc && !s2d_off && b.ups && b.kh == 2 && b.kw == 2 &&
+                    tc_make_geometry_s2d(b.cout, b.cin, &t.geo_dgrad) == 0;
       if (net->precision == OCTSEG_BF16 && !net->disable_tc && b.index > 0 &&
           tc_supported(b.kh, b.kw, b.cout, b.cin, 0, kTcTileH, kTcTileW) &&
-          tc_make_geometry(b.kh, b.kw, b.cout, b.cin, 0, &t.geo_dgrad, b.kh - 1 - (b.kh - 1) / 2,
-                           b.kw - 1 - (b.kw - 1) / 2) == 0) {
+          (t.dgrad_s2d || tc_make_geometry(b.kh, b.kw, b.cout, b.cin, 0, &t.geo_dgrad, b.kh - 1 - (b.kh - 1) / 2,
+                                           b.kw - 1 - (b.kw - 1) / 2) == 0)) {
         t.geo_dgrad_ok = true;
         const size_t elems = (size_t)t.geo_dgrad.n_tiles_n * t.geo_dgrad.cin_chunks * t.geo_dgrad.ksteps * 2 *
                              t.geo_dgrad.n_cols * 8;
