@@ -1012,6 +1012,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int k = 0; k < 4; ++k)
                   h2[k] = bn_relu_pack2(v[u][2 * k], v[u][2 * k + 1], sc[2 * k], sc[2 * k + 1], sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
               }
+              if constexpr (ST == 1) {
+                // training forward of the narrow up-convs (<= 16 channels per parity): batch statistics in registers
+                if (inside) {
+#pragma unroll
+                  for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                      const float o = fmaxf(fmaf(__uint_as_float(v[u][k]), sc[k], sh[k]), relu_floor);
+                      if (c8 == 0) { st_s[k] += o; st_q[k] = fmaf(o, o, st_q[k]); }
+                      else { st_s[8 + k] += o; st_q[8 + k] = fmaf(o, o, st_q[8 + k]); }
+                    }
+                }
+              }
               if (inside) {
                 __nv_bfloat16 *dst = p.out + (long long)img * p.out_img_stride + (long long)c8 * plane_elems +
                                      ((long long)(2 * y + py) * p.out_w + 2 * x) * 8;
@@ -1861,6 +1874,7 @@ int tc_launch(const TcPlan &plan, cudaStream_t st) {
     switch (tc_epi_kind(plan.p)) {
       case 1: return tc_launch_k<0, 1, 1>(plan, st);
       case 2: return tc_launch_k<0, 2, 1>(plan, st);
+      case 4: if (plan.p.scale_mod <= 16) return tc_launch_k<0, 4, 1>(plan, st); break;
       case 5: return tc_launch_k<0, 5, 1>(plan, st);
       case 6: return tc_launch_k<0, 6, 1>(plan, st);
     }
