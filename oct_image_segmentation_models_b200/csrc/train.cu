@@ -535,14 +535,17 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
       View<const T> dpool = make_view((const T *)g_ptr, n, g_planes_total, g_plane0, f8, t.h / 2, t.w / 2);
       View<const T> dskip = make_view((const T *)S->dcat[b.level], n, 2 * f8, f8, f8, t.h, t.w);
       View<T> tot = make_view((T *)S->gB[b.level], n, f8, 0, f8, t.h, t.w);
-      if (launch_pool_bwd_add<T>(ac, dpool, dskip, tot, st)) return 1;
+      // ... and the BatchNorm-backward reductions of this block while the totals are in registers
+      if (launch_pool_bwd_add_bnred<T>(ac, dpool, dskip, tot, zc, t.mean, t.invstd, P + net->params[b.p_gamma].offset,
+                                       P + net->params[b.p_beta].offset, sums_of(bi, 1), st))
+        return 1;
       ++net->launches;
       da = make_view((const T *)S->gB[b.level], n, f8, 0, f8, t.h, t.w);
     }
     const T *mask = (use_dropout && b.dropout_after) ? (const T *)S->mask : nullptr;
     const float *gamma = P + net->params[b.p_gamma].offset, *beta = P + net->params[b.p_beta].offset;
     prof.begin(PH_BNB);
-    if (launch_bn_bwd_reduce<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, sums_of(bi, 1), st)) return 1;
+    if (!b.pool_after && launch_bn_bwd_reduce<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, sums_of(bi, 1), st)) return 1;
     View<T> dz = make_view((T *)t.dz, n, f8, 0, f8, t.h, t.w);
     if (launch_bn_bwd_apply<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, sums_of(bi, 1), (long long)n * t.h * t.w, dz,
                                G + net->params[b.p_gamma].offset, G + net->params[b.p_beta].offset, st))

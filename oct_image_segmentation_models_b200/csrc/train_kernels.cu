@@ -765,11 +765,34 @@ int launch_bn_bwd_apply(View<const T> da, View<const T> z, const float *mean, co
 // ---------------------------------------------------------------------------------
 // max-pool backward + skip add: first max in window scan order gets the pooled gradient
 // ---------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) pool_bwd_add_kernel(View<const T> a, View<const T> d_pooled,
-                                                           View<const T> d_skip, View<T> out, int has_skip) {
+// BnRed (optional): the BatchNorm-backward reductions of THIS block (sum dy, sum dy * zhat over the batch, dy = da where the
+// ReLU was active) are accumulated from the fp32 totals while they are in registers, so bn_bwd_reduce_kernel -- a
+// second read of da and z -- is not launched for the encoder-final blocks.
+struct BnRed {
+  const float *mean, *invstd, *gamma, *beta;   // [c] of the block whose output gradient this kernel produces
+  double *sums;                                // [2c]: sum(dy), sum(dy * zhat); zeroed by the caller
+};
+
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(256, 2) pool_bwd_add_kernel(View<const T> a, View<const T> d_pooled,
+                                                           View<const T> d_skip, View<T> out, int has_skip,
+                                                           View<const T> z, BnRed bn, int c) {
   const int Ho = d_pooled.h, Wo = d_pooled.w;
   const int pl = blockIdx.y, b = blockIdx.z;
+  // per-channel constants through shared memory (broadcast reads): zhat = z * inv - mean * inv, ReLU active <=> z * sc + sh > 0
+  __shared__ float s_inv[8], s_minv[8], s_sc[8], s_sh[8];
+  float acc[16];
+  if constexpr (STATS) {
+    if (threadIdx.x < 8) {
+      const int ch = pl * 8 + threadIdx.x;
+      const float inv = bn.invstd[ch], sc = bn.gamma[ch] * inv;
+      s_inv[threadIdx.x] = inv; s_minv[threadIdx.x] = bn.mean[ch] * inv;
+      s_sc[threadIdx.x] = sc; s_sh[threadIdx.x] = bn.beta[ch] - bn.mean[ch] * sc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Ho * Wo; i += gridDim.x * blockDim.x) {
     const int x = i % Wo, y = i / Wo;
     const long long base = (((long long)pl * a.h + 2 * y) * a.w + 2 * x) * 8;
@@ -781,6 +804,11 @@ __global__ void __launch_bounds__(256) pool_bwd_add_kernel(View<const T> a, View
     if (has_skip) {
       const T *sp = d_skip.ptr + b * d_skip.img_stride + base;
       o00 = load8(sp); o01 = load8(sp + 8); o10 = load8(sp + row); o11 = load8(sp + row + 8);
+    }
+    Raw8<T> rz[4];
+    if constexpr (STATS) {
+      const T *zp = z.ptr + b * z.img_stride + base;        // z is dense with the same plane grid as `a`
+      rz[0] = load_raw8(zp); rz[1] = load_raw8(zp + 8); rz[2] = load_raw8(zp + row); rz[3] = load_raw8(zp + row + 8);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -796,7 +824,22 @@ __global__ void __launch_bounds__(256) pool_bwd_add_kernel(View<const T> a, View
     }
     T *op = out.ptr + b * out.img_stride + base;
     store8(op, o00); store8(op + 8, o01); store8(op + row, o10); store8(op + row + 8, o11);
+    if constexpr (STATS) {
+      const Vec8f *oo[4] = {&o00, &o01, &o10, &o11};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const Vec8f zz = cvt8(rz[j]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float zh = fmaf(zz.v[k], s_inv[k], -s_minv[k]);
+          const float dy = (fmaf(zz.v[k], s_sc[k], s_sh[k]) > 0.f) ? oo[j]->v[k] : 0.f;
+          acc[k] += dy;
+          acc[8 + k] = fmaf(dy, zh, acc[8 + k]);
+        }
+      }
+    }
   }
+  if constexpr (STATS) block_reduce16_to_double(acc, bn.sums, bn.sums + c, pl * 8);
 }
 
 template <typename T>
@@ -804,7 +847,22 @@ int launch_pool_bwd_add(View<const T> a, View<const T> d_pooled, View<const T> d
                         cudaStream_t st) {
   const int hw = d_pooled.h * d_pooled.w;
   dim3 grid(std::max(1, std::min((hw + 255) / 256, 64)), d_pooled.planes, d_pooled.n);
-  pool_bwd_add_kernel<T><<<grid, 256, 0, st>>>(a, d_pooled, d_skip, da_total, d_skip.ptr != nullptr);
+  pool_bwd_add_kernel<T, false><<<grid, 256, 0, st>>>(a, d_pooled, d_skip, da_total, d_skip.ptr != nullptr, View<const T>{},
+                                                      BnRed{}, 0);
+  OCTSEG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// + the BatchNorm-backward reductions of the block (z dense, no dropout on it)
+template <typename T>
+int launch_pool_bwd_add_bnred(View<const T> a, View<const T> d_pooled, View<const T> d_skip, View<T> da_total, View<const T> z,
+                              const float *mean, const float *invstd, const float *gamma, const float *beta, double *sums,
+                              cudaStream_t st) {
+  const int hw = d_pooled.h * d_pooled.w;
+  // >= 8 windows per thread: every block ends with 16 double atomics on the same 16 words per plane
+  dim3 grid(std::max(1, std::min((hw + 2047) / 2048, 64)), d_pooled.planes, d_pooled.n);
+  BnRed bn{mean, invstd, gamma, beta, sums};
+  pool_bwd_add_kernel<T, true><<<grid, 256, 0, st>>>(a, d_pooled, d_skip, da_total, d_skip.ptr != nullptr, z, bn, z.planes * 8);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1099,6 +1157,8 @@ int launch_adam(float *p, const float *g, float *m, float *v, long long n, const
                                       const float *, const float *, const T *, const double *, long long,   \
                                       View<T>, float *, float *, cudaStream_t);                             \
   template int launch_pool_bwd_add<T>(View<const T>, View<const T>, View<const T>, View<T>, cudaStream_t);  \
+  template int launch_pool_bwd_add_bnred<T>(View<const T>, View<const T>, View<const T>, View<T>, View<const T>, const float *,  \
+                                            const float *, const float *, const float *, double *, cudaStream_t);  \
   template int launch_wgrad<T>(View<const T>, View<const T>, int, int, int, int, int, int, int, float *,    \
                                float *, cudaStream_t);                                                      \
   template int launch_image_to_blocked<T>(const void *, int, int, int, int, int, T *, cudaStream_t);         \

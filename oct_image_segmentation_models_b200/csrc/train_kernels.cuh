@@ -62,6 +62,11 @@ int launch_bn_bwd_apply(View<const T> da, View<const T> z, const float *mean, co
 template <typename T>
 int launch_pool_bwd_add(View<const T> a, View<const T> d_pooled, View<const T> d_skip, View<T> da_total,
                         cudaStream_t st);
+// same + the BatchNorm-backward reductions (sum dy, sum dy * zhat) of the block, see pool_bwd_add_kernel
+template <typename T>
+int launch_pool_bwd_add_bnred(View<const T> a, View<const T> d_pooled, View<const T> d_skip, View<T> da_total, View<const T> z,
+                              const float *mean, const float *invstd, const float *gamma, const float *beta, double *sums,
+                              cudaStream_t st);
 
 // nearest x2 up-sampling into a dense tensor, and its adjoint (2x2 sum-pool)
 template <typename T>

@@ -1,8 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-echo "=== 12 epilogue warps"; timeout 300 python tools/predict_bench.py bf16 fp32
-echo "=== 16 epilogue warps"; OCTSEG_LIB=$PWD/tools/liboctseg_epi16.so timeout 300 python tools/predict_bench.py bf16 fp32
-echo "=== 12 again"; timeout 300 python tools/predict_bench.py bf16 fp32
+echo "=== tests"; timeout 900 python -m pytest tests/test_gpu_backward_kernels.py tests/test_gpu_train.py -x -q 2>&1 | tail -5
+for b in 256 32; do
+  echo "=== train_bench $b"; timeout 300 python tools/train_bench.py $b 20 2>&1 | tail -1
+done
+OCTSEG_TRAIN_PROFILE=2 timeout 300 python tools/train_bench.py 256 2 2>&1 | sed 's/\[train detail\] //' > gpurun_out/prof_256.txt; grep "pool_bwd\|profile" gpurun_out/prof_256.txt | tail -5
 } > gpurun_out/r2b_run1.log 2>&1
 cat gpurun_out/r2b_run1.log
