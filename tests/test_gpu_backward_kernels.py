@@ -55,7 +55,7 @@ CASES = [(1, 2, 32, 24), (2, 2, 32, 16), (3, 1, 32, 32), (4, 2, 16, 16), (5, 2, 
          # row-walking weight gradient of the narrow layers: enough tiles per persistent CTA to wrap its TMA stage ring
          # (8 -> 8: 960 tiles of 32x32 over 148 CTAs, 6 stages), the 16 -> 16 variant, and the up-conv read from the
          # LOW-res tensor over several tiles with a partial one
-         (1, 30, 256, 128), (3, 6, 128, 64), (19, 4, 64, 40)]
+         (1, 30, 256, 128), (3, 6, 128, 64), (19, 4, 64, 40), (17, 3, 64, 64), (14, 5, 64, 96), (13, 3, 32, 48)]
 
 
 @pytest.mark.parametrize("idx,n,h,w", CASES)
