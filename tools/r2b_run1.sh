@@ -1,10 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-{
-echo "=== tests"; timeout 900 python -m pytest tests/test_gpu_backward_kernels.py tests/test_gpu_train.py -x -q 2>&1 | tail -5
-for b in 256 32; do
-  echo "=== train_bench $b"; timeout 300 python tools/train_bench.py $b 20 2>&1 | tail -1
-done
-OCTSEG_TRAIN_PROFILE=2 timeout 300 python tools/train_bench.py 256 2 2>&1 | sed 's/\[train detail\] //' > gpurun_out/prof_256.txt; grep "wgrad\|profile" gpurun_out/prof_256.txt | tail -23
-} > gpurun_out/r2b_run1.log 2>&1
-cat gpurun_out/r2b_run1.log
+O=gpurun_out
+OCTSEG_TRAIN_GRAPH=0 python tools/train_steps.py 64 3 > $O/plain_train.log 2>&1 || exit 1
+OCTSEG_TRAIN_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/r2b_launches_all.csv python tools/train_steps.py 64 3 > $O/ncu_tr1.log 2>&1
+python tools/prof_predict.py bf16 3 > $O/plain_p.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/r2b_launches_predict_bf16_all.csv python tools/prof_predict.py bf16 3 > $O/ncu_p1.log 2>&1
+python tools/prof_predict.py fp32 3 > $O/plain_p2.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/r2b_launches_predict_fp32_all.csv python tools/prof_predict.py fp32 3 > $O/ncu_p2.log 2>&1
+ls -la $O | tail -8
