@@ -1,8 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-O=gpurun_out
-OCTSEG_TRAIN_GRAPH=0 python tools/train_steps.py 64 3 > $O/plain_train.log 2>&1 || exit 1
-OCTSEG_TRAIN_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/r2b_launches_all.csv python tools/train_steps.py 64 3 > $O/ncu_tr1.log 2>&1
-python tools/prof_predict.py bf16 3 > $O/plain_p.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/r2b_launches_predict_bf16_all.csv python tools/prof_predict.py bf16 3 > $O/ncu_p1.log 2>&1
-python tools/prof_predict.py fp32 3 > $O/plain_p2.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/r2b_launches_predict_fp32_all.csv python tools/prof_predict.py fp32 3 > $O/ncu_p2.log 2>&1
-ls -la $O | tail -8
+{
+for v in 0 1 0 1; do
+  echo "=== OCTSEG_ONE_D2H_STREAM=$v"; OCTSEG_ONE_D2H_STREAM=$v timeout 300 python bench.py --steps 300 --no-train --no-wide --no-cfg5 --no-fp32 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value',round(d['value']),'e2e',round(d['e2e']['value']),'sync',round(d['e2e']['sync_call']['value']),'probs',round(d['e2e_probs']['value']))"
+done
+echo "=== api tests"; timeout 600 python -m pytest tests/test_gpu_api.py -x -q -m gpu 2>&1 | tail -3
+} > gpurun_out/r2b_run1.log 2>&1
+cat gpurun_out/r2b_run1.log
