@@ -111,7 +111,8 @@ constexpr int kTcThreads = (4 + kTcEpiWarps) * 32;
 // EPI: epilogue specialisation chosen on the host (tc_epi_kind) so that every layer type gets its own
 // register allocation: 0 = generic chunk loop (wide layers, unpaired pixel shuffle, wide fused head),
 // 1 = 8-column layers (batched TMEM loads; plain / pool / fused head), 2 = 16-column plain / pool layers,
-// 3 = stem pixel groups, 4 = paired pixel-shuffle up-conv.  Dead paths are dropped at compile time.
+// 3 = stem pixel groups, 4 = paired pixel-shuffle up-conv, 9 = generic chunk loop that stores only the 2x2 sums of its outputs
+// (data gradient of the wide up-conv).  Dead paths are dropped at compile time.
 // ST: 1 = the epilogue also accumulates per-channel sum / sum of squares of its fp32 output (training forward)
 template <int HK, int EPI, int ST = 0>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -875,25 +876,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
               uint4 pk;
               uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk);
-              if constexpr (ST == 0) {
-                if (p.pool_sum) {
-                  // data gradient of the up-conv: only the 2x2 sums of the fp32 outputs are stored (partners: lanes ^1, ^8)
-                  float o[8];
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) {
-                    o[k] = fmaxf(fmaf(__uint_as_float(v[bb][u][k]), sc[k], sh[k]), relu_floor);
-                    o[k] += __shfl_xor_sync(0xffffffffu, o[k], 1);
-                    o[k] += __shfl_xor_sync(0xffffffffu, o[k], 8);
-                  }
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) h2[k] = pack2(o[2 * k], o[2 * k + 1], p.fp16);
-                  if (inside && !(px & 1) && !(r & 1))
-                    *reinterpret_cast<uint4 *>(p.pool_out + (long long)img * p.pool_img_stride +
-                                               (long long)(co0 >> 3) * (plane_elems >> 2) +
-                                               ((long long)(y >> 1) * (p.out_w >> 1) + (x >> 1)) * 8) = pk;
-                  continue;
-                }
-              }
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 h2[k] = bn_relu_pack2(v[bb][u][2 * k], v[bb][u][2 * k + 1], sc[2 * k], sc[2 * k + 1], sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
@@ -1114,7 +1096,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
               uint4 pk;
               uint32_t *h2 = reinterpret_cast<uint32_t *>(&pk);
-              if (p.pool_sum) {
+              if constexpr (EPI == 9) {
                 // data gradient of the up-conv: only the 2x2 sums of the fp32 outputs are stored (partners: lanes ^1, ^8)
                 float o[8];
 #pragma unroll
@@ -1136,7 +1118,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 h2[k] = bn_relu_pack2(v[u][2 * k], v[u][2 * k + 1], sc[2 * k], sc[2 * k + 1], sh[2 * k], sh[2 * k + 1], floor2, p.fp16);
               if (inside)
                 *reinterpret_cast<uint4 *>(p.out + (long long)img * p.out_img_stride + (long long)(co0 >> 3) * plane_elems + off) = pk;
-              if (p.pool_out) {
+              if (EPI != 9 && p.pool_out) {
                 // 2x2 max on the packed bf16 pairs (max commutes with the monotonic rounding):
                 // partners are lanes ^1 (x) and ^8 (row) of this warp
 #pragma unroll
@@ -1849,6 +1831,7 @@ bool tc_head_fusable(int num_classes) { return num_classes >= 2 && num_classes <
 // epilogue specialisation of a plan (see conv_tc_kernel)
 static int tc_epi_kind(const TcConvParams &p) {
   const bool one_ntile = p.n_tiles_n == 1;
+  if (p.pool_sum) return 9;                                         // generic chunk loop storing 2x2 sums only
   if (p.split) return 7;
   if (p.row_mul == 2) return p.scale_mod == 8 ? 5 : 6;
   if (p.mode == 3) return 3;
@@ -1880,9 +1863,9 @@ int tc_launch(const TcPlan &plan, cudaStream_t st) {
     }
     return tc_launch_k<0, 8>(plan, st);
   }
-  if (plan.p.pool_sum && (plan.p.mode != 0 || (tc_epi_kind(plan.p) != 0 && tc_epi_kind(plan.p) != 2))) {
-    set_error("tc launch: sum-pool epilogue exists for the plain 16-column and generic epilogues only");
-    return 1;
+  if (plan.p.pool_sum) {
+    if (plan.p.mode != 0 || plan.p.stats || plan.p.split || plan.p.row_mul != 1) { set_error("tc launch: sum-pool epilogue not applicable"); return 1; }
+    return tc_launch_k<0, 9>(plan, st);
   }
   if (plan.p.mode != 2) {
     switch (tc_epi_kind(plan.p)) {
