@@ -20,7 +20,10 @@
 //     LOW-res tile and the epilogue scatters them (pixel shuffle) straight into the
 //     up-conv's plane range of the concat buffer;
 //   * accumulators sit in TMEM (double buffered), the epilogue applies the folded
-//     BatchNorm scale/shift + ReLU and stores one 16 B vector per pixel per plane.
+//     BatchNorm scale/shift + ReLU and stores one 16 B vector per pixel per plane;
+//   * the data gradient of that up-conv is a stride-2 3x3 conv over dz: the producer fetches the
+//     four pixel parities of dz as four sub-tiles through stride-2 5-D tensor maps, after which every
+//     tap is again a shifted descriptor on one of the sub-tiles (tc_make_geometry_s2d).
 //
 // Warp roles (512 threads, 1 CTA/SM, persistent over super-tiles):
 //   warp 0        : TMEM allocator; lane 0 = TMA producer (A halo tiles + packed weights)

@@ -194,6 +194,8 @@ enum { PH_CONV = 0, PH_BNF, PH_POOLF, PH_HEAD, PH_POOLB, PH_BNB, PH_WGRAD, PH_DG
 template <typename T>
 static int wgrad_dispatch(octseg_net *net, View<const T> a_in, View<const T> dz, int kh, int kw, int pt, int pl, int ups,
                           int cin, int cout, float *dW, float *db, cudaStream_t st) {
+  // kernel launches of the chosen path (gpu_launches in bench.py): tcgen05 = kernel + split-K reduce + two bias stages,
+  // row-walking kernel = 1, deep kernel = kernel + bias gradient, CUDA cores = 1
   if constexpr (sizeof(T) == 2) {
     if (!net->disable_tc) {
       TrainState *S = reinterpret_cast<TrainState *>(net->train);
@@ -202,12 +204,16 @@ static int wgrad_dispatch(octseg_net *net, View<const T> a_in, View<const T> dz,
       if (!tc_off && S && S->d_wg_scratch && wgrad_tc_applicable(kh, kw, cin, cout, ups, dz.h, dz.w) &&
           a_in.h == dz.h && a_in.w == dz.w && a_in.img_stride == (long long)a_in.planes * a_in.h * a_in.w * 8 &&
           dz.img_stride == (long long)dz.planes * dz.h * dz.w * 8 &&
-          (size_t)wgrad_tc_scratch_floats(kh, kw, cin, cout, dz.n, dz.h, dz.w) <= S->wg_scratch_floats)
+          (size_t)wgrad_tc_scratch_floats(kh, kw, cin, cout, dz.n, dz.h, dz.w) <= S->wg_scratch_floats) {
+        net->launches += 4;
         return launch_wgrad_tc(a_in, dz, kh, kw, pt, pl, cin, cout, dW, db, S->d_wg_scratch, S->wg_scratch_floats,
                                net->d_status, st);
+      }
+      net->launches += wgrad_rows_applicable(kh, kw, cin, ups) ? 1 : 2;
       return launch_wgrad_mma(a_in, dz, kh, kw, pt, pl, ups, cin, cout, dW, db, net->d_status, st);
     }
   }
+  ++net->launches;
   return launch_wgrad<T>(a_in, dz, kh, kw, pt, pl, ups, cin, cout, dW, db, st);
 }
 
@@ -434,6 +440,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
   const int nblk = (int)net->blocks.size();
   const BlockSpec &head = net->blocks.back();
   if (launch_step_advance(S->d_state, S->tc.learning_rate, S->tc.beta_1, S->tc.beta_2, st)) return 1;
+  ++net->launches;
   PhaseProf prof;
   prof.on = std::getenv("OCTSEG_TRAIN_PROFILE") != nullptr;
   prof.detail = prof.on && std::getenv("OCTSEG_TRAIN_PROFILE")[0] == '2';
@@ -473,12 +480,16 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
       if (launch_conv_first<T>(d_img, dtype, n, h, w, b.cin, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cout,
                                S->d_ones, P + net->params[b.p_bias].offset, 0, z, st))
         return 1;
+      ++net->launches;
     } else if (t.tc_fwd) {
       if (tc_launch(t.plan_fwd, st)) return 1;
       ++net->launches;
-    } else if (launch_conv_direct<T>(in, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout,
-                                     b.ups ? 1 : 0, S->d_ones, P + net->params[b.p_bias].offset, 0, z, st))
-      return 1;
+    } else {
+      if (launch_conv_direct<T>(in, P + net->params[b.p_kernel].offset, b.kh, b.kw, b.cin, b.cout, b.ups ? 1 : 0, S->d_ones,
+                                P + net->params[b.p_bias].offset, 0, z, st))
+        return 1;
+      ++net->launches;
+    }
     View<const T> zc = make_view((const T *)t.z, n, b.cout / 8, 0, b.cout / 8, t.h, t.w);
     prof.begin(PH_BNF);
     if (!t.stats_fused) {      // the tensor-core conv's epilogue has already accumulated sum(z), sum(z^2)
@@ -496,7 +507,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
                                     net->d_params + net->params[b.p_mean].offset, net->d_params + net->params[b.p_var].offset,
                                     t.mean, t.invstd, t.scale, t.shift, mask, a, po, st))
       return 1;
-    net->launches += 2;
+    ++net->launches;
   }
   // ------------------------------- loss + head backward -------------------------------
   const BlockSpec &last = net->blocks[nblk - 2];
@@ -545,11 +556,15 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
     const T *mask = (use_dropout && b.dropout_after) ? (const T *)S->mask : nullptr;
     const float *gamma = P + net->params[b.p_gamma].offset, *beta = P + net->params[b.p_beta].offset;
     prof.begin(PH_BNB);
-    if (!b.pool_after && launch_bn_bwd_reduce<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, sums_of(bi, 1), st)) return 1;
+    if (!b.pool_after) {
+      if (launch_bn_bwd_reduce<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, sums_of(bi, 1), st)) return 1;
+      ++net->launches;
+    }
     View<T> dz = make_view((T *)t.dz, n, f8, 0, f8, t.h, t.w);
     if (launch_bn_bwd_apply<T>(da, zc, t.mean, t.invstd, gamma, beta, mask, sums_of(bi, 1), (long long)n * t.h * t.w, dz,
                                G + net->params[b.p_gamma].offset, G + net->params[b.p_beta].offset, st))
       return 1;
+    ++net->launches;
     View<const T> dzc = make_view((const T *)t.dz, n, f8, 0, f8, t.h, t.w);
     View<const T> in = block_input<T>(net, b, n);
     const int pt = (b.kh - 1) / 2, pl = (b.kw - 1) / 2;
@@ -565,7 +580,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
                             G + net->params[b.p_bias].offset, wst))
         return 1;
       if (launch_stem_wgrad_extract(S->d_stem_tmp, taps, b.cin, b.cout, G + net->params[b.p_kernel].offset, wst)) return 1;
-      net->launches += 4;
+      ++net->launches;
       break;
     }
     if (b.ups && sizeof(T) == 2 && !net->disable_tc && !wgrad_rows_applicable(b.kh, b.kw, b.cin, 1)) {
@@ -573,6 +588,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
       // of a tensor the forward pass never stores) and run the plain 2x2 weight gradient on it
       View<T> up = make_view((T *)S->up_scratch, n, b.cin / 8, 0, b.cin / 8, t.h, t.w);
       if (launch_upsample2x<T>(in, up, wst)) return 1;
+      ++net->launches;
       View<const T> upc = make_view((const T *)S->up_scratch, n, b.cin / 8, 0, b.cin / 8, t.h, t.w);
       if (wgrad_dispatch<T>(net, upc, dzc, b.kh, b.kw, pt, pl, 0, b.cin, b.cout, G + net->params[b.p_kernel].offset,
                             G + net->params[b.p_bias].offset, wst))
@@ -649,7 +665,7 @@ static int train_step_t(octseg_net *net, const void *d_img, int dtype, const uin
       g_planes_total = b.cin / 8; g_plane0 = 0;
     }
     (void)pb;
-    net->launches += 5;
+    net->launches += t.tc_dgrad ? 1 : 2;        // data gradient: one tensor-core conv, or weight transform + direct conv
   }
   // ------------------------------- all-reduce + optimizer -------------------------------
   if (dual) {

@@ -8,6 +8,13 @@
 // every filter tap is just a different row address -- the same no-im2col idea as conv_tc.
 // CTAs are persistent over pixel tiles and keep their dW block in registers; one smem
 // reduction + one global atomic per element per CTA at the end.
+//
+// Kernels in this file, in the order launch_wgrad_mma tries them:
+//   wgrad_rows_kernel    Cin = 8 / 16 / 32 (3x3 and 2x2) and the 64-channel up-conv: warps walk the input rows of a band,
+//                        one ldmatrix per (dx, plane) pair feeds all kh taps; reads the up-conv's LOW-res input directly
+//   wgrad_deep_kernel    Cin >= 32 otherwise (64 -> 32 3x3 in the default net): MP x NP warp tiling of the output block
+//   wgrad_mma_tma_kernel / wgrad_mma_kernel   the first TMA-pipelined / staged kernels, kept for shapes the others refuse
+// (layers with Cin, Cout >= 64 go to the tcgen05 kernel in wgrad_tc.cu before this file is reached)
 #include <cuda_bf16.h>
 
 #include <algorithm>
