@@ -1413,6 +1413,23 @@ static double tc_folded_weight(const TcGeometry &g, const float *w, int s, int h
   return g.split ? val : (double)valf;
 }
 
+// s2d geometry (tc_make_geometry_s2d): weight of K half (s, hf), input channel kk of its plane, output column col, summed
+// from the up-conv's FORWARD kernel w[2][2][g.cout][g.cin]
+__host__ __device__ __forceinline__ float s2d_weight(const TcGeometry &g, const float *__restrict__ w, int s, int hf, int kk, int col) {
+  const int P = g.cin / 8, v = g.half_pl[s][hf], par = v / P, cz = (v - par * P) * 8 + kk;
+  const int py = par >> 1, px = par & 1;
+  const int a = py ? (g.half_ty[s][hf] ? 1 : -1) : 0, b = px ? (g.half_tx[s][hf] ? 1 : -1) : 0;
+  float val = 0.f;
+  for (int ky = 0; ky < 2; ++ky) {
+    if ((a == -1 && ky != 1) || (a == 1 && ky != 0)) continue;
+    for (int kx = 0; kx < 2; ++kx) {
+      if ((b == -1 && kx != 1) || (b == 1 && kx != 0)) continue;
+      val += w[(((long long)ky * 2 + kx) * g.cout + col) * g.cin + cz];
+    }
+  }
+  return val;
+}
+
 void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> *out, int fp16) {
   const size_t per_step = (size_t)2 * g.n_cols * 8;
   out->assign((size_t)g.n_tiles_n * g.cin_chunks * g.ksteps * per_step, 0);
@@ -1427,7 +1444,10 @@ void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> 
             if (col >= g.cols_valid) continue;
             for (int kk = 0; kk < 8; ++kk) {
               uint16_t bits;
-              if (!g.split) {
+              if (g.s2d) {
+                const float val = s2d_weight(g, w, s, hf, kk, col);
+                bits = fp16 ? f2h(val) : f2bf(val);
+              } else if (!g.split) {
                 const float val = (float)tc_folded_weight(g, w, s, hf, plane * 8 + kk, col);
                 bits = fp16 ? f2h(val) : f2bf(val);
               } else {
@@ -1448,23 +1468,6 @@ void tc_pack_weights(const TcGeometry &g, const float *w, std::vector<uint16_t> 
 
 // Device-side twin of tc_pack_weights (training: the weights change every step).
 // transposed=1 packs the data-gradient operator: W'[a][b][ci'][co'] = w[kh-1-a][kw-1-b][co'][ci']
-// s2d geometry (tc_make_geometry_s2d): weight of K half (s, hf), input channel kk of its plane, output column col, summed
-// from the up-conv's FORWARD kernel w[2][2][g.cout][g.cin]
-__device__ __forceinline__ float s2d_weight(const TcGeometry &g, const float *__restrict__ w, int s, int hf, int kk, int col) {
-  const int P = g.cin / 8, v = g.half_pl[s][hf], par = v / P, cz = (v - par * P) * 8 + kk;
-  const int py = par >> 1, px = par & 1;
-  const int a = py ? (g.half_ty[s][hf] ? 1 : -1) : 0, b = px ? (g.half_tx[s][hf] ? 1 : -1) : 0;
-  float val = 0.f;
-  for (int ky = 0; ky < 2; ++ky) {
-    if ((a == -1 && ky != 1) || (a == 1 && ky != 0)) continue;
-    for (int kx = 0; kx < 2; ++kx) {
-      if ((b == -1 && kx != 1) || (b == 1 && kx != 0)) continue;
-      val += w[(((long long)ky * 2 + kx) * g.cout + col) * g.cin + cz];
-    }
-  }
-  return val;
-}
-
 // where w is the forward kernel [kh][kw][g.cout][g.cin] (g describes the dgrad conv).
 __global__ void tc_pack_kernel(TcGeometry g, const float *__restrict__ w, int transposed,
                                __nv_bfloat16 *__restrict__ out, long long total) {

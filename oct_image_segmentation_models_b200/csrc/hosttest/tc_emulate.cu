@@ -300,8 +300,89 @@ static int run_split(int kh, int kw, int cin, int cout, int ups, int n, int h, i
   return ok ? 0 : 1;
 }
 
+// Data gradient of the up-conv on the low-res grid (tc_make_geometry_s2d): the stage holds the four pixel parities of the
+// high-res dz as sub-tiles [parity][plane][row][px] (what the four stride-2 tensor maps deliver), every K half is a tap-shifted
+// read of one sub-tile.  Checked against the adjoint of z = conv2x2(upsample2x(a)) written out directly.
+static int run_s2d(int cz, int cout, int n, int h, int w) {      // (h, w) = low-res grid
+  TcGeometry g;
+  if (tc_make_geometry_s2d(cz, cout, &g)) { printf("s2d geometry failed\n"); return 1; }
+  TcConvParams p; size_t smem;
+  if (tc_fill_params(g, n, h, w, &p, &smem)) return 1;
+  const int H = 2 * h, W = 2 * w, P = cz / 8;
+  std::mt19937 rng(3);
+  std::uniform_real_distribution<float> U(-1, 1);
+  std::vector<float> wt((size_t)4 * cout * cz);                 // forward kernel [2][2][cin_up = cout][cout_up = cz]
+  for (auto &v : wt) v = U(rng);
+  std::vector<uint16_t> dz((size_t)n * cz * H * W);              // blocked [n][P][H][W][8]
+  for (auto &v : dz) v = f2bf(U(rng));
+  std::vector<uint16_t> wp;
+  tc_pack_weights(g, wt.data(), &wp);
+  std::vector<double> out((size_t)n * h * w * cout, 1e30), ref((size_t)n * h * w * cout, 0);
+  // reference: d(a)[Y][X][ci] = sum over (y, x, ky, kx) with (y + ky) >> 1 == Y, (x + kx) >> 1 == X of W[ky][kx][ci][co] dz[y][x][co]
+  for (int b = 0; b < n; ++b) for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) for (int ky = 0; ky < 2; ++ky) for (int kx = 0; kx < 2; ++kx) {
+    const int Y = (y + ky) >> 1, X = (x + kx) >> 1;
+    if (Y >= h || X >= w) continue;                             // the forward read zero padding there
+    for (int co = 0; co < cz; ++co) {
+      const double d = bf2f(dz[((((size_t)b * P + co / 8) * H + y) * W + x) * 8 + (co & 7)]);
+      for (int ci = 0; ci < cout; ++ci)
+        ref[(((size_t)b * h + Y) * w + X) * cout + ci] += d * bf2f(f2bf(wt[(((size_t)ky * 2 + kx) * cout + ci) * cz + co]));
+    }
+  }
+  std::vector<uint8_t> stage(p.a_stage_bytes + 4096, 0xFF);
+  if (p.a_tx_bytes != (uint32_t)(4 * P * p.box_w * p.box_h * 16)) { printf("s2d: a_tx_bytes\n"); return 1; }
+  for (int tile = 0; tile < p.num_tiles; ++tile) {
+    int n_tile = tile % p.n_tiles_n, t = tile / p.n_tiles_n;
+    int tx = t % p.tiles_x; t /= p.tiles_x; int ty = t % p.tiles_y; int img = t / p.tiles_y;
+    const int MT = p.mt_x * p.mt_y;
+    std::vector<double> D((size_t)MT * 128 * p.n_cols, 0.0);
+    for (int par = 0; par < 4; ++par) {                         // the four TMA loads: parity map = base + (py * W + px) pixels
+      const int py = par >> 1, px = par & 1;
+      uint16_t *s16 = reinterpret_cast<uint16_t *>(stage.data() + (size_t)par * p.s2d_part_bytes);
+      for (int pc = 0; pc < P; ++pc) for (int r = 0; r < p.box_h; ++r) for (int c = 0; c < p.box_w; ++c) for (int e = 0; e < 8; ++e) {
+        const int X = tx * p.mt_x * kTcTileW - p.pad_x + c, Y = ty * p.mt_y * kTcTileH - p.pad_y + r;
+        uint16_t v = 0;
+        if (X >= 0 && X < w && Y >= 0 && Y < h) v = dz[((((size_t)img * P + pc) * H + 2 * Y + py) * W + 2 * X + px) * 8 + e];
+        s16[(((size_t)pc * p.box_h + r) * p.box_w + c) * 8 + e] = v;
+      }
+    }
+    for (int ks = 0; ks < p.ksteps; ++ks) {
+      const uint16_t *bbase = wp.data() + ((size_t)n_tile * p.ksteps + ks) * 2 * p.n_cols * 8;
+      for (int t2 = 0; t2 < MT; ++t2) for (int m = 0; m < 128; ++m) for (int k = 0; k < 16; ++k) {
+        const int iy = t2 / p.mt_x, ix = t2 % p.mt_x;
+        size_t aoff = p.a_off[ks] + (size_t)iy * kTcTileH * p.box_w * 16 + (size_t)ix * 128 + (size_t)(k / 8) * p.a_lbo[ks] +
+                      (size_t)(m / 8) * p.box_w * 16 + (m % 8) * 16 + (k % 8) * 2;
+        if (aoff + 2 > p.a_stage_bytes) { printf("s2d A read out of stage\n"); return 1; }
+        const float av = bf2f(*reinterpret_cast<uint16_t *>(stage.data() + aoff));
+        for (int nn = 0; nn < p.n_cols; ++nn) {
+          size_t boff = (size_t)(k / 8) * p.n_cols * 16 + (size_t)(nn / 8) * 128 + (nn % 8) * 16 + (k % 8) * 2;
+          D[((size_t)t2 * 128 + m) * p.n_cols + nn] += (double)av * bf2f(bbase[boff / 2]);
+        }
+      }
+    }
+    for (int t2 = 0; t2 < MT; ++t2) for (int m = 0; m < 128; ++m) {
+      const int iy = t2 / p.mt_x, ix = t2 % p.mt_x;
+      const int y = (ty * p.mt_y + iy) * kTcTileH + (m >> 3), xx = (tx * p.mt_x + ix) * kTcTileW + (m & 7);
+      if (y >= h || xx >= w) continue;
+      for (int j = 0; j < p.n_cols; ++j) {
+        const int col = n_tile * p.n_cols + j;
+        if (col >= p.cols_valid) break;
+        out[(((size_t)img * h + y) * w + xx) * cout + col] = D[((size_t)t2 * 128 + m) * p.n_cols + j];
+      }
+    }
+  }
+  double maxerr = 0, maxref = 0;
+  for (size_t i = 0; i < ref.size(); ++i) { maxerr = std::max(maxerr, std::fabs(out[i] - ref[i])); maxref = std::max(maxref, std::fabs(ref[i])); }
+  printf("s2d cz %d cout %d %dx%dx%d: mt %dx%d ksteps %d n_cols %d a_st %d part %u | max err %.4g (ref max %.3g) %s\n", cz, cout, n, h, w,
+         p.mt_x, p.mt_y, p.ksteps, p.n_cols, p.a_stages, p.s2d_part_bytes, maxerr, maxref, maxerr < 0.02 * maxref ? "OK" : "MISMATCH");
+  return maxerr < 0.02 * maxref ? 0 : 1;
+}
+
 int main() {
   int bad = 0;
+  bad += run_s2d(8, 16, 2, 32, 24);       // up3 of the default net: 9 single-plane halves (one dummy)
+  bad += run_s2d(8, 16, 3, 64, 64);       // super-tiles
+  bad += run_s2d(16, 32, 1, 20, 12);      // plane pairs, ragged tiles
+  bad += run_s2d(32, 64, 1, 16, 16);
   bad += run_split(3, 3, 8, 8, 0, 2, 32, 24);
   bad += run_split(3, 3, 16, 8, 0, 1, 20, 12);
   bad += run_split(3, 3, 8, 16, 0, 40, 64, 64);
