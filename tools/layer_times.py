@@ -20,6 +20,8 @@ eng = UNetEngine(precision="bf16", **cfg)
 eng.set_weights(synthetic_weights(seed=1, **cfg))
 blocks = unet_blocks(**cfg)
 N, H, W = (64, 512, 512) if cfg.get("start_neurons", 8) == 8 else (8, 1024, 512)
+if os.environ.get("OCTSEG_LT_SHAPE"):            # e.g. OCTSEG_LT_SHAPE=32,512,256: the per-GPU batch of the 8-GPU training run
+    N, H, W = (int(v) for v in os.environ["OCTSEG_LT_SHAPE"].split(","))
 rng = np.random.default_rng(0)
 sel = [int(a) for a in sys.argv[2:]] if len(sys.argv) > 2 else list(range(1, len(blocks) - 1))
 for idx in sel:
