@@ -868,8 +868,8 @@ int launch_pool_bwd_add_bnred(View<const T> a, View<const T> d_pooled, View<cons
 }
 
 // ---------------------------------------------------------------------------------
-// nearest x2 up-sampling (materialised only for the up-conv's weight gradient) and its adjoint,
-// the 2x2 sum-pool (gradient of the up-sampling in front of the decoder's 2x2 conv)
+// nearest x2 up-sampling, materialised only for the weight gradient of the >= 128-channel up-conv (tcgen05 kernel); the
+// narrower up-convs read the low-res tensor, and the adjoint (2x2 sum-pool) lives in the data-gradient conv
 // ---------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_kernel(View<const T> in, View<T> out) {
@@ -894,30 +894,6 @@ template <typename T>
 int launch_upsample2x(View<const T> in, View<T> out, cudaStream_t st) {
   dim3 grid(std::max(1, std::min((in.h * in.w + 255) / 256, 64)), in.planes, in.n);
   upsample2x_kernel<T><<<grid, 256, 0, st>>>(in, out);
-  OCTSEG_CUDA(cudaGetLastError());
-  return 0;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) sumpool2x_kernel(View<const T> in, View<T> out) {
-  const int pl = blockIdx.y, b = blockIdx.z;
-  const int h = out.h, w = out.w;
-  const T *ib = in.ptr + b * in.img_stride + (long long)pl * (4LL * h * w) * 8;
-  T *ob = out.ptr + b * out.img_stride + (long long)pl * h * w * 8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h * w; i += gridDim.x * blockDim.x) {
-    const int x = i % w, y = i / w;
-    const T *p = ib + ((long long)(2 * y) * (2 * w) + 2 * x) * 8;
-    const Vec8f a = load8(p), c = load8(p + 8), d = load8(p + (long long)2 * w * 8), e = load8(p + (long long)2 * w * 8 + 8);
-    Vec8f o;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o.v[k] = (a.v[k] + c.v[k]) + (d.v[k] + e.v[k]);
-    store8(ob + (long long)i * 8, o);
-  }
-}
-template <typename T>
-int launch_sumpool2x(View<const T> in, View<T> out, cudaStream_t st) {
-  dim3 grid(std::max(1, std::min((out.h * out.w + 255) / 256, 64)), out.planes, out.n);
-  sumpool2x_kernel<T><<<grid, 256, 0, st>>>(in, out);
   OCTSEG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1162,8 +1138,7 @@ int launch_adam(float *p, const float *g, float *m, float *v, long long n, const
   template int launch_wgrad<T>(View<const T>, View<const T>, int, int, int, int, int, int, int, float *,    \
                                float *, cudaStream_t);                                                      \
   template int launch_image_to_blocked<T>(const void *, int, int, int, int, int, T *, cudaStream_t);         \
-  template int launch_upsample2x<T>(View<const T>, View<T>, cudaStream_t);                                  \
-  template int launch_sumpool2x<T>(View<const T>, View<T>, cudaStream_t);
+  template int launch_upsample2x<T>(View<const T>, View<T>, cudaStream_t);
 INST(float)
 INST(__nv_bfloat16)
 

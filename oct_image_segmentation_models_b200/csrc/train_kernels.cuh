@@ -68,11 +68,9 @@ int launch_pool_bwd_add_bnred(View<const T> a, View<const T> d_pooled, View<cons
                               const float *mean, const float *invstd, const float *gamma, const float *beta, double *sums,
                               cudaStream_t st);
 
-// nearest x2 up-sampling into a dense tensor, and its adjoint (2x2 sum-pool)
+// nearest x2 up-sampling into a dense tensor (weight gradient of the wide up-conv only)
 template <typename T>
 int launch_upsample2x(View<const T> in, View<T> out, cudaStream_t st);
-template <typename T>
-int launch_sumpool2x(View<const T> in, View<T> out, cudaStream_t st);
 
 // weight gradient (accumulates with atomics into zero-initialised dW [kh][kw][cin][cout], db [cout])
 template <typename T>
