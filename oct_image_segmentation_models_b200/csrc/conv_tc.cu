@@ -1773,7 +1773,9 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r5 != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (s2d) failed: " + std::to_string((int)r5)); return 1; }
     }
-    if (!plan->dev_maps) OCTSEG_CUDA(cudaMalloc(&plan->dev_maps, sizeof(maps)));
+    // re-planning (new batch / image size): kernels of the previous step may still be queued with the old maps
+    if (plan->dev_maps) OCTSEG_CUDA(cudaDeviceSynchronize());
+    else OCTSEG_CUDA(cudaMalloc(&plan->dev_maps, sizeof(maps)));
     OCTSEG_CUDA(cudaMemcpy(plan->dev_maps, maps, sizeof(maps), cudaMemcpyHostToDevice));
     p.s2d_maps = reinterpret_cast<const CUtensorMap *>(plan->dev_maps);
   }

@@ -277,3 +277,33 @@ def test_wide_net_bf16_train_step_runs_on_tcgen05_and_tracks_oracle():
     b = np.concatenate([grads_ref[i].numpy().ravel() for i in keep])
     cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
     assert cos >= 0.97, cos
+
+
+def test_bf16_step_after_a_batch_size_change_equals_a_fresh_handle():
+    """The last batch of an epoch is smaller: every tensor-core plan (incl. the strided parity tensor maps of the low-res
+    up-conv data gradient, which live in device memory) is rebuilt for the new batch size while the previous step may still
+    be queued.  With a zero learning rate the weights stay put, so the step after the change must give the loss and the
+    gradients of a handle that has only ever seen the small batch."""
+    from oct_image_segmentation_models_b200.engine import UNetEngine
+    cfg = dict(input_channels=1, num_classes=4)
+    weights = synthetic_weights(seed=5, random_bn_stats=True, **cfg)
+    big_x, big_y = synthetic_batch(41, 6, 64, 64, 4)
+    small_x, small_y = synthetic_batch(42, 2, 64, 64, 4)
+    out = []
+    for warm in (True, False):
+        eng = UNetEngine(precision="bf16", **cfg)
+        eng.set_weights(weights)
+        eng.train_begin(CW, learning_rate=0.0, dropout_rate=0.0, global_batch=2)
+        if warm:
+            for _ in range(3):
+                eng.train_step(big_x, big_y)          # the third call replays the captured graph of the big batch
+        loss = eng.train_step(small_x, small_y)
+        out.append((loss, eng.get_grads()))
+        eng.close()
+    (la, ga), (lb, gb) = out
+    assert abs(la - lb) <= 1e-4 * max(1.0, abs(lb)), (la, lb)
+    for a, b in zip(ga, gb):
+        if a is None:
+            continue
+        scale = max(float(np.abs(b).max()), 1e-6)
+        assert float(np.abs(a - b).max()) <= 2e-3 * scale + 1e-6      # atomics order only
