@@ -1773,9 +1773,11 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r5 != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (s2d) failed: " + std::to_string((int)r5)); return 1; }
     }
-    // re-planning (new batch / image size): kernels of the previous step may still be queued with the old maps
-    if (plan->dev_maps) OCTSEG_CUDA(cudaDeviceSynchronize());
-    else OCTSEG_CUDA(cudaMalloc(&plan->dev_maps, sizeof(maps)));
+    // Re-planning (new batch / image size): kernels of the previous step may still be queued with the old maps, and a tensor
+    // map that is rewritten in place in global memory needs a tensormap-proxy fence in every CTA that uses it afterwards.
+    // A fresh buffer per plan avoids both: the old one stays untouched until the plan is released.
+    if (plan->dev_maps) { plan->retired.push_back(plan->dev_maps); plan->dev_maps = nullptr; }
+    OCTSEG_CUDA(cudaMalloc(&plan->dev_maps, sizeof(maps)));
     OCTSEG_CUDA(cudaMemcpy(plan->dev_maps, maps, sizeof(maps), cudaMemcpyHostToDevice));
     p.s2d_maps = reinterpret_cast<const CUtensorMap *>(plan->dev_maps);
   }
@@ -1810,6 +1812,8 @@ int tc_make_plan(const TcGeometry &g, const __nv_bfloat16 *in, int n, int h, int
 
 void tc_release_plan(TcPlan *plan) {
   if (plan->dev_maps) cudaFree(plan->dev_maps);
+  for (void *q : plan->retired) cudaFree(q);
+  plan->retired.clear();
   plan->dev_maps = nullptr;
   plan->valid = false;
 }

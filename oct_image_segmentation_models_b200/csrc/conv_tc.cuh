@@ -77,6 +77,8 @@ struct TcPlan {
   size_t smem_bytes = 0;
   int grid = 0;
   void *dev_maps = nullptr;    // s2d plans: the four parity tensor maps in device memory (owned; tc_release_plan)
+  std::vector<void *> retired; // map buffers of earlier shapes: kept (512 B each) so that a re-plan never rewrites an address the
+                               // GPU may still hold a cached descriptor of, or that queued kernels still read
 };
 void tc_release_plan(TcPlan *plan);
 
